@@ -1,0 +1,234 @@
+"""Host-side mirror of the reference's Model/model.py for the progressive inference path.
+
+Same public names, constructor arguments, state_dict keys and (under a fixed torch seed) the same
+random initialisation as the reference (Model/model.py: UNetModel :190-310, GaussianDiffusion
+:376-642, cosine_beta_schedule :366-372), but every forward computation is executed by
+libipdm_b200.so:
+  * `UNetModel` only *holds* parameters (so checkpoints `proj_model-N` / `img_model-N` load
+    unchanged); `forward` hands x and t to the tcgen05 UNet plan.
+  * `GaussianDiffusion.guided_reverse_process` hands the whole iteration structure to
+    `ipdm_guided_process` (one stream, no host round trips); the extra keyword `noise=` carries a
+    caller-supplied tape [count,B,1,H,W] in the reference's randn_like order, `seed=` keys the
+    in-kernel Philox generator otherwise.
+Out of scope here (reference lines): ddim_sample / sparse_guided_reverse_process
+:654-759, train_losses :645-652, Yeo-Johnson :762-807, adaptive t_start=None :582-613.
+"""
+import math
+from copy import copy
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from _ipdm_boot import engine as _eng
+from Dataset.npz_data_loader import miu2pixel  # noqa: F401  (re-export, as the reference does)
+
+
+def _group_count(channels):
+    if channels % 32 == 0:
+        return 32
+    if channels < 32:
+        return channels
+    divisors = []
+    for i in range(1, int(math.sqrt(channels)) + 1):
+        if channels % i == 0:
+            divisors.append(i)
+            if channels // i != i:
+                divisors.append(channels // i)
+    divisors = np.array(divisors)
+    return int(divisors[np.argmin((divisors - 32) ** 2)])
+
+
+def norm_layer(channels):
+    return nn.GroupNorm(_group_count(channels), channels)
+
+
+def timestep_embedding(timesteps, dim, max_period=10000, dtype=torch.float32):
+    half = dim // 2
+    freqs = torch.exp(-math.log(max_period) * torch.arange(start=0, end=half) / half).type(dtype).to(timesteps.device)
+    args = timesteps[:, None] * freqs[None]
+    emb = torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
+    if dim % 2:
+        emb = torch.cat([emb, torch.zeros_like(emb[:, :1])], dim=-1)
+    return emb
+
+
+class TimestepBlock(nn.Module):
+    pass
+
+
+class TimestepEmbedSequential(nn.Sequential, TimestepBlock):
+    """Parameter container only; execution order lives in the CUDA plan."""
+
+
+def _conv_norm_act(cin, cout):
+    return nn.Sequential(norm_layer(cin), nn.SiLU(), nn.Conv2d(cin, cout, kernel_size=3, padding=1))
+
+
+class ResidualBlock(TimestepBlock):
+    def __init__(self, in_channels, out_channels, time_channels, dropout):
+        super().__init__()
+        self.conv1 = _conv_norm_act(in_channels, out_channels)
+        self.time_emb = nn.Sequential(nn.SiLU(), nn.Linear(time_channels, out_channels))
+        self.conv2 = _conv_norm_act(out_channels, out_channels)
+        self.shortcut = nn.Conv2d(in_channels, out_channels, kernel_size=1) if in_channels != out_channels else nn.Identity()
+
+
+class AttentionBlock(nn.Module):
+    def __init__(self, channels, num_heads=1):
+        super().__init__()
+        assert channels % num_heads == 0
+        self.num_heads = num_heads
+        self.norm = norm_layer(channels)
+        self.qkv = nn.Conv2d(channels, channels * 3, kernel_size=1, bias=False)
+        self.proj = nn.Conv2d(channels, channels, kernel_size=1)
+
+
+class Upsample(nn.Module):
+    def __init__(self, channels, use_conv):
+        super().__init__()
+        if not use_conv:
+            raise NotImplementedError("conv_resample=False is not used by any shipped config")
+        self.use_conv = use_conv
+        self.conv = nn.Conv2d(channels, channels, kernel_size=3, padding=1)
+
+
+class Downsample(nn.Module):
+    def __init__(self, channels, use_conv):
+        super().__init__()
+        if not use_conv:
+            raise NotImplementedError("conv_resample=False is not used by any shipped config")
+        self.use_conv = use_conv
+        self.op = nn.Conv2d(channels, channels, kernel_size=3, stride=2, padding=1)
+
+
+class UNetModel(nn.Module):
+    def __init__(self, in_channels=3, model_channels=128, out_channels=3, num_res_blocks=2, attention_resolutions=(8, 16),
+                 dropout=0, channel_mult=(1, 2, 2, 2), conv_resample=True, num_heads=4, pre_downsample_times=1):
+        super().__init__()
+        self.in_channels, self.model_channels, self.out_channels = in_channels, model_channels, out_channels
+        self.num_res_blocks, self.attention_resolutions, self.dropout = num_res_blocks, attention_resolutions, dropout
+        self.channel_mult, self.conv_resample, self.num_heads = channel_mult, conv_resample, num_heads
+        self.precision = "tf32"
+        self._handle = None
+        self._handle_key = None
+
+        tdim = model_channels * 4
+        self.time_embed = nn.Sequential(nn.Linear(model_channels, tdim), nn.SiLU(), nn.Linear(tdim, tdim))
+        width = lambda m: int(m * model_channels)
+        ch = width(channel_mult[0])
+        self.down_blocks = nn.ModuleList([TimestepEmbedSequential(nn.Conv2d(in_channels, ch, kernel_size=3, padding=1))])
+        skip_chans, ds, mults = [ch], 1, list(channel_mult[1:])
+        for level, mult in enumerate(mults):
+            for _ in range(num_res_blocks):
+                parts = [ResidualBlock(ch, width(mult), tdim, dropout)]
+                ch = width(mult)
+                if ds in attention_resolutions:
+                    parts.append(AttentionBlock(ch, num_heads=num_heads))
+                self.down_blocks.append(TimestepEmbedSequential(*parts))
+                skip_chans.append(ch)
+            if level != len(mults) - 1:
+                self.down_blocks.append(TimestepEmbedSequential(Downsample(ch, conv_resample)))
+                skip_chans.append(ch)
+                ds *= 2
+        self.middle_block = TimestepEmbedSequential(ResidualBlock(ch, ch, tdim, dropout), AttentionBlock(ch, num_heads=num_heads),
+                                                    ResidualBlock(ch, ch, tdim, dropout))
+        self.up_blocks = nn.ModuleList([])
+        for level, mult in list(enumerate(mults))[::-1]:
+            for i in range(num_res_blocks + 1):
+                parts = [ResidualBlock(ch + skip_chans.pop(), width(mult), tdim, dropout)]
+                ch = width(mult)
+                if ds in attention_resolutions:
+                    parts.append(AttentionBlock(ch, num_heads=num_heads))
+                if level and i == num_res_blocks:
+                    parts.append(Upsample(ch, conv_resample))
+                    ds //= 2
+                self.up_blocks.append(TimestepEmbedSequential(*parts))
+        self.out = _conv_norm_act(ch, out_channels)
+
+    # -- CUDA plan ---------------------------------------------------------------------------
+    def set_precision(self, precision):
+        if precision != self.precision:
+            self.precision, self._handle = precision, None
+
+    def _weights_key(self):
+        return (self.precision,) + tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def cuda_handle(self):
+        """Packs the current parameters for the CUDA plan (re-packed if any parameter changed)."""
+        key = self._weights_key()
+        if self._handle is None or key != self._handle_key:
+            cfg = _eng.unet_config(self.in_channels, self.model_channels, self.out_channels, self.num_res_blocks,
+                                   list(self.attention_resolutions), list(self.channel_mult), self.num_heads, self.precision)
+            self._handle = _eng.UNetHandle(cfg, self.state_dict())
+            self._handle_key = key
+        return self._handle
+
+    def forward(self, x, timesteps):
+        """x [N,C,H,W] on the GPU; `timesteps` must hold one value for the whole batch (model.py:564)."""
+        t = timesteps.reshape(-1)
+        t0 = int(t[0])
+        if t.numel() > 1 and not bool((t == t0).all()):
+            raise NotImplementedError("per-sample timesteps are a training feature; the inference path shares t across the batch")
+        return self.cuda_handle().forward(x.contiguous().float(), t0)
+
+
+# ---------------------------------------------------------------------------------------------
+def cosine_beta_schedule(timesteps, s=0.008, schedule_power=1):
+    if s != 0.008:
+        raise NotImplementedError("only the reference offset s=0.008 is built into the schedule kernel")
+    return torch.from_numpy(_eng.cosine_beta_schedule(timesteps, schedule_power))
+
+
+class GaussianDiffusion:
+    def __init__(self, timesteps=1000, beta_schedule='linear', schedule_power=1):
+        if beta_schedule != 'cosine':
+            raise NotImplementedError("the progressive path uses beta_schedule='cosine' (train_test_utils.py:221-245)")
+        self.timesteps, self.schedule_power = timesteps, schedule_power
+        self.betas = cosine_beta_schedule(timesteps, schedule_power=schedule_power)
+        self.alphas = 1. - self.betas
+        self.alphas_cumprod = torch.cumprod(self.alphas, axis=0)
+        self.alphas_cumprod_prev = torch.nn.functional.pad(self.alphas_cumprod[:-1], (1, 0), value=1.)
+        self.sqrt_alphas_cumprod = torch.sqrt(self.alphas_cumprod)
+        self.sqrt_one_minus_alphas_cumprod = torch.sqrt(1.0 - self.alphas_cumprod)
+        self.log_one_minus_alphas_cumprod = torch.log(1.0 - self.alphas_cumprod)
+        self.sqrt_recip_alphas_cumprod = torch.sqrt(1.0 / self.alphas_cumprod)
+        self.sqrt_recipm1_alphas_cumprod = torch.sqrt(1.0 / self.alphas_cumprod - 1)
+        self.posterior_variance = self.betas * (1.0 - self.alphas_cumprod_prev) / (1.0 - self.alphas_cumprod)
+        self.posterior_log_variance_clipped = torch.log(self.posterior_variance.clamp(min=1e-20))
+        self.posterior_mean_coef1 = self.betas * torch.sqrt(self.alphas_cumprod_prev) / (1.0 - self.alphas_cumprod)
+        self.posterior_mean_coef2 = (1.0 - self.alphas_cumprod_prev) * torch.sqrt(self.alphas) / (1.0 - self.alphas_cumprod)
+
+    def _extract(self, a, t, x_shape):
+        out = a.to(t.device).gather(0, t).float()
+        return out.reshape(t.shape[0], *((1,) * (len(x_shape) - 1)))
+
+    def q_sample(self, x_start, t, noise=None, seed=0):
+        ts = int(t.reshape(-1)[0])
+        return _eng.q_sample(x_start.contiguous(), float(self.sqrt_alphas_cumprod[ts].float()),
+                             float(self.sqrt_one_minus_alphas_cumprod[ts].float()), noise=noise, seed=seed)
+
+    @torch.no_grad()
+    def guided_reverse_process(self, model, img, t_start=None, clip=True, lambda_ratio=1, eta=0.5, save_states=False,
+                               mode="img", constant_guidance=None, noise=None, seed=0, **kwargs):
+        if kwargs.get("only_convertor", False):
+            return [img], None, None
+        if kwargs.get("normal", False):
+            raise NotImplementedError("normal=True (Yeo-Johnson) is off in every shipped config and not on the B200 path")
+        if save_states:
+            raise NotImplementedError("save_states=True copies every reverse step to the host; not on the B200 path")
+        ks = kwargs.get("kernel_size_proj" if mode == "proj" else "kernel_size_img", 4)
+        amp = kwargs.get("amplitude_proj" if mode == "proj" else "amplitude_img", 7.0)
+        p = _eng.guided_params(mode, copy(t_start), clip, lambda_ratio, eta, constant_guidance, ks, amp, self.schedule_power,
+                               self.timesteps, seed)
+        img = img.contiguous().float()
+        ldct = kwargs.get("ldct", None)
+        out = _eng.guided_process(model.cuda_handle(), p, img, None if ldct is None else ldct.contiguous().float(), noise)
+        return [out[k] for k in range(out.shape[0])], [], None
+
+    def sparse_guided_reverse_process(self, *a, **k):
+        raise NotImplementedError("sample_method='sparse' (DDIM, model.py:654-759) is outside the B200 hot path (SURVEY N3)")
+
+
+def yeo_johnson_transform(img_tensor):
+    raise NotImplementedError("normal=True (Yeo-Johnson, model.py:762-807) is off in every shipped config")

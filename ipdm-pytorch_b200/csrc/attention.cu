@@ -1,0 +1,226 @@
+// Flash-style self-attention on tcgen05/TMEM for the UNet's AttentionBlock (Model/model.py:135-155):
+//   attn = softmax((q*s)(k*s)^T), s = d^-1/4 ;  h = attn . v         heads = 4, d = 64, T up to 7125
+// The [T,T] score matrix is never materialised (the reference allocates 812 MB per slice at T = 7125).
+//
+// Inputs come straight from the qkv 1x1 GEMM epilogue (conv_tc.cu): q and k live in the NHWC qkv tensor
+// [B][T][3C] (head h: q at channel 3dh, k at 3dh+d, the reference's reshape(B*heads, 3d, T).chunk(3)),
+// v is stored transposed [B][heads][d][t_pad] so that P.V^T is a K-major UMMA like everything else.
+//
+// CTA = 128 queries of one (slice, head); 64-key blocks stream through a 2-stage TMA ring.
+//   warp 4 lane*: TMA producer            warp 5 lane*: MMA issuer (+ TMEM alloc)
+//   warps 0-3  : one query row per thread (row == TMEM lane): online softmax in registers,
+//                P written to shared memory in the 128B-swizzled K-major layout UMMA expects,
+//                O accumulated in registers (O_blk = P.V is a fresh TMEM tile per key block).
+// S = QK^T: kind::tf32 M=128 N=64 K=8 x8;  O_blk = P V: M=128 N=64 K=8 x8.  Out-of-range keys are
+// zero-filled by TMA and masked to -inf; out-of-range query rows are computed and dropped.
+#include "common.cuh"
+#include "tc.cuh"
+#include "unet_ops.cuh"
+
+namespace ipdm {
+
+constexpr int AT_BQ = 128, AT_BKV = 64, AT_D = 64;
+constexpr int AT_THREADS = 192;
+constexpr int AT_Q_BYTES = 2 * AT_BQ * 128;          // 2 channel chunks x [128 rows x 128 B]
+constexpr int AT_K_BYTES = 2 * AT_BKV * 128;         // 2 channel chunks x [64 keys x 128 B]
+constexpr int AT_V_BYTES = 2 * AT_D * 128;           // 2 key chunks x [64 d-rows x 128 B]
+constexpr int AT_P_BYTES = 2 * AT_BQ * 128;          // 2 key chunks x [128 rows x 128 B]
+constexpr int AT_STAGE = AT_K_BYTES + AT_V_BYTES;
+constexpr int AT_OFF_KV = AT_Q_BYTES;
+constexpr int AT_OFF_P = AT_OFF_KV + 2 * AT_STAGE;
+constexpr int AT_OFF_BAR = AT_OFF_P + AT_P_BYTES;
+constexpr int AT_SMEM = AT_OFF_BAR + 16 * 8 + 1024;
+
+__global__ void __launch_bounds__(AT_THREADS)
+attention_kernel(const __grid_constant__ AttentionParams P) {
+    extern __shared__ uint8_t at_smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)at_smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = (uint64_t*)(smem + AT_OFF_BAR);
+    uint64_t* q_full = bars;            // 1
+    uint64_t* kv_full = bars + 1;       // 2
+    uint64_t* kv_empty = bars + 3;      // 2
+    uint64_t* s_full = bars + 5;
+    uint64_t* p_full = bars + 6;        // 128 arrivals
+    uint64_t* o_full = bars + 7;
+    uint32_t* tmem_slot = (uint32_t*)(bars + 8);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * AT_BQ, head = blockIdx.y, b = blockIdx.z;
+    const int nkv = (P.T + AT_BKV - 1) / AT_BKV;
+
+    if (threadIdx.x == 0) {
+        tc::mbar_init(q_full, 1);
+        for (int i = 0; i < 2; ++i) { tc::mbar_init(&kv_full[i], 1); tc::mbar_init(&kv_empty[i], 1); }
+        tc::mbar_init(s_full, 1); tc::mbar_init(p_full, 128); tc::mbar_init(o_full, 1);
+        tc::fence_barrier_init();
+    }
+    if (warp == 5) tc::tmem_alloc(tmem_slot, 128);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 64;
+
+    if (warp == 4) {
+        if (tc::elect_one()) {
+            tc::mbar_expect_tx(q_full, AT_Q_BYTES);
+            for (int c = 0; c < 2; ++c)
+                tc::tma_load_3d(smem + c * (AT_BQ * 128), &P.mapQ, q_full, head * 3 * AT_D + c * 32, q0, b);
+            for (int j = 0; j < nkv; ++j) {
+                const int s = j & 1;
+                tc::mbar_wait(&kv_empty[s], ((uint32_t)(j >> 1) & 1u) ^ 1u);
+                tc::mbar_expect_tx(&kv_full[s], AT_STAGE);
+                uint8_t* sk = smem + AT_OFF_KV + s * AT_STAGE;
+                uint8_t* sv = sk + AT_K_BYTES;
+                for (int c = 0; c < 2; ++c) {
+                    tc::tma_load_3d(sk + c * (AT_BKV * 128), &P.mapK, &kv_full[s], head * 3 * AT_D + AT_D + c * 32, j * AT_BKV, b);
+                    tc::tma_load_3d(sv + c * (AT_D * 128), &P.mapV, &kv_full[s], j * AT_BKV + c * 32, head * AT_D, b);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 5) {
+        if (tc::elect_one()) {
+            constexpr uint32_t idesc = tc::make_idesc(tc::FMT_TF32, 128, 64);
+            const uint32_t sQ = tc::smem_u32(smem), sP = tc::smem_u32(smem + AT_OFF_P);
+            auto issue_S = [&](int j) {
+                const int s = j & 1;
+                tc::mbar_wait(&kv_full[s], (uint32_t)(j >> 1) & 1u);
+                tc::tc_fence_after();
+                const uint32_t sK = tc::smem_u32(smem + AT_OFF_KV + s * AT_STAGE);
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        tc::umma_tf32(tmem_S, tc::smem_desc_k_sw128(sQ + c * (AT_BQ * 128)) + (uint64_t)(k * 2),
+                                      tc::smem_desc_k_sw128(sK + c * (AT_BKV * 128)) + (uint64_t)(k * 2), idesc, (uint32_t)((c | k) != 0));
+                tc::umma_commit(s_full);
+            };
+            tc::mbar_wait(q_full, 0);
+            issue_S(0);
+            for (int j = 0; j < nkv; ++j) {
+                const int s = j & 1;
+                tc::mbar_wait(p_full, (uint32_t)j & 1u);
+                tc::tc_fence_after();
+                const uint32_t sV = tc::smem_u32(smem + AT_OFF_KV + s * AT_STAGE + AT_K_BYTES);
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        tc::umma_tf32(tmem_O, tc::smem_desc_k_sw128(sP + c * (AT_BQ * 128)) + (uint64_t)(k * 2),
+                                      tc::smem_desc_k_sw128(sV + c * (AT_D * 128)) + (uint64_t)(k * 2), idesc, (uint32_t)((c | k) != 0));
+                tc::umma_commit(o_full);
+                tc::umma_commit(&kv_empty[s]);
+                if (j + 1 < nkv) issue_S(j + 1);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ---------------- softmax / accumulate: one query row per thread ----------------
+        const int r = warp * 32 + lane;
+        const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+        float m_run = -INFINITY, l_run = 0.f;
+        float o_acc[AT_D];
+#pragma unroll
+        for (int i = 0; i < AT_D; ++i) o_acc[i] = 0.f;
+        uint8_t* prow = smem + AT_OFF_P + (r >> 3) * 1024 + (r & 7) * 128;
+        const int sw = r & 7;
+        for (int j = 0; j < nkv; ++j) {
+            tc::mbar_wait(s_full, (uint32_t)j & 1u);
+            tc::tc_fence_after();
+            uint32_t sr[2][32];
+            tc::tmem_ld32(tmem_S + lane_off, sr[0]);
+            tc::tmem_ld32(tmem_S + lane_off + 32, sr[1]);
+            tc::tmem_ld_wait();
+            const int nvalid = P.T - j * AT_BKV;           // keys beyond T are masked
+            float mx = -INFINITY;
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    float v = __uint_as_float(sr[h][i]);
+                    v = (h * 32 + i < nvalid) ? v : -INFINITY;
+                    sr[h][i] = __float_as_uint(v);
+                    mx = fmaxf(mx, v);
+                }
+            const float m_new = fmaxf(m_run, mx);
+            const float alpha = exp2f((m_run - m_new) * P.scale_log2);
+            const float mb = m_new * P.scale_log2;
+            float rs = 0.f;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    float4 pv;
+                    pv.x = exp2f(fmaf(__uint_as_float(sr[h][4 * u]), P.scale_log2, -mb));
+                    pv.y = exp2f(fmaf(__uint_as_float(sr[h][4 * u + 1]), P.scale_log2, -mb));
+                    pv.z = exp2f(fmaf(__uint_as_float(sr[h][4 * u + 2]), P.scale_log2, -mb));
+                    pv.w = exp2f(fmaf(__uint_as_float(sr[h][4 * u + 3]), P.scale_log2, -mb));
+                    rs += (pv.x + pv.y) + (pv.z + pv.w);
+                    *reinterpret_cast<float4*>(prow + h * (AT_BQ * 128) + ((u ^ sw) << 4)) = pv;
+                }
+            }
+            l_run = fmaf(l_run, alpha, rs);
+            m_run = m_new;
+            tc::fence_proxy_async();                         // generic-proxy smem writes -> visible to the MMA (async proxy)
+            tc::tc_fence_before();
+            tc::mbar_arrive(p_full);
+            tc::mbar_wait(o_full, (uint32_t)j & 1u);
+            tc::tc_fence_after();
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                uint32_t orr[32];
+                tc::tmem_ld32(tmem_O + lane_off + h * 32, orr);
+                tc::tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) o_acc[h * 32 + i] = fmaf(o_acc[h * 32 + i], alpha, __uint_as_float(orr[i]));
+            }
+        }
+        const int t = q0 + r;
+        if (t < P.T) {
+            const float inv = 1.0f / l_run;
+            float4* op = reinterpret_cast<float4*>(P.out + ((size_t)b * P.T + t) * P.C + head * AT_D);
+#pragma unroll
+            for (int i = 0; i < AT_D / 4; ++i)
+                op[i] = make_float4(o_acc[4 * i] * inv, o_acc[4 * i + 1] * inv, o_acc[4 * i + 2] * inv, o_acc[4 * i + 3] * inv);
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 5) tc::tmem_dealloc(tmem_base, 128);
+}
+
+int attention_prepare(AttentionParams& P, const AttentionDesc& d) {
+    IPDM_REQUIRE(d.head_dim == AT_D && d.C == d.heads * AT_D, "attention: head_dim must be 64 (got %d)", d.head_dim);
+    IPDM_REQUIRE(d.t_pad % 4 == 0 && d.t_pad >= d.T, "attention: t_pad must be a multiple of 4");
+    memset(&P, 0, sizeof(P));
+    const uint64_t dq[3] = {(uint64_t)3 * d.C, (uint64_t)d.T, (uint64_t)d.batch};
+    const uint64_t sq[2] = {(uint64_t)3 * d.C * 4, (uint64_t)d.T * 3 * d.C * 4};
+    const uint32_t bq[3] = {32, AT_BQ, 1}, bk[3] = {32, AT_BKV, 1};
+    IPDM_CHECK(tmap_encode(&P.mapQ, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, d.qk, dq, sq, bq, CU_TENSOR_MAP_SWIZZLE_128B));
+    IPDM_CHECK(tmap_encode(&P.mapK, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, d.qk, dq, sq, bk, CU_TENSOR_MAP_SWIZZLE_128B));
+    const uint64_t dv[3] = {(uint64_t)d.T, (uint64_t)d.heads * AT_D, (uint64_t)d.batch};
+    const uint64_t sv[2] = {(uint64_t)d.t_pad * 4, (uint64_t)d.heads * AT_D * d.t_pad * 4};
+    const uint32_t bv[3] = {32, AT_D, 1};
+    IPDM_CHECK(tmap_encode(&P.mapV, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, d.vt, dv, sv, bv, CU_TENSOR_MAP_SWIZZLE_128B));
+    P.out = d.out; P.batch = d.batch; P.T = d.T; P.heads = d.heads; P.C = d.C;
+    P.scale_log2 = 1.4426950408889634f / sqrtf((float)AT_D);      // (d^-1/4)^2 * log2(e)
+    return IPDM_OK;
+}
+
+int attention_launch(const AttentionParams& P, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        IPDM_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
+        configured = true;
+    }
+    dim3 grid((P.T + AT_BQ - 1) / AT_BQ, P.heads, P.batch);
+    attention_kernel<<<grid, AT_THREADS, AT_SMEM, st>>>(P);
+    count_launch();
+    IPDM_CHECK_LAUNCH();
+    return IPDM_OK;
+}
+
+double attention_flops(const AttentionDesc& d) { return 4.0 * d.batch * d.heads * (double)d.T * d.T * AT_D; }
+
+}  // namespace ipdm

@@ -1,0 +1,74 @@
+// Shared helpers for libipdm_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdarg>
+
+#include "../../include/ipdm_b200.h"
+
+namespace ipdm {
+
+// ---- error plumbing: no exceptions cross the C ABI (include/ipdm_b200.h) ----
+void set_error(const char* fmt, ...);
+const char* last_error();
+
+#define IPDM_CHECK_CUDA(expr)                                                                    \
+    do {                                                                                         \
+        cudaError_t _e = (expr);                                                                 \
+        if (_e != cudaSuccess) {                                                                 \
+            ::ipdm::set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return IPDM_ERR_CUDA;                                                                \
+        }                                                                                        \
+    } while (0)
+
+#define IPDM_REQUIRE(cond, ...)                                                                  \
+    do {                                                                                         \
+        if (!(cond)) {                                                                           \
+            ::ipdm::set_error(__VA_ARGS__);                                                      \
+            return IPDM_ERR_ARG;                                                                 \
+        }                                                                                        \
+    } while (0)
+
+#define IPDM_CHECK(expr)                                                                         \
+    do {                                                                                         \
+        int _rc = (expr);                                                                        \
+        if (_rc != IPDM_OK) return _rc;                                                          \
+    } while (0)
+
+#define IPDM_CHECK_LAUNCH() IPDM_CHECK_CUDA(cudaGetLastError())
+
+constexpr int kNumSMs = 148;
+
+inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// kernel launch counter (bench.py reports it as gpu_launches)
+extern unsigned long long g_launch_count;
+inline void count_launch(int n = 1) { g_launch_count += (unsigned long long)n; }
+
+// ---- device helpers ----
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ float4 ld_stream(const float4* p) {
+    float4 r;
+    asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_stream(float4* p, const float4& v) {
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+__device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
+
+}  // namespace ipdm

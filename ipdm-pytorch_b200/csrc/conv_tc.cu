@@ -1,0 +1,311 @@
+// Implicit-GEMM convolution on the 5th-generation tensor cores (tcgen05 + TMEM), fed by TMA.
+// Covers every dense contraction of the reference UNet (Model/model.py: Conv2d 3x3 :101,113,165,
+// stride-2 Conv2d :180, 1x1 shortcut / qkv / proj :117,142,143) whose channel counts reach the
+// tensor-core path (C_in >= 16 after padding to 32, C_out in {16, 64, 128, ...}).
+//
+// Layout: activations NHWC fp32 with a channel stride that is a multiple of 32 (pad channels are 0),
+// weights repacked as [tap][C_out][K] (K = input channels in virtual-concat order, K-major).
+// GEMM view per CTA: D[128 pixels, BLOCK_N] += A_tap[128 pixels, 32 ch] * W_tap[BLOCK_N, 32 ch]^T over
+// (tap, 32-channel chunk).  The A tile of a tap is ONE 4-D TMA box {32 ch, TW, TH, 1} of the NHWC
+// tensor at pixel offset (dx-1, dy-1): out-of-image coordinates are zero-filled by TMA, which is exactly
+// the convolution's zero padding and also covers ragged image sizes (228, 57, 29 ... columns).
+// Stride-2 convolutions read four parity sub-lattices of the input through four tensor maps.
+// Two virtual-concat sources (torch.cat([h, skip]) :306) are two tensor maps walked back to back.
+//
+// Roles (128 threads): warp 0 lane* = TMA producer, warp 1 lane* = MMA issuer (tcgen05.mma
+// kind::tf32, M=128, N=BLOCK_N, K=8 x4 per 128-byte stage), warp 2 = TMEM allocator; then all four
+// warps run the epilogue: tcgen05.ld 32 lanes x 32 columns, + bias[t] (+ residual), 128-bit NHWC stores.
+// 3 stages x 32 KB of shared memory -> two CTAs per SM, so one CTA's epilogue overlaps the other's
+// main loop without a persistent scheduler.
+#include "common.cuh"
+#include "tc.cuh"
+#include "unet_ops.cuh"
+
+#include <mutex>
+
+namespace ipdm {
+
+// ------------------------------------------------------------------------------------------------
+// driver entry point for cuTensorMapEncodeTiled
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    });
+    return fn;
+}
+
+int tmap_encode(CUtensorMap* out, CUtensorMapDataType dtype, int rank, const void* base, const uint64_t* dims,
+                const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz) {
+    EncodeTiledFn fn = get_encode();
+    if (!fn) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return IPDM_ERR_CUDA; }
+    cuuint64_t d[5], s[4];
+    cuuint32_t b[5], es[5];
+    for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; es[i] = 1; }
+    for (int i = 0; i + 1 < rank; ++i) s[i] = strides_bytes[i];
+    CUresult r = fn(out, dtype, (cuuint32_t)rank, const_cast<void*>(base), d, s, b, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dims %llu %llu %llu %llu, box %u %u %u %u)", (int)r, rank,
+                  (unsigned long long)d[0], (unsigned long long)(rank > 1 ? d[1] : 0), (unsigned long long)(rank > 2 ? d[2] : 0),
+                  (unsigned long long)(rank > 3 ? d[3] : 0), b[0], rank > 1 ? b[1] : 0, rank > 2 ? b[2] : 0, rank > 3 ? b[3] : 0);
+        return IPDM_ERR_CUDA;
+    }
+    return IPDM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel
+// ------------------------------------------------------------------------------------------------
+constexpr int TC_THREADS = 128;
+constexpr int TC_KC = 32;                 // fp32 elements per 128-byte operand row
+constexpr int TC_A_BYTES = 128 * 128;
+
+template <int BLOCK_N, int STAGES>
+struct TcSmem {
+    static constexpr int B_BYTES = BLOCK_N * 128;
+    static constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
+    static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+    static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 1) * 8 + 16 + 1024;   // + alignment slack
+};
+
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS)
+conv_tc_kernel(const __grid_constant__ ConvTcParams P) {
+    using S = TcSmem<BLOCK_N, STAGES>;
+    constexpr int TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* full = (uint64_t*)(smem + S::BAR_OFF);
+    uint64_t* empty = full + STAGES;
+    uint64_t* accum = empty + STAGES;
+    uint32_t* tmem_slot = (uint32_t*)(accum + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_per_img = P.tiles_x * P.tiles_y;
+    const int b = blockIdx.x / tiles_per_img;
+    const int tr = blockIdx.x - b * tiles_per_img;
+    const int tyi = tr / P.tiles_x, txi = tr - tyi * P.tiles_x;
+    const int TW = 1 << P.tw_log2, TH = 128 >> P.tw_log2;
+    const int x0 = txi * TW, y0 = tyi * TH;
+    const int n0 = blockIdx.y * BLOCK_N;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < STAGES; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
+        tc::mbar_init(accum, 1);
+        tc::fence_barrier_init();
+    }
+    if (warp == 2) tc::tmem_alloc(tmem_slot, TMEM_COLS);
+    if (warp == 0 && lane == 0) {
+        tc::prefetch_tmap(&P.mapA[0]);
+        tc::prefetch_tmap(&P.mapB);
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int nk = P.nk0 + P.nk1;
+    const int total = P.ntaps * nk;
+
+    if (warp == 0) {
+        if (tc::elect_one()) {
+            for (int it = 0; it < total; ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+                tc::mbar_wait(&empty[s], ph ^ 1u);
+                tc::mbar_expect_tx(&full[s], S::STAGE_BYTES);
+                const int tap = it / nk, kc = it - tap * nk;
+                const int dy = P.ntaps == 9 ? tap / 3 : 1, dx = P.ntaps == 9 ? tap - (tap / 3) * 3 : 1;
+                uint8_t* sA = smem + s * S::STAGE_BYTES;
+                uint8_t* sB = sA + TC_A_BYTES;
+                if (P.stride == 1) {
+                    const bool first = kc < P.nk0;
+                    tc::tma_load_4d(sA, first ? &P.mapA[0] : &P.mapA[1], &full[s], (first ? kc : kc - P.nk0) * TC_KC,
+                                    x0 + dx - 1, y0 + dy - 1, b);
+                } else {
+                    const int py = dy != 1, px = dx != 1;
+                    tc::tma_load_4d(sA, &P.mapA[py * 2 + px], &full[s], kc * TC_KC, x0 + (dx == 0 ? -1 : 0),
+                                    y0 + (dy == 0 ? -1 : 0), b);
+                }
+                tc::tma_load_2d(sB, &P.mapB, &full[s], kc * TC_KC, tap * P.cout_rows + n0);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (tc::elect_one()) {
+            constexpr uint32_t idesc = tc::make_idesc(tc::FMT_TF32, 128, BLOCK_N);
+            for (int it = 0; it < total; ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+                tc::mbar_wait(&full[s], ph);
+                tc::tc_fence_after();
+                const uint32_t sA = tc::smem_u32(smem + s * S::STAGE_BYTES);
+                const uint64_t adesc = tc::smem_desc_k_sw128(sA), bdesc = tc::smem_desc_k_sw128(sA + TC_A_BYTES);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)          // 4 x (K = 8 tf32 = 32 bytes) inside the 128-byte swizzle atom
+                    tc::umma_tf32(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (uint32_t)((it | k) != 0));
+                tc::umma_commit(&empty[s]);          // frees the stage once these MMAs have read it
+            }
+            tc::umma_commit(accum);
+        }
+        __syncwarp();
+    }
+
+    // ---------------- epilogue: TMEM -> registers -> (+bias, +residual) -> NHWC global ----------------
+    tc::mbar_wait(accum, 0);
+    tc::tc_fence_after();
+    const int m = warp * 32 + lane;                  // accumulator row == TMEM lane == pixel inside the tile
+    const int py = y0 + (m >> P.tw_log2), px = x0 + (m & (TW - 1));
+    const bool valid = py < P.H && px < P.W;
+    const size_t pix = ((size_t)b * P.H + py) * P.W + px;
+    const float* bias = P.bias ? P.bias + (P.t_dev ? (size_t)(*P.t_dev) * P.bias_t_stride : 0) : nullptr;
+    constexpr int CHUNK = BLOCK_N < 32 ? 16 : 32;
+#pragma unroll 1
+    for (int cc = 0; cc < BLOCK_N; cc += CHUNK) {
+        __syncwarp();
+        uint32_t r[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)cc;
+        if constexpr (CHUNK == 32) tc::tmem_ld32(taddr, r);
+        else { uint32_t r16[16]; tc::tmem_ld16(taddr, r16);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) r[i] = r16[i]; }
+        tc::tmem_ld_wait();
+        const int n = n0 + cc;
+        if (!valid || n >= P.cout) continue;
+        float v[CHUNK];
+#pragma unroll
+        for (int i = 0; i < CHUNK; ++i) v[i] = __uint_as_float(r[i]) + (bias ? __ldg(bias + n + i) : 0.f);
+        if (P.res) {
+            const float4* rp = reinterpret_cast<const float4*>(P.res + pix * P.res_cs + n);
+#pragma unroll
+            for (int i = 0; i < CHUNK / 4; ++i) { const float4 t = __ldg(rp + i); v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w; }
+        }
+        if (P.qkv_mode && ((n % (3 * P.head_dim)) >= 2 * P.head_dim)) {
+            // V of one head: write transposed, [b][head][d][t_pad] (token contiguous), so P.V^T is K-major for attention
+            const int head = n / (3 * P.head_dim), d0 = n % (3 * P.head_dim) - 2 * P.head_dim;
+            const size_t tok = (size_t)py * P.W + px;
+            float* vt = P.vt + (((size_t)b * P.heads + head) * P.head_dim + d0) * P.t_pad + tok;
+#pragma unroll
+            for (int i = 0; i < CHUNK; ++i) vt[(size_t)i * P.t_pad] = v[i];
+        } else {
+            float4* op = reinterpret_cast<float4*>(P.out + pix * P.out_cs + n);
+#pragma unroll
+            for (int i = 0; i < CHUNK / 4; ++i) op[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        }
+    }
+    if (valid && !P.qkv_mode && blockIdx.y == gridDim.y - 1)     // keep the channel padding of the output at zero
+        for (int c = P.cout; c < P.out_cs; ++c) P.out[pix * P.out_cs + c] = 0.f;
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tc::tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static int pick_tw_log2(int H, int W) {
+    int best = 3; long long best_area = -1;
+    for (int l = 3; l <= 7; ++l) {
+        const int tw = 1 << l, th = 128 >> l;
+        const long long area = (long long)ceil_div(W, tw) * tw * ceil_div(H, th) * th;
+        if (best_area < 0 || area < best_area || (area == best_area && l > best)) { best = l; best_area = area; }
+    }
+    return best;
+}
+
+int conv_tc_prepare(ConvTcParams& P, const ConvTcDesc& d) {
+    IPDM_REQUIRE(d.nsrc >= 1 && d.nsrc <= 2, "conv_tc: 1 or 2 sources");
+    IPDM_REQUIRE(d.stride == 1 || (d.stride == 2 && d.nsrc == 1), "conv_tc: stride 2 takes one source");
+    IPDM_REQUIRE(d.ntaps == 1 || d.ntaps == 9, "conv_tc: 1x1 or 3x3");
+    memset(&P, 0, sizeof(P));
+    const int Hin = d.src[0].h, Win = d.src[0].w;
+    P.H = d.stride == 1 ? Hin : (Hin + 1) / 2;      // k=3, pad=1, stride 2 -> floor((H-1)/2)+1
+    P.W = d.stride == 1 ? Win : (Win + 1) / 2;
+    P.tw_log2 = pick_tw_log2(P.H, P.W);
+    const int TW = 1 << P.tw_log2, TH = 128 >> P.tw_log2;
+    P.tiles_x = ceil_div(P.W, TW); P.tiles_y = ceil_div(P.H, TH);
+    P.batch = d.src[0].n;
+    P.ntaps = d.ntaps; P.stride = d.stride;
+    P.cout = d.cout; P.block_n = d.cout >= 128 ? 128 : (d.cout >= 64 ? 64 : 16);
+    IPDM_REQUIRE(d.cout % P.block_n == 0, "conv_tc: C_out %d not a multiple of the N tile %d", d.cout, P.block_n);
+    P.cout_rows = d.cout;
+    int ktot = 0;
+    for (int s = 0; s < d.nsrc; ++s) {
+        const TensorNHWC& t = d.src[s];
+        IPDM_REQUIRE(t.cs % TC_KC == 0 && ((uintptr_t)t.p % 16) == 0, "conv_tc: source channel stride %d must be a multiple of 32", t.cs);
+        IPDM_REQUIRE(t.h == Hin && t.w == Win && t.n == P.batch, "conv_tc: concat sources differ in shape");
+        (s == 0 ? P.nk0 : P.nk1) = t.cs / TC_KC;
+        ktot += t.cs;
+        if (d.stride == 1) {
+            const uint64_t dims[4] = {(uint64_t)t.cs, (uint64_t)t.w, (uint64_t)t.h, (uint64_t)t.n};
+            const uint64_t str[3] = {(uint64_t)t.cs * 4, (uint64_t)t.w * t.cs * 4, (uint64_t)t.h * t.w * t.cs * 4};
+            const uint32_t box[4] = {TC_KC, (uint32_t)TW, (uint32_t)TH, 1};
+            IPDM_CHECK(tmap_encode(&P.mapA[s], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, t.p, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B));
+        } else {
+            for (int py = 0; py < 2; ++py)
+                for (int px = 0; px < 2; ++px) {
+                    const uint64_t wp = (uint64_t)(t.w - px + 1) / 2, hp = (uint64_t)(t.h - py + 1) / 2;
+                    const uint64_t dims[4] = {(uint64_t)t.cs, wp ? wp : 1, hp ? hp : 1, (uint64_t)t.n};
+                    const uint64_t str[3] = {(uint64_t)t.cs * 8, (uint64_t)t.w * t.cs * 8, (uint64_t)t.h * t.w * t.cs * 4};
+                    const uint32_t box[4] = {TC_KC, (uint32_t)TW, (uint32_t)TH, 1};
+                    const float* base = t.p + ((size_t)py * t.w + px) * t.cs;
+                    IPDM_CHECK(tmap_encode(&P.mapA[py * 2 + px], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B));
+                }
+        }
+    }
+    IPDM_REQUIRE(ktot == d.w_k, "conv_tc: packed weight K %d != sum of source channel strides %d", d.w_k, ktot);
+    {
+        const uint64_t dims[2] = {(uint64_t)d.w_k, (uint64_t)d.ntaps * d.cout};
+        const uint64_t str[1] = {(uint64_t)d.w_k * 4};
+        const uint32_t box[2] = {TC_KC, (uint32_t)P.block_n};
+        IPDM_CHECK(tmap_encode(&P.mapB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, d.w_packed, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B));
+    }
+    P.out = d.out.p; P.out_cs = d.out.cs;
+    IPDM_REQUIRE(d.qkv_mode || (d.out.h == P.H && d.out.w == P.W && d.out.n == P.batch && d.out.cs % 4 == 0 && d.out.c >= d.cout),
+                 "conv_tc: output tensor shape mismatch");
+    P.bias = d.bias; P.bias_t_stride = d.bias_t_stride; P.t_dev = d.t_dev;
+    P.res = d.res.p; P.res_cs = d.res.cs;
+    P.qkv_mode = d.qkv_mode; P.vt = d.vt; P.t_pad = d.t_pad; P.heads = d.heads; P.head_dim = d.head_dim;
+    return IPDM_OK;
+}
+
+template <int BN, int ST>
+static int launch_tc(const ConvTcParams& P, cudaStream_t st) {
+    static bool configured = false;
+    constexpr int smem = TcSmem<BN, ST>::TOTAL;
+    if (!configured) {
+        IPDM_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    dim3 grid(P.tiles_x * P.tiles_y * P.batch, P.cout / BN);
+    conv_tc_kernel<BN, ST><<<grid, TC_THREADS, smem, st>>>(P);
+    count_launch();
+    IPDM_CHECK_LAUNCH();
+    return IPDM_OK;
+}
+
+int conv_tc_launch(const ConvTcParams& P, cudaStream_t st) {
+    switch (P.block_n) {
+        case 128: return launch_tc<128, 3>(P, st);
+        case 64: return launch_tc<64, 4>(P, st);
+        case 16: return launch_tc<16, 4>(P, st);
+    }
+    set_error("conv_tc_launch: unsupported N tile %d", P.block_n);
+    return IPDM_ERR_UNSUPPORTED;
+}
+
+double conv_tc_flops(const ConvTcParams& P) {
+    return 2.0 * P.batch * P.H * P.W * (double)P.cout * P.ntaps * (P.nk0 + P.nk1) * TC_KC;
+}
+
+}  // namespace ipdm

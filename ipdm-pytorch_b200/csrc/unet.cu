@@ -1,0 +1,674 @@
+// UNet noise predictor: architecture builder, weight repacking and the per-shape execution plan.
+// Mirrors the reference's Model/model.py UNetModel.__init__ :190-281 (block structure, channel
+// plan, attention placement) and UNetModel.forward :283-310 (skip stack, concat, upsample-to-size).
+//
+// A plan is a flat list of kernel launches over NHWC fp32 tensors carved from one arena with
+// liveness-based reuse; it is built once per (batch, H, W) and replayed on the caller's stream with
+// no allocation, no host synchronisation and no timestep-dependent host work (the timestep is a
+// device scalar that selects the row of each ResBlock's precomputed bias+time-embedding table).
+#include "unet_ops.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <map>
+#include <memory>
+#include <tuple>
+#include <vector>
+
+namespace ipdm {
+
+static int round_up(int a, int b) { return (a + b - 1) / b * b; }
+static int alloc_cs(int c) { return c >= 16 ? round_up(c, 32) : c; }
+
+static int gn_groups(int c) {           // norm_layer, model.py:82-90
+    if (c % 32 == 0) return 32;
+    if (c < 32) return c;
+    int best = 1; long long bd = -1;
+    for (int i = 1; i * i <= c; ++i)
+        if (c % i == 0)
+            for (int f : {i, c / i}) {
+                const long long dd = (long long)(f - 32) * (f - 32);
+                if (bd < 0 || dd < bd) { bd = dd; best = f; }   // first minimum in the reference's factor order
+            }
+    return best;
+}
+
+struct GNW { float* gamma = nullptr; float* beta = nullptr; int C = 0, groups = 0; };
+struct ConvW {
+    int cin = 0, cout = 0, k = 0;
+    std::vector<float> w_host, b_host;       // PyTorch layout [cout][cin][k][k], [cout]
+    float* w_dev = nullptr; float* b_dev = nullptr;
+    bool tc = false; int c0 = 0, cs0 = 0, c1 = 0, cs1 = 0, kpad = 0;
+};
+struct ResW { GNW gn1, gn2; ConvW conv1, conv2, shortcut; bool has_shortcut = false; std::vector<float> temb_w, temb_b; float* bias1_t = nullptr; int cin = 0, cout = 0; };
+struct AttnW { GNW norm; ConvW qkv, proj; int C = 0; };
+struct LayerRef { enum Kind { CONV_IN, RES, ATTN, DOWN, UP } kind; int idx; };
+typedef std::vector<LayerRef> Block;
+
+struct VTensor { int n = 0, h = 0, w = 0, c = 0, cs = 0; int def = -1, last = -1; size_t off = 0; bool external = false; };
+
+struct Op {
+    enum Kind { GN_STATS, GN_APPLY, CONV_TC, CONV_DIRECT, UPSAMPLE, ATTN } kind;
+    int src[2] = {-1, -1}; int nsrc = 0; int dst = -1, res = -1, aux = -1;
+    const GNW* gn = nullptr; int norm_slot = -1; int act = 1;
+    const ConvW* cw = nullptr; const float* bias = nullptr; int bias_t_stride = 0; bool use_t = false;
+    int stride = 1, upsample = 0, qkv = 0;
+    // materialised
+    ConvTcParams tcp; ConvDirectDesc cd; GroupNormDesc gd; TensorNHWC out_t, src_t; AttentionParams ap; AttentionDesc ad;
+    double flops = 0;
+};
+
+struct Plan {
+    int B = 0, H = 0, W = 0;
+    std::vector<VTensor> vt;
+    std::vector<Op> ops;
+    float* arena = nullptr; size_t arena_bytes = 0;
+    float* norm_buf = nullptr; double* gn_partials = nullptr;
+    int x_id = -1, eps_id = -1, first_op = -1, last_op = -1;
+    double flops = 0;
+    ~Plan() { cudaFree(arena); cudaFree(norm_buf); cudaFree(gn_partials); }
+};
+
+}  // namespace ipdm
+
+using namespace ipdm;
+
+struct ipdm_unet {
+    ipdm_unet_config cfg;
+    std::vector<ConvW> convs;           // conv_in, downs, ups, out conv
+    std::vector<ResW> res;
+    std::vector<AttnW> attn;
+    std::vector<Block> down_blocks, up_blocks;
+    Block middle;
+    GNW out_gn; int out_conv = -1;
+    std::vector<float*> dev_allocs;
+    int* t_dev = nullptr;
+    int heads = 4;
+    std::map<std::tuple<int, int, int>, std::unique_ptr<Plan>> plans;
+    ~ipdm_unet() { for (float* p : dev_allocs) cudaFree(p); cudaFree(t_dev); }
+};
+
+namespace ipdm {
+
+// ------------------------------------------------------------------------------------------------
+// weights
+// ------------------------------------------------------------------------------------------------
+struct Reader {
+    const float* p; size_t n, pos = 0; bool ok = true;
+    std::vector<float> take(size_t k) {
+        if (pos + k > n) { ok = false; return std::vector<float>(k, 0.f); }
+        std::vector<float> v(p + pos, p + pos + k); pos += k; return v;
+    }
+};
+
+static int upload(ipdm_unet* net, const std::vector<float>& h, float** out) {
+    float* d = nullptr;
+    IPDM_CHECK_CUDA(cudaMalloc(&d, std::max<size_t>(h.size(), 1) * sizeof(float)));
+    IPDM_CHECK_CUDA(cudaMemcpy(d, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
+    net->dev_allocs.push_back(d);
+    *out = d;
+    return IPDM_OK;
+}
+
+static void read_conv(Reader& r, ConvW& c, int cin, int cout, int k, bool bias) {
+    c.cin = cin; c.cout = cout; c.k = k;
+    c.w_host = r.take((size_t)cout * cin * k * k);
+    if (bias) c.b_host = r.take(cout);
+}
+static int read_gn(ipdm_unet* net, Reader& r, GNW& g, int C) {
+    g.C = C; g.groups = gn_groups(C);
+    IPDM_CHECK(upload(net, r.take(C), &g.gamma));
+    IPDM_CHECK(upload(net, r.take(C), &g.beta));
+    return IPDM_OK;
+}
+
+static bool wants_tc(int cin_total, int cout) { return cout % 16 == 0 && cin_total >= 16 && (cout >= 64 || cin_total >= 64); }
+
+// K layout of a tensor-core conv: channel c of the virtual concat -> column c (c < c0) or cs0 + (c - c0)
+static int pack_conv(ipdm_unet* net, ConvW& c, int c0, int c1, bool raw_sources, int force = -1) {
+    const int kk = c.k * c.k;
+    c.tc = force < 0 ? wants_tc(c.cin, c.cout) : force != 0;
+    if (c.tc) {
+        c.c0 = c0; c.c1 = c1;
+        if (raw_sources) { c.cs0 = alloc_cs(c0); c.cs1 = c1 ? alloc_cs(c1) : 0; }
+        else { c.c0 = c.cin; c.c1 = 0; c.cs0 = round_up(c.cin, 32); c.cs1 = 0; }
+        IPDM_REQUIRE(c.cs0 % 32 == 0 && c.cs1 % 32 == 0, "pack_conv: source strides %d/%d are not multiples of 32", c.cs0, c.cs1);
+        c.kpad = c.cs0 + c.cs1;
+        std::vector<float> p((size_t)kk * c.cout * c.kpad, 0.f);
+        for (int co = 0; co < c.cout; ++co)
+            for (int ci = 0; ci < c.cin; ++ci) {
+                const int col = ci < c.c0 ? ci : c.cs0 + (ci - c.c0);
+                for (int t = 0; t < kk; ++t) p[((size_t)t * c.cout + co) * c.kpad + col] = c.w_host[((size_t)co * c.cin + ci) * kk + t];
+            }
+        IPDM_CHECK(upload(net, p, &c.w_dev));
+    } else {
+        std::vector<float> p((size_t)kk * c.cin * c.cout);
+        for (int co = 0; co < c.cout; ++co)
+            for (int ci = 0; ci < c.cin; ++ci)
+                for (int t = 0; t < kk; ++t) p[((size_t)t * c.cin + ci) * c.cout + co] = c.w_host[((size_t)co * c.cin + ci) * kk + t];
+        IPDM_CHECK(upload(net, p, &c.w_dev));
+    }
+    if (!c.b_host.empty()) IPDM_CHECK(upload(net, c.b_host, &c.b_dev));
+    return IPDM_OK;
+}
+
+static inline float silu_h(float x) { return x / (1.0f + std::exp(-x)); }
+
+// architecture walk shared by create() and param_count(): calls back for every parameter tensor in state_dict order
+struct ArchVisitor {
+    virtual void conv_in(int cin, int cout) = 0;
+    virtual void res(int c0, int c1, int cout, int where) = 0;      // where: 0 down, 1 middle, 2 up ; input = cat(c0, c1)
+    virtual void attn(int c, int where) = 0;
+    virtual void down(int c) = 0;
+    virtual void up(int c) = 0;
+    virtual void begin_block(int where) = 0;
+    virtual void out(int c, int cout) = 0;
+    virtual void time_embed(int mc, int tdim) = 0;
+    virtual ~ArchVisitor() {}
+};
+
+static void walk_arch(const ipdm_unet_config& cfg, ArchVisitor& v) {
+    const int mc = cfg.model_channels, tdim = mc * 4;
+    auto is_attn = [&](int ds) { for (int i = 0; i < cfg.n_attn; ++i) if (cfg.attention_resolutions[i] == ds) return true; return false; };
+    v.time_embed(mc, tdim);
+    int ch = (int)(cfg.channel_mult[0] * mc);
+    v.begin_block(0); v.conv_in(cfg.in_channels, ch);
+    std::vector<int> chans{ch};
+    int ds = 1;
+    const int nm = cfg.n_mult - 1;
+    for (int level = 0; level < nm; ++level) {
+        const int oc = (int)(cfg.channel_mult[level + 1] * mc);
+        for (int i = 0; i < cfg.num_res_blocks; ++i) {
+            v.begin_block(0); v.res(ch, 0, oc, 0); ch = oc;
+            if (is_attn(ds)) v.attn(ch, 0);
+            chans.push_back(ch);
+        }
+        if (level != nm - 1) { v.begin_block(0); v.down(ch); chans.push_back(ch); ds *= 2; }
+    }
+    v.begin_block(1); v.res(ch, 0, ch, 1); v.attn(ch, 1); v.res(ch, 0, ch, 1);
+    for (int level = nm - 1; level >= 0; --level) {
+        const int oc = (int)(mc * cfg.channel_mult[level + 1]);
+        for (int i = 0; i <= cfg.num_res_blocks; ++i) {
+            const int skip = chans.back(); chans.pop_back();
+            v.begin_block(2); v.res(ch, skip, oc, 2); ch = oc;
+            if (is_attn(ds)) v.attn(ch, 2);
+            if (level && i == cfg.num_res_blocks) { v.up(ch); ds /= 2; }
+        }
+    }
+    v.out(ch, cfg.out_channels);
+}
+
+struct CountVisitor : ArchVisitor {
+    long long n = 0;
+    void conv(int ci, int co, int k, bool b = true) { n += (long long)co * ci * k * k + (b ? co : 0); }
+    void time_embed(int mc, int tdim) override { n += (long long)tdim * mc + tdim + (long long)tdim * tdim + tdim; tdim_ = tdim; }
+    void conv_in(int ci, int co) override { conv(ci, co, 3); }
+    void res(int c0, int c1, int co, int) override {
+        const int ci = c0 + c1;
+        n += 2 * ci; conv(ci, co, 3); n += (long long)co * tdim_ + co; n += 2 * co; conv(co, co, 3);
+        if (ci != co) conv(ci, co, 1);
+    }
+    void attn(int c, int) override { n += 2 * c; conv(c, 3 * c, 1, false); conv(c, c, 1); }
+    void down(int c) override { conv(c, c, 3); }
+    void up(int c) override { conv(c, c, 3); }
+    void begin_block(int) override {}
+    void out(int c, int co) override { n += 2 * c; conv(c, co, 3); }
+    int tdim_ = 0;
+};
+
+struct BuildVisitor : ArchVisitor {
+    ipdm_unet* net; Reader& r; int rc = IPDM_OK; int tdim = 0, mc = 0;
+    std::vector<float> te_w0, te_b0, te_w1, te_b1;
+    Block* cur = nullptr;
+    BuildVisitor(ipdm_unet* n, Reader& rd) : net(n), r(rd) {}
+    void fail(int c) { if (rc == IPDM_OK) rc = c; }
+    void time_embed(int mc_, int tdim_) override {
+        mc = mc_; tdim = tdim_;
+        te_w0 = r.take((size_t)tdim * mc); te_b0 = r.take(tdim); te_w1 = r.take((size_t)tdim * tdim); te_b1 = r.take(tdim);
+    }
+    void begin_block(int where) override {
+        if (where == 0) { net->down_blocks.emplace_back(); cur = &net->down_blocks.back(); }
+        else if (where == 1) cur = &net->middle;
+        else { net->up_blocks.emplace_back(); cur = &net->up_blocks.back(); }
+    }
+    void conv_in(int ci, int co) override {
+        net->convs.emplace_back(); read_conv(r, net->convs.back(), ci, co, 3, true);
+        fail(pack_conv(net, net->convs.back(), ci, 0, true));
+        cur->push_back({LayerRef::CONV_IN, (int)net->convs.size() - 1});
+    }
+    void res(int c0, int c1, int co, int) override {
+        net->res.emplace_back(); ResW& w = net->res.back();
+        const int ci = c0 + c1; w.cin = ci; w.cout = co;
+        fail(read_gn(net, r, w.gn1, ci)); read_conv(r, w.conv1, ci, co, 3, true);
+        w.temb_w = r.take((size_t)co * tdim); w.temb_b = r.take(co);
+        fail(read_gn(net, r, w.gn2, co)); read_conv(r, w.conv2, co, co, 3, true);
+        w.has_shortcut = ci != co;
+        if (w.has_shortcut) read_conv(r, w.shortcut, ci, co, 1, true);
+        fail(pack_conv(net, w.conv1, ci, 0, false));
+        fail(pack_conv(net, w.conv2, co, 0, false));
+        if (w.has_shortcut) fail(pack_conv(net, w.shortcut, c0, c1, true));
+        cur->push_back({LayerRef::RES, (int)net->res.size() - 1});
+    }
+    void attn(int c, int) override {
+        net->attn.emplace_back(); AttnW& a = net->attn.back(); a.C = c;
+        fail(read_gn(net, r, a.norm, c)); read_conv(r, a.qkv, c, 3 * c, 1, false); read_conv(r, a.proj, c, c, 1, true);
+        fail(pack_conv(net, a.qkv, c, 0, false)); fail(pack_conv(net, a.proj, c, 0, false));
+        if (!a.qkv.tc || !a.proj.tc || c % (64 * net->heads) != 0 || c / net->heads != 64) {
+            set_error("attention block with %d channels / %d heads is not supported (head_dim must be 64)", c, net->heads);
+            fail(IPDM_ERR_UNSUPPORTED);
+        }
+        cur->push_back({LayerRef::ATTN, (int)net->attn.size() - 1});
+    }
+    void down(int c) override {
+        net->convs.emplace_back(); read_conv(r, net->convs.back(), c, c, 3, true);
+        fail(pack_conv(net, net->convs.back(), c, 0, true));
+        cur->push_back({LayerRef::DOWN, (int)net->convs.size() - 1});
+    }
+    void up(int c) override {
+        net->convs.emplace_back(); read_conv(r, net->convs.back(), c, c, 3, true);
+        fail(pack_conv(net, net->convs.back(), c, 0, true));
+        cur->push_back({LayerRef::UP, (int)net->convs.size() - 1});
+    }
+    void out(int c, int co) override {
+        fail(read_gn(net, r, net->out_gn, c));
+        net->convs.emplace_back(); read_conv(r, net->convs.back(), c, co, 3, true);
+        fail(pack_conv(net, net->convs.back(), c, 0, false));
+        net->out_conv = (int)net->convs.size() - 1;
+    }
+};
+
+// bias1_t[t][co] = conv1.bias[co] + Linear(SiLU(time_embed(timestep_embedding(t))))[co]   (model.py:14-32, 218-222, 105-108, 128)
+static int build_time_tables(ipdm_unet* net, const BuildVisitor& bv) {
+    const int mc = bv.mc, tdim = bv.tdim, T = net->cfg.max_t, half = mc / 2;
+    std::vector<float> emb((size_t)T * tdim);
+    for (int t = 0; t < T; ++t) {
+        std::vector<float> te(mc), h(tdim);
+        for (int i = 0; i < half; ++i) {
+            const float f = (float)std::exp(-std::log(10000.0) * i / half);
+            te[i] = std::cos((float)t * f); te[half + i] = std::sin((float)t * f);
+        }
+        for (int o = 0; o < tdim; ++o) { double a = bv.te_b0[o]; for (int i = 0; i < mc; ++i) a += (double)bv.te_w0[(size_t)o * mc + i] * te[i]; h[o] = silu_h((float)a); }
+        for (int o = 0; o < tdim; ++o) { double a = bv.te_b1[o]; for (int i = 0; i < tdim; ++i) a += (double)bv.te_w1[(size_t)o * tdim + i] * h[i]; emb[(size_t)t * tdim + o] = silu_h((float)a); }
+    }   // emb now holds SiLU(time_embed(.)), the input of every block's time_emb Linear
+    for (ResW& w : net->res) {
+        std::vector<float> tab((size_t)T * w.cout);
+        for (int t = 0; t < T; ++t)
+            for (int o = 0; o < w.cout; ++o) {
+                double a = w.temb_b[o];
+                for (int i = 0; i < tdim; ++i) a += (double)w.temb_w[(size_t)o * tdim + i] * emb[(size_t)t * tdim + i];
+                tab[(size_t)t * w.cout + o] = (float)((double)w.conv1.b_host[o] + a);
+            }
+        IPDM_CHECK(upload(net, tab, &w.bias1_t));
+    }
+    return IPDM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// plan construction
+// ------------------------------------------------------------------------------------------------
+struct PlanBuilder {
+    ipdm_unet* net; Plan* pl;
+    int norm_slots = 0; int max_c = 0;
+    int new_tensor(int n, int h, int w, int c, int cs) {
+        VTensor t; t.n = n; t.h = h; t.w = w; t.c = c; t.cs = cs;
+        pl->vt.push_back(t); return (int)pl->vt.size() - 1;
+    }
+    int act(int h, int w, int c) { return new_tensor(pl->B, h, w, c, alloc_cs(c)); }
+    void touch(int id, int opi) { if (id < 0) return; VTensor& t = pl->vt[id]; if (t.def < 0) t.def = opi; t.last = std::max(t.last, opi); }
+    int push(Op& o) {
+        const int i = (int)pl->ops.size();
+        for (int s = 0; s < o.nsrc; ++s) touch(o.src[s], i);
+        touch(o.dst, i); touch(o.res, i); touch(o.aux, i);
+        pl->ops.push_back(o); return i;
+    }
+    int cin_of(const int* src, int nsrc) { int c = 0; for (int i = 0; i < nsrc; ++i) c += pl->vt[src[i]].c; return c; }
+
+    // GroupNorm(+SiLU) followed by a conv; returns nothing, writes `dst`
+    void norm_conv(const int* src, int nsrc, const GNW& gn, const ConvW& cw, int dst, int res, const float* bias, int bstride, bool use_t, int act_silu) {
+        Op st; st.kind = Op::GN_STATS; st.nsrc = nsrc; st.src[0] = src[0]; st.src[1] = nsrc > 1 ? src[1] : -1; st.gn = &gn; st.norm_slot = norm_slots++;
+        max_c = std::max(max_c, gn.C);
+        push(st);
+        const VTensor& s0 = pl->vt[src[0]];
+        if (cw.tc) {
+            const int a = new_tensor(pl->B, s0.h, s0.w, gn.C, round_up(gn.C, 32));
+            Op ap; ap.kind = Op::GN_APPLY; ap.nsrc = nsrc; ap.src[0] = src[0]; ap.src[1] = st.src[1]; ap.gn = &gn; ap.norm_slot = st.norm_slot; ap.dst = a; ap.act = act_silu;
+            push(ap);
+            Op cv; cv.kind = Op::CONV_TC; cv.nsrc = 1; cv.src[0] = a; cv.cw = &cw; cv.dst = dst; cv.res = res; cv.bias = bias; cv.bias_t_stride = bstride; cv.use_t = use_t;
+            push(cv);
+        } else {
+            Op cv; cv.kind = Op::CONV_DIRECT; cv.nsrc = nsrc; cv.src[0] = src[0]; cv.src[1] = st.src[1]; cv.cw = &cw; cv.dst = dst; cv.res = res;
+            cv.bias = bias; cv.bias_t_stride = bstride; cv.use_t = use_t; cv.norm_slot = st.norm_slot; cv.gn = &gn;
+            push(cv);
+        }
+    }
+    void plain_conv(const int* src, int nsrc, const ConvW& cw, int dst, int res, int stride, int upsample) {
+        Op cv; cv.kind = cw.tc ? Op::CONV_TC : Op::CONV_DIRECT; cv.nsrc = nsrc; cv.src[0] = src[0]; cv.src[1] = nsrc > 1 ? src[1] : -1;
+        cv.cw = &cw; cv.dst = dst; cv.res = res; cv.bias = cw.b_dev; cv.stride = stride; cv.upsample = upsample;
+        push(cv);
+    }
+    int res_block(const ResW& w, const int* src, int nsrc) {
+        const VTensor s0 = pl->vt[src[0]];
+        const int h1 = act(s0.h, s0.w, w.cout);
+        norm_conv(src, nsrc, w.gn1, w.conv1, h1, -1, w.bias1_t, w.cout, true, 1);
+        int resid = src[0];
+        if (w.has_shortcut) { resid = act(s0.h, s0.w, w.cout); plain_conv(src, nsrc, w.shortcut, resid, -1, 1, 0); }
+        const int out = act(s0.h, s0.w, w.cout);
+        norm_conv(&h1, 1, w.gn2, w.conv2, out, resid, w.conv2.b_dev, 0, false, 1);
+        return out;
+    }
+    int attn_block(const AttnW& a, int x) {
+        const VTensor s = pl->vt[x];
+        const int T = s.h * s.w, tpad = round_up(T, 4);
+        const int qk = new_tensor(pl->B, s.h, s.w, 3 * a.C, 3 * a.C);
+        const int vt = new_tensor(pl->B, 1, 1, a.C * tpad, a.C * tpad);
+        Op st; st.kind = Op::GN_STATS; st.nsrc = 1; st.src[0] = x; st.gn = &a.norm; st.norm_slot = norm_slots++; max_c = std::max(max_c, a.C); push(st);
+        const int an = new_tensor(pl->B, s.h, s.w, a.C, a.C);
+        Op ap; ap.kind = Op::GN_APPLY; ap.nsrc = 1; ap.src[0] = x; ap.gn = &a.norm; ap.norm_slot = st.norm_slot; ap.dst = an; ap.act = 0; push(ap);
+        Op q; q.kind = Op::CONV_TC; q.nsrc = 1; q.src[0] = an; q.cw = &a.qkv; q.dst = qk; q.aux = vt; q.qkv = 1; push(q);
+        const int o = new_tensor(pl->B, s.h, s.w, a.C, a.C);
+        Op at; at.kind = Op::ATTN; at.nsrc = 1; at.src[0] = qk; at.aux = vt; at.dst = o; push(at);
+        const int out = act(s.h, s.w, a.C);
+        Op pj; pj.kind = Op::CONV_TC; pj.nsrc = 1; pj.src[0] = o; pj.cw = &a.proj; pj.dst = out; pj.res = x; pj.bias = a.proj.b_dev; push(pj);
+        return out;
+    }
+    int run_block(const Block& blk, const int* src_in, int nsrc_in, int up_h, int up_w) {
+        int cur[2] = {src_in[0], nsrc_in > 1 ? src_in[1] : -1}; int ncur = nsrc_in;
+        for (const LayerRef& l : blk) {
+            int out = -1;
+            const VTensor s0 = pl->vt[cur[0]];
+            switch (l.kind) {
+                case LayerRef::CONV_IN: out = act(s0.h, s0.w, net->convs[l.idx].cout); plain_conv(cur, 1, net->convs[l.idx], out, -1, 1, 0); break;
+                case LayerRef::RES: out = res_block(net->res[l.idx], cur, ncur); break;
+                case LayerRef::ATTN: out = attn_block(net->attn[l.idx], cur[0]); break;
+                case LayerRef::DOWN: out = act((s0.h + 1) / 2, (s0.w + 1) / 2, s0.c); plain_conv(cur, 1, net->convs[l.idx], out, -1, 2, 0); break;
+                case LayerRef::UP: {
+                    const ConvW& cw = net->convs[l.idx];
+                    out = act(up_h, up_w, s0.c);
+                    if (cw.tc) {
+                        const int u = act(up_h, up_w, s0.c);
+                        Op up; up.kind = Op::UPSAMPLE; up.nsrc = 1; up.src[0] = cur[0]; up.dst = u; push(up);
+                        plain_conv(&u, 1, cw, out, -1, 1, 0);
+                    } else plain_conv(cur, 1, cw, out, -1, 1, 1);
+                } break;
+            }
+            cur[0] = out; cur[1] = -1; ncur = 1;
+        }
+        return cur[0];
+    }
+};
+
+static TensorNHWC resolve(const Plan& pl, int id) {
+    TensorNHWC t;
+    if (id < 0) return t;
+    const VTensor& v = pl.vt[id];
+    t.n = v.n; t.h = v.h; t.w = v.w; t.c = v.c; t.cs = v.cs;
+    t.p = v.external ? nullptr : (float*)((char*)pl.arena + v.off);
+    return t;
+}
+
+static int build_plan(ipdm_unet* net, int B, int H, int W, Plan** out) {
+    std::unique_ptr<Plan> pl(new Plan());
+    pl->B = B; pl->H = H; pl->W = W;
+    PlanBuilder pb{net, pl.get()};
+    pl->x_id = pb.new_tensor(B, H, W, net->cfg.in_channels, net->cfg.in_channels); pl->vt[pl->x_id].external = true;
+    pl->eps_id = pb.new_tensor(B, H, W, net->cfg.out_channels, net->cfg.out_channels); pl->vt[pl->eps_id].external = true;
+
+    // ---- forward wiring (model.py:283-310) ----
+    std::vector<int> hs;
+    int h = pl->x_id;
+    for (const Block& blk : net->down_blocks) { h = pb.run_block(blk, &h, 1, 0, 0); hs.push_back(h); }
+    h = pb.run_block(net->middle, &h, 1, 0, 0);
+    int h_ = hs.back(); hs.pop_back();
+    for (const Block& blk : net->up_blocks) {
+        const int cat[2] = {h, h_};
+        if (!hs.empty()) { h_ = hs.back(); hs.pop_back(); }
+        h = pb.run_block(blk, cat, 2, pl->vt[h_].h, pl->vt[h_].w);
+    }
+    pb.norm_conv(&h, 1, net->out_gn, net->convs[net->out_conv], pl->eps_id, -1, net->convs[net->out_conv].b_dev, 0, false, 1);
+    pl->first_op = 0; pl->last_op = (int)pl->ops.size() - 1;
+    IPDM_REQUIRE(pl->ops[0].kind == Op::CONV_DIRECT && pl->ops.back().kind == Op::CONV_DIRECT,
+                 "unet: first and last convolutions must be on the direct path (in/out channels too wide)");
+
+    // ---- arena assignment: first-fit over tensors sorted by definition, freeing at last use ----
+    struct Blk { size_t off, size; };
+    std::vector<Blk> free_list; size_t top = 0;
+    std::vector<std::vector<int>> expire(pl->ops.size() + 1);
+    std::vector<int> order;
+    for (int i = 0; i < (int)pl->vt.size(); ++i) if (!pl->vt[i].external && pl->vt[i].def >= 0) order.push_back(i);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return pl->vt[a].def < pl->vt[b].def; });
+    size_t oi = 0;
+    auto bytes_of = [&](const VTensor& t) { return ((size_t)t.n * t.h * t.w * t.cs * sizeof(float) + 1023) & ~(size_t)1023; };
+    for (int op = 0; op < (int)pl->ops.size(); ++op) {
+        while (oi < order.size() && pl->vt[order[oi]].def == op) {
+            VTensor& t = pl->vt[order[oi]];
+            const size_t need = bytes_of(t);
+            int best = -1;
+            for (int f = 0; f < (int)free_list.size(); ++f)
+                if (free_list[f].size >= need && (best < 0 || free_list[f].size < free_list[best].size)) best = f;
+            if (best >= 0) {
+                t.off = free_list[best].off;
+                free_list[best].off += need; free_list[best].size -= need;
+                if (free_list[best].size == 0) free_list.erase(free_list.begin() + best);
+            } else { t.off = top; top += need; }
+            expire[t.last].push_back(order[oi]);
+            ++oi;
+        }
+        for (int id : expire[op]) {          // release after this op; merge neighbours
+            const VTensor& t = pl->vt[id];
+            free_list.push_back({t.off, bytes_of(t)});
+            std::sort(free_list.begin(), free_list.end(), [](const Blk& a, const Blk& b) { return a.off < b.off; });
+            for (size_t f = 0; f + 1 < free_list.size();)
+                if (free_list[f].off + free_list[f].size == free_list[f + 1].off) { free_list[f].size += free_list[f + 1].size; free_list.erase(free_list.begin() + f + 1); }
+                else ++f;
+        }
+    }
+    pl->arena_bytes = top;
+    IPDM_CHECK_CUDA(cudaMalloc(&pl->arena, std::max<size_t>(top, 1024)));
+    IPDM_CHECK_CUDA(cudaMemset(pl->arena, 0, std::max<size_t>(top, 1024)));
+    const size_t norm_floats = (size_t)pb.norm_slots * 2 * B * pb.max_c;
+    IPDM_CHECK_CUDA(cudaMalloc(&pl->norm_buf, std::max<size_t>(norm_floats, 1) * sizeof(float)));
+    IPDM_CHECK_CUDA(cudaMalloc(&pl->gn_partials, (size_t)B * GN_MAX_BLOCKS * pb.max_c * 2 * sizeof(double)));
+
+    // ---- materialise descriptors ----
+    for (Op& o : pl->ops) {
+        float* nscale = o.norm_slot >= 0 ? pl->norm_buf + (size_t)o.norm_slot * 2 * B * pb.max_c : nullptr;
+        float* nshift = nscale ? nscale + (size_t)B * pb.max_c : nullptr;
+        switch (o.kind) {
+            case Op::GN_STATS:
+            case Op::GN_APPLY: {
+                GroupNormDesc& g = o.gd;
+                g.nsrc = o.nsrc; g.src[0] = resolve(*pl, o.src[0]); if (o.nsrc > 1) g.src[1] = resolve(*pl, o.src[1]);
+                g.groups = o.gn->groups; g.gamma = o.gn->gamma; g.beta = o.gn->beta; g.scale = nscale; g.shift = nshift; g.partials = pl->gn_partials;
+                if (o.kind == Op::GN_APPLY) o.out_t = resolve(*pl, o.dst);
+            } break;
+            case Op::CONV_TC: {
+                ConvTcDesc d;
+                d.nsrc = o.nsrc; d.src[0] = resolve(*pl, o.src[0]); if (o.nsrc > 1) d.src[1] = resolve(*pl, o.src[1]);
+                d.ntaps = o.cw->k * o.cw->k; d.stride = o.stride; d.cout = o.cw->cout; d.w_packed = o.cw->w_dev; d.w_k = o.cw->kpad;
+                d.bias = o.bias; d.bias_t_stride = o.bias_t_stride; d.t_dev = o.use_t ? net->t_dev : nullptr;
+                if (o.res >= 0) d.res = resolve(*pl, o.res);
+                d.out = resolve(*pl, o.dst);
+                if (o.qkv) {
+                    const TensorNHWC v = resolve(*pl, o.aux);
+                    d.qkv_mode = 1; d.vt = v.p; d.heads = net->heads; d.head_dim = o.cw->cin / net->heads; d.t_pad = v.c / o.cw->cin;
+                }
+                IPDM_CHECK(conv_tc_prepare(o.tcp, d));
+                o.flops = 2.0 * B * o.tcp.H * o.tcp.W * (double)o.cw->cin * o.cw->cout * d.ntaps;
+            } break;
+            case Op::CONV_DIRECT: {
+                ConvDirectDesc& d = o.cd;
+                d.nsrc = o.nsrc; d.src[0] = resolve(*pl, o.src[0]); if (o.nsrc > 1) d.src[1] = resolve(*pl, o.src[1]);
+                d.norm_scale = o.gn ? nscale : nullptr; d.norm_shift = o.gn ? nshift : nullptr;
+                d.ksize = o.cw->k; d.stride = o.stride; d.upsample = o.upsample; d.cin = o.cw->cin; d.cout = o.cw->cout; d.w = o.cw->w_dev;
+                d.bias = o.bias; d.bias_t_stride = o.bias_t_stride; d.t_dev = o.use_t ? net->t_dev : nullptr;
+                if (o.res >= 0) d.res = resolve(*pl, o.res);
+                d.out = resolve(*pl, o.dst);
+                o.flops = conv_direct_flops(d);
+            } break;
+            case Op::UPSAMPLE: o.src_t = resolve(*pl, o.src[0]); o.out_t = resolve(*pl, o.dst); break;
+            case Op::ATTN: {
+                const TensorNHWC qk = resolve(*pl, o.src[0]), v = resolve(*pl, o.aux), ot = resolve(*pl, o.dst);
+                AttentionDesc& a = o.ad;
+                a.qk = qk.p; a.vt = v.p; a.out = ot.p; a.batch = B; a.T = qk.h * qk.w; a.C = ot.c; a.heads = net->heads; a.head_dim = a.C / a.heads;
+                a.t_pad = v.c / a.C;
+                IPDM_CHECK(attention_prepare(o.ap, a));
+                o.flops = attention_flops(a);
+            } break;
+        }
+        pl->flops += o.flops;
+    }
+    *out = pl.get();
+    net->plans[std::make_tuple(B, H, W)] = std::move(pl);
+    return IPDM_OK;
+}
+
+__global__ void set_int_kernel(int* p, int v) { *p = v; }
+
+static int run_plan(ipdm_unet* net, Plan* pl, const float* x, int t, float* eps, cudaStream_t st) {
+    set_int_kernel<<<1, 1, 0, st>>>(net->t_dev, t);
+    count_launch();
+    for (size_t i = 0; i < pl->ops.size(); ++i) {
+        Op& o = pl->ops[i];
+        switch (o.kind) {
+            case Op::GN_STATS: IPDM_CHECK(groupnorm_stats_launch(o.gd, st)); break;
+            case Op::GN_APPLY: IPDM_CHECK(groupnorm_apply_launch(o.gd, o.out_t, o.act, st)); break;
+            case Op::CONV_TC: IPDM_CHECK(conv_tc_launch(o.tcp, st)); break;
+            case Op::CONV_DIRECT: {
+                ConvDirectDesc d = o.cd;
+                if ((int)i == pl->first_op) d.src[0].p = const_cast<float*>(x);
+                if ((int)i == pl->last_op) d.out.p = eps;
+                IPDM_CHECK(conv_direct_launch(d, st));
+            } break;
+            case Op::UPSAMPLE: IPDM_CHECK(upsample_nearest_launch(o.src_t, o.out_t, st)); break;
+            case Op::ATTN: IPDM_CHECK(attention_launch(o.ap, st)); break;
+        }
+    }
+    return IPDM_OK;
+}
+
+static int get_plan(ipdm_unet* net, int B, int H, int W, Plan** out) {
+    auto it = net->plans.find(std::make_tuple(B, H, W));
+    if (it != net->plans.end()) { *out = it->second.get(); return IPDM_OK; }
+    return build_plan(net, B, H, W, out);
+}
+
+}  // namespace ipdm
+
+extern "C" long long ipdm_unet_param_count(const ipdm_unet_config* cfg) {
+    if (!cfg || cfg->n_mult < 2 || cfg->n_mult > 8) return -1;
+    CountVisitor cv; walk_arch(*cfg, cv); return cv.n;
+}
+
+extern "C" int ipdm_unet_create(ipdm_unet** out, const ipdm_unet_config* cfg, const float* weights_host, size_t n_weights) {
+    IPDM_REQUIRE(out && cfg && weights_host, "ipdm_unet_create: null argument");
+    IPDM_REQUIRE(cfg->n_mult >= 2 && cfg->n_mult <= 8 && cfg->n_attn >= 0 && cfg->n_attn <= 8, "ipdm_unet_create: bad config");
+    IPDM_REQUIRE(cfg->precision == IPDM_PREC_TF32, "ipdm_unet_create: only IPDM_PREC_TF32 is implemented in this build");
+    const long long expect = ipdm_unet_param_count(cfg);
+    IPDM_REQUIRE((long long)n_weights == expect, "ipdm_unet_create: got %zu weights, the config needs %lld", n_weights, expect);
+    std::unique_ptr<ipdm_unet> net(new ipdm_unet());
+    net->cfg = *cfg; net->heads = cfg->num_heads;
+    if (net->cfg.max_t <= 0) net->cfg.max_t = 64;
+    IPDM_CHECK_CUDA(cudaMalloc(&net->t_dev, sizeof(int)));
+    Reader r{weights_host, n_weights};
+    // conservative reserves so that references into the vectors stay valid while blocks are appended
+    net->convs.reserve(256); net->res.reserve(256); net->attn.reserve(256); net->down_blocks.reserve(256); net->up_blocks.reserve(256);
+    BuildVisitor bv(net.get(), r);
+    walk_arch(net->cfg, bv);
+    IPDM_CHECK(bv.rc);
+    IPDM_REQUIRE(r.ok && r.pos == n_weights, "ipdm_unet_create: weight buffer walk ended at %zu of %zu", r.pos, n_weights);
+    IPDM_CHECK(build_time_tables(net.get(), bv));
+    *out = net.release();
+    return IPDM_OK;
+}
+
+extern "C" int ipdm_unet_destroy(ipdm_unet* net) { delete net; return IPDM_OK; }
+
+extern "C" int ipdm_unet_forward(ipdm_unet* net, const float* x, int t, float* eps, int batch, int h, int w, void* stream) {
+    IPDM_REQUIRE(net && x && eps && batch > 0 && h > 0 && w > 0, "ipdm_unet_forward: bad arguments");
+    IPDM_REQUIRE(t >= 0 && t < net->cfg.max_t, "ipdm_unet_forward: timestep %d outside the precomputed range [0, %d)", t, net->cfg.max_t);
+    Plan* pl = nullptr;
+    IPDM_CHECK(get_plan(net, batch, h, w, &pl));
+    return run_plan(net, pl, x, t, eps, (cudaStream_t)stream);
+}
+
+extern "C" double ipdm_unet_flops(const ipdm_unet* cnet, int batch, int h, int w) {
+    ipdm_unet* net = const_cast<ipdm_unet*>(cnet);
+    Plan* pl = nullptr;
+    if (!net || get_plan(net, batch, h, w, &pl) != IPDM_OK) return -1.0;
+    return pl->flops;
+}
+
+// ------------------------------------------------------------------------------------------------
+// single-op entry points for the per-kernel parity tests (tests/test_unet_kernels_gpu.py)
+// ------------------------------------------------------------------------------------------------
+static TensorNHWC mk(const float* p, int n, int h, int w, int c, int cs) {
+    TensorNHWC t; t.p = const_cast<float*>(p); t.n = n; t.h = h; t.w = w; t.c = c; t.cs = cs; return t;
+}
+
+extern "C" int ipdm_debug_conv(const float* src0, int c0, int cs0, const float* src1, int c1, int cs1, int n, int h, int w,
+                               const float* w_host, const float* bias_host, int cout, int k, int stride, int upsample_h,
+                               int upsample_w, const float* norm_scale, const float* norm_shift, const float* res, int res_cs,
+                               float* out, int out_cs, int use_tc, void* stream) {
+    IPDM_REQUIRE(src0 && w_host && out, "ipdm_debug_conv: null argument");
+    ipdm_unet holder;
+    ConvW cw; cw.cin = c0 + c1; cw.cout = cout; cw.k = k;
+    cw.w_host.assign(w_host, w_host + (size_t)cout * cw.cin * k * k);
+    if (bias_host) cw.b_host.assign(bias_host, bias_host + cout);
+    IPDM_CHECK(pack_conv(&holder, cw, c0, c1, true, use_tc));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int hin = upsample_h > 0 ? upsample_h : h, win = upsample_w > 0 ? upsample_w : w;
+    const int ho = stride == 1 ? hin : (hin + 1) / 2, wo = stride == 1 ? win : (win + 1) / 2;
+    int rc;
+    if (use_tc) {
+        IPDM_REQUIRE(cs0 == cw.cs0 && (c1 == 0 || cs1 == cw.cs1), "ipdm_debug_conv: tensor-core sources need channel strides %d / %d", cw.cs0, cw.cs1);
+        IPDM_REQUIRE(upsample_h == 0 && !norm_scale, "ipdm_debug_conv: upsample / fused norm are direct-path features");
+        ConvTcDesc d; d.nsrc = c1 ? 2 : 1; d.src[0] = mk(src0, n, h, w, c0, cs0); if (c1) d.src[1] = mk(src1, n, h, w, c1, cs1);
+        d.ntaps = k * k; d.stride = stride; d.cout = cout; d.w_packed = cw.w_dev; d.w_k = cw.kpad; d.bias = cw.b_dev;
+        if (res) d.res = mk(res, n, ho, wo, cout, res_cs);
+        d.out = mk(out, n, ho, wo, cout, out_cs);
+        ConvTcParams P;
+        IPDM_CHECK(conv_tc_prepare(P, d));
+        rc = conv_tc_launch(P, st);
+    } else {
+        ConvDirectDesc d; d.nsrc = c1 ? 2 : 1; d.src[0] = mk(src0, n, h, w, c0, cs0); if (c1) d.src[1] = mk(src1, n, h, w, c1, cs1);
+        d.norm_scale = norm_scale; d.norm_shift = norm_shift; d.ksize = k; d.stride = stride; d.upsample = upsample_h > 0;
+        d.cin = cw.cin; d.cout = cout; d.w = cw.w_dev; d.bias = cw.b_dev;
+        if (res) d.res = mk(res, n, ho, wo, cout, res_cs);
+        d.out = mk(out, n, ho, wo, cout, out_cs);
+        rc = conv_direct_launch(d, st);
+    }
+    cudaStreamSynchronize(st);      // the packed weights are freed when `holder` goes out of scope
+    return rc;
+}
+
+extern "C" int ipdm_debug_groupnorm(const float* src0, int c0, int cs0, const float* src1, int c1, int cs1, int n, int h, int w,
+                                    const float* gamma_host, const float* beta_host, int act_silu, float* scale_out,
+                                    float* shift_out, float* out, int out_cs, void* stream) {
+    IPDM_REQUIRE(src0 && gamma_host && beta_host && scale_out && shift_out, "ipdm_debug_groupnorm: null argument");
+    ipdm_unet holder;
+    const int C = c0 + c1;
+    GNW g; g.C = C; g.groups = gn_groups(C);
+    IPDM_CHECK(upload(&holder, std::vector<float>(gamma_host, gamma_host + C), &g.gamma));
+    IPDM_CHECK(upload(&holder, std::vector<float>(beta_host, beta_host + C), &g.beta));
+    double* partials = nullptr;
+    IPDM_CHECK_CUDA(cudaMalloc(&partials, (size_t)n * GN_MAX_BLOCKS * C * 2 * sizeof(double)));
+    GroupNormDesc d; d.nsrc = c1 ? 2 : 1; d.src[0] = mk(src0, n, h, w, c0, cs0); if (c1) d.src[1] = mk(src1, n, h, w, c1, cs1);
+    d.groups = g.groups; d.gamma = g.gamma; d.beta = g.beta; d.scale = scale_out; d.shift = shift_out; d.partials = partials;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = groupnorm_stats_launch(d, st);
+    if (rc == IPDM_OK && out) rc = groupnorm_apply_launch(d, mk(out, n, h, w, C, out_cs), act_silu, st);
+    cudaStreamSynchronize(st);
+    cudaFree(partials);
+    return rc;
+}
+
+extern "C" int ipdm_debug_attention(const float* qk, const float* vt, float* out, int batch, int T, int t_pad, int heads, int C, void* stream) {
+    AttentionDesc a; a.qk = qk; a.vt = vt; a.out = out; a.batch = batch; a.T = T; a.t_pad = t_pad; a.heads = heads; a.C = C; a.head_dim = C / heads;
+    AttentionParams P;
+    IPDM_CHECK(attention_prepare(P, a));
+    return attention_launch(P, (cudaStream_t)stream);
+}
+
+extern "C" int ipdm_debug_upsample(const float* src, int n, int hs, int ws, int cs, float* dst, int hd, int wd, void* stream) {
+    return upsample_nearest_launch(mk(src, n, hs, ws, cs, cs), mk(dst, n, hd, wd, cs, cs), (cudaStream_t)stream);
+}

@@ -1,0 +1,307 @@
+// CUDA-core kernels of the UNet noise predictor (NHWC fp32): direct convolution for the thin
+// full-resolution layers, GroupNorm statistics / apply+SiLU, nearest-neighbour resize.
+// Reference semantics: Model/model.py norm_layer :82-90, ResidualBlock :95-130, Upsample :160-171,
+// Downsample :175-185, UNetModel.out :277-281.
+#include "unet_ops.cuh"
+
+#include <algorithm>
+
+namespace ipdm {
+
+// ------------------------------------------------------------------------------------------------
+// direct convolution: one output pixel per thread, all (<= 16) output channels in registers.
+// The CTA stages the input halo tile in shared memory as planes [c][y][x] (conflict-free reads for
+// neighbouring pixels) and applies GroupNorm+SiLU / virtual concat / nearest upsample while loading.
+// Memory-bound layers (C <= 24 at 2000x912 / 1000x456): 4*(C_in + C_out) bytes per pixel.
+// ------------------------------------------------------------------------------------------------
+struct ConvDirectParams {
+    const float* src0; const float* src1;
+    int c0, cs0, c1, cs1;                 // channels / channel stride of each source
+    int hs, ws;                           // source spatial size
+    int hin, win;                         // conv-input spatial size (== source, or the upsampled size)
+    int hout, wout;
+    float up_sy, up_sx; int upsample;
+    const float* nscale; const float* nshift;
+    int ksize, stride, cin, cout, co_tiles;
+    const float* w; const float* bias; int bias_t_stride; const int* t_dev;
+    const float* res; int res_cs;
+    float* out; int out_cs;
+};
+
+constexpr int CD_TX = 32, CD_TY = 8;
+
+template <int COUT_T>
+__global__ void __launch_bounds__(CD_TX * CD_TY)
+conv_direct_kernel(const ConvDirectParams P) {
+    extern __shared__ float cd_smem[];
+    const int K = P.ksize, pad = K / 2;
+    const int tin_w = (CD_TX - 1) * P.stride + K, tin_h = (CD_TY - 1) * P.stride + K;
+    const int plane = tin_w * tin_h + 1;                      // +1: de-phase the planes across banks
+    float* tile = cd_smem;                                    // [cin][plane]
+    float* wsm = cd_smem + (((size_t)P.cin * plane + 3) & ~(size_t)3);   // [K*K][cin][COUT_T], 16-byte aligned
+    const int n = blockIdx.z / P.co_tiles;
+    const int co_base = (blockIdx.z - n * P.co_tiles) * COUT_T;   // C_out > 16: tiles of COUT_T output channels
+    const int ox0 = blockIdx.x * CD_TX, oy0 = blockIdx.y * CD_TY;
+    const int ix0 = ox0 * P.stride - pad, iy0 = oy0 * P.stride - pad;
+    const int tid = threadIdx.y * CD_TX + threadIdx.x;
+
+    // weights -> smem, zero-padded to COUT_T output channels
+    const int wtot = K * K * P.cin * COUT_T;
+    for (int i = tid; i < wtot; i += CD_TX * CD_TY) {
+        const int co = i % COUT_T, rest = i / COUT_T;
+        wsm[i] = co_base + co < P.cout ? __ldg(P.w + (size_t)rest * P.cout + co_base + co) : 0.f;
+    }
+    // input halo tile -> smem planes
+    const int tot = tin_w * tin_h * P.cin;
+    for (int i = tid; i < tot; i += CD_TX * CD_TY) {
+        const int c = i % P.cin, pix = i / P.cin;
+        const int ly = pix / tin_w, lx = pix - ly * tin_w;
+        const int iy = iy0 + ly, ix = ix0 + lx;
+        float v = 0.f;
+        if (iy >= 0 && iy < P.hin && ix >= 0 && ix < P.win) {
+            int sy = iy, sx = ix;
+            if (P.upsample) {
+                sy = min((int)floorf((float)iy * P.up_sy), P.hs - 1);
+                sx = min((int)floorf((float)ix * P.up_sx), P.ws - 1);
+            }
+            const size_t sp = ((size_t)n * P.hs + sy) * P.ws + sx;
+            v = c < P.c0 ? __ldg(P.src0 + sp * P.cs0 + c) : __ldg(P.src1 + sp * P.cs1 + (c - P.c0));
+            if (P.nscale) {
+                v = fmaf(v, __ldg(P.nscale + (size_t)n * P.cin + c), __ldg(P.nshift + (size_t)n * P.cin + c));
+                v = silu(v);
+            }
+        }
+        tile[(size_t)c * plane + pix] = v;
+    }
+    __syncthreads();
+
+    const int ox = ox0 + threadIdx.x, oy = oy0 + threadIdx.y;
+    float acc[COUT_T];
+#pragma unroll
+    for (int i = 0; i < COUT_T; ++i) acc[i] = 0.f;
+    const int lbase = threadIdx.y * P.stride * tin_w + threadIdx.x * P.stride;
+    for (int tap = 0; tap < K * K; ++tap) {
+        const int dy = tap / K, dx = tap - dy * K;
+        const float* tp = tile + lbase + dy * tin_w + dx;
+        const float4* wp = reinterpret_cast<const float4*>(wsm + (size_t)tap * P.cin * COUT_T);
+        for (int c = 0; c < P.cin; ++c) {
+            const float v = tp[(size_t)c * plane];
+#pragma unroll
+            for (int q = 0; q < COUT_T / 4; ++q) {
+                const float4 w4 = wp[c * (COUT_T / 4) + q];
+                acc[4 * q] = fmaf(v, w4.x, acc[4 * q]);
+                acc[4 * q + 1] = fmaf(v, w4.y, acc[4 * q + 1]);
+                acc[4 * q + 2] = fmaf(v, w4.z, acc[4 * q + 2]);
+                acc[4 * q + 3] = fmaf(v, w4.w, acc[4 * q + 3]);
+            }
+        }
+    }
+    if (ox >= P.wout || oy >= P.hout) return;
+    const size_t op = ((size_t)n * P.hout + oy) * P.wout + ox;
+    const float* bias = P.bias ? P.bias + (P.t_dev ? (size_t)(*P.t_dev) * P.bias_t_stride : 0) : nullptr;
+#pragma unroll
+    for (int i = 0; i < COUT_T; ++i) {
+        const int co = co_base + i;
+        if (co < P.cout) {
+            float v = acc[i] + (bias ? __ldg(bias + co) : 0.f);
+            if (P.res) v += __ldg(P.res + op * P.res_cs + co);
+            P.out[op * P.out_cs + co] = v;
+        } else if (co < P.out_cs) {
+            P.out[op * P.out_cs + co] = 0.f;
+        }
+    }
+    if (co_base + COUT_T >= P.cout)
+        for (int co = co_base + COUT_T; co < P.out_cs; ++co) P.out[op * P.out_cs + co] = 0.f;
+}
+
+int conv_direct_launch(const ConvDirectDesc& d, cudaStream_t st) {
+    ConvDirectParams P{};
+    const TensorNHWC& s0 = d.src[0];
+    P.src0 = s0.p; P.c0 = s0.c; P.cs0 = s0.cs;
+    if (d.nsrc == 2) { P.src1 = d.src[1].p; P.c1 = d.src[1].c; P.cs1 = d.src[1].cs; }
+    IPDM_REQUIRE(d.cin == P.c0 + P.c1, "conv_direct: C_in %d != %d + %d", d.cin, P.c0, P.c1);
+    IPDM_REQUIRE(d.cout >= 1, "conv_direct: C_out %d", d.cout);
+    IPDM_REQUIRE(d.ksize == 1 || d.ksize == 3, "conv_direct: 1x1 or 3x3");
+    P.hs = s0.h; P.ws = s0.w;
+    P.upsample = d.upsample;
+    P.hin = d.upsample ? d.out.h : s0.h; P.win = d.upsample ? d.out.w : s0.w;
+    P.up_sy = (float)s0.h / (float)P.hin; P.up_sx = (float)s0.w / (float)P.win;
+    P.hout = d.stride == 1 ? P.hin : (P.hin + 2 * (d.ksize / 2) - d.ksize) / 2 + 1;
+    P.wout = d.stride == 1 ? P.win : (P.win + 2 * (d.ksize / 2) - d.ksize) / 2 + 1;
+    IPDM_REQUIRE(d.out.h == P.hout && d.out.w == P.wout && d.out.n == s0.n, "conv_direct: output shape mismatch (%dx%d vs %dx%d)",
+                 d.out.h, d.out.w, P.hout, P.wout);
+    P.nscale = d.norm_scale; P.nshift = d.norm_shift;
+    P.ksize = d.ksize; P.stride = d.stride; P.cin = d.cin; P.cout = d.cout;
+    P.w = d.w; P.bias = d.bias; P.bias_t_stride = d.bias_t_stride; P.t_dev = d.t_dev;
+    P.res = d.res.p; P.res_cs = d.res.cs;
+    P.out = d.out.p; P.out_cs = d.out.cs;
+    const int ct = d.cout <= 4 ? 4 : (d.cout <= 8 ? 8 : 16);
+    P.co_tiles = (d.cout + ct - 1) / ct;
+    const int tin_w = (CD_TX - 1) * d.stride + d.ksize, tin_h = (CD_TY - 1) * d.stride + d.ksize;
+    const size_t smem = ((((size_t)d.cin * (tin_w * tin_h + 1) + 3) & ~(size_t)3) + (size_t)d.ksize * d.ksize * d.cin * ct) * sizeof(float);
+    IPDM_REQUIRE(smem <= 200 * 1024, "conv_direct: tile needs %zu bytes of shared memory", smem);
+    dim3 grid(ceil_div(P.wout, CD_TX), ceil_div(P.hout, CD_TY), s0.n * P.co_tiles), block(CD_TX, CD_TY);
+    auto go = [&](auto kern) -> int {
+        if (smem > 48 * 1024) IPDM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, block, smem, st>>>(P);
+        return IPDM_OK;
+    };
+    int rc = ct == 4 ? go(conv_direct_kernel<4>) : (ct == 8 ? go(conv_direct_kernel<8>) : go(conv_direct_kernel<16>));
+    IPDM_CHECK(rc);
+    count_launch();
+    IPDM_CHECK_LAUNCH();
+    return IPDM_OK;
+}
+
+double conv_direct_flops(const ConvDirectDesc& d) {
+    return 2.0 * d.out.n * d.out.h * d.out.w * (double)d.cin * d.cout * d.ksize * d.ksize;
+}
+
+// ------------------------------------------------------------------------------------------------
+// GroupNorm statistics
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gn_partial_kernel(const float* __restrict__ src, int C, int cs, size_t npix, double* __restrict__ partials, int c_off, int Ctot) {
+    __shared__ float red[256][8];
+    const int n = blockIdx.y, V = C / 4;
+    const int R = 256 / V > 0 ? 256 / V : 1;                    // pixel rows handled in parallel
+    const int TA = R * V;
+    const int t = threadIdx.x;
+    float4 s = make_float4(0, 0, 0, 0), q = make_float4(0, 0, 0, 0);
+    if (t < TA) {
+        const int cv = t % V, prow = t / V;
+        const float* base = src + (size_t)n * npix * cs + 4 * cv;
+        for (size_t pix = (size_t)blockIdx.x * R + prow; pix < npix; pix += (size_t)gridDim.x * R) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(base + pix * cs));
+            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+            q.x = fmaf(v.x, v.x, q.x); q.y = fmaf(v.y, v.y, q.y); q.z = fmaf(v.z, v.z, q.z); q.w = fmaf(v.w, v.w, q.w);
+        }
+    }
+    red[t][0] = s.x; red[t][1] = s.y; red[t][2] = s.z; red[t][3] = s.w;
+    red[t][4] = q.x; red[t][5] = q.y; red[t][6] = q.z; red[t][7] = q.w;
+    __syncthreads();
+    for (int c = t; c < C; c += 256) {
+        const int cv = c / 4, comp = c % 4;
+        double a = 0, b = 0;
+        for (int r = 0; r < R; ++r) { a += red[r * V + cv][comp]; b += red[r * V + cv][4 + comp]; }
+        double* o = partials + (((size_t)n * gridDim.x + blockIdx.x) * Ctot + c_off + c) * 2;
+        o[0] = a; o[1] = b;
+    }
+}
+
+__global__ void gn_finalize_kernel(const double* __restrict__ partials, int nblk, int Ctot, int groups, double count,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                   float* __restrict__ scale, float* __restrict__ shift) {
+    const int n = blockIdx.x, cpg = Ctot / groups;
+    for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+        double a = 0, b = 0;
+        for (int blk = 0; blk < nblk; ++blk)
+            for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+                const double* o = partials + (((size_t)n * nblk + blk) * Ctot + c) * 2;
+                a += o[0]; b += o[1];
+            }
+        const double mean = a / count;
+        double var = b / count - mean * mean;
+        var = var < 0 ? 0 : var;
+        const double rstd = 1.0 / sqrt(var + (double)eps);
+        for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+            const double ga = gamma[c];
+            scale[(size_t)n * Ctot + c] = (float)(ga * rstd);
+            shift[(size_t)n * Ctot + c] = (float)((double)beta[c] - mean * ga * rstd);
+        }
+    }
+}
+
+int groupnorm_stats_launch(const GroupNormDesc& d, cudaStream_t st) {
+    int Ctot = 0;
+    for (int s = 0; s < d.nsrc; ++s) Ctot += d.src[s].c;
+    IPDM_REQUIRE(Ctot % d.groups == 0, "groupnorm: %d channels not divisible by %d groups", Ctot, d.groups);
+    const TensorNHWC& s0 = d.src[0];
+    const size_t npix = (size_t)s0.h * s0.w;
+    const int R0 = std::max(1, 256 / (s0.c / 4));
+    const int nblk = (int)std::min<size_t>(GN_MAX_BLOCKS, (npix + R0 - 1) / R0);   // one partial grid for all sources
+    int c_off = 0;
+    for (int s = 0; s < d.nsrc; ++s) {
+        const TensorNHWC& t = d.src[s];
+        IPDM_REQUIRE(t.c % 4 == 0 && t.cs % 4 == 0 && t.c <= 1024, "groupnorm: channel count %d must be a multiple of 4", t.c);
+        gn_partial_kernel<<<dim3(nblk, s0.n), 256, 0, st>>>(t.p, t.c, t.cs, npix, d.partials, c_off, Ctot);
+        count_launch();
+        c_off += t.c;
+    }
+    gn_finalize_kernel<<<s0.n, 64, 0, st>>>(d.partials, nblk, Ctot, d.groups, (double)npix * (Ctot / d.groups), d.gamma, d.beta, d.eps,
+                                            d.scale, d.shift);
+    count_launch();
+    IPDM_CHECK_LAUNCH();
+    return IPDM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// GroupNorm apply + SiLU (+ virtual concat, + channel padding) -> operand tensor of a tensor-core conv
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gn_apply_kernel(const float* __restrict__ s0, int c0, int cs0, const float* __restrict__ s1, int c1, int cs1,
+                const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ out, int ocs,
+                size_t npix_per_slice, size_t nvec_total, int act) {
+    const int Ctot = c0 + c1, V = ocs / 4;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < nvec_total; i += (size_t)gridDim.x * 256) {
+        const size_t pix = i / V;
+        const int c = (int)(i - pix * V) * 4;
+        const int n = (int)(pix / npix_per_slice);
+        float4 o = make_float4(0, 0, 0, 0);
+        if (c < Ctot) {
+            const float4 v = c < c0 ? __ldg(reinterpret_cast<const float4*>(s0 + pix * cs0 + c))
+                                    : __ldg(reinterpret_cast<const float4*>(s1 + pix * cs1 + (c - c0)));
+            const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + (size_t)n * Ctot + c));
+            const float4 sh = __ldg(reinterpret_cast<const float4*>(shift + (size_t)n * Ctot + c));
+            o.x = fmaf(v.x, sc.x, sh.x); o.y = fmaf(v.y, sc.y, sh.y); o.z = fmaf(v.z, sc.z, sh.z); o.w = fmaf(v.w, sc.w, sh.w);
+            if (act) { o.x = silu(o.x); o.y = silu(o.y); o.z = silu(o.z); o.w = silu(o.w); }
+        }
+        *reinterpret_cast<float4*>(out + pix * ocs + c) = o;
+    }
+}
+
+int groupnorm_apply_launch(const GroupNormDesc& d, const TensorNHWC& out, int act_silu, cudaStream_t st) {
+    const TensorNHWC& a = d.src[0];
+    const int c1 = d.nsrc == 2 ? d.src[1].c : 0;
+    IPDM_REQUIRE(out.cs % 4 == 0 && out.cs >= a.c + c1 && a.c % 4 == 0, "groupnorm_apply: bad channel layout");
+    const size_t npix = (size_t)a.h * a.w, nvec = (size_t)a.n * npix * (out.cs / 4);
+    const int grid = (int)std::min<size_t>((size_t)kNumSMs * 8, (nvec + 255) / 256);
+    gn_apply_kernel<<<grid, 256, 0, st>>>(a.p, a.c, a.cs, d.nsrc == 2 ? d.src[1].p : nullptr, c1, d.nsrc == 2 ? d.src[1].cs : 0,
+                                          d.scale, d.shift, out.p, out.cs, npix, nvec, act_silu);
+    count_launch();
+    IPDM_CHECK_LAUNCH();
+    return IPDM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// nearest resize
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+upsample_kernel(const float* __restrict__ src, int hs, int ws, int scs, float* __restrict__ dst, int hd, int wd, int dcs,
+                float sy, float sx, size_t nvec_total) {
+    const int V = dcs / 4;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < nvec_total; i += (size_t)gridDim.x * 256) {
+        const size_t pix = i / V;
+        const int c = (int)(i - pix * V) * 4;
+        const int x = (int)(pix % wd);
+        const size_t r = pix / wd;
+        const int y = (int)(r % hd), n = (int)(r / hd);
+        const int yy = min((int)floorf((float)y * sy), hs - 1), xx = min((int)floorf((float)x * sx), ws - 1);
+        float4 v = make_float4(0, 0, 0, 0);
+        if (c < scs) v = __ldg(reinterpret_cast<const float4*>(src + (((size_t)n * hs + yy) * ws + xx) * scs + c));
+        *reinterpret_cast<float4*>(dst + pix * dcs + c) = v;
+    }
+}
+
+int upsample_nearest_launch(const TensorNHWC& src, const TensorNHWC& dst, cudaStream_t st) {
+    IPDM_REQUIRE(src.cs % 4 == 0 && dst.cs % 4 == 0 && dst.cs >= src.cs && src.n == dst.n, "upsample: bad layout");
+    const size_t nvec = dst.pixels() * (dst.cs / 4);
+    const int grid = (int)std::min<size_t>((size_t)kNumSMs * 8, (nvec + 255) / 256);
+    upsample_kernel<<<grid, 256, 0, st>>>(src.p, src.h, src.w, src.cs, dst.p, dst.h, dst.w, dst.cs, (float)src.h / dst.h,
+                                          (float)src.w / dst.w, nvec);
+    count_launch();
+    IPDM_CHECK_LAUNCH();
+    return IPDM_OK;
+}
+
+}  // namespace ipdm

@@ -1,0 +1,102 @@
+// Internal op interfaces of the UNet noise predictor (host launchers; kernels live in *.cu).
+#pragma once
+#include "common.cuh"
+#include <cuda.h>
+#include <cstring>
+
+namespace ipdm {
+
+// Activation tensor: NHWC fp32, `cs` >= c floats per pixel (pad channels hold zeros).
+struct TensorNHWC {
+    float* p = nullptr;
+    int n = 0, h = 0, w = 0, c = 0, cs = 0;
+    size_t pixels() const { return (size_t)n * h * w; }
+    size_t elems() const { return pixels() * cs; }
+};
+
+// ---- tensor-core implicit GEMM convolution (conv_tc.cu) ---------------------------------------------
+struct ConvTcDesc {
+    int nsrc = 1;
+    TensorNHWC src[2];          // virtual concat along channels; both padded to multiples of 32
+    int ntaps = 9, stride = 1;
+    int cout = 0;
+    const float* w_packed = nullptr;   // [ntaps][cout][w_k]
+    int w_k = 0;
+    const float* bias = nullptr;       // [cout] or table [max_t][bias_t_stride]
+    int bias_t_stride = 0;
+    const int* t_dev = nullptr;        // device scalar: current timestep (selects the bias row)
+    TensorNHWC res;                    // optional residual, same pixels as the output
+    TensorNHWC out;
+    int qkv_mode = 0; float* vt = nullptr; int t_pad = 0, heads = 0, head_dim = 0;
+};
+
+struct ConvTcParams {
+    CUtensorMap mapA[4];
+    CUtensorMap mapB;
+    int H, W, tiles_x, tiles_y, tw_log2, batch;
+    int ntaps, stride, nk0, nk1;
+    int cout, cout_rows, block_n;
+    float* out; int out_cs;
+    const float* bias; int bias_t_stride; const int* t_dev;
+    const float* res; int res_cs;
+    int qkv_mode; float* vt; int t_pad, heads, head_dim;
+};
+
+int conv_tc_prepare(ConvTcParams& P, const ConvTcDesc& d);
+int conv_tc_launch(const ConvTcParams& P, cudaStream_t st);
+double conv_tc_flops(const ConvTcParams& P);
+
+// ---- direct (CUDA-core) convolution for thin layers (unet_kernels.cu) -------------------------------
+struct ConvDirectDesc {
+    int nsrc = 1;
+    TensorNHWC src[2];                 // virtual concat
+    const float* norm_scale = nullptr; // optional fused GroupNorm+SiLU on load: y = silu(x*scale[n][c] + shift[n][c])
+    const float* norm_shift = nullptr; //   both [batch][cin_total]
+    int ksize = 3, stride = 1;
+    int upsample = 0;                  // 1: sources are nearest-upsampled to (out.h, out.w) before the conv
+    int cin = 0, cout = 0;
+    const float* w = nullptr;          // [ksize*ksize][cin][cout]; C_out > 16 is processed in tiles of 16
+    const float* bias = nullptr; int bias_t_stride = 0; const int* t_dev = nullptr;
+    TensorNHWC res;
+    TensorNHWC out;                    // pad channels (c..cs) are written as zeros
+};
+int conv_direct_launch(const ConvDirectDesc& d, cudaStream_t st);
+double conv_direct_flops(const ConvDirectDesc& d);
+
+// ---- GroupNorm (unet_kernels.cu) ---------------------------------------------------------------------
+// statistics over (H, W, C/G) per slice and group -> per-(slice, channel) affine y = x*scale + shift
+struct GroupNormDesc {
+    int nsrc = 1;
+    TensorNHWC src[2];                 // virtual concat
+    int groups = 0;
+    const float* gamma = nullptr;      // [C]
+    const float* beta = nullptr;
+    float eps = 1e-5f;
+    float* scale = nullptr;            // [batch][C] out
+    float* shift = nullptr;
+    double* partials = nullptr;        // workspace [batch][GN_MAX_BLOCKS][C][2]
+};
+constexpr int GN_MAX_BLOCKS = 128;
+int groupnorm_stats_launch(const GroupNormDesc& d, cudaStream_t st);
+// out[n][y][x][c] = act(src*scale + shift) (c < C; act = SiLU or identity), 0 for pad channels; out.cs may exceed C
+int groupnorm_apply_launch(const GroupNormDesc& d, const TensorNHWC& out, int act_silu, cudaStream_t st);
+
+// nearest-neighbour resize (F.interpolate(mode="nearest") index rule), NHWC
+int upsample_nearest_launch(const TensorNHWC& src, const TensorNHWC& dst, cudaStream_t st);
+
+// ---- attention (attention.cu) --------------------------------------------------------------------------
+struct AttentionDesc {
+    const float* qk = nullptr;  // NHWC [B][T][3*C]: per head h, q at channel 3*d*h, k at 3*d*h + d
+    const float* vt = nullptr;  // [B][heads][d][t_pad]
+    float* out = nullptr;       // NHWC [B][T][C], channel = h*d + dd
+    int batch = 0, T = 0, t_pad = 0, heads = 0, head_dim = 0, C = 0;
+};
+struct AttentionParams {
+    CUtensorMap mapQ, mapK, mapV;
+    float* out; int batch, T, heads, C; float scale_log2;
+};
+int attention_prepare(AttentionParams& P, const AttentionDesc& d);
+int attention_launch(const AttentionParams& P, cudaStream_t st);
+double attention_flops(const AttentionDesc& d);
+
+}  // namespace ipdm

@@ -1,0 +1,15 @@
+"""Import shim: the package directory is named `ipdm-pytorch_b200` (not a valid Python identifier).
+
+`import ipdm_pytorch_b200` loads `ipdm-pytorch_b200/__init__.py` as a regular package, so
+`ipdm_pytorch_b200.engine`, `ipdm_pytorch_b200.synthetic` ... resolve inside that directory.
+"""
+import importlib.util
+import os
+import sys
+
+_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ipdm-pytorch_b200")
+_spec = importlib.util.spec_from_file_location(__name__, os.path.join(_dir, "__init__.py"),
+                                               submodule_search_locations=[_dir])
+_mod = importlib.util.module_from_spec(_spec)
+sys.modules[__name__] = _mod
+_spec.loader.exec_module(_mod)
