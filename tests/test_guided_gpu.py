@@ -1,0 +1,78 @@
+"""GPU parity: guided partial reverse process (ipdm_guided_process) vs goldens from the unmodified reference."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden, rel_l2
+from inputs import IMG_CFG, PROJ_CFG, noise_tape, small_img_input, small_proj_input
+
+pytestmark = pytest.mark.gpu
+GRP_TOL = 2e-3      # rel-L2 of every recorded iterate after 45 (proj) / 60 (img) TF32 UNet calls with injected noise
+
+
+def _tape(shape, count, seed, dev):
+    return torch.stack(noise_tape(shape, count, seed)).to(dev).contiguous()
+
+
+def test_proj_domain_adaptive_lambda_two_slices(cuda):
+    from Model.model import GaussianDiffusion, UNetModel
+    g = golden("grp_small")
+    torch.manual_seed(0)
+    net = UNetModel(**PROJ_CFG).to(cuda).eval()
+    gd = GaussianDiffusion(1000, "cosine", schedule_power=5)
+    xs = [small_proj_input(200 + s) for s in (0, 1)]
+    tapes = [_tape(xs[0].shape, 48, 300 + s, cuda) for s in (0, 1)]
+    kw = dict(t_start=[15, 15, 15], clip=False, lambda_ratio=1, eta=0.5, mode="proj", constant_guidance=None,
+              kernel_size_proj=4, amplitude_proj=7, only_convertor=False, normal=False)
+    # batch of two different slices == the reference run per slice at B = 1
+    x = torch.cat(xs).to(cuda)
+    noise = torch.cat(tapes, dim=1).contiguous()                        # [48, 2, 1, H, W]
+    res, _, ns = gd.guided_reverse_process(net, x, noise=noise, **kw)
+    assert ns is None and len(res) == 4
+    for s in (0, 1):
+        got = np.stack([r[s, 0].cpu().numpy() for r in res])
+        err = [rel_l2(got[k], g[f"proj{s}"][k]) for k in range(4)]
+        print(f"proj slice {s}: rel-L2 per iterate {['%.2e' % e for e in err]}")
+        assert max(err) < GRP_TOL
+    one, _, _ = gd.guided_reverse_process(net, xs[1].to(cuda), noise=tapes[1], **kw)
+    assert rel_l2(one[-1].cpu().numpy(), res[-1][1:2].cpu().numpy()) < 1e-5
+
+
+def test_img_domain_constant_guidance_and_ultra(cuda):
+    from Model.model import GaussianDiffusion, UNetModel
+    g = golden("grp_small")
+    torch.manual_seed(1)
+    net = UNetModel(**IMG_CFG).to(cuda).eval()
+    gd = GaussianDiffusion(1000, "cosine", schedule_power=1)
+    for s in (0, 1):
+        x = small_img_input(400 + s).to(cuda)
+        tape = _tape(x.shape, 66, 500 + s, cuda)
+        common = dict(model=net, clip=True, lambda_ratio=10, mode="img", ldct=x, kernel_size_img=4, amplitude_img=30,
+                      only_convertor=False, normal=False)
+        res, _, _ = gd.guided_reverse_process(img=x, t_start=[15, 15, 15], eta=0.7, constant_guidance=0.45, noise=tape[:48].contiguous(), **common)
+        res2, _, _ = gd.guided_reverse_process(img=res[-1], t_start=[5, 5, 5], eta=0.6, constant_guidance=0.6, noise=tape[48:].contiguous(), **common)
+        got = np.stack([r[0, 0].cpu().numpy() for r in res + res2])
+        err = [rel_l2(got[k], g[f"img{s}"][k]) for k in range(8)]
+        print(f"img slice {s}: rel-L2 per iterate {['%.2e' % e for e in err]}")
+        assert max(err) < GRP_TOL
+        assert got.min() >= 0 and got.max() <= 1                       # clip_img clamps every iterate to [0,1]
+
+
+def test_philox_path_is_deterministic_and_unsupported_modes_fail_loudly(cuda):
+    from Model.model import GaussianDiffusion, UNetModel
+    torch.manual_seed(1)
+    net = UNetModel(**IMG_CFG).to(cuda).eval()
+    gd = GaussianDiffusion(1000, "cosine", schedule_power=1)
+    x = small_img_input(3, n=32).to(cuda)
+    kw = dict(model=net, img=x, t_start=[3, 2], clip=True, eta=0.7, mode="img", constant_guidance=0.45, ldct=x, only_convertor=False, normal=False)
+    a, _, _ = gd.guided_reverse_process(seed=7, **kw)
+    b, _, _ = gd.guided_reverse_process(seed=7, **kw)
+    c, _, _ = gd.guided_reverse_process(seed=8, **kw)
+    assert len(a) == 3 and torch.equal(a[-1], b[-1]) and not torch.equal(a[-1], c[-1])
+    assert torch.allclose(a[2], (a[0] + a[1]) / 2)
+    with pytest.raises(NotImplementedError):
+        gd.guided_reverse_process(net, x, t_start=None, mode="img", constant_guidance=0.45, ldct=x, only_convertor=False)
+    with pytest.raises(RuntimeError):
+        gd.guided_reverse_process(net, x, t_start=[2], mode="img", constant_guidance=None, ldct=x, only_convertor=False)
+    out, _, _ = gd.guided_reverse_process(net, x, t_start=[2], mode="img", constant_guidance=0.45, ldct=x, only_convertor=True)
+    assert out[0] is x

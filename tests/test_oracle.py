@@ -1,0 +1,108 @@
+"""CPU: pins the oracle restatement (oracle/) to golden vectors produced by the UNMODIFIED reference
+(oracle/make_golden.py, run in the build container).  The reference ships no tests of its own."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden, rel_l2
+from inputs import IMG_CFG, PROJ_CFG, noise_tape, small_img_input, small_proj_input, unet_small_input
+from oracle import fbp_oracle, ipdm_oracle as O
+
+
+def test_schedule_tables_match_reference():
+    g = golden("schedule")
+    for name, p in (("proj", 5), ("img", 1)):
+        tab = O.Tables(1000, p)
+        for attr in ("betas", "alphas_cumprod", "sqrt_alphas_cumprod", "sqrt_one_minus_alphas_cumprod", "sqrt_recip_alphas_cumprod",
+                     "sqrt_recipm1_alphas_cumprod", "posterior_variance", "posterior_log_variance_clipped", "posterior_mean_coef1",
+                     "posterior_mean_coef2"):
+            np.testing.assert_array_equal(getattr(tab, attr).numpy()[:64], g[f"{name}_{attr}"])
+    np.testing.assert_array_equal(O.cosine_beta_schedule(15, schedule_power=1).numpy(), g["lambda_cosine_15"])
+    np.testing.assert_array_equal(O.cosine_beta_schedule(5, schedule_power=10).numpy(), g["lambda_cosine_5_p10"])
+
+
+def test_known_answer_constants():
+    """SURVEY.md Appendix A table (computed from the reference formulas)."""
+    p, i = O.Tables(1000, 5), O.Tables(1000, 1)
+    assert abs(float(p.sqrt_one_minus_alphas_cumprod[15]) - 0.078734) < 5e-7
+    assert abs(float(i.sqrt_one_minus_alphas_cumprod[15]) - 0.035255) < 5e-7
+    assert abs(float(p.posterior_mean_coef1[5]) - 0.204554) < 5e-7
+    assert abs(float(i.posterior_mean_coef2[14]) - 0.903209) < 5e-7
+    lam = O.cosine_beta_schedule(15, schedule_power=1).numpy()
+    assert abs(lam[0] - 0.0133) < 5e-5 and lam[14] == 0.999
+
+
+def test_lambda_curves_match_reference():
+    g = golden("curves")
+    for kind in ("proj", "img"):
+        np.testing.assert_allclose(O.lambda_curve(g["x"], kind), g[kind], rtol=2e-6, atol=1e-6)
+    z1, z2 = O.curve_coefficients("proj")
+    assert abs(np.polyval(z1, 1.0) - 19.953) < 2e-3 and abs(np.polyval(z2, 2.75) + 0.190) < 2e-3
+
+
+@pytest.mark.parametrize("name,cfg", [("proj", PROJ_CFG), ("img", IMG_CFG)])
+def test_unet_oracle_matches_reference(name, cfg):
+    g = golden("unet_small")
+    seed, x, t = unet_small_input(name)
+    torch.manual_seed(seed)
+    net = O.UNetOracle(**cfg).eval()
+    assert sum(p.numel() for p in net.parameters()) == int(g[f"{name}_nparams"])
+    assert abs(sum(p.double().sum().item() for p in net.parameters()) - float(g[f"{name}_wsum"])) < 1e-6
+    y = net(x, torch.full((1,), t, dtype=torch.long)).numpy()
+    assert rel_l2(y, g[f"{name}_y"]) < 1e-5
+
+
+def test_guided_process_oracle_matches_reference_proj():
+    g = golden("grp_small")
+    torch.manual_seed(0)
+    net = O.UNetOracle(**PROJ_CFG).eval()
+    x = small_proj_input(200)
+    res = O.guided_reverse_process(net, O.Tables(1000, 5), x, [15, 15, 15], clip=False, lambda_ratio=1, eta=0.5, mode="proj",
+                                   constant_guidance=None, noise=iter(noise_tape(x.shape, 48, 300)), kernel_size=4, amplitude=7.0)
+    got = np.stack([r.numpy()[0, 0] for r in res])
+    assert got.shape == g["proj0"].shape
+    assert rel_l2(got, g["proj0"]) < 2e-5
+
+
+def test_guided_process_oracle_matches_reference_img():
+    g = golden("grp_small")
+    torch.manual_seed(1)
+    net = O.UNetOracle(**IMG_CFG).eval()
+    x = small_img_input(400)
+    tape = noise_tape(x.shape, 66, 500)
+    tab = O.Tables(1000, 1)
+    res = O.guided_reverse_process(net, tab, x, [15, 15, 15], clip=True, lambda_ratio=10, eta=0.7, mode="img",
+                                   constant_guidance=0.45, noise=iter(tape[:48]), ldct=x)
+    res += O.guided_reverse_process(net, tab, res[-1], [5, 5, 5], clip=True, lambda_ratio=10, eta=0.6, mode="img",
+                                    constant_guidance=0.6, noise=iter(tape[48:]), ldct=x)
+    got = np.stack([r.numpy()[0, 0] for r in res])
+    assert rel_l2(got, g["img0"]) < 2e-5
+
+
+def test_fbp_oracle_tables_and_image_match_reference():
+    import ipdm_pytorch_b200.synthetic as S
+    g = golden("fbp_slice0")
+    T = fbp_oracle.Tables()
+    np.testing.assert_array_equal(T.h, g["h_RL"])
+    np.testing.assert_array_equal(T.nda, g["nda"])
+    np.testing.assert_array_equal(T.theta, g["theta"])
+    np.testing.assert_array_equal(T.r.reshape(512, 512)[1::4, 2::4], g["r_sub"])
+    np.testing.assert_array_equal(T.phi.reshape(512, 512)[1::4, 2::4], g["phi_sub"])
+    assert float(g["simens_theta_maxabs_rad"]) < 1e-6          # Simens_theta.txt == arange(0, 360, .18) deg
+    ld, nd, img = S.make_slice(0)
+    rec = fbp_oracle.convert(ld[None])[0]
+    assert rel_l2(rec, g["ld"]) < 1e-5                         # measured 2.8e-6 (libm / summation-order differences)
+    # domain property: FBP of the clean synthetic sinogram reproduces the phantom inside the body
+    assert float(g["nd_rmse_in_body"]) < 0.006
+
+
+def test_sharpen_and_conversions():
+    x = small_img_input(7)
+    y = O.tensor_sharpen(x, 42)
+    k = torch.full((3, 3), -2.0); k[1, 1] = 42
+    ref = torch.nn.functional.conv2d(x, (k / 26)[None, None], padding=1)
+    assert torch.allclose(y, ref)
+    assert O.tensor_sharpen(x, -1) is x
+    mu = torch.tensor([0.0, 0.183, 0.5, 1.0])
+    pix = O.miu2pixel(mu)
+    assert pix[0] == 0 and abs(float(pix[1]) - (1024 - 24) / 4096) < 1e-6 and pix[3] == 1

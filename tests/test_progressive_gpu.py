@@ -1,0 +1,90 @@
+"""GPU parity at BASELINE config 1: one full 2000x912 -> 512x512 progressive slice through the reference-facing
+API (`progressive_domain_denoiser`, update_opt(convertor="FBP"), t_start_proj=[15,15,15], ultra_img_denoise) against
+the golden produced by the UNMODIFIED reference on CPU with the same seeds, weights and injected noise
+(tests/golden/full_slice0.npz, oracle/make_golden.py full; 672 s on 8 host cores)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import PKG, golden, rel_l2
+
+pytestmark = pytest.mark.gpu
+HU_PER_MU = 1e3 / 0.183
+
+
+def _model(tmp_path, extra=None):
+    from Config.default_config import default_cfg
+    from Utils.train_test_utils import progressive_domain_denoiser
+    opt = default_cfg(["--load_option_path", os.path.join(PKG, "Config/Mayo-Config/test_progressive_option.json"), "--device", "cuda:0"])
+    opt.load_img_model_path = opt.load_proj_model_path = None
+    opt.test_dataset_path_FD_img = opt.test_dataset_path_LD_img = opt.test_dataset_path_FD_proj = opt.test_dataset_path_LD_proj = None
+    torch.manual_seed(0)
+    model = progressive_domain_denoiser(opt, result_save_path=str(tmp_path))
+    cfg = dict(convertor="FBP", save_it_state_img=False, save_it_state_proj=False, ultra_img_denoise=True)
+    cfg.update(extra or {})
+    model.update_opt(cfg)
+    return model
+
+
+def test_art_convertor_fails_loudly_until_switched(cuda, tmp_path):
+    from Config.default_config import default_cfg
+    from Utils.train_test_utils import progressive_domain_denoiser
+    opt = default_cfg(["--mode", "test_img", "--device", "cuda:0", "--convertor", "ART"])
+    m = progressive_domain_denoiser(opt, result_save_path=str(tmp_path))
+    with pytest.raises(RuntimeError, match="FBP"):
+        m.convertor(torch.zeros(1, 2000, 912))
+    m.update_opt(dict(convertor="FBP", bogus_key=1))
+    assert m.opt.convertor == "FBP" and m._fbp is not None and not hasattr(m.opt, "bogus_key")
+    assert os.path.exists(os.path.join(str(tmp_path), "IPDM_default", "save_models", "option.json"))
+    m.reset_opt()
+    assert m.opt.convertor == "ART"
+
+
+def test_full_slice_matches_reference_golden(cuda, tmp_path):
+    import ipdm_pytorch_b200.synthetic as S
+    from inputs import noise_tape
+    g = golden("full_slice0")
+    model = _model(tmp_path)
+    ld, nd, img = S.make_slice(0)
+    model.data_sample_load(ldct=torch.zeros(1, 1, 512, 512), ldproj=torch.from_numpy(ld)[None, None], fdproj=None,
+                           fdct=torch.from_numpy(img)[None, None])
+    model.temp_clear()
+    pn = torch.stack(noise_tape((1, 1, 2000, 912), 48, 9527)).to(cuda)
+    inn = torch.stack(noise_tape((1, 1, 512, 512), 66, 19527)).to(cuda)
+    out = model.progressive_denoiser(save_proj_state=True, noise=(pn, inn))
+    torch.cuda.synchronize()
+    assert tuple(out.shape) == (1, 1, 512, 512) and out.is_cuda
+    # stage 1: the four projection-domain iterates (strided sample of the golden)
+    perr = []
+    for k in range(1, 5):
+        mine = model.proj_denoise_result[f"iter_{k}"][0, 0]
+        perr.append(rel_l2(mine[1::4, 2::4], g[f"proj_iter{k}_sub"]))
+    # stage 2: FBP of the averaged iterate
+    rec = model.proj_denoise_convert2img_result["iter_1"][0, 0]
+    ferr = rel_l2(rec[1::4, 2::4], g["fbp_img_sub"])
+    # stage 3: final image
+    fin = model.progressive_denoise_result["iter_1"][0, 0]
+    assert np.isfinite(fin).all() and fin.min() >= 0 and fin.max() <= 1
+    rmse_hu = float(np.sqrt(np.mean((fin.astype(np.float64) - g["final"]) ** 2))) * HU_PER_MU
+    print(f"full slice: proj iterates rel-L2 {['%.2e' % e for e in perr]}; FBP image rel-L2 {ferr:.2e}; final RMSE {rmse_hu:.2f} HU "
+          f"(final image spans [{g['final'].min():.2f}, {g['final'].max():.2f}] mu with random-init weights)")
+    assert max(perr) < 5e-3
+    assert ferr < 2e-2
+    np.savez_compressed(os.path.join(os.environ.get("GRAFT_REPO_ROOT", "."), "gpurun_out", "full_slice_gpu.npz") if os.path.isdir("gpurun_out") else str(tmp_path / "x.npz"),
+                        final=fin, fbp=rec, proj4=model.proj_denoise_result["iter_4"][0, 0][1::4, 2::4])
+
+
+def test_batch_of_two_slices_equals_single_slices_philox(cuda, tmp_path):
+    """Drop-in API with B = 2 and the in-kernel generator: finite, clamped, deterministic, per-slice independent shapes."""
+    import ipdm_pytorch_b200.synthetic as S
+    model = _model(tmp_path, dict(t_start_proj=[2, 1], t_start_img=[2, 1], noise_seed=11))
+    ld = np.stack([S.make_slice(s)[0] for s in (0, 1)])
+    model.data_sample_load(ldct=None, ldproj=torch.from_numpy(ld)[:, None], fdproj=None, fdct=None)
+    a = model.progressive_denoiser().clone()
+    b = model.progressive_denoiser()
+    assert tuple(a.shape) == (2, 1, 512, 512) and torch.equal(a, b)
+    assert torch.isfinite(a).all() and float(a.min()) >= 0 and float(a.max()) <= 1
+    assert model.progressive_denoise_result[-1].shape == (2, 1, 512, 512)
+    assert model.proj_denoise_convert2img_result["iter_1"].shape == (2, 1, 512, 512)

@@ -1,0 +1,71 @@
+"""GPU parity: whole UNet forward (tcgen05 plan, through the C ABI) vs the reference golden and the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden, rel_l2
+from inputs import IMG_CFG, PROJ_CFG, unet_small_input
+
+pytestmark = pytest.mark.gpu
+UNET_TF32_TOL = 5e-3        # whole-net rel-L2 with kind::tf32 contractions (fp32 CPU reference)
+
+
+@pytest.mark.parametrize("name,cfg", [("proj", PROJ_CFG), ("img", IMG_CFG)])
+def test_small_forward_matches_reference_golden(cuda, name, cfg):
+    from Model.model import UNetModel
+    g = golden("unet_small")
+    seed, x, t = unet_small_input(name)
+    torch.manual_seed(seed)
+    net = UNetModel(**cfg).to(cuda).eval()
+    y = net(x.to(cuda), torch.full((1,), t, device=cuda, dtype=torch.long)).cpu().numpy()
+    assert np.isfinite(y).all()
+    err = rel_l2(y, g[f"{name}_y"])
+    print(f"UNet {name} small forward vs reference golden: rel-L2 {err:.3e}")
+    assert err < UNET_TF32_TOL
+
+
+@pytest.mark.parametrize("name,cfg,shape", [("proj", PROJ_CFG, (2, 1, 96, 64)), ("img", IMG_CFG, (3, 1, 48, 80))])
+def test_batched_forward_matches_oracle_per_slice(cuda, name, cfg, shape):
+    from Model.model import UNetModel
+    from oracle.ipdm_oracle import UNetOracle
+    torch.manual_seed(5)
+    net = UNetModel(**cfg).eval()
+    ora = UNetOracle(**cfg).eval()
+    ora.load_state_dict(net.state_dict())
+    x = torch.randn(shape, generator=torch.Generator().manual_seed(9))
+    net = net.to(cuda)
+    for t in (0, 14):
+        y = net(x.to(cuda), torch.full((1,), t, device=cuda, dtype=torch.long)).cpu()
+        want = ora(x, torch.full((1,), t, dtype=torch.long))
+        assert rel_l2(y.numpy(), want.numpy()) < UNET_TF32_TOL, t
+    # a slice of a batch equals the same slice run alone (no cross-slice coupling)
+    y1 = net(x[1:2].to(cuda).contiguous(), torch.full((1,), 14, device=cuda, dtype=torch.long)).cpu()
+    assert rel_l2(y1.numpy(), y[1:2].numpy()) < 1e-6
+
+
+def test_checkpoint_roundtrip_and_repack(cuda, tmp_path):
+    """state_dict files in the reference's format load unchanged and trigger a re-pack of the CUDA weights."""
+    from Model.model import UNetModel
+    from Utils.loggerx import load_network
+    torch.manual_seed(1)
+    a = UNetModel(**IMG_CFG).to(cuda).eval()
+    torch.manual_seed(2)
+    b = UNetModel(**IMG_CFG).to(cuda).eval()
+    x = torch.randn(1, 1, 32, 32, device=cuda)
+    t = torch.zeros(1, dtype=torch.long, device=cuda)
+    ya, yb = a(x, t), b(x, t)
+    assert not torch.allclose(ya, yb)
+    path = tmp_path / "img_model-20"
+    torch.save({"module." + k: v for k, v in a.state_dict().items()}, path)
+    b.load_state_dict(load_network(str(path)))
+    assert torch.equal(b(x, t), ya)
+
+
+def test_flop_model_matches_survey(cuda):
+    """Algorithmic FLOPs of one forward at the real sizes (1275.98 / 924.16 GFLOP)."""
+    from Model.model import UNetModel
+    torch.manual_seed(0)
+    p = UNetModel(**PROJ_CFG).to(cuda)
+    assert abs(p.cuda_handle().flops(1, 2000, 912) / 1e9 - 1275.98) < 1.0
+    i = UNetModel(**IMG_CFG).to(cuda)
+    assert abs(i.cuda_handle().flops(1, 512, 512) / 1e9 - 924.16) < 1.0

@@ -1,0 +1,213 @@
+"""GPU parity, one UNet building block at a time (ipdm_debug_* entry points) vs plain PyTorch fp32 on the CPU.
+
+Tolerances: CUDA-core kernels are fp32 (1e-5 rel-L2); tcgen05 kind::tf32 contractions carry a 10-bit
+mantissa on both operands (<= 2e-3 rel-L2 for these K, the error the reference itself has on an
+Ampere+ GPU with its default allow_tf32=True)."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+TF32_TOL = 2e-3
+FP32_TOL = 1e-5
+
+
+def nhwc(x, cs=None):
+    n, c, h, w = x.shape
+    cs = c if cs is None else cs
+    out = torch.zeros(n, h, w, cs, dtype=torch.float32)
+    out[..., :c] = x.permute(0, 2, 3, 1)
+    return out.contiguous()
+
+
+def nchw(y, c):
+    return y[..., :c].permute(0, 3, 1, 2).contiguous()
+
+
+def alloc_cs(c):
+    return (c + 31) // 32 * 32 if c >= 16 else c
+
+
+def _p(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def run_conv(cuda, x0, x1, weight, bias, k, stride, use_tc, res=None, up=None, norm=None):
+    from ipdm_pytorch_b200 import _lib
+    n, c0, h, w = x0.shape
+    c1 = 0 if x1 is None else x1.shape[1]
+    cs0, cs1 = (alloc_cs(c0), alloc_cs(c1)) if use_tc else (c0, c1)
+    cout = weight.shape[0]
+    hin, win = (h, w) if up is None else up
+    ho, wo = (hin, win) if stride == 1 else ((hin + 1) // 2, (win + 1) // 2)
+    ocs = alloc_cs(cout)
+    a0 = nhwc(x0, cs0).to(cuda)
+    a1 = None if x1 is None else nhwc(x1, cs1).to(cuda)
+    r = None if res is None else nhwc(res, ocs).to(cuda)
+    out = torch.full((n, ho, wo, ocs), float("nan"), device=cuda)
+    wh = weight.contiguous().float()
+    bh = None if bias is None else bias.contiguous().float()
+    sc = sh = None
+    if norm is not None:
+        sc, sh = [t.to(cuda).contiguous() for t in norm]
+    rc = _lib.lib().ipdm_debug_conv(_p(a0), c0, cs0, _p(a1), c1, cs1, n, h, w, _p(wh), _p(bh), cout, k, stride,
+                                    0 if up is None else up[0], 0 if up is None else up[1], _p(sc), _p(sh), _p(r), ocs, _p(out), ocs,
+                                    int(use_tc), None)
+    _lib.check(rc, "ipdm_debug_conv")
+    torch.cuda.synchronize()
+    full = out.cpu()
+    if ocs > cout:
+        assert float(full[..., cout:].abs().max()) == 0.0              # channel padding stays zero
+    return nchw(full, cout)
+
+
+def ref_conv(x0, x1, weight, bias, k, stride, res=None, up=None, norm=None):
+    x = x0 if x1 is None else torch.cat([x0, x1], 1)
+    if norm is not None:
+        x = F.silu(x * norm[0][:, :, None, None] + norm[1][:, :, None, None])
+    if up is not None:
+        x = F.interpolate(x, size=up, mode="nearest")
+    y = F.conv2d(x, weight, bias, stride=stride, padding=k // 2)
+    return y if res is None else y + res
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    return scale * torch.randn(*shape, generator=torch.Generator().manual_seed(seed))
+
+
+# ---- direct (CUDA core) path: the thin full-resolution layers of the proj net --------------------
+@pytest.mark.parametrize("c0,c1,cout,k,stride,hw", [
+    (1, 0, 4, 3, 1, (40, 70)), (4, 0, 8, 3, 1, (33, 65)), (4, 0, 8, 1, 1, (33, 65)), (8, 0, 8, 3, 2, (25, 57)),
+    (16, 8, 16, 3, 1, (21, 47)), (8, 4, 8, 1, 1, (21, 47)), (8, 0, 1, 3, 1, (40, 70)), (16, 0, 16, 3, 2, (50, 38)),
+    (1, 0, 64, 3, 1, (32, 32)), (64, 0, 1, 3, 1, (24, 40)),
+])
+def test_direct_conv(cuda, c0, c1, cout, k, stride, hw):
+    x0 = rnd(2, c0, *hw, seed=1)
+    x1 = rnd(2, c1, *hw, seed=2) if c1 else None
+    w = rnd(cout, c0 + c1, k, k, seed=3, scale=0.2)
+    b = rnd(cout, seed=4)
+    ho, wo = hw if stride == 1 else ((hw[0] + 1) // 2, (hw[1] + 1) // 2)
+    res = rnd(2, cout, ho, wo, seed=5) if (stride == 1 and k == 3) else None
+    got = run_conv(cuda, x0, x1, w, b, k, stride, False, res=res)
+    assert rel_l2(got.numpy(), ref_conv(x0, x1, w, b, k, stride, res=res).numpy()) < FP32_TOL
+
+
+def test_direct_conv_fused_norm_and_upsample(cuda):
+    x0, x1 = rnd(2, 16, 20, 30, seed=1), rnd(2, 8, 20, 30, seed=2)
+    sc, sh = 1 + 0.3 * rnd(2, 24, seed=6), 0.2 * rnd(2, 24, seed=7)
+    w, b = rnd(16, 24, 3, 3, seed=3, scale=0.2), rnd(16, seed=4)
+    got = run_conv(cuda, x0, x1, w, b, 3, 1, False, norm=(sc, sh))
+    assert rel_l2(got.numpy(), ref_conv(x0, x1, w, b, 3, 1, norm=(sc, sh)).numpy()) < 2e-5
+    xs = rnd(2, 16, 13, 19, seed=8)                                    # 13x19 -> 25x38 (odd target, like 63 -> 125)
+    w2 = rnd(16, 16, 3, 3, seed=9, scale=0.2)
+    got = run_conv(cuda, xs, None, w2, b, 3, 1, False, up=(25, 38))
+    assert rel_l2(got.numpy(), ref_conv(xs, None, w2, b, 3, 1, up=(25, 38)).numpy()) < FP32_TOL
+
+
+# ---- GroupNorm ------------------------------------------------------------------------------------
+@pytest.mark.parametrize("c0,c1,hw", [(8, 0, (40, 70)), (16, 8, (21, 47)), (128, 16, (13, 10)), (256, 128, (7, 5)), (64, 0, (32, 32)), (12, 0, (9, 11))])
+def test_groupnorm_stats_and_apply(cuda, c0, c1, hw):
+    from ipdm_pytorch_b200 import _lib
+    from oracle.ipdm_oracle import gn_groups
+    C = c0 + c1
+    x0 = 0.5 + 2 * rnd(2, c0, *hw, seed=1)
+    x1 = -1 + rnd(2, c1, *hw, seed=2) if c1 else None
+    gamma, beta = 1 + 0.2 * rnd(C, seed=3), 0.1 * rnd(C, seed=4)
+    a0 = nhwc(x0, alloc_cs(c0)).to(cuda)
+    a1 = None if x1 is None else nhwc(x1, alloc_cs(c1)).to(cuda)
+    ocs = (C + 31) // 32 * 32
+    sc, sh = torch.empty(2, C, device=cuda), torch.empty(2, C, device=cuda)
+    out = torch.full((2, hw[0], hw[1], ocs), float("nan"), device=cuda)
+    for act in (1, 0):
+        rc = _lib.lib().ipdm_debug_groupnorm(_p(a0), c0, alloc_cs(c0), _p(a1), c1, alloc_cs(c1), 2, hw[0], hw[1], _p(gamma.contiguous()),
+                                             _p(beta.contiguous()), act, _p(sc), _p(sh), _p(out), ocs, None)
+        _lib.check(rc, "ipdm_debug_groupnorm")
+        x = x0 if x1 is None else torch.cat([x0, x1], 1)
+        want = F.group_norm(x, gn_groups(C), gamma, beta, eps=1e-5)
+        want = F.silu(want) if act else want
+        full = out.cpu()
+        assert rel_l2(nchw(full, C).numpy(), want.numpy()) < 2e-5
+        assert ocs == C or float(full[..., C:].abs().max()) == 0.0
+    lin = x * sc.cpu()[:, :, None, None] + sh.cpu()[:, :, None, None]
+    assert rel_l2(lin.numpy(), F.group_norm(x, gn_groups(C), gamma, beta, eps=1e-5).numpy()) < 2e-5
+
+
+# ---- tensor-core implicit GEMM ----------------------------------------------------------------------
+@pytest.mark.parametrize("c0,c1,cout,k,stride,hw", [
+    (128, 0, 128, 3, 1, (25, 19)),      # ragged tile edges
+    (128, 0, 128, 3, 1, (16, 8)),       # exactly one 128-pixel tile
+    (256, 0, 256, 3, 1, (7, 5)),        # two N tiles, tiny image
+    (128, 128, 128, 3, 1, (13, 10)),    # virtual concat
+    (128, 16, 128, 3, 1, (25, 19)),     # 144 -> 128 (skip padded to 32)
+    (128, 16, 16, 3, 1, (25, 19)),      # 144 -> 16, N = 16 tile
+    (16, 0, 128, 3, 1, (25, 19)),       # 16 -> 128, K padded to 32
+    (128, 0, 128, 3, 2, (25, 19)),      # stride 2, odd size
+    (256, 0, 256, 3, 2, (14, 10)),      # stride 2, even size
+    (256, 0, 768, 1, 1, (7, 5)),        # qkv-like 1x1
+    (256, 128, 256, 1, 1, (13, 10)),    # 1x1 shortcut over a concat
+    (64, 0, 64, 3, 1, (32, 32)),        # img net, N = 64 tile
+    (128, 64, 64, 3, 1, (32, 32)),
+])
+def test_tc_conv(cuda, c0, c1, cout, k, stride, hw):
+    x0 = rnd(2, c0, *hw, seed=1)
+    x1 = rnd(2, c1, *hw, seed=2) if c1 else None
+    w = rnd(cout, c0 + c1, k, k, seed=3, scale=(1.0 / ((c0 + c1) * k * k)) ** 0.5)
+    b = rnd(cout, seed=4)
+    ho, wo = hw if stride == 1 else ((hw[0] + 1) // 2, (hw[1] + 1) // 2)
+    res = rnd(2, cout, ho, wo, seed=5) if stride == 1 else None
+    got = run_conv(cuda, x0, x1, w, b, k, stride, True, res=res)
+    want = ref_conv(x0, x1, w, b, k, stride, res=res)
+    assert torch.isfinite(got).all()
+    err = rel_l2(got.numpy(), want.numpy())
+    print(f"tc conv {c0}+{c1}->{cout} k{k} s{stride} {hw}: rel-L2 {err:.2e}")
+    assert err < TF32_TOL
+
+
+def test_tc_conv_full_size_row_shapes(cuda):
+    """The proj net's real row widths (228, 114, 57, 29) at reduced height, batch 1."""
+    for hw, c in (((24, 228), 128), ((20, 114), 128), ((16, 57), 256), ((9, 29), 256)):
+        x = rnd(1, c, *hw, seed=hw[1])
+        w = rnd(c, c, 3, 3, seed=3, scale=(1.0 / (9 * c)) ** 0.5)
+        got = run_conv(cuda, x, None, w, None, 3, 1, True)
+        assert rel_l2(got.numpy(), ref_conv(x, None, w, None, 3, 1).numpy()) < TF32_TOL, hw
+
+
+# ---- attention ----------------------------------------------------------------------------------------
+@pytest.mark.parametrize("hw,batch", [((7, 5), 2), ((13, 10), 1), ((25, 19), 2), ((32, 32), 1)])
+def test_attention(cuda, hw, batch):
+    from ipdm_pytorch_b200 import _lib
+    C, heads, d = 256, 4, 64
+    T = hw[0] * hw[1]
+    tpad = (T + 3) // 4 * 4
+    qkv = rnd(batch, 3 * C, *hw, seed=T)
+    q, k, v = qkv.reshape(batch * heads, 3 * d, T).chunk(3, dim=1)
+    sc = 1.0 / (d ** 0.25)
+    att = torch.einsum("bct,bcs->bts", q * sc, k * sc).softmax(dim=-1)
+    want = torch.einsum("bts,bcs->bct", att, v).reshape(batch, C, *hw)
+    qk_nhwc = nhwc(qkv).to(cuda)                                        # [B,H,W,3C]; v channels are ignored by the kernel
+    vt = torch.zeros(batch, heads, d, tpad)
+    vt[..., :T] = v.reshape(batch, heads, d, T)
+    out = torch.full((batch, hw[0], hw[1], C), float("nan"), device=cuda)
+    rc = _lib.lib().ipdm_debug_attention(_p(qk_nhwc), _p(vt.to(cuda).contiguous()), _p(out), batch, T, tpad, heads, C, None)
+    _lib.check(rc, "ipdm_debug_attention")
+    torch.cuda.synchronize()
+    got = nchw(out.cpu(), C)
+    assert torch.isfinite(got).all()
+    err = rel_l2(got.numpy(), want.numpy())
+    print(f"attention T={T}: rel-L2 {err:.2e}")
+    assert err < TF32_TOL
+
+
+def test_upsample_nearest_index_rule(cuda):
+    from ipdm_pytorch_b200 import _lib
+    for (hs, ws), (hd, wd) in (((63, 29), (125, 57)), ((4, 3), (7, 5)), ((16, 16), (32, 32))):
+        x = rnd(2, 32, hs, ws, seed=hs)
+        src = nhwc(x).to(cuda)
+        dst = torch.empty(2, hd, wd, 32, device=cuda)
+        _lib.check(_lib.lib().ipdm_debug_upsample(_p(src), 2, hs, ws, 32, _p(dst), hd, wd, None), "ipdm_debug_upsample")
+        assert torch.equal(nchw(dst.cpu(), 32), F.interpolate(x, size=(hd, wd), mode="nearest"))
