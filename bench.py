@@ -1,0 +1,280 @@
+#!/usr/bin/env python
+"""Benchmark of the IPDM domain-progressive inference path (BASELINE.json metric: slices/sec).
+
+    python bench.py --gpus N --steps K --warmup W            # this build (libipdm_b200.so), one rank per GPU
+    python bench.py --impl reference --gpus N --steps K ...   # the reference algorithm on the host CPU (oracle port)
+
+A "step" is one pass of the whole hot path over one batch of synthetic slices per GPU:
+projection-domain guided process (t_start_proj) -> FBP -> sharpen -> image-domain guided process
+(t_start_img) -> "ultra" pass [5,5,5], i.e. `progressive_denoiser` of the reference with
+convertor="FBP", ultra_img_denoise=True on 2000x912 sinograms -> 512x512 images.
+`value` is timed with inputs resident in HBM; `e2e` goes through the reference-facing API
+(`progressive_domain_denoiser.data_sample_load` + `.progressive_denoiser`) from pinned host buffers
+to a host result.  Slices are sharded across ranks with no collective on the data path (weak
+scaling); the only collective is the final gather of the [B,1,512,512] results.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(REPO, "ipdm-pytorch_b200")
+for p in (REPO, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+HBM_FALLBACK_GBS, TENSOR_FALLBACK_TFLOPS = 6650.0, 1590.0        # /opt/skills/guides/B200_PROFILING.md
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=4, help="slices per GPU per step")
+    ap.add_argument("--precision", default="tf32")
+    ap.add_argument("--t_start_proj", type=int, nargs="+", default=[15, 15, 15])
+    ap.add_argument("--t_start_img", type=int, nargs="+", default=[15, 15, 15])
+    ap.add_argument("--skip_cpu_baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return dict(hbm=d["hbm_gbs"], tensor=d.get("bf16_tflops_sustained", d["bf16_tflops"]), which="measured (MEASURED_PEAKS.json; sustained bf16)")
+    return dict(hbm=HBM_FALLBACK_GBS, tensor=TENSOR_FALLBACK_TFLOPS, which="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower() == "active" for r in self.rows)]
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons, samples=len(sm))
+
+
+# -------------------------------------------------------------------------------------------------
+# CPU legs (oracle port): the reference algorithm on the host cores, bounded sample
+# -------------------------------------------------------------------------------------------------
+def cpu_reference_sample(t_start_proj, t_start_img):
+    """Times one proj-UNet forward, one img-UNet forward, one FBP and one sampler step of the oracle on the host and
+    extrapolates one slice: n_proj*t_proj + n_img*t_img + t_fbp + steps*t_step (the reference is serial per slice)."""
+    import numpy as np
+    import torch
+    from oracle import ipdm_oracle as O
+    torch.manual_seed(0)
+    pnet, inet = O.UNetOracle(**O.PROJ_UNET).eval(), O.UNetOracle(**O.IMG_UNET).eval()
+    g = torch.Generator().manual_seed(0)
+    xp, xi = 3 * torch.rand(1, 1, 2000, 912, generator=g), 0.2 * torch.rand(1, 1, 512, 512, generator=g)
+    t0 = time.perf_counter(); ep = pnet(xp, torch.full((1,), 7, dtype=torch.long)); t_proj = time.perf_counter() - t0
+    t0 = time.perf_counter(); ei = inet(xi, torch.full((1,), 7, dtype=torch.long)); t_img = time.perf_counter() - t0
+    tab = O.Tables(1000, 5)
+    t0 = time.perf_counter(); O.p_sample_condition(tab, ep, xp, xp, 7, 0.4, False, torch.randn(xp.shape, generator=g)); t_sp = time.perf_counter() - t0
+    t0 = time.perf_counter(); O.p_sample_condition(tab, ei, xi, xi, 7, 0.45, True, torch.randn(xi.shape, generator=g)); t_si = time.perf_counter() - t0
+    t0 = time.perf_counter(); O.fbp_convert(xp[:, 0].numpy()); t_fbp = time.perf_counter() - t0
+    n_proj, n_img = sum(t_start_proj), sum(t_start_img) + 15
+    per_slice = n_proj * (t_proj + t_sp) + n_img * (t_img + t_si) + t_fbp
+    return dict(per_slice_s=per_slice, t_proj=t_proj, t_img=t_img, t_fbp=t_fbp, cores=torch.get_num_threads(),
+                sample=f"1 proj UNet fwd 2000x912 ({t_proj:.2f}s) + 1 img UNet fwd 512x512 ({t_img:.2f}s) + 1 sampler step each "
+                       f"+ 1 FBP ({t_fbp:.2f}s, C oracle, OpenMP); extrapolated to {n_proj}+{n_img} forwards per slice")
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    vals, last = [], None
+    for i in range(args.warmup + args.steps):
+        last = cpu_reference_sample(args.t_start_proj, args.t_start_img)
+        if i >= args.warmup:
+            vals.append(last["per_slice_s"])
+        if i == 0 and last["per_slice_s"] > 0 and (args.warmup + args.steps) * 25 > 600:
+            pass
+    per_slice = sum(vals) / len(vals)
+    v = 1.0 / per_slice
+    line = dict(metric="ipdm_progressive_slices_per_sec", value=v, unit="slices/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=per_slice * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                impl="reference",
+                config=dict(workload=workload_name(args, 1), note="reference algorithm (oracle port: torch CPU UNet + C FBP) on the host; "
+                            "the Python reference itself cannot travel to the GPU box; one slice at a time (the reference cannot batch)"),
+                cpu_baseline=dict(value=v, unit="slices/s", cores=last["cores"], kind="port", sample=last["sample"]),
+                e2e=dict(value=v, unit="slices/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line))
+
+
+def workload_name(args, batch):
+    return (f"IPDM progressive inference, convertor=FBP, t_start_proj={args.t_start_proj}, t_start_img={args.t_start_img} + ultra [5,5,5], "
+            f"{batch} slice(s)/GPU/step, sinogram 2000x912 -> image 512x512, random-init UNets (28.4M + 29.1M params)")
+
+
+# -------------------------------------------------------------------------------------------------
+# B200 arm
+# -------------------------------------------------------------------------------------------------
+def run_b200(args, rank, world, local_rank):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from Config.default_config import default_cfg
+    from ipdm_pytorch_b200 import engine, synthetic
+    from Utils.train_test_utils import progressive_domain_denoiser
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    B = args.batch
+    import tempfile
+    opt = default_cfg(["--load_option_path", os.path.join(PKG, "Config/Mayo-Config/test_progressive_option.json"), "--device", f"cuda:{local_rank}"])
+    opt.load_img_model_path = opt.load_proj_model_path = None
+    for k in ("test_dataset_path_FD_img", "test_dataset_path_LD_img", "test_dataset_path_FD_proj", "test_dataset_path_LD_proj"):
+        setattr(opt, k, None)
+    torch.manual_seed(0)
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = progressive_domain_denoiser(opt, result_save_path=tempfile.mkdtemp(prefix="ipdm_bench_"))
+        model.update_opt(dict(convertor="FBP", save_it_state_img=False, save_it_state_proj=False, ultra_img_denoise=True,
+                              t_start_proj=args.t_start_proj, t_start_img=args.t_start_img, precision=args.precision, noise_seed=1234 + rank))
+    # synthetic slices of this rank's shard (weak scaling: B per GPU), pinned on the host
+    host = torch.from_numpy(synthetic.cheap_sinogram(B, seed=100 + rank))[:, None].contiguous().pin_memory()
+    host_out = torch.empty(B, 1, 512, 512).pin_memory()
+    resident = host.to(dev)
+
+    def step_resident():
+        model.ldproj = resident
+        return model.progressive_denoiser()
+
+    def step_e2e():
+        model.ldproj = host.to(dev, non_blocking=True)
+        out = model.progressive_denoiser()
+        host_out.copy_(out, non_blocking=True)
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            out = fn()
+        b.record()
+        barrier()
+        ms = a.elapsed_time(b)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms, out
+
+    for _ in range(args.warmup):
+        step_resident()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    engine.launch_count_reset()
+    ms, out = timed(step_resident, args.steps)
+    launches = engine.launch_count()
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:                                   # the only collective: final gather of the results
+        gathered = torch.empty(world * B, 1, 512, 512, device=dev)
+        dist.all_gather_into_tensor(gathered, out.contiguous())
+    step_e2e()
+    ms_e2e, _ = timed(step_e2e, args.steps)
+
+    if rank != 0:
+        return
+    value = world * B * args.steps / (ms / 1e3)
+    e2e = world * B * args.steps / (ms_e2e / 1e3)
+    # per-family profile of ONE extra step (CUDA events around every launch, on the launching stream)
+    engine.profile_enable(True)
+    step_resident()
+    prof = engine.profile_collect()
+    engine.profile_enable(False)
+    pk = peaks()
+    tc_ms, tc_flops, tc_n = prof["conv_tc"]
+    total_prof_ms = sum(v[0] for v in prof.values())
+    roof = dict(bound="tensor", kernel="conv_tc_kernel (tcgen05 kind::tf32 implicit-GEMM conv)", achieved=tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms else None,
+                peak=pk["tensor"], unit="TFLOP/s", traffic=None, peak_source=pk["which"],
+                note="achieved = FLOPs issued by all conv_tc launches of one step / their summed CUDA-event time; peak is dense bf16 "
+                     "(a kind::tf32 MMA runs at half that rate, so 0.5 is this kernel's ceiling in tf32 mode)",
+                share_of_step=tc_ms / total_prof_ms if total_prof_ms else None, launches_per_step=tc_n)
+    roof["frac"] = roof["achieved"] / roof["peak"] if roof["achieved"] else None
+    families = {}
+    for k, (m, w, n) in prof.items():
+        unit = "TFLOP/s" if k in ("conv_tc", "attention") else "GB/s"
+        rate = (w / (m * 1e-3) / (1e12 if unit == "TFLOP/s" else 1e9)) if m else None
+        families[k] = dict(ms=round(m, 3), launches=n, rate=None if rate is None else round(rate, 2), unit=unit,
+                           frac_of_peak=None if rate is None else round(rate / (pk["tensor"] if unit == "TFLOP/s" else pk["hbm"]), 4))
+    p_flops = model.proj_model.cuda_handle().flops(B, 2000, 912)
+    i_flops = model.img_model.cuda_handle().flops(B, 512, 512)
+    step_flops = sum(args.t_start_proj) * p_flops + (sum(args.t_start_img) + 15) * i_flops
+    line = dict(metric="ipdm_progressive_slices_per_sec", value=value, unit="slices/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
+                ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype={"tf32": "tf32 (fp32 state, tcgen05 kind::tf32, fp32 accumulate)", "fp32": "f32 (3xTF32)", "bf16": "bf16"}[args.precision],
+                data="synthetic",
+                config=dict(workload=workload_name(args, B), global_batch=world * B, parallelism=f"slice-sharded x{world}, no data-path collective",
+                            l2="working set (activation arena of several GB per step) >> 126 MB L2; no explicit flush needed",
+                            noise="in-kernel Philox4x32-10", unet_tflop_per_step=step_flops / 1e12),
+                e2e=dict(value=e2e, unit="slices/s", h2d_bytes_per_step=int(host.numel() * 4), d2h_bytes_per_step=int(host_out.numel() * 4),
+                         ms_per_step=ms_e2e / args.steps),
+                gpu_launches=int(launches), clocks=clocks, roofline=roof, kernel_families=families,
+                unet_effective_tflops=step_flops * args.steps / (ms * 1e-3) / 1e12)
+    if not args.skip_cpu_baseline:
+        c = cpu_reference_sample(args.t_start_proj, args.t_start_img)
+        line["cpu_baseline"] = dict(value=1.0 / c["per_slice_s"], unit="slices/s", cores=c["cores"], kind="port", sample=c["sample"])
+    print(json.dumps(line))
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    import torch
+    import torch.distributed as dist
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_b200(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -45,6 +45,14 @@ int ipdm_abi_version(void);
 unsigned long long ipdm_launch_count(void);
 void ipdm_launch_count_reset(void);
 
+/* Per-kernel-family profiler for bench.py: when enabled, every launch is bracketed by CUDA events on its
+ * stream.  Families (index): 0 conv_tc (work = FLOPs issued), 1 attention (FLOPs), 2 conv_direct (bytes),
+ * 3 groupnorm (bytes), 4 upsample (bytes), 5 fbp_filter (bytes), 6 fbp_backproject (compulsory bytes),
+ * 7 sampler step (algorithmic bytes).  collect() synchronises the device and sums per family. */
+#define IPDM_PROF_KINDS 8
+void ipdm_profile_enable(int on);
+int ipdm_profile_collect(double ms_out[IPDM_PROF_KINDS], double work_out[IPDM_PROF_KINDS], long long launches_out[IPDM_PROF_KINDS]);
+
 /* ------------------------------------------------------------------------------------------
  * FBP convertor.  Replaces Recon/FBP_kernel.py: FBP.__init__ :27-67 (tables), FBP.convert
  * :86-122, conv_pj/conv_kernel :125-143 (ramp filter), fbp_cpu/fbp_kernel :146-184

@@ -2,6 +2,7 @@
 #include "common.cuh"
 
 #include <cstring>
+#include <vector>
 
 namespace ipdm {
 
@@ -16,7 +17,34 @@ void set_error(const char* fmt, ...) {
 }
 const char* last_error() { return g_err; }
 
+bool g_prof_on = false;
+struct ProfRec { int kind; cudaEvent_t a, b; double work; };
+static std::vector<ProfRec> g_prof;
+static cudaEvent_t g_prof_open[PROF_KINDS];
+void prof_begin(int kind, cudaStream_t st) {
+    cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); g_prof_open[kind] = e;
+}
+void prof_end(int kind, cudaStream_t st, double work) {
+    cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st);
+    g_prof.push_back({kind, g_prof_open[kind], e, work});
+}
+
 }  // namespace ipdm
+
+extern "C" void ipdm_profile_enable(int on) {
+    ipdm::g_prof_on = on != 0;
+    if (on) { for (auto& r : ipdm::g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); } ipdm::g_prof.clear(); }
+}
+extern "C" int ipdm_profile_collect(double* ms_out, double* work_out, long long* launches_out) {
+    using namespace ipdm;
+    IPDM_CHECK_CUDA(cudaDeviceSynchronize());
+    for (int k = 0; k < PROF_KINDS; ++k) { ms_out[k] = 0; work_out[k] = 0; launches_out[k] = 0; }
+    for (auto& r : g_prof) {
+        float ms = 0; cudaEventElapsedTime(&ms, r.a, r.b);
+        ms_out[r.kind] += ms; work_out[r.kind] += r.work; launches_out[r.kind] += 1;
+    }
+    return IPDM_OK;
+}
 
 extern "C" const char* ipdm_last_error(void) { return ipdm::last_error(); }
 extern "C" int ipdm_abi_version(void) { return 1; }

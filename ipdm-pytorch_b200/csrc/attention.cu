@@ -156,6 +156,7 @@ attention_kernel(const __grid_constant__ AttentionParams P) {
                     pv.y = exp2f(fmaf(__uint_as_float(sr[h][4 * u + 1]), P.scale_log2, -mb));
                     pv.z = exp2f(fmaf(__uint_as_float(sr[h][4 * u + 2]), P.scale_log2, -mb));
                     pv.w = exp2f(fmaf(__uint_as_float(sr[h][4 * u + 3]), P.scale_log2, -mb));
+                    pv.x = tf32_rn(pv.x); pv.y = tf32_rn(pv.y); pv.z = tf32_rn(pv.z); pv.w = tf32_rn(pv.w);   // P is an MMA operand
                     rs += (pv.x + pv.y) + (pv.z + pv.w);
                     *reinterpret_cast<float4*>(prow + h * (AT_BQ * 128) + ((u ^ sw) << 4)) = pv;
                 }
@@ -182,7 +183,8 @@ attention_kernel(const __grid_constant__ AttentionParams P) {
             float4* op = reinterpret_cast<float4*>(P.out + ((size_t)b * P.T + t) * P.C + head * AT_D);
 #pragma unroll
             for (int i = 0; i < AT_D / 4; ++i)
-                op[i] = make_float4(o_acc[4 * i] * inv, o_acc[4 * i + 1] * inv, o_acc[4 * i + 2] * inv, o_acc[4 * i + 3] * inv);
+                op[i] = make_float4(tf32_rn(o_acc[4 * i] * inv), tf32_rn(o_acc[4 * i + 1] * inv), tf32_rn(o_acc[4 * i + 2] * inv),
+                                    tf32_rn(o_acc[4 * i + 3] * inv));              // operand of the proj 1x1 GEMM
         }
     }
     tc::tc_fence_before();
@@ -215,6 +217,7 @@ int attention_launch(const AttentionParams& P, cudaStream_t st) {
         configured = true;
     }
     dim3 grid((P.T + AT_BQ - 1) / AT_BQ, P.heads, P.batch);
+    ProfScope prof(PROF_ATTENTION, st, 4.0 * P.batch * P.heads * (double)P.T * P.T * AT_D);
     attention_kernel<<<grid, AT_THREADS, AT_SMEM, st>>>(P);
     count_launch();
     IPDM_CHECK_LAUNCH();

@@ -4,6 +4,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdarg>
+#include <cstring>
 
 #include "../../include/ipdm_b200.h"
 
@@ -46,6 +47,18 @@ inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 extern unsigned long long g_launch_count;
 inline void count_launch(int n = 1) { g_launch_count += (unsigned long long)n; }
 
+// per-kernel-family profiler (off by default): CUDA events around every launch, summed by family.
+enum ProfKind { PROF_CONV_TC = 0, PROF_ATTENTION, PROF_CONV_DIRECT, PROF_GROUPNORM, PROF_UPSAMPLE, PROF_FBP_FILTER,
+                PROF_FBP_BACKPROJECT, PROF_SAMPLER, PROF_KINDS };
+extern bool g_prof_on;
+void prof_begin(int kind, cudaStream_t st);
+void prof_end(int kind, cudaStream_t st, double work);
+struct ProfScope {
+    int kind; cudaStream_t st; double work;
+    ProfScope(int k, cudaStream_t s, double w) : kind(k), st(s), work(w) { if (g_prof_on) prof_begin(kind, st); }
+    ~ProfScope() { if (g_prof_on) prof_end(kind, st, work); }
+};
+
 // ---- device helpers ----
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -70,5 +83,21 @@ __device__ __forceinline__ void st_stream(float4* p, const float4& v) {
 }
 
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
+
+// Round to the nearest TF32 value (10-bit mantissa).  The tensor core only reads the upper 19 bits of an
+// fp32 operand, i.e. it TRUNCATES; truncation shrinks every product coherently (measured: 4.3e-4 rel-L2 on a
+// K=1152 conv), whereas pre-rounded operands leave only zero-mean noise.  Operand producers call this.
+__device__ __forceinline__ float tf32_rn(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+inline float tf32_rn_host(float x) {
+    uint32_t b; memcpy(&b, &x, 4);
+    if ((b & 0x7F800000u) == 0x7F800000u) return x;
+    b += 0x00000FFFu + ((b >> 13) & 1u);
+    b &= 0xFFFFE000u;
+    float y; memcpy(&y, &b, 4); return y;
+}
 
 }  // namespace ipdm

@@ -190,6 +190,10 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams P) {
 #pragma unroll
             for (int i = 0; i < CHUNK / 4; ++i) { const float4 t = __ldg(rp + i); v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w; }
         }
+        if (P.qkv_mode) {                            // q, k, v are operands of the attention MMAs: round to nearest tf32
+#pragma unroll
+            for (int i = 0; i < CHUNK; ++i) v[i] = tf32_rn(v[i]);
+        }
         if (P.qkv_mode && ((n % (3 * P.head_dim)) >= 2 * P.head_dim)) {
             // V of one head: write transposed, [b][head][d][t_pad] (token contiguous), so P.V^T is K-major for attention
             const int head = n / (3 * P.head_dim), d0 = n % (3 * P.head_dim) - 2 * P.head_dim;
@@ -295,6 +299,7 @@ static int launch_tc(const ConvTcParams& P, cudaStream_t st) {
 }
 
 int conv_tc_launch(const ConvTcParams& P, cudaStream_t st) {
+    ProfScope prof(PROF_CONV_TC, st, conv_tc_flops(P));      // padded-K FLOPs actually issued to the tensor pipe
     switch (P.block_n) {
         case 128: return launch_tc<128, 3>(P, st);
         case 64: return launch_tc<64, 4>(P, st);

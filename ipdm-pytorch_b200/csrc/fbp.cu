@@ -319,6 +319,7 @@ extern "C" int ipdm_fbp_tables(const ipdm_fbp_plan* p, double* theta, float* nda
 
 extern "C" int ipdm_fbp_filter(ipdm_fbp_plan* p, const float* sino, float* q, int batch, int flip, void* stream) {
     IPDM_REQUIRE(p && sino && q && batch > 0, "ipdm_fbp_filter: bad arguments");
+    ProfScope prof(PROF_FBP_FILTER, (cudaStream_t)stream, 2.0 * 4 * batch * (double)NV * ND);
     fbp_filter_kernel<<<batch * NV, FILT_THREADS, 0, (cudaStream_t)stream>>>(sino, q, p->d_wcos, p->d_htap, p->h0,
                                                                              p->dtheta, flip);
     count_launch();
@@ -329,6 +330,7 @@ extern "C" int ipdm_fbp_filter(ipdm_fbp_plan* p, const float* sino, float* q, in
 extern "C" int ipdm_fbp_backproject(ipdm_fbp_plan* p, const float* q, float* img, int batch, int flip, void* stream) {
     IPDM_REQUIRE(p && q && img && batch > 0, "ipdm_fbp_backproject: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
+    ProfScope prof(PROF_FBP_BACKPROJECT, st, 4.0 * batch * ((double)NV * ND + (double)NP * NP));   // compulsory bytes (8.345 MB / slice)
     // tile height: keep >= ~4 CTAs per SM in flight for small batches, fattest tile otherwise
     if (batch >= 4) {
         fbp_backproject_kernel<4><<<dim3(NP / 32, NP / 32, batch), 256, 0, st>>>(q, img, p->d_cs, p->inv_da, p->u_off, flip);

@@ -481,6 +481,7 @@ extern "C" int ipdm_sampler_step(const float* x_t, const float* x0c, const float
     IPDM_REQUIRE(batch == 1 || n % 4 == 0, "ipdm_sampler_step: H*W must be a multiple of 4 for batch > 1");
     IPDM_REQUIRE(lam_map == nullptr || ks > 0, "ipdm_sampler_step: ks must be positive with a lambda map");
     cudaStream_t st = (cudaStream_t)stream;
+    ProfScope prof(PROF_SAMPLER, st, (lam_map ? 44.0 : 32.0) * batch * (double)h * w);        // algorithmic bytes
     Ws ws = carve(workspace, batch);
     StepCoef k{coef7[0], coef7[1], coef7[2], coef7[3], coef7[4], coef7[5], coef7[6]};
     const int nblk = (int)std::min<size_t>(MOM_BLOCKS, (n / 4 + MOM_THREADS - 1) / MOM_THREADS > 0 ? (n / 4 + MOM_THREADS - 1) / MOM_THREADS : 1);

@@ -138,7 +138,7 @@ static int pack_conv(ipdm_unet* net, ConvW& c, int c0, int c1, bool raw_sources,
         for (int co = 0; co < c.cout; ++co)
             for (int ci = 0; ci < c.cin; ++ci) {
                 const int col = ci < c.c0 ? ci : c.cs0 + (ci - c.c0);
-                for (int t = 0; t < kk; ++t) p[((size_t)t * c.cout + co) * c.kpad + col] = c.w_host[((size_t)co * c.cin + ci) * kk + t];
+                for (int t = 0; t < kk; ++t) p[((size_t)t * c.cout + co) * c.kpad + col] = tf32_rn_host(c.w_host[((size_t)co * c.cin + ci) * kk + t]);
             }
         IPDM_CHECK(upload(net, p, &c.w_dev));
     } else {
@@ -364,7 +364,7 @@ struct PlanBuilder {
         Op st; st.kind = Op::GN_STATS; st.nsrc = 1; st.src[0] = x; st.gn = &a.norm; st.norm_slot = norm_slots++; max_c = std::max(max_c, a.C); push(st);
         const int an = new_tensor(pl->B, s.h, s.w, a.C, a.C);
         Op ap; ap.kind = Op::GN_APPLY; ap.nsrc = 1; ap.src[0] = x; ap.gn = &a.norm; ap.norm_slot = st.norm_slot; ap.dst = an; ap.act = 0; push(ap);
-        Op q; q.kind = Op::CONV_TC; q.nsrc = 1; q.src[0] = an; q.cw = &a.qkv; q.dst = qk; q.aux = vt; q.qkv = 1; push(q);
+        Op q; q.kind = Op::CONV_TC; q.nsrc = 1; q.src[0] = an; q.cw = &a.qkv; q.dst = qk; q.aux = vt; q.qkv = 1; push(q);   // epilogue rounds q,k,v to tf32
         const int o = new_tensor(pl->B, s.h, s.w, a.C, a.C);
         Op at; at.kind = Op::ATTN; at.nsrc = 1; at.src[0] = qk; at.aux = vt; at.dst = o; push(at);
         const int out = act(s.h, s.w, a.C);

@@ -141,6 +141,7 @@ int conv_direct_launch(const ConvDirectDesc& d, cudaStream_t st) {
     const size_t smem = ((((size_t)d.cin * (tin_w * tin_h + 1) + 3) & ~(size_t)3) + (size_t)d.ksize * d.ksize * d.cin * ct) * sizeof(float);
     IPDM_REQUIRE(smem <= 200 * 1024, "conv_direct: tile needs %zu bytes of shared memory", smem);
     dim3 grid(ceil_div(P.wout, CD_TX), ceil_div(P.hout, CD_TY), s0.n * P.co_tiles), block(CD_TX, CD_TY);
+    ProfScope prof(PROF_CONV_DIRECT, st, 4.0 * s0.n * ((double)s0.h * s0.w * d.cin + (double)P.hout * P.wout * d.cout));   // bytes
     auto go = [&](auto kern) -> int {
         if (smem > 48 * 1024) IPDM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, block, smem, st>>>(P);
@@ -218,6 +219,7 @@ int groupnorm_stats_launch(const GroupNormDesc& d, cudaStream_t st) {
     IPDM_REQUIRE(Ctot % d.groups == 0, "groupnorm: %d channels not divisible by %d groups", Ctot, d.groups);
     const TensorNHWC& s0 = d.src[0];
     const size_t npix = (size_t)s0.h * s0.w;
+    ProfScope prof(PROF_GROUPNORM, st, 4.0 * s0.n * (double)npix * Ctot);
     const int R0 = std::max(1, 256 / (s0.c / 4));
     const int nblk = (int)std::min<size_t>(GN_MAX_BLOCKS, (npix + R0 - 1) / R0);   // one partial grid for all sources
     int c_off = 0;
@@ -255,6 +257,7 @@ gn_apply_kernel(const float* __restrict__ s0, int c0, int cs0, const float* __re
             const float4 sh = __ldg(reinterpret_cast<const float4*>(shift + (size_t)n * Ctot + c));
             o.x = fmaf(v.x, sc.x, sh.x); o.y = fmaf(v.y, sc.y, sh.y); o.z = fmaf(v.z, sc.z, sh.z); o.w = fmaf(v.w, sc.w, sh.w);
             if (act) { o.x = silu(o.x); o.y = silu(o.y); o.z = silu(o.z); o.w = silu(o.w); }
+            o.x = tf32_rn(o.x); o.y = tf32_rn(o.y); o.z = tf32_rn(o.z); o.w = tf32_rn(o.w);   // operand of a tcgen05 kind::tf32 MMA
         }
         *reinterpret_cast<float4*>(out + pix * ocs + c) = o;
     }
@@ -266,6 +269,7 @@ int groupnorm_apply_launch(const GroupNormDesc& d, const TensorNHWC& out, int ac
     IPDM_REQUIRE(out.cs % 4 == 0 && out.cs >= a.c + c1 && a.c % 4 == 0, "groupnorm_apply: bad channel layout");
     const size_t npix = (size_t)a.h * a.w, nvec = (size_t)a.n * npix * (out.cs / 4);
     const int grid = (int)std::min<size_t>((size_t)kNumSMs * 8, (nvec + 255) / 256);
+    ProfScope prof(PROF_GROUPNORM, st, 4.0 * a.n * (double)npix * (a.c + c1 + out.cs));
     gn_apply_kernel<<<grid, 256, 0, st>>>(a.p, a.c, a.cs, d.nsrc == 2 ? d.src[1].p : nullptr, c1, d.nsrc == 2 ? d.src[1].cs : 0,
                                           d.scale, d.shift, out.p, out.cs, npix, nvec, act_silu);
     count_launch();
@@ -289,6 +293,7 @@ upsample_kernel(const float* __restrict__ src, int hs, int ws, int scs, float* _
         const int yy = min((int)floorf((float)y * sy), hs - 1), xx = min((int)floorf((float)x * sx), ws - 1);
         float4 v = make_float4(0, 0, 0, 0);
         if (c < scs) v = __ldg(reinterpret_cast<const float4*>(src + (((size_t)n * hs + yy) * ws + xx) * scs + c));
+        v.x = tf32_rn(v.x); v.y = tf32_rn(v.y); v.z = tf32_rn(v.z); v.w = tf32_rn(v.w);      // feeds a tensor-core conv only
         *reinterpret_cast<float4*>(dst + pix * dcs + c) = v;
     }
 }
@@ -297,6 +302,7 @@ int upsample_nearest_launch(const TensorNHWC& src, const TensorNHWC& dst, cudaSt
     IPDM_REQUIRE(src.cs % 4 == 0 && dst.cs % 4 == 0 && dst.cs >= src.cs && src.n == dst.n, "upsample: bad layout");
     const size_t nvec = dst.pixels() * (dst.cs / 4);
     const int grid = (int)std::min<size_t>((size_t)kNumSMs * 8, (nvec + 255) / 256);
+    ProfScope prof(PROF_UPSAMPLE, st, 4.0 * ((double)src.elems() + dst.elems()));
     upsample_kernel<<<grid, 256, 0, st>>>(src.p, src.h, src.w, src.cs, dst.p, dst.h, dst.w, dst.cs, (float)src.h / dst.h,
                                           (float)src.w / dst.w, nvec);
     count_launch();

@@ -44,6 +44,20 @@ def launch_count_reset():
     _lib.lib().ipdm_launch_count_reset()
 
 
+PROF_FAMILIES = ("conv_tc", "attention", "conv_direct", "groupnorm", "upsample", "fbp_filter", "fbp_backproject", "sampler")
+
+
+def profile_enable(on=True):
+    _lib.lib().ipdm_profile_enable(int(bool(on)))
+
+
+def profile_collect():
+    """{family: (milliseconds, work, launches)}; work is FLOPs for conv_tc / attention, bytes otherwise."""
+    ms, work, n = (ctypes.c_double * 8)(), (ctypes.c_double * 8)(), (ctypes.c_longlong * 8)()
+    check(_lib.lib().ipdm_profile_collect(ms, work, n), "ipdm_profile_collect")
+    return {f: (ms[i], work[i], int(n[i])) for i, f in enumerate(PROF_FAMILIES)}
+
+
 # ---------------------------------------------------------------------------------------------
 # FBP convertor
 # ---------------------------------------------------------------------------------------------

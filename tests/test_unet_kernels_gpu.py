@@ -131,7 +131,7 @@ def test_groupnorm_stats_and_apply(cuda, c0, c1, hw):
         want = F.group_norm(x, gn_groups(C), gamma, beta, eps=1e-5)
         want = F.silu(want) if act else want
         full = out.cpu()
-        assert rel_l2(nchw(full, C).numpy(), want.numpy()) < 2e-5
+        assert rel_l2(nchw(full, C).numpy(), want.numpy()) < 4e-4     # the applied tensor is rounded to tf32 (MMA operand)
         assert ocs == C or float(full[..., C:].abs().max()) == 0.0
     lin = x * sc.cpu()[:, :, None, None] + sh.cpu()[:, :, None, None]
     assert rel_l2(lin.numpy(), F.group_norm(x, gn_groups(C), gamma, beta, eps=1e-5).numpy()) < 2e-5
@@ -178,7 +178,7 @@ def test_tc_conv_full_size_row_shapes(cuda):
 
 
 # ---- attention ----------------------------------------------------------------------------------------
-@pytest.mark.parametrize("hw,batch", [((7, 5), 2), ((13, 10), 1), ((25, 19), 2), ((32, 32), 1)])
+@pytest.mark.parametrize("hw,batch", [((7, 5), 2), ((13, 10), 1), ((25, 19), 2), ((32, 32), 1), ((63, 29), 1), ((125, 57), 1)])
 def test_attention(cuda, hw, batch):
     from ipdm_pytorch_b200 import _lib
     C, heads, d = 256, 4, 64
