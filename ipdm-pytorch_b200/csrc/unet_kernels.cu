@@ -159,8 +159,15 @@ double conv_direct_flops(const ConvDirectDesc& d) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// GroupNorm statistics
+// GroupNorm statistics: HBM-bound single read of the tensor (4 B / element).
+//   gn_partial_kernel   grid (nblk, slices): a CTA strides over pixel rows; thread t always sees the same
+//                       4-channel vector (t % V), four independent 128-bit loads in flight per thread;
+//                       fp32 per-thread sums, fixed-order fp64 combine per channel -> partials[n][blk][c][2]
+//   gn_finalize_kernel  grid (groups, slices): fixed-order fp64 reduction over blocks x channels-in-group
+//                       -> per-(slice, channel) scale = gamma*rstd, shift = beta - mean*gamma*rstd
 // ------------------------------------------------------------------------------------------------
+constexpr int GN_UNROLL = 4;
+
 __global__ void __launch_bounds__(256)
 gn_partial_kernel(const float* __restrict__ src, int C, int cs, size_t npix, double* __restrict__ partials, int c_off, int Ctot) {
     __shared__ float red[256][8];
@@ -172,8 +179,20 @@ gn_partial_kernel(const float* __restrict__ src, int C, int cs, size_t npix, dou
     if (t < TA) {
         const int cv = t % V, prow = t / V;
         const float* base = src + (size_t)n * npix * cs + 4 * cv;
-        for (size_t pix = (size_t)blockIdx.x * R + prow; pix < npix; pix += (size_t)gridDim.x * R) {
-            const float4 v = __ldg(reinterpret_cast<const float4*>(base + pix * cs));
+        const size_t stride = (size_t)gridDim.x * R;
+        size_t pix = (size_t)blockIdx.x * R + prow;
+        for (; pix + (GN_UNROLL - 1) * stride < npix; pix += GN_UNROLL * stride) {
+            float4 v[GN_UNROLL];
+#pragma unroll
+            for (int u = 0; u < GN_UNROLL; ++u) v[u] = ld_stream(reinterpret_cast<const float4*>(base + (pix + u * stride) * cs));
+#pragma unroll
+            for (int u = 0; u < GN_UNROLL; ++u) {
+                s.x += v[u].x; s.y += v[u].y; s.z += v[u].z; s.w += v[u].w;
+                q.x = fmaf(v[u].x, v[u].x, q.x); q.y = fmaf(v[u].y, v[u].y, q.y); q.z = fmaf(v[u].z, v[u].z, q.z); q.w = fmaf(v[u].w, v[u].w, q.w);
+            }
+        }
+        for (; pix < npix; pix += stride) {
+            const float4 v = ld_stream(reinterpret_cast<const float4*>(base + pix * cs));
             s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
             q.x = fmaf(v.x, v.x, q.x); q.y = fmaf(v.y, v.y, q.y); q.z = fmaf(v.z, v.z, q.z); q.w = fmaf(v.w, v.w, q.w);
         }
@@ -190,26 +209,33 @@ gn_partial_kernel(const float* __restrict__ src, int C, int cs, size_t npix, dou
     }
 }
 
-__global__ void gn_finalize_kernel(const double* __restrict__ partials, int nblk, int Ctot, int groups, double count,
-                                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                                   float* __restrict__ scale, float* __restrict__ shift) {
-    const int n = blockIdx.x, cpg = Ctot / groups;
-    for (int g = threadIdx.x; g < groups; g += blockDim.x) {
-        double a = 0, b = 0;
-        for (int blk = 0; blk < nblk; ++blk)
-            for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
-                const double* o = partials + (((size_t)n * nblk + blk) * Ctot + c) * 2;
-                a += o[0]; b += o[1];
-            }
-        const double mean = a / count;
-        double var = b / count - mean * mean;
-        var = var < 0 ? 0 : var;
-        const double rstd = 1.0 / sqrt(var + (double)eps);
-        for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
-            const double ga = gamma[c];
-            scale[(size_t)n * Ctot + c] = (float)(ga * rstd);
-            shift[(size_t)n * Ctot + c] = (float)((double)beta[c] - mean * ga * rstd);
-        }
+__global__ void __launch_bounds__(128)
+gn_finalize_kernel(const double* __restrict__ partials, int nblk, int Ctot, int groups, double count,
+                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                   float* __restrict__ scale, float* __restrict__ shift) {
+    __shared__ double sa[128], sb[128];
+    const int g = blockIdx.x, n = blockIdx.y, cpg = Ctot / groups;
+    double a = 0, b = 0;
+    const int total = nblk * cpg;
+    for (int i = threadIdx.x; i < total; i += 128) {
+        const int blk = i / cpg, c = g * cpg + (i - blk * cpg);
+        const double* o = partials + (((size_t)n * nblk + blk) * Ctot + c) * 2;
+        a += o[0]; b += o[1];
+    }
+    sa[threadIdx.x] = a; sb[threadIdx.x] = b;
+    __syncthreads();
+    for (int o = 64; o > 0; o >>= 1) {
+        if (threadIdx.x < o) { sa[threadIdx.x] += sa[threadIdx.x + o]; sb[threadIdx.x] += sb[threadIdx.x + o]; }
+        __syncthreads();
+    }
+    const double mean = sa[0] / count;
+    double var = sb[0] / count - mean * mean;
+    var = var < 0 ? 0 : var;
+    const double rstd = 1.0 / sqrt(var + (double)eps);
+    for (int c = g * cpg + threadIdx.x; c < (g + 1) * cpg; c += 128) {
+        const double ga = gamma[c];
+        scale[(size_t)n * Ctot + c] = (float)(ga * rstd);
+        shift[(size_t)n * Ctot + c] = (float)((double)beta[c] - mean * ga * rstd);
     }
 }
 
@@ -221,7 +247,9 @@ int groupnorm_stats_launch(const GroupNormDesc& d, cudaStream_t st) {
     const size_t npix = (size_t)s0.h * s0.w;
     ProfScope prof(PROF_GROUPNORM, st, 4.0 * s0.n * (double)npix * Ctot);
     const int R0 = std::max(1, 256 / (s0.c / 4));
-    const int nblk = (int)std::min<size_t>(GN_MAX_BLOCKS, (npix + R0 - 1) / R0);   // one partial grid for all sources
+    // one partial grid for all sources: enough CTAs to cover the machine a few times, at least 2 unrolled trips each
+    int nblk = (int)std::min<size_t>(GN_MAX_BLOCKS, (npix + (size_t)R0 * 2 * GN_UNROLL - 1) / ((size_t)R0 * 2 * GN_UNROLL));
+    nblk = std::max(1, std::min(nblk, std::max(1, kNumSMs * 6 / s0.n)));
     int c_off = 0;
     for (int s = 0; s < d.nsrc; ++s) {
         const TensorNHWC& t = d.src[s];
@@ -230,36 +258,50 @@ int groupnorm_stats_launch(const GroupNormDesc& d, cudaStream_t st) {
         count_launch();
         c_off += t.c;
     }
-    gn_finalize_kernel<<<s0.n, 64, 0, st>>>(d.partials, nblk, Ctot, d.groups, (double)npix * (Ctot / d.groups), d.gamma, d.beta, d.eps,
-                                            d.scale, d.shift);
+    gn_finalize_kernel<<<dim3(d.groups, s0.n), 128, 0, st>>>(d.partials, nblk, Ctot, d.groups, (double)npix * (Ctot / d.groups), d.gamma, d.beta,
+                                                            d.eps, d.scale, d.shift);
     count_launch();
     IPDM_CHECK_LAUNCH();
     return IPDM_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
-// GroupNorm apply + SiLU (+ virtual concat, + channel padding) -> operand tensor of a tensor-core conv
+// GroupNorm apply + SiLU (+ virtual concat, + channel padding) -> operand tensor of a tensor-core conv.
+// HBM-bound: 4 B read + 4 B written per element; two independent 128-bit loads in flight per thread.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 gn_apply_kernel(const float* __restrict__ s0, int c0, int cs0, const float* __restrict__ s1, int c1, int cs1,
                 const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ out, int ocs,
                 size_t npix_per_slice, size_t nvec_total, int act) {
     const int Ctot = c0 + c1, V = ocs / 4;
-    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < nvec_total; i += (size_t)gridDim.x * 256) {
-        const size_t pix = i / V;
-        const int c = (int)(i - pix * V) * 4;
-        const int n = (int)(pix / npix_per_slice);
-        float4 o = make_float4(0, 0, 0, 0);
-        if (c < Ctot) {
-            const float4 v = c < c0 ? __ldg(reinterpret_cast<const float4*>(s0 + pix * cs0 + c))
-                                    : __ldg(reinterpret_cast<const float4*>(s1 + pix * cs1 + (c - c0)));
-            const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + (size_t)n * Ctot + c));
-            const float4 sh = __ldg(reinterpret_cast<const float4*>(shift + (size_t)n * Ctot + c));
-            o.x = fmaf(v.x, sc.x, sh.x); o.y = fmaf(v.y, sc.y, sh.y); o.z = fmaf(v.z, sc.z, sh.z); o.w = fmaf(v.w, sc.w, sh.w);
-            if (act) { o.x = silu(o.x); o.y = silu(o.y); o.z = silu(o.z); o.w = silu(o.w); }
-            o.x = tf32_rn(o.x); o.y = tf32_rn(o.y); o.z = tf32_rn(o.z); o.w = tf32_rn(o.w);   // operand of a tcgen05 kind::tf32 MMA
+    const size_t stride = (size_t)gridDim.x * 256;
+    for (size_t i0 = (size_t)blockIdx.x * 256 + threadIdx.x; i0 < nvec_total; i0 += 2 * stride) {
+        float4 v[2]; size_t pix[2]; int c[2]; bool live[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const size_t i = i0 + u * stride;
+            live[u] = i < nvec_total;
+            pix[u] = live[u] ? i / V : 0;
+            c[u] = live[u] ? (int)(i - pix[u] * V) * 4 : 0;
+            v[u] = make_float4(0, 0, 0, 0);
+            if (live[u] && c[u] < Ctot)
+                v[u] = c[u] < c0 ? ld_stream(reinterpret_cast<const float4*>(s0 + pix[u] * cs0 + c[u]))
+                                 : ld_stream(reinterpret_cast<const float4*>(s1 + pix[u] * cs1 + (c[u] - c0)));
         }
-        *reinterpret_cast<float4*>(out + pix * ocs + c) = o;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (!live[u]) continue;
+            float4 o = make_float4(0, 0, 0, 0);
+            if (c[u] < Ctot) {
+                const int n = (int)(pix[u] / npix_per_slice);
+                const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + (size_t)n * Ctot + c[u]));
+                const float4 sh = __ldg(reinterpret_cast<const float4*>(shift + (size_t)n * Ctot + c[u]));
+                o.x = fmaf(v[u].x, sc.x, sh.x); o.y = fmaf(v[u].y, sc.y, sh.y); o.z = fmaf(v[u].z, sc.z, sh.z); o.w = fmaf(v[u].w, sc.w, sh.w);
+                if (act) { o.x = silu(o.x); o.y = silu(o.y); o.z = silu(o.z); o.w = silu(o.w); }
+                o.x = tf32_rn(o.x); o.y = tf32_rn(o.y); o.z = tf32_rn(o.z); o.w = tf32_rn(o.w);   // operand of a tcgen05 kind::tf32 MMA
+            }
+            *reinterpret_cast<float4*>(out + pix[u] * ocs + c[u]) = o;
+        }
     }
 }
 
@@ -268,9 +310,9 @@ int groupnorm_apply_launch(const GroupNormDesc& d, const TensorNHWC& out, int ac
     const int c1 = d.nsrc == 2 ? d.src[1].c : 0;
     IPDM_REQUIRE(out.cs % 4 == 0 && out.cs >= a.c + c1 && a.c % 4 == 0, "groupnorm_apply: bad channel layout");
     const size_t npix = (size_t)a.h * a.w, nvec = (size_t)a.n * npix * (out.cs / 4);
-    const int grid = (int)std::min<size_t>((size_t)kNumSMs * 8, (nvec + 255) / 256);
+    const int grid = (int)std::min<size_t>((size_t)kNumSMs * 16, (nvec + 511) / 512);
     ProfScope prof(PROF_GROUPNORM, st, 4.0 * a.n * (double)npix * (a.c + c1 + out.cs));
-    gn_apply_kernel<<<grid, 256, 0, st>>>(a.p, a.c, a.cs, d.nsrc == 2 ? d.src[1].p : nullptr, c1, d.nsrc == 2 ? d.src[1].cs : 0,
+    gn_apply_kernel<<<std::max(grid, 1), 256, 0, st>>>(a.p, a.c, a.cs, d.nsrc == 2 ? d.src[1].p : nullptr, c1, d.nsrc == 2 ? d.src[1].cs : 0,
                                           d.scale, d.shift, out.p, out.cs, npix, nvec, act_silu);
     count_launch();
     IPDM_CHECK_LAUNCH();

@@ -76,7 +76,7 @@ struct GroupNormDesc {
     float* shift = nullptr;
     double* partials = nullptr;        // workspace [batch][GN_MAX_BLOCKS][C][2]
 };
-constexpr int GN_MAX_BLOCKS = 128;
+constexpr int GN_MAX_BLOCKS = 888;        // 6 CTAs per SM
 int groupnorm_stats_launch(const GroupNormDesc& d, cudaStream_t st);
 // out[n][y][x][c] = act(src*scale + shift) (c < C; act = SiLU or identity), 0 for pad channels; out.cs may exceed C
 int groupnorm_apply_launch(const GroupNormDesc& d, const TensorNHWC& out, int act_silu, cudaStream_t st);
