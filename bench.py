@@ -151,13 +151,15 @@ def run_b200(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     B = args.batch
+    import contextlib
+    import io
     import tempfile
-    opt = default_cfg(["--load_option_path", os.path.join(PKG, "Config/Mayo-Config/test_progressive_option.json"), "--device", f"cuda:{local_rank}"])
+    with contextlib.redirect_stdout(io.StringIO()):          # the reference's option loader prints; stdout carries ONE JSON line
+        opt = default_cfg(["--load_option_path", os.path.join(PKG, "Config/Mayo-Config/test_progressive_option.json"), "--device", f"cuda:{local_rank}"])
     opt.load_img_model_path = opt.load_proj_model_path = None
     for k in ("test_dataset_path_FD_img", "test_dataset_path_LD_img", "test_dataset_path_FD_proj", "test_dataset_path_LD_proj"):
         setattr(opt, k, None)
     torch.manual_seed(0)
-    import contextlib, io
     with contextlib.redirect_stdout(io.StringIO()):
         model = progressive_domain_denoiser(opt, result_save_path=tempfile.mkdtemp(prefix="ipdm_bench_"))
         model.update_opt(dict(convertor="FBP", save_it_state_img=False, save_it_state_proj=False, ultra_img_denoise=True,

@@ -70,8 +70,8 @@ class FBPPlan:
         check(_lib.lib().ipdm_fbp_plan_create(ctypes.byref(self._h), int(max_batch)), "ipdm_fbp_plan_create")
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            _lib.lib().ipdm_fbp_plan_destroy(self._h)
+        if getattr(self, "_h", None) and _lib is not None and getattr(_lib, "_lib", None) is not None:
+            _lib._lib.ipdm_fbp_plan_destroy(self._h)
             self._h = None
 
     @staticmethod
@@ -254,8 +254,8 @@ class UNetHandle:
               "ipdm_unet_create")
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            _lib.lib().ipdm_unet_destroy(self._h)
+        if getattr(self, "_h", None) and _lib is not None and getattr(_lib, "_lib", None) is not None:
+            _lib._lib.ipdm_unet_destroy(self._h)
             self._h = None
 
     def forward(self, x, t, out=None):
