@@ -209,8 +209,9 @@ def run_b200(args, rank, world, local_rank):
     launches = engine.launch_count()
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:                                   # the only collective: final gather of the results
-        gathered = torch.empty(world * B, 1, 512, 512, device=dev)
-        dist.all_gather_into_tensor(gathered, out.contiguous())
+        from ipdm_pytorch_b200.sharding import gather_slices
+        gathered = gather_slices(out.contiguous(), world * B)
+        assert gathered.shape[0] == world * B
     step_e2e()
     ms_e2e, _ = timed(step_e2e, args.steps)
 

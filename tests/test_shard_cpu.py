@@ -7,11 +7,8 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 
-def shard_range(n_slices, rank, world):
-    """Contiguous slice range of `rank`: slices[r*B/W : (r+1)*B/W], remainders to the first ranks."""
-    base, rem = divmod(n_slices, world)
-    start = rank * base + min(rank, rem)
-    return start, start + base + (1 if rank < rem else 0)
+import conftest  # noqa: F401  (sys.path)
+from ipdm_pytorch_b200.sharding import gather_slices, shard_range
 
 
 def _worker(rank, world, port, n_slices, out):
@@ -21,11 +18,9 @@ def _worker(rank, world, port, n_slices, out):
     local = torch.arange(a, b, dtype=torch.float32)[:, None, None, None].expand(b - a, 1, 4, 4).contiguous() * 2 + 1   # "denoise" slice i -> 2i+1
     ms = torch.tensor([10.0 + rank])
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)                       # timing: max over ranks
-    sizes = [shard_range(n_slices, r, world) for r in range(world)]
-    parts = [torch.empty(e - s, 1, 4, 4) for s, e in sizes]
-    dist.all_gather(parts, local)                                   # the only collective: final gather
+    full = gather_slices(local, n_slices)                           # the only collective: final gather
     if rank == 0:
-        out.put((float(ms), torch.cat(parts)[:, 0, 0, 0].tolist()))
+        out.put((float(ms), full[:, 0, 0, 0].tolist()))
     dist.destroy_process_group()
 
 
