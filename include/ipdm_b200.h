@@ -200,7 +200,8 @@ int ipdm_guided_process(ipdm_unet* net, const ipdm_guided_params* p, const float
  * weights / affine parameters are HOST arrays in PyTorch layout.  They replace nothing in the
  * reference; they expose the building blocks of ipdm_unet_forward one at a time:
  *   conv        nn.Conv2d 3x3 / 1x1, stride 1 / 2, over a virtual concat of two sources
- *               (Model/model.py:101,113,117,142,143,165,180,306); use_tc picks tcgen05 or CUDA-core path;
+ *               (Model/model.py:101,113,117,142,143,165,180,306); use_tc: 0 CUDA-core path, 1 tcgen05 kind::tf32,
+ *               2 tcgen05 3xTF32 (fp32-accurate);
  *               the direct path can fuse GroupNorm+SiLU on load and a nearest upsample (:168).
  *   groupnorm   norm_layer(C) statistics -> per-(slice, channel) scale/shift (+ optional apply, +SiLU) (:82-90)
  *   attention   AttentionBlock core (:148-153) from q,k in NHWC [B,T,3C] and v transposed [B,heads,d,t_pad]
@@ -212,8 +213,9 @@ int ipdm_debug_conv(const float* src0_dev, int c0, int cs0, const float* src1_de
 int ipdm_debug_groupnorm(const float* src0_dev, int c0, int cs0, const float* src1_dev, int c1, int cs1, int n, int h, int w,
                          const float* gamma_host, const float* beta_host, int act_silu, float* scale_out_dev,
                          float* shift_out_dev, float* out_dev, int out_cs, void* stream);
-int ipdm_debug_attention(const float* qk_dev, const float* vt_dev, float* out_dev, int batch, int T, int t_pad, int heads, int C,
-                         void* stream);
+/* qk_lo_dev / vt_lo_dev: NULL (tf32 mode: qk, vt are used as they are) or the tf32 "lo" parts for the 3xTF32 fp32 mode */
+int ipdm_debug_attention(const float* qk_dev, const float* vt_dev, const float* qk_lo_dev, const float* vt_lo_dev, float* out_dev,
+                         int batch, int T, int t_pad, int heads, int C, void* stream);
 int ipdm_debug_upsample(const float* src_dev, int n, int hs, int ws, int cs, float* dst_dev, int hd, int wd, void* stream);
 
 #ifdef __cplusplus

@@ -74,7 +74,7 @@ _SIGNATURES = {
                                        vp, ctypes.c_int, ctypes.c_int, vp]),
     "ipdm_debug_groupnorm": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                             ctypes.c_int, vp, vp, ctypes.c_int, vp, vp, vp, ctypes.c_int, vp]),
-    "ipdm_debug_attention": (ctypes.c_int, [vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp]),
+    "ipdm_debug_attention": (ctypes.c_int, [vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp]),
     "ipdm_debug_upsample": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, ctypes.c_int, ctypes.c_int, vp]),
 }
 

@@ -25,17 +25,32 @@ constexpr int AT_Q_BYTES = 2 * AT_BQ * 128;          // 2 channel chunks x [128 
 constexpr int AT_K_BYTES = 2 * AT_BKV * 128;         // 2 channel chunks x [64 keys x 128 B]
 constexpr int AT_V_BYTES = 2 * AT_D * 128;           // 2 key chunks x [64 d-rows x 128 B]
 constexpr int AT_P_BYTES = 2 * AT_BQ * 128;          // 2 key chunks x [128 rows x 128 B]
-constexpr int AT_STAGE = AT_K_BYTES + AT_V_BYTES;
-constexpr int AT_OFF_KV = AT_Q_BYTES;
-constexpr int AT_OFF_P = AT_OFF_KV + 2 * AT_STAGE;
-constexpr int AT_OFF_BAR = AT_OFF_P + AT_P_BYTES;
-constexpr int AT_SMEM = AT_OFF_BAR + 16 * 8 + 1024;
+// SPLIT = fp32-accurate 3xTF32 mode: q, k, v arrive as tf32 hi/lo pairs (written by the qkv GEMM epilogue), the softmax
+// threads write P as hi/lo, and every product is hi*hi + hi*lo + lo*hi.  One K/V stage instead of two (192 KB of smem).
+template <bool SPLIT>
+struct AtL {
+    static constexpr int M = SPLIT ? 2 : 1;                   // hi (+ lo) copies of every operand tile
+    static constexpr int NST = SPLIT ? 1 : 2;
+    static constexpr int STAGE = M * (AT_K_BYTES + AT_V_BYTES);
+    static constexpr int OFF_QLO = AT_Q_BYTES;
+    static constexpr int OFF_KV = M * AT_Q_BYTES;
+    static constexpr int OFF_KLO = AT_K_BYTES;                // inside a stage: K_hi [K_lo] V_hi [V_lo]
+    static constexpr int OFF_V = M * AT_K_BYTES;
+    static constexpr int OFF_VLO = OFF_V + AT_V_BYTES;
+    static constexpr int OFF_P = OFF_KV + NST * STAGE;
+    static constexpr int OFF_PLO = OFF_P + AT_P_BYTES;
+    static constexpr int OFF_BAR = OFF_P + M * AT_P_BYTES;
+    static constexpr int SMEM = OFF_BAR + 16 * 8 + 1024;
+};
 
+template <bool SPLIT>
 __global__ void __launch_bounds__(AT_THREADS)
 attention_kernel(const __grid_constant__ AttentionParams P) {
+    using L = AtL<SPLIT>;
+    constexpr int NST = L::NST;
     extern __shared__ uint8_t at_smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)at_smem_raw + 1023) & ~(uintptr_t)1023);
-    uint64_t* bars = (uint64_t*)(smem + AT_OFF_BAR);
+    uint64_t* bars = (uint64_t*)(smem + L::OFF_BAR);
     uint64_t* q_full = bars;            // 1
     uint64_t* kv_full = bars + 1;       // 2
     uint64_t* kv_empty = bars + 3;      // 2
@@ -63,18 +78,24 @@ attention_kernel(const __grid_constant__ AttentionParams P) {
 
     if (warp == 4) {
         if (tc::elect_one()) {
-            tc::mbar_expect_tx(q_full, AT_Q_BYTES);
-            for (int c = 0; c < 2; ++c)
+            tc::mbar_expect_tx(q_full, L::M * AT_Q_BYTES);
+            for (int c = 0; c < 2; ++c) {
                 tc::tma_load_3d(smem + c * (AT_BQ * 128), &P.mapQ, q_full, head * 3 * AT_D + c * 32, q0, b);
+                if constexpr (SPLIT) tc::tma_load_3d(smem + L::OFF_QLO + c * (AT_BQ * 128), &P.mapQlo, q_full, head * 3 * AT_D + c * 32, q0, b);
+            }
             for (int j = 0; j < nkv; ++j) {
-                const int s = j & 1;
-                tc::mbar_wait(&kv_empty[s], ((uint32_t)(j >> 1) & 1u) ^ 1u);
-                tc::mbar_expect_tx(&kv_full[s], AT_STAGE);
-                uint8_t* sk = smem + AT_OFF_KV + s * AT_STAGE;
-                uint8_t* sv = sk + AT_K_BYTES;
+                const int s = j % NST;
+                tc::mbar_wait(&kv_empty[s], ((uint32_t)(j / NST) & 1u) ^ 1u);
+                tc::mbar_expect_tx(&kv_full[s], L::STAGE);
+                uint8_t* sk = smem + L::OFF_KV + s * L::STAGE;
+                uint8_t* sv = sk + L::OFF_V;
                 for (int c = 0; c < 2; ++c) {
                     tc::tma_load_3d(sk + c * (AT_BKV * 128), &P.mapK, &kv_full[s], head * 3 * AT_D + AT_D + c * 32, j * AT_BKV, b);
                     tc::tma_load_3d(sv + c * (AT_D * 128), &P.mapV, &kv_full[s], j * AT_BKV + c * 32, head * AT_D, b);
+                    if constexpr (SPLIT) {
+                        tc::tma_load_3d(sk + L::OFF_KLO + c * (AT_BKV * 128), &P.mapKlo, &kv_full[s], head * 3 * AT_D + AT_D + c * 32, j * AT_BKV, b);
+                        tc::tma_load_3d(sk + L::OFF_VLO + c * (AT_D * 128), &P.mapVlo, &kv_full[s], j * AT_BKV + c * 32, head * AT_D, b);
+                    }
                 }
             }
         }
@@ -82,33 +103,45 @@ attention_kernel(const __grid_constant__ AttentionParams P) {
     } else if (warp == 5) {
         if (tc::elect_one()) {
             constexpr uint32_t idesc = tc::make_idesc(tc::FMT_TF32, 128, 64);
-            const uint32_t sQ = tc::smem_u32(smem), sP = tc::smem_u32(smem + AT_OFF_P);
+            const uint32_t sQ = tc::smem_u32(smem), sP = tc::smem_u32(smem + L::OFF_P);
             auto issue_S = [&](int j) {
-                const int s = j & 1;
-                tc::mbar_wait(&kv_full[s], (uint32_t)(j >> 1) & 1u);
+                const int s = j % NST;
+                tc::mbar_wait(&kv_full[s], (uint32_t)(j / NST) & 1u);
                 tc::tc_fence_after();
-                const uint32_t sK = tc::smem_u32(smem + AT_OFF_KV + s * AT_STAGE);
+                const uint32_t sK = tc::smem_u32(smem + L::OFF_KV + s * L::STAGE);
 #pragma unroll
                 for (int c = 0; c < 2; ++c)
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        tc::umma_tf32(tmem_S, tc::smem_desc_k_sw128(sQ + c * (AT_BQ * 128)) + (uint64_t)(k * 2),
-                                      tc::smem_desc_k_sw128(sK + c * (AT_BKV * 128)) + (uint64_t)(k * 2), idesc, (uint32_t)((c | k) != 0));
+                    for (int k = 0; k < 4; ++k) {
+                        const uint64_t qd = tc::smem_desc_k_sw128(sQ + c * (AT_BQ * 128)) + (uint64_t)(k * 2);
+                        const uint64_t kd = tc::smem_desc_k_sw128(sK + c * (AT_BKV * 128)) + (uint64_t)(k * 2);
+                        tc::umma_tf32(tmem_S, qd, kd, idesc, (uint32_t)((c | k) != 0));
+                        if constexpr (SPLIT) {
+                            tc::umma_tf32(tmem_S, qd, tc::smem_desc_k_sw128(sK + L::OFF_KLO + c * (AT_BKV * 128)) + (uint64_t)(k * 2), idesc, 1u);
+                            tc::umma_tf32(tmem_S, tc::smem_desc_k_sw128(sQ + L::OFF_QLO + c * (AT_BQ * 128)) + (uint64_t)(k * 2), kd, idesc, 1u);
+                        }
+                    }
                 tc::umma_commit(s_full);
             };
             tc::mbar_wait(q_full, 0);
             issue_S(0);
             for (int j = 0; j < nkv; ++j) {
-                const int s = j & 1;
+                const int s = j % NST;
                 tc::mbar_wait(p_full, (uint32_t)j & 1u);
                 tc::tc_fence_after();
-                const uint32_t sV = tc::smem_u32(smem + AT_OFF_KV + s * AT_STAGE + AT_K_BYTES);
+                const uint32_t sV = tc::smem_u32(smem + L::OFF_KV + s * L::STAGE + L::OFF_V);
 #pragma unroll
                 for (int c = 0; c < 2; ++c)
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        tc::umma_tf32(tmem_O, tc::smem_desc_k_sw128(sP + c * (AT_BQ * 128)) + (uint64_t)(k * 2),
-                                      tc::smem_desc_k_sw128(sV + c * (AT_D * 128)) + (uint64_t)(k * 2), idesc, (uint32_t)((c | k) != 0));
+                    for (int k = 0; k < 4; ++k) {
+                        const uint64_t pd = tc::smem_desc_k_sw128(sP + c * (AT_BQ * 128)) + (uint64_t)(k * 2);
+                        const uint64_t vd = tc::smem_desc_k_sw128(sV + c * (AT_D * 128)) + (uint64_t)(k * 2);
+                        tc::umma_tf32(tmem_O, pd, vd, idesc, (uint32_t)((c | k) != 0));
+                        if constexpr (SPLIT) {
+                            tc::umma_tf32(tmem_O, pd, tc::smem_desc_k_sw128(sV + AT_V_BYTES + c * (AT_D * 128)) + (uint64_t)(k * 2), idesc, 1u);
+                            tc::umma_tf32(tmem_O, tc::smem_desc_k_sw128(sP + AT_P_BYTES + c * (AT_BQ * 128)) + (uint64_t)(k * 2), vd, idesc, 1u);
+                        }
+                    }
                 tc::umma_commit(o_full);
                 tc::umma_commit(&kv_empty[s]);
                 if (j + 1 < nkv) issue_S(j + 1);
@@ -123,7 +156,7 @@ attention_kernel(const __grid_constant__ AttentionParams P) {
         float o_acc[AT_D];
 #pragma unroll
         for (int i = 0; i < AT_D; ++i) o_acc[i] = 0.f;
-        uint8_t* prow = smem + AT_OFF_P + (r >> 3) * 1024 + (r & 7) * 128;
+        uint8_t* prow = smem + L::OFF_P + (r >> 3) * 1024 + (r & 7) * 128;
         const int sw = r & 7;
         for (int j = 0; j < nkv; ++j) {
             tc::mbar_wait(s_full, (uint32_t)j & 1u);
@@ -156,9 +189,17 @@ attention_kernel(const __grid_constant__ AttentionParams P) {
                     pv.y = exp2f(fmaf(__uint_as_float(sr[h][4 * u + 1]), P.scale_log2, -mb));
                     pv.z = exp2f(fmaf(__uint_as_float(sr[h][4 * u + 2]), P.scale_log2, -mb));
                     pv.w = exp2f(fmaf(__uint_as_float(sr[h][4 * u + 3]), P.scale_log2, -mb));
-                    pv.x = tf32_rn(pv.x); pv.y = tf32_rn(pv.y); pv.z = tf32_rn(pv.z); pv.w = tf32_rn(pv.w);   // P is an MMA operand
-                    rs += (pv.x + pv.y) + (pv.z + pv.w);
-                    *reinterpret_cast<float4*>(prow + h * (AT_BQ * 128) + ((u ^ sw) << 4)) = pv;
+                    float4 ph;
+                    ph.x = tf32_rn(pv.x); ph.y = tf32_rn(pv.y); ph.z = tf32_rn(pv.z); ph.w = tf32_rn(pv.w);   // P is an MMA operand
+                    if constexpr (SPLIT) {
+                        rs += (pv.x + pv.y) + (pv.z + pv.w);
+                        float4 pl;
+                        pl.x = tf32_rn(pv.x - ph.x); pl.y = tf32_rn(pv.y - ph.y); pl.z = tf32_rn(pv.z - ph.z); pl.w = tf32_rn(pv.w - ph.w);
+                        *reinterpret_cast<float4*>(prow + AT_P_BYTES + h * (AT_BQ * 128) + ((u ^ sw) << 4)) = pl;
+                    } else {
+                        rs += (ph.x + ph.y) + (ph.z + ph.w);
+                    }
+                    *reinterpret_cast<float4*>(prow + h * (AT_BQ * 128) + ((u ^ sw) << 4)) = ph;
                 }
             }
             l_run = fmaf(l_run, alpha, rs);
@@ -183,8 +224,9 @@ attention_kernel(const __grid_constant__ AttentionParams P) {
             float4* op = reinterpret_cast<float4*>(P.out + ((size_t)b * P.T + t) * P.C + head * AT_D);
 #pragma unroll
             for (int i = 0; i < AT_D / 4; ++i)
-                op[i] = make_float4(tf32_rn(o_acc[4 * i] * inv), tf32_rn(o_acc[4 * i + 1] * inv), tf32_rn(o_acc[4 * i + 2] * inv),
-                                    tf32_rn(o_acc[4 * i + 3] * inv));              // operand of the proj 1x1 GEMM
+                op[i] = SPLIT ? make_float4(o_acc[4 * i] * inv, o_acc[4 * i + 1] * inv, o_acc[4 * i + 2] * inv, o_acc[4 * i + 3] * inv)
+                              : make_float4(tf32_rn(o_acc[4 * i] * inv), tf32_rn(o_acc[4 * i + 1] * inv), tf32_rn(o_acc[4 * i + 2] * inv),
+                                            tf32_rn(o_acc[4 * i + 3] * inv));      // tf32 mode: operand of the proj 1x1 GEMM
         }
     }
     tc::tc_fence_before();
@@ -205,6 +247,13 @@ int attention_prepare(AttentionParams& P, const AttentionDesc& d) {
     const uint64_t sv[2] = {(uint64_t)d.t_pad * 4, (uint64_t)d.heads * AT_D * d.t_pad * 4};
     const uint32_t bv[3] = {32, AT_D, 1};
     IPDM_CHECK(tmap_encode(&P.mapV, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, d.vt, dv, sv, bv, CU_TENSOR_MAP_SWIZZLE_128B));
+    P.split = d.qk_lo != nullptr;
+    if (P.split) {
+        IPDM_REQUIRE(d.vt_lo != nullptr, "attention: fp32 mode needs both qk_lo and vt_lo");
+        IPDM_CHECK(tmap_encode(&P.mapQlo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, d.qk_lo, dq, sq, bq, CU_TENSOR_MAP_SWIZZLE_128B));
+        IPDM_CHECK(tmap_encode(&P.mapKlo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, d.qk_lo, dq, sq, bk, CU_TENSOR_MAP_SWIZZLE_128B));
+        IPDM_CHECK(tmap_encode(&P.mapVlo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, d.vt_lo, dv, sv, bv, CU_TENSOR_MAP_SWIZZLE_128B));
+    }
     P.out = d.out; P.batch = d.batch; P.T = d.T; P.heads = d.heads; P.C = d.C;
     P.scale_log2 = 1.4426950408889634f / sqrtf((float)AT_D);      // (d^-1/4)^2 * log2(e)
     return IPDM_OK;
@@ -212,13 +261,16 @@ int attention_prepare(AttentionParams& P, const AttentionDesc& d) {
 
 int attention_launch(const AttentionParams& P, cudaStream_t st) {
     static bool configured = false;
+    static_assert(AtL<true>::SMEM <= 227 * 1024, "fp32-mode attention tiles do not fit in shared memory");
     if (!configured) {
-        IPDM_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
+        IPDM_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AtL<false>::SMEM));
+        IPDM_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AtL<true>::SMEM));
         configured = true;
     }
     dim3 grid((P.T + AT_BQ - 1) / AT_BQ, P.heads, P.batch);
-    ProfScope prof(PROF_ATTENTION, st, 4.0 * P.batch * P.heads * (double)P.T * P.T * AT_D);
-    attention_kernel<<<grid, AT_THREADS, AT_SMEM, st>>>(P);
+    ProfScope prof(PROF_ATTENTION, st, (P.split ? 3.0 : 1.0) * 4.0 * P.batch * P.heads * (double)P.T * P.T * AT_D);
+    if (P.split) attention_kernel<true><<<grid, AT_THREADS, AtL<true>::SMEM, st>>>(P);
+    else attention_kernel<false><<<grid, AT_THREADS, AtL<false>::SMEM, st>>>(P);
     count_launch();
     IPDM_CHECK_LAUNCH();
     return IPDM_OK;

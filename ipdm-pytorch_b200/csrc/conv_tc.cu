@@ -70,24 +70,34 @@ constexpr int TC_THREADS = 128;
 constexpr int TC_KC = 32;                 // fp32 elements per 128-byte operand row
 constexpr int TC_A_BYTES = 128 * 128;
 
-template <int BLOCK_N, int STAGES>
+// SPLIT = fp32-accurate "3xTF32" mode: every fp32 operand x is used as x_hi + x_lo (x_hi = rn_tf32(x), x_lo =
+// rn_tf32(x - x_hi)) and D += A_hi B_hi + A_hi B_lo + A_lo B_hi.  Weights are split on the host (two packed arrays, two
+// TMA loads); the activation tile is split in shared memory by warps 2-3 right after the TMA lands (the split is
+// elementwise, so the 128B swizzle is irrelevant to it), then handed to the MMA warp through a `ready` barrier.
+template <int BLOCK_N, int STAGES, bool SPLIT>
 struct TcSmem {
     static constexpr int B_BYTES = BLOCK_N * 128;
-    static constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
+    static constexpr int OFF_ALO = TC_A_BYTES;
+    static constexpr int OFF_B = SPLIT ? 2 * TC_A_BYTES : TC_A_BYTES;
+    static constexpr int OFF_BLO = OFF_B + B_BYTES;
+    static constexpr int STAGE_BYTES = OFF_B + (SPLIT ? 2 : 1) * B_BYTES;
+    static constexpr int TX_BYTES = TC_A_BYTES + (SPLIT ? 2 : 1) * B_BYTES;
     static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
-    static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 1) * 8 + 16 + 1024;   // + alignment slack
+    static constexpr int TOTAL = BAR_OFF + (3 * STAGES + 1) * 8 + 16 + 1024;   // + alignment slack
 };
+constexpr int TC_SPLIT_THREADS = 64;
 
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int STAGES, bool SPLIT>
 __global__ void __launch_bounds__(TC_THREADS)
 conv_tc_kernel(const __grid_constant__ ConvTcParams P) {
-    using S = TcSmem<BLOCK_N, STAGES>;
+    using S = TcSmem<BLOCK_N, STAGES, SPLIT>;
     constexpr int TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t* full = (uint64_t*)(smem + S::BAR_OFF);
     uint64_t* empty = full + STAGES;
-    uint64_t* accum = empty + STAGES;
+    uint64_t* ready = empty + STAGES;
+    uint64_t* accum = ready + STAGES;
     uint32_t* tmem_slot = (uint32_t*)(accum + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -100,7 +110,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams P) {
     const int n0 = blockIdx.y * BLOCK_N;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < STAGES; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
+        for (int i = 0; i < STAGES; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); tc::mbar_init(&ready[i], TC_SPLIT_THREADS); }
         tc::mbar_init(accum, 1);
         tc::fence_barrier_init();
     }
@@ -123,11 +133,11 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams P) {
                 const int s = it % STAGES;
                 const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
                 tc::mbar_wait(&empty[s], ph ^ 1u);
-                tc::mbar_expect_tx(&full[s], S::STAGE_BYTES);
+                tc::mbar_expect_tx(&full[s], S::TX_BYTES);
                 const int tap = it / nk, kc = it - tap * nk;
                 const int dy = P.ntaps == 9 ? tap / 3 : 1, dx = P.ntaps == 9 ? tap - (tap / 3) * 3 : 1;
                 uint8_t* sA = smem + s * S::STAGE_BYTES;
-                uint8_t* sB = sA + TC_A_BYTES;
+                uint8_t* sB = sA + S::OFF_B;
                 if (P.stride == 1) {
                     const bool first = kc < P.nk0;
                     tc::tma_load_4d(sA, first ? &P.mapA[0] : &P.mapA[1], &full[s], (first ? kc : kc - P.nk0) * TC_KC,
@@ -138,6 +148,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams P) {
                                     y0 + (dy == 0 ? -1 : 0), b);
                 }
                 tc::tma_load_2d(sB, &P.mapB, &full[s], kc * TC_KC, tap * P.cout_rows + n0);
+                if constexpr (SPLIT) tc::tma_load_2d(sA + S::OFF_BLO, &P.mapBlo, &full[s], kc * TC_KC, tap * P.cout_rows + n0);
             }
         }
         __syncwarp();
@@ -147,18 +158,44 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams P) {
             for (int it = 0; it < total; ++it) {
                 const int s = it % STAGES;
                 const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-                tc::mbar_wait(&full[s], ph);
+                tc::mbar_wait(SPLIT ? &ready[s] : &full[s], ph);
                 tc::tc_fence_after();
                 const uint32_t sA = tc::smem_u32(smem + s * S::STAGE_BYTES);
-                const uint64_t adesc = tc::smem_desc_k_sw128(sA), bdesc = tc::smem_desc_k_sw128(sA + TC_A_BYTES);
+                const uint64_t adesc = tc::smem_desc_k_sw128(sA), bdesc = tc::smem_desc_k_sw128(sA + S::OFF_B);
 #pragma unroll
-                for (int k = 0; k < 4; ++k)          // 4 x (K = 8 tf32 = 32 bytes) inside the 128-byte swizzle atom
+                for (int k = 0; k < 4; ++k) {        // 4 x (K = 8 tf32 = 32 bytes) inside the 128-byte swizzle atom
                     tc::umma_tf32(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (uint32_t)((it | k) != 0));
+                    if constexpr (SPLIT) {
+                        const uint64_t alo = tc::smem_desc_k_sw128(sA + S::OFF_ALO), blo = tc::smem_desc_k_sw128(sA + S::OFF_BLO);
+                        tc::umma_tf32(tmem_base, adesc + (uint64_t)(k * 2), blo + (uint64_t)(k * 2), idesc, 1u);
+                        tc::umma_tf32(tmem_base, alo + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, 1u);
+                    }
+                }
                 tc::umma_commit(&empty[s]);          // frees the stage once these MMAs have read it
             }
             tc::umma_commit(accum);
         }
         __syncwarp();
+    } else if constexpr (SPLIT) {
+        // warps 2-3: split the activation tile of every stage into tf32 hi (in place) and lo (second buffer)
+        const int st = threadIdx.x - 64;
+        for (int it = 0; it < total; ++it) {
+            const int s = it % STAGES;
+            const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+            tc::mbar_wait(&full[s], ph);
+            float4* a = reinterpret_cast<float4*>(smem + s * S::STAGE_BYTES);
+            float4* lo = reinterpret_cast<float4*>(smem + s * S::STAGE_BYTES + S::OFF_ALO);
+#pragma unroll 4
+            for (int i = st; i < TC_A_BYTES / 16; i += TC_SPLIT_THREADS) {
+                const float4 v = a[i];
+                float4 h, l;
+                h.x = tf32_rn(v.x); h.y = tf32_rn(v.y); h.z = tf32_rn(v.z); h.w = tf32_rn(v.w);
+                l.x = tf32_rn(v.x - h.x); l.y = tf32_rn(v.y - h.y); l.z = tf32_rn(v.z - h.z); l.w = tf32_rn(v.w - h.w);
+                a[i] = h; lo[i] = l;
+            }
+            tc::fence_proxy_async();                 // generic-proxy writes -> visible to the tensor core's async proxy
+            tc::mbar_arrive(&ready[s]);
+        }
     }
 
     // ---------------- epilogue: TMEM -> registers -> (+bias, +residual) -> NHWC global ----------------
@@ -190,18 +227,32 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams P) {
 #pragma unroll
             for (int i = 0; i < CHUNK / 4; ++i) { const float4 t = __ldg(rp + i); v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w; }
         }
-        if (P.qkv_mode) {                            // q, k, v are operands of the attention MMAs: round to nearest tf32
+        if (P.qkv_mode && !SPLIT) {                  // q, k, v are operands of the attention MMAs: round to nearest tf32
 #pragma unroll
             for (int i = 0; i < CHUNK; ++i) v[i] = tf32_rn(v[i]);
+        }
+        float lo[CHUNK];
+        if (P.qkv_mode && SPLIT) {                   // fp32 mode: hand q, k, v to the attention kernel as tf32 hi / lo pairs
+#pragma unroll
+            for (int i = 0; i < CHUNK; ++i) { const float h = tf32_rn(v[i]); lo[i] = tf32_rn(v[i] - h); v[i] = h; }
         }
         if (P.qkv_mode && ((n % (3 * P.head_dim)) >= 2 * P.head_dim)) {
             // V of one head: write transposed, [b][head][d][t_pad] (token contiguous), so P.V^T is K-major for attention
             const int head = n / (3 * P.head_dim), d0 = n % (3 * P.head_dim) - 2 * P.head_dim;
             const size_t tok = (size_t)py * P.W + px;
-            float* vt = P.vt + (((size_t)b * P.heads + head) * P.head_dim + d0) * P.t_pad + tok;
+            const size_t vo = (((size_t)b * P.heads + head) * P.head_dim + d0) * P.t_pad + tok;
 #pragma unroll
-            for (int i = 0; i < CHUNK; ++i) vt[(size_t)i * P.t_pad] = v[i];
+            for (int i = 0; i < CHUNK; ++i) P.vt[vo + (size_t)i * P.t_pad] = v[i];
+            if (SPLIT) {
+#pragma unroll
+                for (int i = 0; i < CHUNK; ++i) P.vt_lo[vo + (size_t)i * P.t_pad] = lo[i];
+            }
         } else {
+            if (P.qkv_mode && SPLIT) {
+                float4* lp = reinterpret_cast<float4*>(P.out_lo + pix * P.out_cs + n);
+#pragma unroll
+                for (int i = 0; i < CHUNK / 4; ++i) lp[i] = make_float4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+            }
             float4* op = reinterpret_cast<float4*>(P.out + pix * P.out_cs + n);
 #pragma unroll
             for (int i = 0; i < CHUNK / 4; ++i) op[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
@@ -273,6 +324,8 @@ int conv_tc_prepare(ConvTcParams& P, const ConvTcDesc& d) {
         const uint64_t str[1] = {(uint64_t)d.w_k * 4};
         const uint32_t box[2] = {TC_KC, (uint32_t)P.block_n};
         IPDM_CHECK(tmap_encode(&P.mapB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, d.w_packed, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B));
+        P.split = d.w_packed_lo != nullptr;
+        if (P.split) IPDM_CHECK(tmap_encode(&P.mapBlo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, d.w_packed_lo, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B));
     }
     P.out = d.out.p; P.out_cs = d.out.cs;
     IPDM_REQUIRE(d.qkv_mode || (d.out.h == P.H && d.out.w == P.W && d.out.n == P.batch && d.out.cs % 4 == 0 && d.out.c >= d.cout),
@@ -280,19 +333,22 @@ int conv_tc_prepare(ConvTcParams& P, const ConvTcDesc& d) {
     P.bias = d.bias; P.bias_t_stride = d.bias_t_stride; P.t_dev = d.t_dev;
     P.res = d.res.p; P.res_cs = d.res.cs;
     P.qkv_mode = d.qkv_mode; P.vt = d.vt; P.t_pad = d.t_pad; P.heads = d.heads; P.head_dim = d.head_dim;
+    P.out_lo = d.out_lo; P.vt_lo = d.vt_lo;
+    IPDM_REQUIRE(!(d.qkv_mode && P.split) || (d.out_lo && d.vt_lo), "conv_tc: the fp32-mode qkv epilogue needs out_lo and vt_lo");
     return IPDM_OK;
 }
 
-template <int BN, int ST>
+template <int BN, int ST, bool SPLIT>
 static int launch_tc(const ConvTcParams& P, cudaStream_t st) {
     static bool configured = false;
-    constexpr int smem = TcSmem<BN, ST>::TOTAL;
+    constexpr int smem = TcSmem<BN, ST, SPLIT>::TOTAL;
+    static_assert(smem <= 227 * 1024, "stage ring does not fit in shared memory");
     if (!configured) {
-        IPDM_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        IPDM_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, ST, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
     }
     dim3 grid(P.tiles_x * P.tiles_y * P.batch, P.cout / BN);
-    conv_tc_kernel<BN, ST><<<grid, TC_THREADS, smem, st>>>(P);
+    conv_tc_kernel<BN, ST, SPLIT><<<grid, TC_THREADS, smem, st>>>(P);
     count_launch();
     IPDM_CHECK_LAUNCH();
     return IPDM_OK;
@@ -300,17 +356,25 @@ static int launch_tc(const ConvTcParams& P, cudaStream_t st) {
 
 int conv_tc_launch(const ConvTcParams& P, cudaStream_t st) {
     ProfScope prof(PROF_CONV_TC, st, conv_tc_flops(P));      // padded-K FLOPs actually issued to the tensor pipe
-    switch (P.block_n) {
-        case 128: return launch_tc<128, 3>(P, st);
-        case 64: return launch_tc<64, 4>(P, st);
-        case 16: return launch_tc<16, 4>(P, st);
+    if (P.split) {
+        switch (P.block_n) {
+            case 128: return launch_tc<128, 3, true>(P, st);
+            case 64: return launch_tc<64, 4, true>(P, st);
+            case 16: return launch_tc<16, 4, true>(P, st);
+        }
+    } else {
+        switch (P.block_n) {
+            case 128: return launch_tc<128, 3, false>(P, st);
+            case 64: return launch_tc<64, 4, false>(P, st);
+            case 16: return launch_tc<16, 4, false>(P, st);
+        }
     }
     set_error("conv_tc_launch: unsupported N tile %d", P.block_n);
     return IPDM_ERR_UNSUPPORTED;
 }
 
 double conv_tc_flops(const ConvTcParams& P) {
-    return 2.0 * P.batch * P.H * P.W * (double)P.cout * P.ntaps * (P.nk0 + P.nk1) * TC_KC;
+    return (P.split ? 3.0 : 1.0) * 2.0 * P.batch * P.H * P.W * (double)P.cout * P.ntaps * (P.nk0 + P.nk1) * TC_KC;
 }
 
 }  // namespace ipdm

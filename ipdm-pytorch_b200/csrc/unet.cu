@@ -37,7 +37,7 @@ struct GNW { float* gamma = nullptr; float* beta = nullptr; int C = 0, groups = 
 struct ConvW {
     int cin = 0, cout = 0, k = 0;
     std::vector<float> w_host, b_host;       // PyTorch layout [cout][cin][k][k], [cout]
-    float* w_dev = nullptr; float* b_dev = nullptr;
+    float* w_dev = nullptr; float* w_dev_lo = nullptr; float* b_dev = nullptr;
     bool tc = false; int c0 = 0, cs0 = 0, c1 = 0, cs1 = 0, kpad = 0;
 };
 struct ResW { GNW gn1, gn2; ConvW conv1, conv2, shortcut; bool has_shortcut = false; std::vector<float> temb_w, temb_b; float* bias1_t = nullptr; int cin = 0, cout = 0; };
@@ -49,7 +49,7 @@ struct VTensor { int n = 0, h = 0, w = 0, c = 0, cs = 0; int def = -1, last = -1
 
 struct Op {
     enum Kind { GN_STATS, GN_APPLY, CONV_TC, CONV_DIRECT, UPSAMPLE, ATTN } kind;
-    int src[2] = {-1, -1}; int nsrc = 0; int dst = -1, res = -1, aux = -1;
+    int src[2] = {-1, -1}; int nsrc = 0; int dst = -1, res = -1, aux = -1, aux2 = -1, aux3 = -1;
     const GNW* gn = nullptr; int norm_slot = -1; int act = 1;
     const ConvW* cw = nullptr; const float* bias = nullptr; int bias_t_stride = 0; bool use_t = false;
     int stride = 1, upsample = 0, qkv = 0;
@@ -84,6 +84,7 @@ struct ipdm_unet {
     std::vector<float*> dev_allocs;
     int* t_dev = nullptr;
     int heads = 4;
+    int precision = IPDM_PREC_TF32;
     std::map<std::tuple<int, int, int>, std::unique_ptr<Plan>> plans;
     ~ipdm_unet() { for (float* p : dev_allocs) cudaFree(p); cudaFree(t_dev); }
 };
@@ -134,13 +135,20 @@ static int pack_conv(ipdm_unet* net, ConvW& c, int c0, int c1, bool raw_sources,
         else { c.c0 = c.cin; c.c1 = 0; c.cs0 = round_up(c.cin, 32); c.cs1 = 0; }
         IPDM_REQUIRE(c.cs0 % 32 == 0 && c.cs1 % 32 == 0, "pack_conv: source strides %d/%d are not multiples of 32", c.cs0, c.cs1);
         c.kpad = c.cs0 + c.cs1;
-        std::vector<float> p((size_t)kk * c.cout * c.kpad, 0.f);
+        const bool split = net->precision == IPDM_PREC_FP32;       // 3xTF32: w = w_hi + w_lo, both exactly representable in tf32
+        std::vector<float> p((size_t)kk * c.cout * c.kpad, 0.f), plo(split ? p.size() : 0, 0.f);
         for (int co = 0; co < c.cout; ++co)
             for (int ci = 0; ci < c.cin; ++ci) {
                 const int col = ci < c.c0 ? ci : c.cs0 + (ci - c.c0);
-                for (int t = 0; t < kk; ++t) p[((size_t)t * c.cout + co) * c.kpad + col] = tf32_rn_host(c.w_host[((size_t)co * c.cin + ci) * kk + t]);
+                for (int t = 0; t < kk; ++t) {
+                    const float w = c.w_host[((size_t)co * c.cin + ci) * kk + t], hi = tf32_rn_host(w);
+                    const size_t at = ((size_t)t * c.cout + co) * c.kpad + col;
+                    p[at] = hi;
+                    if (split) plo[at] = tf32_rn_host(w - hi);
+                }
             }
         IPDM_CHECK(upload(net, p, &c.w_dev));
+        if (split) IPDM_CHECK(upload(net, plo, &c.w_dev_lo));
     } else {
         std::vector<float> p((size_t)kk * c.cin * c.cout);
         for (int co = 0; co < c.cout; ++co)
@@ -318,7 +326,7 @@ struct PlanBuilder {
     int push(Op& o) {
         const int i = (int)pl->ops.size();
         for (int s = 0; s < o.nsrc; ++s) touch(o.src[s], i);
-        touch(o.dst, i); touch(o.res, i); touch(o.aux, i);
+        touch(o.dst, i); touch(o.res, i); touch(o.aux, i); touch(o.aux2, i); touch(o.aux3, i);
         pl->ops.push_back(o); return i;
     }
     int cin_of(const int* src, int nsrc) { int c = 0; for (int i = 0; i < nsrc; ++i) c += pl->vt[src[i]].c; return c; }
@@ -359,14 +367,17 @@ struct PlanBuilder {
     int attn_block(const AttnW& a, int x) {
         const VTensor s = pl->vt[x];
         const int T = s.h * s.w, tpad = round_up(T, 4);
+        const bool split = net->precision == IPDM_PREC_FP32;
         const int qk = new_tensor(pl->B, s.h, s.w, 3 * a.C, 3 * a.C);
         const int vt = new_tensor(pl->B, 1, 1, a.C * tpad, a.C * tpad);
+        const int qk_lo = split ? new_tensor(pl->B, s.h, s.w, 3 * a.C, 3 * a.C) : -1;
+        const int vt_lo = split ? new_tensor(pl->B, 1, 1, a.C * tpad, a.C * tpad) : -1;
         Op st; st.kind = Op::GN_STATS; st.nsrc = 1; st.src[0] = x; st.gn = &a.norm; st.norm_slot = norm_slots++; max_c = std::max(max_c, a.C); push(st);
         const int an = new_tensor(pl->B, s.h, s.w, a.C, a.C);
         Op ap; ap.kind = Op::GN_APPLY; ap.nsrc = 1; ap.src[0] = x; ap.gn = &a.norm; ap.norm_slot = st.norm_slot; ap.dst = an; ap.act = 0; push(ap);
-        Op q; q.kind = Op::CONV_TC; q.nsrc = 1; q.src[0] = an; q.cw = &a.qkv; q.dst = qk; q.aux = vt; q.qkv = 1; push(q);   // epilogue rounds q,k,v to tf32
+        Op q; q.kind = Op::CONV_TC; q.nsrc = 1; q.src[0] = an; q.cw = &a.qkv; q.dst = qk; q.aux = vt; q.qkv = 1; q.aux2 = qk_lo; q.aux3 = vt_lo; push(q);   // epilogue rounds q,k,v to tf32 (hi/lo pairs in fp32 mode)
         const int o = new_tensor(pl->B, s.h, s.w, a.C, a.C);
-        Op at; at.kind = Op::ATTN; at.nsrc = 1; at.src[0] = qk; at.aux = vt; at.dst = o; push(at);
+        Op at; at.kind = Op::ATTN; at.nsrc = 1; at.src[0] = qk; at.aux = vt; at.aux2 = qk_lo; at.aux3 = vt_lo; at.dst = o; push(at);
         const int out = act(s.h, s.w, a.C);
         Op pj; pj.kind = Op::CONV_TC; pj.nsrc = 1; pj.src[0] = o; pj.cw = &a.proj; pj.dst = out; pj.res = x; pj.bias = a.proj.b_dev; push(pj);
         return out;
@@ -485,12 +496,14 @@ static int build_plan(ipdm_unet* net, int B, int H, int W, Plan** out) {
                 ConvTcDesc d;
                 d.nsrc = o.nsrc; d.src[0] = resolve(*pl, o.src[0]); if (o.nsrc > 1) d.src[1] = resolve(*pl, o.src[1]);
                 d.ntaps = o.cw->k * o.cw->k; d.stride = o.stride; d.cout = o.cw->cout; d.w_packed = o.cw->w_dev; d.w_k = o.cw->kpad;
+                d.w_packed_lo = o.cw->w_dev_lo;
                 d.bias = o.bias; d.bias_t_stride = o.bias_t_stride; d.t_dev = o.use_t ? net->t_dev : nullptr;
                 if (o.res >= 0) d.res = resolve(*pl, o.res);
                 d.out = resolve(*pl, o.dst);
                 if (o.qkv) {
                     const TensorNHWC v = resolve(*pl, o.aux);
                     d.qkv_mode = 1; d.vt = v.p; d.heads = net->heads; d.head_dim = o.cw->cin / net->heads; d.t_pad = v.c / o.cw->cin;
+                    if (o.aux2 >= 0) { d.out_lo = resolve(*pl, o.aux2).p; d.vt_lo = resolve(*pl, o.aux3).p; }
                 }
                 IPDM_CHECK(conv_tc_prepare(o.tcp, d));
                 o.flops = 2.0 * B * o.tcp.H * o.tcp.W * (double)o.cw->cin * o.cw->cout * d.ntaps;
@@ -511,6 +524,7 @@ static int build_plan(ipdm_unet* net, int B, int H, int W, Plan** out) {
                 AttentionDesc& a = o.ad;
                 a.qk = qk.p; a.vt = v.p; a.out = ot.p; a.batch = B; a.T = qk.h * qk.w; a.C = ot.c; a.heads = net->heads; a.head_dim = a.C / a.heads;
                 a.t_pad = v.c / a.C;
+                if (o.aux2 >= 0) { a.qk_lo = resolve(*pl, o.aux2).p; a.vt_lo = resolve(*pl, o.aux3).p; }
                 IPDM_CHECK(attention_prepare(o.ap, a));
                 o.flops = attention_flops(a);
             } break;
@@ -531,7 +545,7 @@ static int run_plan(ipdm_unet* net, Plan* pl, const float* x, int t, float* eps,
         Op& o = pl->ops[i];
         switch (o.kind) {
             case Op::GN_STATS: IPDM_CHECK(groupnorm_stats_launch(o.gd, st)); break;
-            case Op::GN_APPLY: IPDM_CHECK(groupnorm_apply_launch(o.gd, o.out_t, o.act, st)); break;
+            case Op::GN_APPLY: IPDM_CHECK(groupnorm_apply_launch(o.gd, o.out_t, o.act, net->precision != IPDM_PREC_FP32, st)); break;
             case Op::CONV_TC: IPDM_CHECK(conv_tc_launch(o.tcp, st)); break;
             case Op::CONV_DIRECT: {
                 ConvDirectDesc d = o.cd;
@@ -539,7 +553,7 @@ static int run_plan(ipdm_unet* net, Plan* pl, const float* x, int t, float* eps,
                 if ((int)i == pl->last_op) d.out.p = eps;
                 IPDM_CHECK(conv_direct_launch(d, st));
             } break;
-            case Op::UPSAMPLE: IPDM_CHECK(upsample_nearest_launch(o.src_t, o.out_t, st)); break;
+            case Op::UPSAMPLE: IPDM_CHECK(upsample_nearest_launch(o.src_t, o.out_t, net->precision != IPDM_PREC_FP32, st)); break;
             case Op::ATTN: IPDM_CHECK(attention_launch(o.ap, st)); break;
         }
     }
@@ -562,11 +576,12 @@ extern "C" long long ipdm_unet_param_count(const ipdm_unet_config* cfg) {
 extern "C" int ipdm_unet_create(ipdm_unet** out, const ipdm_unet_config* cfg, const float* weights_host, size_t n_weights) {
     IPDM_REQUIRE(out && cfg && weights_host, "ipdm_unet_create: null argument");
     IPDM_REQUIRE(cfg->n_mult >= 2 && cfg->n_mult <= 8 && cfg->n_attn >= 0 && cfg->n_attn <= 8, "ipdm_unet_create: bad config");
-    IPDM_REQUIRE(cfg->precision == IPDM_PREC_TF32, "ipdm_unet_create: only IPDM_PREC_TF32 is implemented in this build");
+    IPDM_REQUIRE(cfg->precision == IPDM_PREC_TF32 || cfg->precision == IPDM_PREC_FP32,
+                 "ipdm_unet_create: precision %d is not implemented (tf32 = 0 and fp32 = 2 are; bf16 is planned)", cfg->precision);
     const long long expect = ipdm_unet_param_count(cfg);
     IPDM_REQUIRE((long long)n_weights == expect, "ipdm_unet_create: got %zu weights, the config needs %lld", n_weights, expect);
     std::unique_ptr<ipdm_unet> net(new ipdm_unet());
-    net->cfg = *cfg; net->heads = cfg->num_heads;
+    net->cfg = *cfg; net->heads = cfg->num_heads; net->precision = cfg->precision;
     if (net->cfg.max_t <= 0) net->cfg.max_t = 64;
     IPDM_CHECK_CUDA(cudaMalloc(&net->t_dev, sizeof(int)));
     Reader r{weights_host, n_weights};
@@ -611,10 +626,11 @@ extern "C" int ipdm_debug_conv(const float* src0, int c0, int cs0, const float* 
                                float* out, int out_cs, int use_tc, void* stream) {
     IPDM_REQUIRE(src0 && w_host && out, "ipdm_debug_conv: null argument");
     ipdm_unet holder;
+    holder.precision = use_tc == 2 ? IPDM_PREC_FP32 : IPDM_PREC_TF32;
     ConvW cw; cw.cin = c0 + c1; cw.cout = cout; cw.k = k;
     cw.w_host.assign(w_host, w_host + (size_t)cout * cw.cin * k * k);
     if (bias_host) cw.b_host.assign(bias_host, bias_host + cout);
-    IPDM_CHECK(pack_conv(&holder, cw, c0, c1, true, use_tc));
+    IPDM_CHECK(pack_conv(&holder, cw, c0, c1, true, use_tc != 0));
     cudaStream_t st = (cudaStream_t)stream;
     const int hin = upsample_h > 0 ? upsample_h : h, win = upsample_w > 0 ? upsample_w : w;
     const int ho = stride == 1 ? hin : (hin + 1) / 2, wo = stride == 1 ? win : (win + 1) / 2;
@@ -623,7 +639,7 @@ extern "C" int ipdm_debug_conv(const float* src0, int c0, int cs0, const float* 
         IPDM_REQUIRE(cs0 == cw.cs0 && (c1 == 0 || cs1 == cw.cs1), "ipdm_debug_conv: tensor-core sources need channel strides %d / %d", cw.cs0, cw.cs1);
         IPDM_REQUIRE(upsample_h == 0 && !norm_scale, "ipdm_debug_conv: upsample / fused norm are direct-path features");
         ConvTcDesc d; d.nsrc = c1 ? 2 : 1; d.src[0] = mk(src0, n, h, w, c0, cs0); if (c1) d.src[1] = mk(src1, n, h, w, c1, cs1);
-        d.ntaps = k * k; d.stride = stride; d.cout = cout; d.w_packed = cw.w_dev; d.w_k = cw.kpad; d.bias = cw.b_dev;
+        d.ntaps = k * k; d.stride = stride; d.cout = cout; d.w_packed = cw.w_dev; d.w_packed_lo = cw.w_dev_lo; d.w_k = cw.kpad; d.bias = cw.b_dev;
         if (res) d.res = mk(res, n, ho, wo, cout, res_cs);
         d.out = mk(out, n, ho, wo, cout, out_cs);
         ConvTcParams P;
@@ -656,19 +672,20 @@ extern "C" int ipdm_debug_groupnorm(const float* src0, int c0, int cs0, const fl
     d.groups = g.groups; d.gamma = g.gamma; d.beta = g.beta; d.scale = scale_out; d.shift = shift_out; d.partials = partials;
     cudaStream_t st = (cudaStream_t)stream;
     int rc = groupnorm_stats_launch(d, st);
-    if (rc == IPDM_OK && out) rc = groupnorm_apply_launch(d, mk(out, n, h, w, C, out_cs), act_silu, st);
+    if (rc == IPDM_OK && out) rc = groupnorm_apply_launch(d, mk(out, n, h, w, C, out_cs), act_silu, 1, st);
     cudaStreamSynchronize(st);
     cudaFree(partials);
     return rc;
 }
 
-extern "C" int ipdm_debug_attention(const float* qk, const float* vt, float* out, int batch, int T, int t_pad, int heads, int C, void* stream) {
-    AttentionDesc a; a.qk = qk; a.vt = vt; a.out = out; a.batch = batch; a.T = T; a.t_pad = t_pad; a.heads = heads; a.C = C; a.head_dim = C / heads;
+extern "C" int ipdm_debug_attention(const float* qk, const float* vt, const float* qk_lo, const float* vt_lo, float* out, int batch, int T,
+                                    int t_pad, int heads, int C, void* stream) {
+    AttentionDesc a; a.qk = qk; a.vt = vt; a.qk_lo = qk_lo; a.vt_lo = vt_lo; a.out = out; a.batch = batch; a.T = T; a.t_pad = t_pad; a.heads = heads; a.C = C; a.head_dim = C / heads;
     AttentionParams P;
     IPDM_CHECK(attention_prepare(P, a));
     return attention_launch(P, (cudaStream_t)stream);
 }
 
 extern "C" int ipdm_debug_upsample(const float* src, int n, int hs, int ws, int cs, float* dst, int hd, int wd, void* stream) {
-    return upsample_nearest_launch(mk(src, n, hs, ws, cs, cs), mk(dst, n, hd, wd, cs, cs), (cudaStream_t)stream);
+    return upsample_nearest_launch(mk(src, n, hs, ws, cs, cs), mk(dst, n, hd, wd, cs, cs), 0, (cudaStream_t)stream);
 }

@@ -272,7 +272,7 @@ int groupnorm_stats_launch(const GroupNormDesc& d, cudaStream_t st) {
 __global__ void __launch_bounds__(256)
 gn_apply_kernel(const float* __restrict__ s0, int c0, int cs0, const float* __restrict__ s1, int c1, int cs1,
                 const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ out, int ocs,
-                size_t npix_per_slice, size_t nvec_total, int act) {
+                size_t npix_per_slice, size_t nvec_total, int act, int rnd) {
     const int Ctot = c0 + c1, V = ocs / 4;
     const size_t stride = (size_t)gridDim.x * 256;
     for (size_t i0 = (size_t)blockIdx.x * 256 + threadIdx.x; i0 < nvec_total; i0 += 2 * stride) {
@@ -298,14 +298,14 @@ gn_apply_kernel(const float* __restrict__ s0, int c0, int cs0, const float* __re
                 const float4 sh = __ldg(reinterpret_cast<const float4*>(shift + (size_t)n * Ctot + c[u]));
                 o.x = fmaf(v[u].x, sc.x, sh.x); o.y = fmaf(v[u].y, sc.y, sh.y); o.z = fmaf(v[u].z, sc.z, sh.z); o.w = fmaf(v[u].w, sc.w, sh.w);
                 if (act) { o.x = silu(o.x); o.y = silu(o.y); o.z = silu(o.z); o.w = silu(o.w); }
-                o.x = tf32_rn(o.x); o.y = tf32_rn(o.y); o.z = tf32_rn(o.z); o.w = tf32_rn(o.w);   // operand of a tcgen05 kind::tf32 MMA
+                if (rnd) { o.x = tf32_rn(o.x); o.y = tf32_rn(o.y); o.z = tf32_rn(o.z); o.w = tf32_rn(o.w); }   // tf32 mode: MMA operand
             }
             *reinterpret_cast<float4*>(out + pix[u] * ocs + c[u]) = o;
         }
     }
 }
 
-int groupnorm_apply_launch(const GroupNormDesc& d, const TensorNHWC& out, int act_silu, cudaStream_t st) {
+int groupnorm_apply_launch(const GroupNormDesc& d, const TensorNHWC& out, int act_silu, int round_tf32, cudaStream_t st) {
     const TensorNHWC& a = d.src[0];
     const int c1 = d.nsrc == 2 ? d.src[1].c : 0;
     IPDM_REQUIRE(out.cs % 4 == 0 && out.cs >= a.c + c1 && a.c % 4 == 0, "groupnorm_apply: bad channel layout");
@@ -313,7 +313,7 @@ int groupnorm_apply_launch(const GroupNormDesc& d, const TensorNHWC& out, int ac
     const int grid = (int)std::min<size_t>((size_t)kNumSMs * 16, (nvec + 511) / 512);
     ProfScope prof(PROF_GROUPNORM, st, 4.0 * a.n * (double)npix * (a.c + c1 + out.cs));
     gn_apply_kernel<<<std::max(grid, 1), 256, 0, st>>>(a.p, a.c, a.cs, d.nsrc == 2 ? d.src[1].p : nullptr, c1, d.nsrc == 2 ? d.src[1].cs : 0,
-                                          d.scale, d.shift, out.p, out.cs, npix, nvec, act_silu);
+                                          d.scale, d.shift, out.p, out.cs, npix, nvec, act_silu, round_tf32);
     count_launch();
     IPDM_CHECK_LAUNCH();
     return IPDM_OK;
@@ -324,7 +324,7 @@ int groupnorm_apply_launch(const GroupNormDesc& d, const TensorNHWC& out, int ac
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 upsample_kernel(const float* __restrict__ src, int hs, int ws, int scs, float* __restrict__ dst, int hd, int wd, int dcs,
-                float sy, float sx, size_t nvec_total) {
+                float sy, float sx, size_t nvec_total, int rnd) {
     const int V = dcs / 4;
     for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < nvec_total; i += (size_t)gridDim.x * 256) {
         const size_t pix = i / V;
@@ -335,18 +335,18 @@ upsample_kernel(const float* __restrict__ src, int hs, int ws, int scs, float* _
         const int yy = min((int)floorf((float)y * sy), hs - 1), xx = min((int)floorf((float)x * sx), ws - 1);
         float4 v = make_float4(0, 0, 0, 0);
         if (c < scs) v = __ldg(reinterpret_cast<const float4*>(src + (((size_t)n * hs + yy) * ws + xx) * scs + c));
-        v.x = tf32_rn(v.x); v.y = tf32_rn(v.y); v.z = tf32_rn(v.z); v.w = tf32_rn(v.w);      // feeds a tensor-core conv only
+        if (rnd) { v.x = tf32_rn(v.x); v.y = tf32_rn(v.y); v.z = tf32_rn(v.z); v.w = tf32_rn(v.w); }   // tf32 mode: feeds a tensor-core conv only
         *reinterpret_cast<float4*>(dst + pix * dcs + c) = v;
     }
 }
 
-int upsample_nearest_launch(const TensorNHWC& src, const TensorNHWC& dst, cudaStream_t st) {
+int upsample_nearest_launch(const TensorNHWC& src, const TensorNHWC& dst, int round_tf32, cudaStream_t st) {
     IPDM_REQUIRE(src.cs % 4 == 0 && dst.cs % 4 == 0 && dst.cs >= src.cs && src.n == dst.n, "upsample: bad layout");
     const size_t nvec = dst.pixels() * (dst.cs / 4);
     const int grid = (int)std::min<size_t>((size_t)kNumSMs * 8, (nvec + 255) / 256);
     ProfScope prof(PROF_UPSAMPLE, st, 4.0 * ((double)src.elems() + dst.elems()));
     upsample_kernel<<<grid, 256, 0, st>>>(src.p, src.h, src.w, src.cs, dst.p, dst.h, dst.w, dst.cs, (float)src.h / dst.h,
-                                          (float)src.w / dst.w, nvec);
+                                          (float)src.w / dst.w, nvec, round_tf32);
     count_launch();
     IPDM_CHECK_LAUNCH();
     return IPDM_OK;

@@ -20,7 +20,8 @@ struct ConvTcDesc {
     TensorNHWC src[2];          // virtual concat along channels; both padded to multiples of 32
     int ntaps = 9, stride = 1;
     int cout = 0;
-    const float* w_packed = nullptr;   // [ntaps][cout][w_k]
+    const float* w_packed = nullptr;   // [ntaps][cout][w_k] (tf32-rounded; the hi part in fp32 mode)
+    const float* w_packed_lo = nullptr;// fp32 (3xTF32) mode: the lo part, same layout; selects the split kernel
     int w_k = 0;
     const float* bias = nullptr;       // [cout] or table [max_t][bias_t_stride]
     int bias_t_stride = 0;
@@ -28,11 +29,13 @@ struct ConvTcDesc {
     TensorNHWC res;                    // optional residual, same pixels as the output
     TensorNHWC out;
     int qkv_mode = 0; float* vt = nullptr; int t_pad = 0, heads = 0, head_dim = 0;
+    float* out_lo = nullptr; float* vt_lo = nullptr;   // qkv epilogue in fp32 mode: q,k,v are written as tf32 hi / lo pairs
 };
 
 struct ConvTcParams {
     CUtensorMap mapA[4];
-    CUtensorMap mapB;
+    CUtensorMap mapB, mapBlo;
+    int split;
     int H, W, tiles_x, tiles_y, tw_log2, batch;
     int ntaps, stride, nk0, nk1;
     int cout, cout_rows, block_n;
@@ -40,6 +43,7 @@ struct ConvTcParams {
     const float* bias; int bias_t_stride; const int* t_dev;
     const float* res; int res_cs;
     int qkv_mode; float* vt; int t_pad, heads, head_dim;
+    float* out_lo; float* vt_lo;
 };
 
 int conv_tc_prepare(ConvTcParams& P, const ConvTcDesc& d);
@@ -79,20 +83,22 @@ struct GroupNormDesc {
 constexpr int GN_MAX_BLOCKS = 888;        // 6 CTAs per SM
 int groupnorm_stats_launch(const GroupNormDesc& d, cudaStream_t st);
 // out[n][y][x][c] = act(src*scale + shift) (c < C; act = SiLU or identity), 0 for pad channels; out.cs may exceed C
-int groupnorm_apply_launch(const GroupNormDesc& d, const TensorNHWC& out, int act_silu, cudaStream_t st);
+int groupnorm_apply_launch(const GroupNormDesc& d, const TensorNHWC& out, int act_silu, int round_tf32, cudaStream_t st);
 
 // nearest-neighbour resize (F.interpolate(mode="nearest") index rule), NHWC
-int upsample_nearest_launch(const TensorNHWC& src, const TensorNHWC& dst, cudaStream_t st);
+int upsample_nearest_launch(const TensorNHWC& src, const TensorNHWC& dst, int round_tf32, cudaStream_t st);
 
 // ---- attention (attention.cu) --------------------------------------------------------------------------
 struct AttentionDesc {
     const float* qk = nullptr;  // NHWC [B][T][3*C]: per head h, q at channel 3*d*h, k at 3*d*h + d
     const float* vt = nullptr;  // [B][heads][d][t_pad]
     float* out = nullptr;       // NHWC [B][T][C], channel = h*d + dd
+    const float* qk_lo = nullptr; const float* vt_lo = nullptr;   // fp32 (3xTF32) mode: tf32 lo parts, same layouts
     int batch = 0, T = 0, t_pad = 0, heads = 0, head_dim = 0, C = 0;
 };
 struct AttentionParams {
-    CUtensorMap mapQ, mapK, mapV;
+    CUtensorMap mapQ, mapK, mapV, mapQlo, mapKlo, mapVlo;
+    int split;
     float* out; int batch, T, heads, C; float scale_log2;
 };
 int attention_prepare(AttentionParams& P, const AttentionDesc& d);

@@ -42,11 +42,12 @@ def test_art_convertor_fails_loudly_until_switched(cuda, tmp_path):
     assert m.opt.convertor == "ART"
 
 
-def test_full_slice_matches_reference_golden(cuda, tmp_path):
+@pytest.mark.parametrize("prec", ["tf32", "fp32"])
+def test_full_slice_matches_reference_golden(cuda, tmp_path, prec):
     import ipdm_pytorch_b200.synthetic as S
     from inputs import noise_tape
     g = golden("full_slice0")
-    model = _model(tmp_path)
+    model = _model(tmp_path, dict(precision=prec))
     ld, nd, img = S.make_slice(0)
     model.data_sample_load(ldct=torch.zeros(1, 1, 512, 512), ldproj=torch.from_numpy(ld)[None, None], fdproj=None,
                            fdct=torch.from_numpy(img)[None, None])
@@ -68,14 +69,12 @@ def test_full_slice_matches_reference_golden(cuda, tmp_path):
     fin = model.progressive_denoise_result["iter_1"][0, 0]
     assert np.isfinite(fin).all() and fin.min() >= 0 and fin.max() <= 1
     rmse_hu = float(np.sqrt(np.mean((fin.astype(np.float64) - g["final"]) ** 2))) * HU_PER_MU
-    print(f"full slice: proj iterates rel-L2 {['%.2e' % e for e in perr]}; FBP image rel-L2 {ferr:.2e}; final RMSE {rmse_hu:.2f} HU "
+    print(f"full slice ({prec}): proj iterates rel-L2 {['%.2e' % e for e in perr]}; FBP image rel-L2 {ferr:.2e}; final RMSE {rmse_hu:.2f} HU "
           f"(final image spans [{g['final'].min():.2f}, {g['final'].max():.2f}] mu with random-init weights)")
     # tf32 mode with RANDOM-INIT weights: the per-forward tf32 error (4e-3 at 2000x912, tests/test_unet_gpu.py) is re-fed
     # 45 times through an untrained, expansive network; DESIGN.md "Parity" reports these numbers and the fp32-mode ones.
-    assert max(perr) < 5e-2
-    assert ferr < 0.2
-    np.savez_compressed(os.path.join(os.environ.get("GRAFT_REPO_ROOT", "."), "gpurun_out", "full_slice_gpu.npz") if os.path.isdir("gpurun_out") else str(tmp_path / "x.npz"),
-                        final=fin, fbp=rec, proj4=model.proj_denoise_result["iter_4"][0, 0][1::4, 2::4])
+    assert max(perr) < (5e-2 if prec == "tf32" else 5e-3)
+    assert ferr < (0.2 if prec == "tf32" else 2e-2)
 
 
 def test_batch_of_two_slices_equals_single_slices_philox(cuda, tmp_path):

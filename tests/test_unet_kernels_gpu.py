@@ -15,6 +15,13 @@ from conftest import rel_l2
 pytestmark = pytest.mark.gpu
 TF32_TOL = 2e-3
 FP32_TOL = 1e-5
+SPLIT_TOL = 2e-5        # tcgen05 3xTF32 ("fp32" precision mode): dropped lo*lo terms ~2^-22, tensor-core fp32 accumulation
+
+
+def tf32_rn(x):
+    """Round to nearest tf32 (ties away from zero, like cvt.rna.tf32.f32)."""
+    b = x.contiguous().view(torch.int32)
+    return ((b + 0x1000) & ~0x1FFF).view(torch.float32)
 
 
 def nhwc(x, cs=None):
@@ -42,6 +49,7 @@ def run_conv(cuda, x0, x1, weight, bias, k, stride, use_tc, res=None, up=None, n
     n, c0, h, w = x0.shape
     c1 = 0 if x1 is None else x1.shape[1]
     cs0, cs1 = (alloc_cs(c0), alloc_cs(c1)) if use_tc else (c0, c1)
+    use_tc = int(use_tc)
     cout = weight.shape[0]
     hin, win = (h, w) if up is None else up
     ho, wo = (hin, win) if stride == 1 else ((hin + 1) // 2, (win + 1) // 2)
@@ -160,12 +168,13 @@ def test_tc_conv(cuda, c0, c1, cout, k, stride, hw):
     b = rnd(cout, seed=4)
     ho, wo = hw if stride == 1 else ((hw[0] + 1) // 2, (hw[1] + 1) // 2)
     res = rnd(2, cout, ho, wo, seed=5) if stride == 1 else None
-    got = run_conv(cuda, x0, x1, w, b, k, stride, True, res=res)
     want = ref_conv(x0, x1, w, b, k, stride, res=res)
-    assert torch.isfinite(got).all()
-    err = rel_l2(got.numpy(), want.numpy())
-    print(f"tc conv {c0}+{c1}->{cout} k{k} s{stride} {hw}: rel-L2 {err:.2e}")
-    assert err < TF32_TOL
+    for mode, tol in ((1, TF32_TOL), (2, SPLIT_TOL)):
+        got = run_conv(cuda, x0, x1, w, b, k, stride, mode, res=res)
+        assert torch.isfinite(got).all()
+        err = rel_l2(got.numpy(), want.numpy())
+        print(f"tc conv {c0}+{c1}->{cout} k{k} s{stride} {hw} mode {'tf32' if mode == 1 else '3xtf32'}: rel-L2 {err:.2e}")
+        assert err < tol
 
 
 def test_tc_conv_full_size_row_shapes(cuda):
@@ -192,15 +201,22 @@ def test_attention(cuda, hw, batch):
     qk_nhwc = nhwc(qkv).to(cuda)                                        # [B,H,W,3C]; v channels are ignored by the kernel
     vt = torch.zeros(batch, heads, d, tpad)
     vt[..., :T] = v.reshape(batch, heads, d, T)
-    out = torch.full((batch, hw[0], hw[1], C), float("nan"), device=cuda)
-    rc = _lib.lib().ipdm_debug_attention(_p(qk_nhwc), _p(vt.to(cuda).contiguous()), _p(out), batch, T, tpad, heads, C, None)
-    _lib.check(rc, "ipdm_debug_attention")
-    torch.cuda.synchronize()
-    got = nchw(out.cpu(), C)
-    assert torch.isfinite(got).all()
-    err = rel_l2(got.numpy(), want.numpy())
-    print(f"attention T={T}: rel-L2 {err:.2e}")
-    assert err < TF32_TOL
+    vt = vt.to(cuda).contiguous()
+    for split, tol in ((False, TF32_TOL), (True, SPLIT_TOL)):
+        out = torch.full((batch, hw[0], hw[1], C), float("nan"), device=cuda)
+        if split:
+            qh, vh = tf32_rn(qk_nhwc), tf32_rn(vt)
+            ql, vl = tf32_rn(qk_nhwc - qh), tf32_rn(vt - vh)
+            rc = _lib.lib().ipdm_debug_attention(_p(qh), _p(vh), _p(ql), _p(vl), _p(out), batch, T, tpad, heads, C, None)
+        else:
+            rc = _lib.lib().ipdm_debug_attention(_p(qk_nhwc), _p(vt), None, None, _p(out), batch, T, tpad, heads, C, None)
+        _lib.check(rc, "ipdm_debug_attention")
+        torch.cuda.synchronize()
+        got = nchw(out.cpu(), C)
+        assert torch.isfinite(got).all()
+        err = rel_l2(got.numpy(), want.numpy())
+        print(f"attention T={T} {'3xtf32' if split else 'tf32'}: rel-L2 {err:.2e}")
+        assert err < tol
 
 
 def test_upsample_nearest_index_rule(cuda):
