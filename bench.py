@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--t_start_proj", type=int, nargs="+", default=[15, 15, 15])
     ap.add_argument("--t_start_img", type=int, nargs="+", default=[15, 15, 15])
     ap.add_argument("--skip_cpu_baseline", action="store_true")
+    ap.add_argument("--cuda_graph", type=int, default=0, help="1: capture the whole progressive pass in one CUDA graph")
     return ap.parse_args()
 
 
@@ -163,7 +164,8 @@ def run_b200(args, rank, world, local_rank):
     with contextlib.redirect_stdout(io.StringIO()):
         model = progressive_domain_denoiser(opt, result_save_path=tempfile.mkdtemp(prefix="ipdm_bench_"))
         model.update_opt(dict(convertor="FBP", save_it_state_img=False, save_it_state_proj=False, ultra_img_denoise=True,
-                              t_start_proj=args.t_start_proj, t_start_img=args.t_start_img, precision=args.precision, noise_seed=1234 + rank))
+                              t_start_proj=args.t_start_proj, t_start_img=args.t_start_img, precision=args.precision, noise_seed=1234 + rank,
+                              cuda_graph=bool(args.cuda_graph)))
     # synthetic slices of this rank's shard (weak scaling: B per GPU), pinned on the host
     host = torch.from_numpy(synthetic.cheap_sinogram(B, seed=100 + rank))[:, None].contiguous().pin_memory()
     host_out = torch.empty(B, 1, 512, 512).pin_memory()
@@ -248,7 +250,7 @@ def run_b200(args, rank, world, local_rank):
                 data="synthetic",
                 config=dict(workload=workload_name(args, B), global_batch=world * B, parallelism=f"slice-sharded x{world}, no data-path collective",
                             l2="working set (activation arena of several GB per step) >> 126 MB L2; no explicit flush needed",
-                            noise="in-kernel Philox4x32-10", unet_tflop_per_step=step_flops / 1e12),
+                            noise="in-kernel Philox4x32-10", cuda_graph=bool(args.cuda_graph), unet_tflop_per_step=step_flops / 1e12),
                 e2e=dict(value=e2e, unit="slices/s", h2d_bytes_per_step=int(host.numel() * 4), d2h_bytes_per_step=int(host_out.numel() * 4),
                          ms_per_step=ms_e2e / args.steps),
                 gpu_launches=int(launches), clocks=clocks, roofline=roof, kernel_families=families,

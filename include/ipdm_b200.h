@@ -112,6 +112,9 @@ int ipdm_sampler_step(const float* x_t_dev, const float* x0c_dev, const float* e
                       float* x_out_dev, int batch, int h, int w, const float coef7[7], float lam_scalar,
                       const float* lam_map_dev, int ks, int clip, int t_nonzero, uint64_t seed, uint64_t call_id,
                       void* workspace_dev, void* stream);
+/* Device-resident half of the Philox key (default 0).  CUDA-graph replays reuse frozen kernel arguments, so callers
+ * bump this epoch between replays to get fresh noise; it is an ordinary stream-ordered update. */
+int ipdm_set_noise_epoch(uint64_t epoch, void* stream);
 /* out = a*x + b*N(0,1) with caller noise or Philox (q_sample) */
 int ipdm_q_sample(const float* x_dev, const float* noise_dev, float* out_dev, float a, float b, size_t n_per_slice,
                   int batch, uint64_t seed, uint64_t call_id, void* stream);

@@ -5,7 +5,7 @@ The flags are declared from one table instead of ~70 add_argument calls.  Refere
 purpose: `type=bool` flags are truthy for any non-empty string; a JSON overlay never overrides a
 flag that was given on the command line; `cfg_load` only merges keys that already exist and prints
 the reference's "no key names ..." line otherwise.  Additive keys of this build: `precision`
-("tf32" | "bf16" | "fp32") and `noise_seed`; their defaults reproduce the reference.
+("tf32" | "fp32"), `noise_seed` and `cuda_graph`; their defaults reproduce the reference.
 """
 import argparse
 import json
@@ -47,7 +47,7 @@ _FLAGS = [
     ("test_dataset_path_LD_proj", str, None, None), ("num_workers", int, 4, None), ("patch", int, [512, 512], "+"),
     ("patch_per_image", int, 4, None), ("dose", float, 0.25, None),
     # additive (B200 build)
-    ("precision", str, "tf32", None), ("noise_seed", int, 0, None),
+    ("precision", str, "tf32", None), ("noise_seed", int, 0, None), ("cuda_graph", bool, False, None),
 ]
 
 

@@ -288,9 +288,52 @@ class progressive_domain_denoiser:
             store["iter_1"] = result[return_idx].cpu().numpy()
         return result[return_idx]
 
+    def _progressive_graphed(self, sharpen_num):
+        """Whole progressive pass as ONE CUDA graph (north_star item 4): captured once per (batch, options) after an eager
+        warm-up that builds every plan, replayed with fresh Philox noise (device-resident epoch) and a refreshed input."""
+        o = self.opt
+        key = (tuple(self.ldproj.shape), tuple(o.t_start_proj), tuple(o.t_start_img), bool(o.ultra_img_denoise), int(sharpen_num),
+               o.precision, bool(o.clip_proj), bool(o.clip_img), o.constant_guidance_proj, o.constant_guidance_img, o.eta_proj, o.eta_img)
+        cache = self.__dict__.setdefault("_graphs", {})
+        if key not in cache:
+            static_in = self.ldproj.clone()
+            self._progressive_eager(static_in, sharpen_num, None, None)            # warm-up: plans, workspaces, attributes
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                outs = self._progressive_eager(static_in, sharpen_num, None, None)
+            cache[key] = (g, static_in, outs)
+        g, static_in, outs = cache[key]
+        self._graph_runs = getattr(self, "_graph_runs", 0) + 1
+        _eng.set_noise_epoch(self._graph_runs)
+        static_in.copy_(self.ldproj, non_blocking=True)
+        g.replay()
+        return outs
+
+    def _progressive_eager(self, ldproj, sharpen_num, pn, inn):
+        o = self.opt
+        result = self._proj_stage(ldproj, pn)
+        recs = [self._convert_device(r) for r in result] if o.save_it_state_proj else [self._convert_device(result[-1])]
+        sharpen = sharpen_num if (o.convertor == "FBP" and o.fbp_sharpen) else -1
+        x = tensor_sharpen(recs[-1], sharpen)
+        out = self._img_stage(x, inn, self.noise_strength)
+        return result, recs, out
+
     def progressive_denoiser(self, save_proj_state=False, convert=True, sharpen_num=42, noise=None):
         """proj stage -> FBP -> sharpen -> img stage, all on the GPU; returns [B,1,512,512] on the device."""
         o = self.opt
+        if getattr(o, "cuda_graph", False) and noise is None and convert:
+            result, recs, out = self._progressive_graphed(sharpen_num)
+            self.proj_temp_clear()
+            self.img_temp_clear()
+            if save_proj_state:
+                for k, r in enumerate(result):
+                    self.proj_denoise_result[f"iter_{k + 1}"] = r.cpu().numpy()
+            for k, r in enumerate(recs):
+                self.proj_denoise_convert2img_result[f"iter_{k + 1}"] = r.cpu().numpy()
+            for k, r in enumerate(out if o.save_it_state_img else out[-1:]):
+                self.progressive_denoise_result[f"iter_{k + 1}"] = r.cpu().numpy()
+            return out[-1]
         pn, inn = (None, None) if noise is None else noise
         result = self._proj_stage(self.ldproj, pn)
         self.proj_temp_clear()

@@ -25,9 +25,14 @@ __device__ __forceinline__ void philox_round(uint32_t& c0, uint32_t& c1, uint32_
     const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
     c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
 }
+// Device-resident part of the Philox key.  Kernel arguments are frozen when a CUDA graph is captured, so the per-run
+// entropy lives here: ipdm_set_noise_epoch() updates it between replays (ordinary stream-ordered memcpy).
+__device__ unsigned long long d_noise_epoch = 0ull;
+
 __device__ __forceinline__ float4 philox_normal4(uint64_t seed, uint64_t call, uint32_t slice, uint32_t quad) {
     uint32_t c0 = quad, c1 = slice, c2 = (uint32_t)call, c3 = (uint32_t)(call >> 32);
-    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    const unsigned long long ep = d_noise_epoch;
+    uint32_t k0 = (uint32_t)seed ^ (uint32_t)(ep * 0x9E3779B97F4A7C15ull >> 32), k1 = (uint32_t)(seed >> 32) ^ (uint32_t)ep;
 #pragma unroll
     for (int r = 0; r < 10; ++r) { philox_round(c0, c1, c2, c3, k0, k1); k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
     const float s = 2.3283064365386963e-10f;                  // 2^-32
@@ -434,6 +439,15 @@ static int grid_for(size_t n, int threads) {
 }  // namespace ipdm
 
 using namespace ipdm;
+
+extern "C" int ipdm_set_noise_epoch(uint64_t epoch, void* stream) {
+    static uint64_t staging[64];
+    static int slot = 0;
+    uint64_t* h = &staging[slot++ & 63];            // the copy is asynchronous: keep the source alive
+    *h = epoch;
+    IPDM_CHECK_CUDA(cudaMemcpyToSymbolAsync(d_noise_epoch, h, sizeof(uint64_t), 0, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return IPDM_OK;
+}
 
 extern "C" int ipdm_lincomb(float* out, float a, const float* x, float b, const float* y, float c, const float* z,
                             size_t n, void* stream) {

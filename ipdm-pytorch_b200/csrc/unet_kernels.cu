@@ -22,96 +22,142 @@ struct ConvDirectParams {
     int hout, wout;
     float up_sy, up_sx; int upsample;
     const float* nscale; const float* nshift;
-    int ksize, stride, cin, cout, co_tiles;
+    int ksize, stride, cin, cout, co_tiles, cin_chunk;
     const float* w; const float* bias; int bias_t_stride; const int* t_dev;
     const float* res; int res_cs;
     float* out; int out_cs;
 };
 
-constexpr int CD_TX = 32, CD_TY = 8;
+// CTA = 16 x 8 threads, each thread 4 horizontally adjacent output pixels x COUT_T channels in registers
+// (64 x 8 output tile).  Input channels are processed in chunks (8, or 4 for stride 2) so the staged halo tile
+// stays ~20-35 KB: per (row tap, channel) a thread reads (4-1)*S+K inputs and 3 weight vectors for 12*COUT_T FFMA.
+constexpr int CD_BX = 16, CD_BY = 8, CD_PX = 4;
+constexpr int CD_TW = CD_BX * CD_PX, CD_TH = CD_BY;
 
-template <int COUT_T>
-__global__ void __launch_bounds__(CD_TX * CD_TY)
+template <int COUT_T, int KS, int STRIDE>
+__global__ void __launch_bounds__(CD_BX * CD_BY)
 conv_direct_kernel(const ConvDirectParams P) {
-    extern __shared__ float cd_smem[];
-    const int K = P.ksize, pad = K / 2;
-    const int tin_w = (CD_TX - 1) * P.stride + K, tin_h = (CD_TY - 1) * P.stride + K;
-    const int plane = tin_w * tin_h + 1;                      // +1: de-phase the planes across banks
-    float* tile = cd_smem;                                    // [cin][plane]
-    float* wsm = cd_smem + (((size_t)P.cin * plane + 3) & ~(size_t)3);   // [K*K][cin][COUT_T], 16-byte aligned
+    extern __shared__ __align__(16) float cd_smem[];
+    constexpr int PAD = KS / 2;
+    constexpr int TIN_W = (CD_TW - 1) * STRIDE + KS, TIN_H = (CD_TH - 1) * STRIDE + KS;
+    constexpr int TIN_WP = (TIN_W + 3) & ~3;                    // row pitch: multiple of 4 floats -> 128-bit smem loads
+    constexpr int PLANE = TIN_WP * TIN_H + 4;                   // +4: de-phase the planes across banks, keep 16-byte alignment
+    constexpr int NI = (CD_PX - 1) * STRIDE + KS;               // inputs per row a thread needs
+    const int chunk = P.cin_chunk;
+    float* tile = cd_smem;                                      // [chunk][PLANE]
+    float* wsm = cd_smem + (((size_t)chunk * PLANE + 3) & ~(size_t)3);   // [KS*KS][chunk][COUT_T], 16-byte aligned
     const int n = blockIdx.z / P.co_tiles;
-    const int co_base = (blockIdx.z - n * P.co_tiles) * COUT_T;   // C_out > 16: tiles of COUT_T output channels
-    const int ox0 = blockIdx.x * CD_TX, oy0 = blockIdx.y * CD_TY;
-    const int ix0 = ox0 * P.stride - pad, iy0 = oy0 * P.stride - pad;
-    const int tid = threadIdx.y * CD_TX + threadIdx.x;
+    const int co_base = (blockIdx.z - n * P.co_tiles) * COUT_T; // C_out > 16: tiles of COUT_T output channels
+    const int ox0 = blockIdx.x * CD_TW, oy0 = blockIdx.y * CD_TH;
+    const int ix0 = ox0 * STRIDE - PAD, iy0 = oy0 * STRIDE - PAD;
+    const int tid = threadIdx.y * CD_BX + threadIdx.x;
+    constexpr int NT = CD_BX * CD_BY;
 
-    // weights -> smem, zero-padded to COUT_T output channels
-    const int wtot = K * K * P.cin * COUT_T;
-    for (int i = tid; i < wtot; i += CD_TX * CD_TY) {
-        const int co = i % COUT_T, rest = i / COUT_T;
-        wsm[i] = co_base + co < P.cout ? __ldg(P.w + (size_t)rest * P.cout + co_base + co) : 0.f;
-    }
-    // input halo tile -> smem planes
-    const int tot = tin_w * tin_h * P.cin;
-    for (int i = tid; i < tot; i += CD_TX * CD_TY) {
-        const int c = i % P.cin, pix = i / P.cin;
-        const int ly = pix / tin_w, lx = pix - ly * tin_w;
-        const int iy = iy0 + ly, ix = ix0 + lx;
-        float v = 0.f;
-        if (iy >= 0 && iy < P.hin && ix >= 0 && ix < P.win) {
-            int sy = iy, sx = ix;
-            if (P.upsample) {
-                sy = min((int)floorf((float)iy * P.up_sy), P.hs - 1);
-                sx = min((int)floorf((float)ix * P.up_sx), P.ws - 1);
+    float acc[CD_PX][COUT_T];
+#pragma unroll
+    for (int p = 0; p < CD_PX; ++p)
+#pragma unroll
+        for (int i = 0; i < COUT_T; ++i) acc[p][i] = 0.f;
+
+    for (int c0 = 0; c0 < P.cin; c0 += chunk) {
+        const int cc = min(chunk, P.cin - c0);
+        __syncthreads();                                        // previous chunk fully consumed
+        // weights of this chunk -> smem, zero-padded to COUT_T output channels
+        for (int i = tid; i < KS * KS * cc * COUT_T; i += NT) {
+            const int co = i % COUT_T, rest = i / COUT_T;       // rest = tap * cc + ci
+            const int tap = rest / cc, ci = rest - tap * cc;
+            wsm[(tap * chunk + ci) * COUT_T + co] = co_base + co < P.cout ? __ldg(P.w + ((size_t)tap * P.cin + c0 + ci) * P.cout + co_base + co) : 0.f;
+        }
+        // input halo tile of this chunk -> smem planes (GroupNorm+SiLU, concat, nearest upsample fused into the load)
+        for (int i = tid; i < TIN_W * TIN_H * cc; i += NT) {
+            const int ci = i % cc, pix = i / cc;
+            const int ly = pix / TIN_W, lx = pix - ly * TIN_W;
+            const int iy = iy0 + ly, ix = ix0 + lx, c = c0 + ci;
+            float v = 0.f;
+            if (iy >= 0 && iy < P.hin && ix >= 0 && ix < P.win) {
+                int sy = iy, sx = ix;
+                if (P.upsample) {
+                    sy = min((int)floorf((float)iy * P.up_sy), P.hs - 1);
+                    sx = min((int)floorf((float)ix * P.up_sx), P.ws - 1);
+                }
+                const size_t sp = ((size_t)n * P.hs + sy) * P.ws + sx;
+                v = c < P.c0 ? __ldg(P.src0 + sp * P.cs0 + c) : __ldg(P.src1 + sp * P.cs1 + (c - P.c0));
+                if (P.nscale) {
+                    v = fmaf(v, __ldg(P.nscale + (size_t)n * P.cin + c), __ldg(P.nshift + (size_t)n * P.cin + c));
+                    v = silu(v);
+                }
             }
-            const size_t sp = ((size_t)n * P.hs + sy) * P.ws + sx;
-            v = c < P.c0 ? __ldg(P.src0 + sp * P.cs0 + c) : __ldg(P.src1 + sp * P.cs1 + (c - P.c0));
-            if (P.nscale) {
-                v = fmaf(v, __ldg(P.nscale + (size_t)n * P.cin + c), __ldg(P.nshift + (size_t)n * P.cin + c));
-                v = silu(v);
+            tile[(size_t)ci * PLANE + ly * TIN_WP + lx] = v;
+        }
+        __syncthreads();
+        const float* tbase = tile + threadIdx.y * STRIDE * TIN_WP + threadIdx.x * CD_PX * STRIDE;
+        for (int ci = 0; ci < cc; ++ci) {
+#pragma unroll
+            for (int dy = 0; dy < KS; ++dy) {
+                float in[NI];
+                const float* tp = tbase + (size_t)ci * PLANE + dy * TIN_WP;
+#pragma unroll
+                for (int k4 = 0; k4 < NI / 4; ++k4) {
+                    const float4 t4 = reinterpret_cast<const float4*>(tp)[k4];
+                    in[4 * k4] = t4.x; in[4 * k4 + 1] = t4.y; in[4 * k4 + 2] = t4.z; in[4 * k4 + 3] = t4.w;
+                }
+#pragma unroll
+                for (int k = (NI / 4) * 4; k < NI; ++k) in[k] = tp[k];
+#pragma unroll
+                for (int dx = 0; dx < KS; ++dx) {
+                    const float4* wp = reinterpret_cast<const float4*>(wsm + ((dy * KS + dx) * chunk + ci) * COUT_T);
+#pragma unroll
+                    for (int q = 0; q < COUT_T / 4; ++q) {
+                        const float4 w4 = wp[q];
+#pragma unroll
+                        for (int p = 0; p < CD_PX; ++p) {
+                            const float v = in[p * STRIDE + dx];
+                            acc[p][4 * q] = fmaf(v, w4.x, acc[p][4 * q]);
+                            acc[p][4 * q + 1] = fmaf(v, w4.y, acc[p][4 * q + 1]);
+                            acc[p][4 * q + 2] = fmaf(v, w4.z, acc[p][4 * q + 2]);
+                            acc[p][4 * q + 3] = fmaf(v, w4.w, acc[p][4 * q + 3]);
+                        }
+                    }
+                }
             }
         }
-        tile[(size_t)c * plane + pix] = v;
     }
-    __syncthreads();
-
-    const int ox = ox0 + threadIdx.x, oy = oy0 + threadIdx.y;
-    float acc[COUT_T];
-#pragma unroll
-    for (int i = 0; i < COUT_T; ++i) acc[i] = 0.f;
-    const int lbase = threadIdx.y * P.stride * tin_w + threadIdx.x * P.stride;
-    for (int tap = 0; tap < K * K; ++tap) {
-        const int dy = tap / K, dx = tap - dy * K;
-        const float* tp = tile + lbase + dy * tin_w + dx;
-        const float4* wp = reinterpret_cast<const float4*>(wsm + (size_t)tap * P.cin * COUT_T);
-        for (int c = 0; c < P.cin; ++c) {
-            const float v = tp[(size_t)c * plane];
-#pragma unroll
-            for (int q = 0; q < COUT_T / 4; ++q) {
-                const float4 w4 = wp[c * (COUT_T / 4) + q];
-                acc[4 * q] = fmaf(v, w4.x, acc[4 * q]);
-                acc[4 * q + 1] = fmaf(v, w4.y, acc[4 * q + 1]);
-                acc[4 * q + 2] = fmaf(v, w4.z, acc[4 * q + 2]);
-                acc[4 * q + 3] = fmaf(v, w4.w, acc[4 * q + 3]);
-            }
-        }
-    }
-    if (ox >= P.wout || oy >= P.hout) return;
-    const size_t op = ((size_t)n * P.hout + oy) * P.wout + ox;
+    const int oy = oy0 + threadIdx.y;
+    if (oy >= P.hout) return;
     const float* bias = P.bias ? P.bias + (P.t_dev ? (size_t)(*P.t_dev) * P.bias_t_stride : 0) : nullptr;
 #pragma unroll
-    for (int i = 0; i < COUT_T; ++i) {
-        const int co = co_base + i;
-        if (co < P.cout) {
-            float v = acc[i] + (bias ? __ldg(bias + co) : 0.f);
-            if (P.res) v += __ldg(P.res + op * P.res_cs + co);
-            P.out[op * P.out_cs + co] = v;
-        } else if (co < P.out_cs) {
-            P.out[op * P.out_cs + co] = 0.f;
+    for (int p = 0; p < CD_PX; ++p) {
+        const int ox = ox0 + threadIdx.x * CD_PX + p;
+        if (ox >= P.wout) continue;
+        const size_t op = ((size_t)n * P.hout + oy) * P.wout + ox;
+#pragma unroll
+        for (int i = 0; i < COUT_T; ++i) {
+            const int co = co_base + i;
+            if (co < P.cout) {
+                float v = acc[p][i] + (bias ? __ldg(bias + co) : 0.f);
+                if (P.res) v += __ldg(P.res + op * P.res_cs + co);
+                P.out[op * P.out_cs + co] = v;
+            } else if (co < P.out_cs) {
+                P.out[op * P.out_cs + co] = 0.f;
+            }
         }
+        if (co_base + COUT_T >= P.cout)
+            for (int co = co_base + COUT_T; co < P.out_cs; ++co) P.out[op * P.out_cs + co] = 0.f;
     }
-    if (co_base + COUT_T >= P.cout)
-        for (int co = co_base + COUT_T; co < P.out_cs; ++co) P.out[op * P.out_cs + co] = 0.f;
+}
+
+template <int COUT_T, int KS, int STRIDE>
+static int launch_direct(const ConvDirectParams& P, int batch, cudaStream_t st) {
+    constexpr int TIN_W = (CD_TW - 1) * STRIDE + KS, TIN_H = (CD_TH - 1) * STRIDE + KS, TIN_WP = (TIN_W + 3) & ~3;
+    const size_t smem = ((((size_t)P.cin_chunk * (TIN_WP * TIN_H + 4) + 3) & ~(size_t)3) + (size_t)KS * KS * P.cin_chunk * COUT_T) * sizeof(float);
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        IPDM_CHECK_CUDA(cudaFuncSetAttribute(conv_direct_kernel<COUT_T, KS, STRIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    dim3 grid(ceil_div(P.wout, CD_TW), ceil_div(P.hout, CD_TH), batch * P.co_tiles), block(CD_BX, CD_BY);
+    conv_direct_kernel<COUT_T, KS, STRIDE><<<grid, block, smem, st>>>(P);
+    return IPDM_OK;
 }
 
 int conv_direct_launch(const ConvDirectDesc& d, cudaStream_t st) {
@@ -122,6 +168,7 @@ int conv_direct_launch(const ConvDirectDesc& d, cudaStream_t st) {
     IPDM_REQUIRE(d.cin == P.c0 + P.c1, "conv_direct: C_in %d != %d + %d", d.cin, P.c0, P.c1);
     IPDM_REQUIRE(d.cout >= 1, "conv_direct: C_out %d", d.cout);
     IPDM_REQUIRE(d.ksize == 1 || d.ksize == 3, "conv_direct: 1x1 or 3x3");
+    IPDM_REQUIRE(d.stride == 1 || (d.stride == 2 && d.ksize == 3), "conv_direct: stride 2 only for 3x3");
     P.hs = s0.h; P.ws = s0.w;
     P.upsample = d.upsample;
     P.hin = d.upsample ? d.out.h : s0.h; P.win = d.upsample ? d.out.w : s0.w;
@@ -137,17 +184,12 @@ int conv_direct_launch(const ConvDirectDesc& d, cudaStream_t st) {
     P.out = d.out.p; P.out_cs = d.out.cs;
     const int ct = d.cout <= 4 ? 4 : (d.cout <= 8 ? 8 : 16);
     P.co_tiles = (d.cout + ct - 1) / ct;
-    const int tin_w = (CD_TX - 1) * d.stride + d.ksize, tin_h = (CD_TY - 1) * d.stride + d.ksize;
-    const size_t smem = ((((size_t)d.cin * (tin_w * tin_h + 1) + 3) & ~(size_t)3) + (size_t)d.ksize * d.ksize * d.cin * ct) * sizeof(float);
-    IPDM_REQUIRE(smem <= 200 * 1024, "conv_direct: tile needs %zu bytes of shared memory", smem);
-    dim3 grid(ceil_div(P.wout, CD_TX), ceil_div(P.hout, CD_TY), s0.n * P.co_tiles), block(CD_TX, CD_TY);
+    P.cin_chunk = std::min(d.cin, d.stride == 2 ? 4 : 8);
     ProfScope prof(PROF_CONV_DIRECT, st, 4.0 * s0.n * ((double)s0.h * s0.w * d.cin + (double)P.hout * P.wout * d.cout));   // bytes
-    auto go = [&](auto kern) -> int {
-        if (smem > 48 * 1024) IPDM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, block, smem, st>>>(P);
-        return IPDM_OK;
-    };
-    int rc = ct == 4 ? go(conv_direct_kernel<4>) : (ct == 8 ? go(conv_direct_kernel<8>) : go(conv_direct_kernel<16>));
+    int rc = IPDM_ERR_UNSUPPORTED;
+#define IPDM_CD(CT) (d.ksize == 1 ? launch_direct<CT, 1, 1>(P, s0.n, st) : (d.stride == 1 ? launch_direct<CT, 3, 1>(P, s0.n, st) : launch_direct<CT, 3, 2>(P, s0.n, st)))
+    rc = ct == 4 ? IPDM_CD(4) : (ct == 8 ? IPDM_CD(8) : IPDM_CD(16));
+#undef IPDM_CD
     IPDM_CHECK(rc);
     count_launch();
     IPDM_CHECK_LAUNCH();

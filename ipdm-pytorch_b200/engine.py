@@ -173,6 +173,11 @@ def clamp_(x, lo=-math.inf, hi=math.inf):
     return x
 
 
+def set_noise_epoch(epoch):
+    """Stream-ordered update of the device-resident half of the Philox key (fresh noise per CUDA-graph replay)."""
+    check(_lib.lib().ipdm_set_noise_epoch(int(epoch) & (2 ** 64 - 1), _stream()), "ipdm_set_noise_epoch")
+
+
 def q_sample(x, a, b, noise=None, seed=0, call_id=0, out=None):
     bsz = x.shape[0]
     out = torch.empty_like(x) if out is None else out

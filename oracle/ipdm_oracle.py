@@ -140,7 +140,7 @@ def gn_groups(c):
 def timestep_embedding(t, dim, max_period=10000):
     """:14-32, [cos | sin]."""
     half = dim // 2
-    freqs = torch.exp(-math.log(max_period) * torch.arange(0, half) / half).float()
+    freqs = torch.exp(-math.log(max_period) * torch.arange(0, half) / half).float().to(t.device)
     args = t[:, None].float() * freqs[None]
     return torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
 
@@ -246,7 +246,7 @@ class UNetOracle(nn.Module):
 
     @torch.no_grad()
     def forward(self, x, timesteps):                # :283-310
-        emb = self.time_embed(timestep_embedding(timesteps, self.model_channels))
+        emb = self.time_embed(timestep_embedding(timesteps.to(x.device), self.model_channels))
         hs, h = [], x
         for m in self.down_blocks:
             h = m(h, emb, None)
@@ -308,7 +308,7 @@ def guided_reverse_process(unet, tab, img, t_start, clip, lambda_ratio, eta, mod
                     lam = lam_cos[i]                                      # 0-dim fp64 tensor as in :552 (ops stay f32)
                 else:
                     I = condition_lambda_map(Lam, i, ts)                  # :554-558
-                    lam = F.interpolate(torch.from_numpy(I), size=img.shape[-2:], mode="nearest")   # :559
+                    lam = F.interpolate(torch.from_numpy(I).to(img.device), size=img.shape[-2:], mode="nearest")   # :559
             else:
                 lam = constant_guidance
             eps = unet(x, torch.full((1,), i, dtype=torch.long))
@@ -321,7 +321,7 @@ def guided_reverse_process(unet, tab, img, t_start, clip, lambda_ratio, eta, mod
             d = d - torch.median(d)
             d = F.avg_pool2d(d, kernel_size)
             d = torch.where(d <= 0, torch.zeros_like(d), d)
-            Lam = lambda_curve(torch.exp(amplitude * d).numpy(), "proj")  # :600, :614
+            Lam = lambda_curve(torch.exp(amplitude * d).cpu().numpy(), "proj")  # :600, :614
         iters_out.append(x.contiguous())
         if constant_guidance is None:
             if it >= 1:

@@ -192,6 +192,30 @@ def case_full_slice():
     return out
 
 
+def case_img_stage_512():
+    """Image-domain stage alone at 512x512 (60 UNet forwards): input = sharpened reference FBP of the low-dose slice."""
+    import torch
+    tmp = tempfile.mkdtemp(prefix="ipdm_ref_")
+    model = build_denoiser(tmp, seed=0)
+    ld, nd, img = SYN.make_slice(0)
+    rec = model.convertor(torch.from_numpy(ld)[None])[:, None]             # reference FBP.convert, CPU tensor [1,1,512,512]
+    x = TTsharpen(rec, 42)
+    with NoiseTape(tape((1, 1, 512, 512), 66, 19527)) as nt:
+        t0 = time.time()
+        res = model.img_denoiser(x, noise_strength=None, save_state=True)
+        total = time.time() - t0
+    assert nt.used == 66
+    out = dict(x=x[0, 0].numpy(), final=res[0, 0].numpy(), total_s=np.float64(total))
+    for k in range(1, 9):
+        out[f"iter{k}_sub"] = model.progressive_denoise_result[f"iter_{k}"][0, 0][1::4, 2::4].copy()
+    return out
+
+
+def TTsharpen(x, n):
+    MM, RF, TT, CFG = load_reference()
+    return TT.tensor_sharpen(x, n)
+
+
 def save(name, d):
     os.makedirs(GOLD, exist_ok=True)
     path = os.path.join(GOLD, name + ".npz")
@@ -214,6 +238,8 @@ def main():
         save("fbp_slice0", case_fbp(RF))
     elif what == "full":
         save("full_slice0", case_full_slice())
+    elif what == "img512":
+        save("img_stage512", case_img_stage_512())
     os.chdir(cwd)
 
 
