@@ -149,7 +149,8 @@ typedef struct ipdm_unet_config {
 } ipdm_unet_config;
 
 #define IPDM_PREC_TF32 0   /* fp32 activations, tcgen05 kind::tf32 contractions, fp32 accumulate (reference GPU default) */
-#define IPDM_PREC_BF16 1   /* bf16 operands for tcgen05 kind::f16, fp32 accumulate / norm statistics */
+#define IPDM_PREC_BF16 1   /* bf16 operands (GroupNorm-apply / upsample outputs, weights) for tcgen05 kind::f16 in the 3x3 convs and
+                              qkv; fp32 residual stream, accumulators, norm statistics, attention and sampler state */
 #define IPDM_PREC_FP32 2   /* fp32 activations, 3xTF32 split contractions (fp32-accurate) */
 
 int ipdm_unet_create(ipdm_unet** out, const ipdm_unet_config* cfg, const float* weights_host, size_t n_weights);
@@ -204,7 +205,8 @@ int ipdm_guided_process(ipdm_unet* net, const ipdm_guided_params* p, const float
  * reference; they expose the building blocks of ipdm_unet_forward one at a time:
  *   conv        nn.Conv2d 3x3 / 1x1, stride 1 / 2, over a virtual concat of two sources
  *               (Model/model.py:101,113,117,142,143,165,180,306); use_tc: 0 CUDA-core path, 1 tcgen05 kind::tf32,
- *               2 tcgen05 3xTF32 (fp32-accurate);
+ *               2 tcgen05 3xTF32 (fp32-accurate), 3 tcgen05 kind::f16 with bf16 operands (src0 is then a bf16 NHWC tensor
+ *               with a channel stride that is a multiple of 64, single source);
  *               the direct path can fuse GroupNorm+SiLU on load and a nearest upsample (:168).
  *   groupnorm   norm_layer(C) statistics -> per-(slice, channel) scale/shift (+ optional apply, +SiLU) (:82-90)
  *   attention   AttentionBlock core (:148-153) from q,k in NHWC [B,T,3C] and v transposed [B,heads,d,t_pad]

@@ -5,7 +5,7 @@ The flags are declared from one table instead of ~70 add_argument calls.  Refere
 purpose: `type=bool` flags are truthy for any non-empty string; a JSON overlay never overrides a
 flag that was given on the command line; `cfg_load` only merges keys that already exist and prints
 the reference's "no key names ..." line otherwise.  Additive keys of this build: `precision`
-("tf32" | "fp32"), `noise_seed` and `cuda_graph`; their defaults reproduce the reference.
+("tf32" | "fp32" | "bf16"), `noise_seed` and `cuda_graph`; their defaults reproduce the reference.
 """
 import argparse
 import json

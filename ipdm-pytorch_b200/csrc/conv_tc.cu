@@ -67,7 +67,7 @@ int tmap_encode(CUtensorMap* out, CUtensorMapDataType dtype, int rank, const voi
 // kernel
 // ------------------------------------------------------------------------------------------------
 constexpr int TC_THREADS = 128;
-constexpr int TC_KC = 32;                 // fp32 elements per 128-byte operand row
+constexpr int TC_KC = 32;                 // fp32 elements per 128-byte operand row (bf16 operands: 64, P.kc)
 constexpr int TC_A_BYTES = 128 * 128;
 
 // SPLIT = fp32-accurate "3xTF32" mode: every fp32 operand x is used as x_hi + x_lo (x_hi = rn_tf32(x), x_lo =
@@ -140,21 +140,22 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams P) {
                 uint8_t* sB = sA + S::OFF_B;
                 if (P.stride == 1) {
                     const bool first = kc < P.nk0;
-                    tc::tma_load_4d(sA, first ? &P.mapA[0] : &P.mapA[1], &full[s], (first ? kc : kc - P.nk0) * TC_KC,
+                    tc::tma_load_4d(sA, first ? &P.mapA[0] : &P.mapA[1], &full[s], (first ? kc : kc - P.nk0) * P.kc,
                                     x0 + dx - 1, y0 + dy - 1, b);
                 } else {
                     const int py = dy != 1, px = dx != 1;
-                    tc::tma_load_4d(sA, &P.mapA[py * 2 + px], &full[s], kc * TC_KC, x0 + (dx == 0 ? -1 : 0),
+                    tc::tma_load_4d(sA, &P.mapA[py * 2 + px], &full[s], kc * P.kc, x0 + (dx == 0 ? -1 : 0),
                                     y0 + (dy == 0 ? -1 : 0), b);
                 }
-                tc::tma_load_2d(sB, &P.mapB, &full[s], kc * TC_KC, tap * P.cout_rows + n0);
-                if constexpr (SPLIT) tc::tma_load_2d(sA + S::OFF_BLO, &P.mapBlo, &full[s], kc * TC_KC, tap * P.cout_rows + n0);
+                tc::tma_load_2d(sB, &P.mapB, &full[s], kc * P.kc, tap * P.cout_rows + n0);
+                if constexpr (SPLIT) tc::tma_load_2d(sA + S::OFF_BLO, &P.mapBlo, &full[s], kc * P.kc, tap * P.cout_rows + n0);
             }
         }
         __syncwarp();
     } else if (warp == 1) {
         if (tc::elect_one()) {
-            constexpr uint32_t idesc = tc::make_idesc(tc::FMT_TF32, 128, BLOCK_N);
+            const bool bf16 = !SPLIT && P.bf16;      // bf16 operands: kind::f16, K = 16 per instruction (still 32 bytes)
+            const uint32_t idesc = tc::make_idesc(bf16 ? tc::FMT_BF16 : tc::FMT_TF32, 128, BLOCK_N);
             for (int it = 0; it < total; ++it) {
                 const int s = it % STAGES;
                 const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
@@ -164,7 +165,8 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams P) {
                 const uint64_t adesc = tc::smem_desc_k_sw128(sA), bdesc = tc::smem_desc_k_sw128(sA + S::OFF_B);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {        // 4 x (K = 8 tf32 = 32 bytes) inside the 128-byte swizzle atom
-                    tc::umma_tf32(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (uint32_t)((it | k) != 0));
+                    if (bf16) tc::umma_f16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (uint32_t)((it | k) != 0));
+                    else tc::umma_tf32(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (uint32_t)((it | k) != 0));
                     if constexpr (SPLIT) {
                         const uint64_t alo = tc::smem_desc_k_sw128(sA + S::OFF_ALO), blo = tc::smem_desc_k_sw128(sA + S::OFF_BLO);
                         tc::umma_tf32(tmem_base, adesc + (uint64_t)(k * 2), blo + (uint64_t)(k * 2), idesc, 1u);
@@ -295,35 +297,41 @@ int conv_tc_prepare(ConvTcParams& P, const ConvTcDesc& d) {
     IPDM_REQUIRE(d.cout % P.block_n == 0, "conv_tc: C_out %d not a multiple of the N tile %d", d.cout, P.block_n);
     P.cout_rows = d.cout;
     int ktot = 0;
+    P.bf16 = d.src[0].bf16;
+    P.kc = P.bf16 ? 64 : 32;
+    const int eb = P.bf16 ? 2 : 4;
+    const CUtensorMapDataType dt = P.bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    IPDM_REQUIRE(!(P.bf16 && d.w_packed_lo), "conv_tc: bf16 operands and the 3xTF32 split are exclusive");
     for (int s = 0; s < d.nsrc; ++s) {
         const TensorNHWC& t = d.src[s];
-        IPDM_REQUIRE(t.cs % TC_KC == 0 && ((uintptr_t)t.p % 16) == 0, "conv_tc: source channel stride %d must be a multiple of 32", t.cs);
+        IPDM_REQUIRE(t.bf16 == P.bf16, "conv_tc: concat sources differ in dtype");
+        IPDM_REQUIRE(t.cs % P.kc == 0 && ((uintptr_t)t.p % 16) == 0, "conv_tc: source channel stride %d must be a multiple of %d", t.cs, P.kc);
         IPDM_REQUIRE(t.h == Hin && t.w == Win && t.n == P.batch, "conv_tc: concat sources differ in shape");
-        (s == 0 ? P.nk0 : P.nk1) = t.cs / TC_KC;
+        (s == 0 ? P.nk0 : P.nk1) = t.cs / P.kc;
         ktot += t.cs;
         if (d.stride == 1) {
             const uint64_t dims[4] = {(uint64_t)t.cs, (uint64_t)t.w, (uint64_t)t.h, (uint64_t)t.n};
-            const uint64_t str[3] = {(uint64_t)t.cs * 4, (uint64_t)t.w * t.cs * 4, (uint64_t)t.h * t.w * t.cs * 4};
-            const uint32_t box[4] = {TC_KC, (uint32_t)TW, (uint32_t)TH, 1};
-            IPDM_CHECK(tmap_encode(&P.mapA[s], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, t.p, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B));
+            const uint64_t str[3] = {(uint64_t)t.cs * eb, (uint64_t)t.w * t.cs * eb, (uint64_t)t.h * t.w * t.cs * eb};
+            const uint32_t box[4] = {(uint32_t)P.kc, (uint32_t)TW, (uint32_t)TH, 1};
+            IPDM_CHECK(tmap_encode(&P.mapA[s], dt, 4, t.p, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B));
         } else {
             for (int py = 0; py < 2; ++py)
                 for (int px = 0; px < 2; ++px) {
                     const uint64_t wp = (uint64_t)(t.w - px + 1) / 2, hp = (uint64_t)(t.h - py + 1) / 2;
                     const uint64_t dims[4] = {(uint64_t)t.cs, wp ? wp : 1, hp ? hp : 1, (uint64_t)t.n};
-                    const uint64_t str[3] = {(uint64_t)t.cs * 8, (uint64_t)t.w * t.cs * 8, (uint64_t)t.h * t.w * t.cs * 4};
-                    const uint32_t box[4] = {TC_KC, (uint32_t)TW, (uint32_t)TH, 1};
-                    const float* base = t.p + ((size_t)py * t.w + px) * t.cs;
-                    IPDM_CHECK(tmap_encode(&P.mapA[py * 2 + px], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B));
+                    const uint64_t str[3] = {(uint64_t)t.cs * 2 * eb, (uint64_t)t.w * t.cs * 2 * eb, (uint64_t)t.h * t.w * t.cs * eb};
+                    const uint32_t box[4] = {(uint32_t)P.kc, (uint32_t)TW, (uint32_t)TH, 1};
+                    const char* base = (const char*)t.p + ((size_t)py * t.w + px) * t.cs * eb;
+                    IPDM_CHECK(tmap_encode(&P.mapA[py * 2 + px], dt, 4, base, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B));
                 }
         }
     }
     IPDM_REQUIRE(ktot == d.w_k, "conv_tc: packed weight K %d != sum of source channel strides %d", d.w_k, ktot);
     {
         const uint64_t dims[2] = {(uint64_t)d.w_k, (uint64_t)d.ntaps * d.cout};
-        const uint64_t str[1] = {(uint64_t)d.w_k * 4};
-        const uint32_t box[2] = {TC_KC, (uint32_t)P.block_n};
-        IPDM_CHECK(tmap_encode(&P.mapB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, d.w_packed, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B));
+        const uint64_t str[1] = {(uint64_t)d.w_k * eb};
+        const uint32_t box[2] = {(uint32_t)P.kc, (uint32_t)P.block_n};
+        IPDM_CHECK(tmap_encode(&P.mapB, dt, 2, d.w_packed, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B));
         P.split = d.w_packed_lo != nullptr;
         if (P.split) IPDM_CHECK(tmap_encode(&P.mapBlo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, d.w_packed_lo, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B));
     }
@@ -374,7 +382,7 @@ int conv_tc_launch(const ConvTcParams& P, cudaStream_t st) {
 }
 
 double conv_tc_flops(const ConvTcParams& P) {
-    return (P.split ? 3.0 : 1.0) * 2.0 * P.batch * P.H * P.W * (double)P.cout * P.ntaps * (P.nk0 + P.nk1) * TC_KC;
+    return (P.split ? 3.0 : 1.0) * 2.0 * P.batch * P.H * P.W * (double)P.cout * P.ntaps * (P.nk0 + P.nk1) * P.kc;
 }
 
 }  // namespace ipdm

@@ -39,13 +39,14 @@ struct ConvW {
     std::vector<float> w_host, b_host;       // PyTorch layout [cout][cin][k][k], [cout]
     float* w_dev = nullptr; float* w_dev_lo = nullptr; float* b_dev = nullptr;
     bool tc = false; int c0 = 0, cs0 = 0, c1 = 0, cs1 = 0, kpad = 0;
+    bool bf16 = false;                       // operands (activation tile and packed weights) are bf16
 };
 struct ResW { GNW gn1, gn2; ConvW conv1, conv2, shortcut; bool has_shortcut = false; std::vector<float> temb_w, temb_b; float* bias1_t = nullptr; int cin = 0, cout = 0; };
 struct AttnW { GNW norm; ConvW qkv, proj; int C = 0; };
 struct LayerRef { enum Kind { CONV_IN, RES, ATTN, DOWN, UP } kind; int idx; };
 typedef std::vector<LayerRef> Block;
 
-struct VTensor { int n = 0, h = 0, w = 0, c = 0, cs = 0; int def = -1, last = -1; size_t off = 0; bool external = false; };
+struct VTensor { int n = 0, h = 0, w = 0, c = 0, cs = 0; int def = -1, last = -1; size_t off = 0; bool external = false; int bf16 = 0; };
 
 struct Op {
     enum Kind { GN_STATS, GN_APPLY, CONV_TC, CONV_DIRECT, UPSAMPLE, ATTN } kind;
@@ -126,12 +127,22 @@ static int read_gn(ipdm_unet* net, Reader& r, GNW& g, int C) {
 static bool wants_tc(int cin_total, int cout) { return cout % 16 == 0 && cin_total >= 16 && (cout >= 64 || cin_total >= 64); }
 
 // K layout of a tensor-core conv: channel c of the virtual concat -> column c (c < c0) or cs0 + (c - c0)
-static int pack_conv(ipdm_unet* net, ConvW& c, int c0, int c1, bool raw_sources, int force = -1) {
+static inline uint16_t bf16_rn_host(float x) {
+    uint32_t b; memcpy(&b, &x, 4);
+    b += 0x7FFFu + ((b >> 16) & 1u);
+    return (uint16_t)(b >> 16);
+}
+
+// operand_tensor: the conv reads a tensor that exists only as its operand (GroupNorm-apply or upsample output), which the
+// bf16 precision mode stores as bf16; raw_sources: the conv reads residual-stream tensors (fp32, virtual concat).
+static int pack_conv(ipdm_unet* net, ConvW& c, int c0, int c1, bool raw_sources, int force = -1, bool operand_tensor = false) {
     const int kk = c.k * c.k;
     c.tc = force < 0 ? wants_tc(c.cin, c.cout) : force != 0;
+    c.bf16 = c.tc && net->precision == IPDM_PREC_BF16 && (operand_tensor || !raw_sources);
     if (c.tc) {
         c.c0 = c0; c.c1 = c1;
-        if (raw_sources) { c.cs0 = alloc_cs(c0); c.cs1 = c1 ? alloc_cs(c1) : 0; }
+        if (c.bf16) { c.c0 = c.cin; c.c1 = 0; c.cs0 = round_up(c.cin, 64); c.cs1 = 0; }
+        else if (raw_sources) { c.cs0 = alloc_cs(c0); c.cs1 = c1 ? alloc_cs(c1) : 0; }
         else { c.c0 = c.cin; c.c1 = 0; c.cs0 = round_up(c.cin, 32); c.cs1 = 0; }
         IPDM_REQUIRE(c.cs0 % 32 == 0 && c.cs1 % 32 == 0, "pack_conv: source strides %d/%d are not multiples of 32", c.cs0, c.cs1);
         c.kpad = c.cs0 + c.cs1;
@@ -147,8 +158,18 @@ static int pack_conv(ipdm_unet* net, ConvW& c, int c0, int c1, bool raw_sources,
                     if (split) plo[at] = tf32_rn_host(w - hi);
                 }
             }
-        IPDM_CHECK(upload(net, p, &c.w_dev));
-        if (split) IPDM_CHECK(upload(net, plo, &c.w_dev_lo));
+        if (c.bf16) {                                   // same [tap][cout][K] layout, 2-byte elements
+            std::vector<float> packed((p.size() + 1) / 2, 0.f);
+            uint16_t* h = reinterpret_cast<uint16_t*>(packed.data());
+            for (int co = 0; co < c.cout; ++co)
+                for (int ci = 0; ci < c.cin; ++ci)
+                    for (int t = 0; t < kk; ++t)
+                        h[((size_t)t * c.cout + co) * c.kpad + ci] = bf16_rn_host(c.w_host[((size_t)co * c.cin + ci) * kk + t]);
+            IPDM_CHECK(upload(net, packed, &c.w_dev));
+        } else {
+            IPDM_CHECK(upload(net, p, &c.w_dev));
+            if (split) IPDM_CHECK(upload(net, plo, &c.w_dev_lo));
+        }
     } else {
         std::vector<float> p((size_t)kk * c.cin * c.cout);
         for (int co = 0; co < c.cout; ++co)
@@ -274,7 +295,7 @@ struct BuildVisitor : ArchVisitor {
     }
     void up(int c) override {
         net->convs.emplace_back(); read_conv(r, net->convs.back(), c, c, 3, true);
-        fail(pack_conv(net, net->convs.back(), c, 0, true));
+        fail(pack_conv(net, net->convs.back(), c, 0, true, -1, true));
         cur->push_back({LayerRef::UP, (int)net->convs.size() - 1});
     }
     void out(int c, int co) override {
@@ -338,7 +359,8 @@ struct PlanBuilder {
         push(st);
         const VTensor& s0 = pl->vt[src[0]];
         if (cw.tc) {
-            const int a = new_tensor(pl->B, s0.h, s0.w, gn.C, round_up(gn.C, 32));
+            const int a = new_tensor(pl->B, s0.h, s0.w, gn.C, cw.bf16 ? round_up(gn.C, 64) : round_up(gn.C, 32));
+            pl->vt[a].bf16 = cw.bf16;
             Op ap; ap.kind = Op::GN_APPLY; ap.nsrc = nsrc; ap.src[0] = src[0]; ap.src[1] = st.src[1]; ap.gn = &gn; ap.norm_slot = st.norm_slot; ap.dst = a; ap.act = act_silu;
             push(ap);
             Op cv; cv.kind = Op::CONV_TC; cv.nsrc = 1; cv.src[0] = a; cv.cw = &cw; cv.dst = dst; cv.res = res; cv.bias = bias; cv.bias_t_stride = bstride; cv.use_t = use_t;
@@ -374,6 +396,7 @@ struct PlanBuilder {
         const int vt_lo = split ? new_tensor(pl->B, 1, 1, a.C * tpad, a.C * tpad) : -1;
         Op st; st.kind = Op::GN_STATS; st.nsrc = 1; st.src[0] = x; st.gn = &a.norm; st.norm_slot = norm_slots++; max_c = std::max(max_c, a.C); push(st);
         const int an = new_tensor(pl->B, s.h, s.w, a.C, a.C);
+        pl->vt[an].bf16 = a.qkv.bf16;
         Op ap; ap.kind = Op::GN_APPLY; ap.nsrc = 1; ap.src[0] = x; ap.gn = &a.norm; ap.norm_slot = st.norm_slot; ap.dst = an; ap.act = 0; push(ap);
         Op q; q.kind = Op::CONV_TC; q.nsrc = 1; q.src[0] = an; q.cw = &a.qkv; q.dst = qk; q.aux = vt; q.qkv = 1; q.aux2 = qk_lo; q.aux3 = vt_lo; push(q);   // epilogue rounds q,k,v to tf32 (hi/lo pairs in fp32 mode)
         const int o = new_tensor(pl->B, s.h, s.w, a.C, a.C);
@@ -396,7 +419,8 @@ struct PlanBuilder {
                     const ConvW& cw = net->convs[l.idx];
                     out = act(up_h, up_w, s0.c);
                     if (cw.tc) {
-                        const int u = act(up_h, up_w, s0.c);
+                        const int u = cw.bf16 ? new_tensor(pl->B, up_h, up_w, s0.c, round_up(s0.c, 64)) : act(up_h, up_w, s0.c);
+                        pl->vt[u].bf16 = cw.bf16;
                         Op up; up.kind = Op::UPSAMPLE; up.nsrc = 1; up.src[0] = cur[0]; up.dst = u; push(up);
                         plain_conv(&u, 1, cw, out, -1, 1, 0);
                     } else plain_conv(cur, 1, cw, out, -1, 1, 1);
@@ -412,7 +436,7 @@ static TensorNHWC resolve(const Plan& pl, int id) {
     TensorNHWC t;
     if (id < 0) return t;
     const VTensor& v = pl.vt[id];
-    t.n = v.n; t.h = v.h; t.w = v.w; t.c = v.c; t.cs = v.cs;
+    t.n = v.n; t.h = v.h; t.w = v.w; t.c = v.c; t.cs = v.cs; t.bf16 = v.bf16;
     t.p = v.external ? nullptr : (float*)((char*)pl.arena + v.off);
     return t;
 }
@@ -448,7 +472,7 @@ static int build_plan(ipdm_unet* net, int B, int H, int W, Plan** out) {
     for (int i = 0; i < (int)pl->vt.size(); ++i) if (!pl->vt[i].external && pl->vt[i].def >= 0) order.push_back(i);
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return pl->vt[a].def < pl->vt[b].def; });
     size_t oi = 0;
-    auto bytes_of = [&](const VTensor& t) { return ((size_t)t.n * t.h * t.w * t.cs * sizeof(float) + 1023) & ~(size_t)1023; };
+    auto bytes_of = [&](const VTensor& t) { return ((size_t)t.n * t.h * t.w * t.cs * (t.bf16 ? 2 : 4) + 1023) & ~(size_t)1023; };
     for (int op = 0; op < (int)pl->ops.size(); ++op) {
         while (oi < order.size() && pl->vt[order[oi]].def == op) {
             VTensor& t = pl->vt[order[oi]];
@@ -576,8 +600,8 @@ extern "C" long long ipdm_unet_param_count(const ipdm_unet_config* cfg) {
 extern "C" int ipdm_unet_create(ipdm_unet** out, const ipdm_unet_config* cfg, const float* weights_host, size_t n_weights) {
     IPDM_REQUIRE(out && cfg && weights_host, "ipdm_unet_create: null argument");
     IPDM_REQUIRE(cfg->n_mult >= 2 && cfg->n_mult <= 8 && cfg->n_attn >= 0 && cfg->n_attn <= 8, "ipdm_unet_create: bad config");
-    IPDM_REQUIRE(cfg->precision == IPDM_PREC_TF32 || cfg->precision == IPDM_PREC_FP32,
-                 "ipdm_unet_create: precision %d is not implemented (tf32 = 0 and fp32 = 2 are; bf16 is planned)", cfg->precision);
+    IPDM_REQUIRE(cfg->precision == IPDM_PREC_TF32 || cfg->precision == IPDM_PREC_FP32 || cfg->precision == IPDM_PREC_BF16,
+                 "ipdm_unet_create: unknown precision %d", cfg->precision);
     const long long expect = ipdm_unet_param_count(cfg);
     IPDM_REQUIRE((long long)n_weights == expect, "ipdm_unet_create: got %zu weights, the config needs %lld", n_weights, expect);
     std::unique_ptr<ipdm_unet> net(new ipdm_unet());
@@ -626,11 +650,11 @@ extern "C" int ipdm_debug_conv(const float* src0, int c0, int cs0, const float* 
                                float* out, int out_cs, int use_tc, void* stream) {
     IPDM_REQUIRE(src0 && w_host && out, "ipdm_debug_conv: null argument");
     ipdm_unet holder;
-    holder.precision = use_tc == 2 ? IPDM_PREC_FP32 : IPDM_PREC_TF32;
+    holder.precision = use_tc == 2 ? IPDM_PREC_FP32 : (use_tc == 3 ? IPDM_PREC_BF16 : IPDM_PREC_TF32);
     ConvW cw; cw.cin = c0 + c1; cw.cout = cout; cw.k = k;
     cw.w_host.assign(w_host, w_host + (size_t)cout * cw.cin * k * k);
     if (bias_host) cw.b_host.assign(bias_host, bias_host + cout);
-    IPDM_CHECK(pack_conv(&holder, cw, c0, c1, true, use_tc != 0));
+    IPDM_CHECK(pack_conv(&holder, cw, c0, c1, true, use_tc != 0, use_tc == 3));
     cudaStream_t st = (cudaStream_t)stream;
     const int hin = upsample_h > 0 ? upsample_h : h, win = upsample_w > 0 ? upsample_w : w;
     const int ho = stride == 1 ? hin : (hin + 1) / 2, wo = stride == 1 ? win : (win + 1) / 2;
@@ -639,6 +663,7 @@ extern "C" int ipdm_debug_conv(const float* src0, int c0, int cs0, const float* 
         IPDM_REQUIRE(cs0 == cw.cs0 && (c1 == 0 || cs1 == cw.cs1), "ipdm_debug_conv: tensor-core sources need channel strides %d / %d", cw.cs0, cw.cs1);
         IPDM_REQUIRE(upsample_h == 0 && !norm_scale, "ipdm_debug_conv: upsample / fused norm are direct-path features");
         ConvTcDesc d; d.nsrc = c1 ? 2 : 1; d.src[0] = mk(src0, n, h, w, c0, cs0); if (c1) d.src[1] = mk(src1, n, h, w, c1, cs1);
+        d.src[0].bf16 = cw.bf16;
         d.ntaps = k * k; d.stride = stride; d.cout = cout; d.w_packed = cw.w_dev; d.w_packed_lo = cw.w_dev_lo; d.w_k = cw.kpad; d.bias = cw.b_dev;
         if (res) d.res = mk(res, n, ho, wo, cout, res_cs);
         d.out = mk(out, n, ho, wo, cout, out_cs);

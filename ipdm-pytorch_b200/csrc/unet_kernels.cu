@@ -5,6 +5,7 @@
 #include "unet_ops.cuh"
 
 #include <algorithm>
+#include <cuda_bf16.h>
 
 namespace ipdm {
 
@@ -22,7 +23,7 @@ struct ConvDirectParams {
     int hout, wout;
     float up_sy, up_sx; int upsample;
     const float* nscale; const float* nshift;
-    int ksize, stride, cin, cout, co_tiles, cin_chunk;
+    int ksize, stride, cin, cout, co_tiles, cin_chunk, vec4;
     const float* w; const float* bias; int bias_t_stride; const int* t_dev;
     const float* res; int res_cs;
     float* out; int out_cs;
@@ -69,6 +70,34 @@ conv_direct_kernel(const ConvDirectParams P) {
             wsm[(tap * chunk + ci) * COUT_T + co] = co_base + co < P.cout ? __ldg(P.w + ((size_t)tap * P.cin + c0 + ci) * P.cout + co_base + co) : 0.f;
         }
         // input halo tile of this chunk -> smem planes (GroupNorm+SiLU, concat, nearest upsample fused into the load)
+        if (P.vec4) {
+            // 128-bit path: one (pixel, 4-channel group) per item; cc is 4 or 8
+            const int vpp = cc >> 2;                            // vectors per pixel (1 or 2)
+            for (int i = tid; i < TIN_W * TIN_H * vpp; i += NT) {
+                const int cv = i & (vpp - 1), pix = i >> (vpp >> 1);
+                const int ly = pix / TIN_W, lx = pix - ly * TIN_W;
+                const int iy = iy0 + ly, ix = ix0 + lx, c = c0 + 4 * cv;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (iy >= 0 && iy < P.hin && ix >= 0 && ix < P.win) {
+                    int sy = iy, sx = ix;
+                    if (P.upsample) {
+                        sy = min((int)floorf((float)iy * P.up_sy), P.hs - 1);
+                        sx = min((int)floorf((float)ix * P.up_sx), P.ws - 1);
+                    }
+                    const size_t sp = ((size_t)n * P.hs + sy) * P.ws + sx;
+                    v = c < P.c0 ? __ldg(reinterpret_cast<const float4*>(P.src0 + sp * P.cs0 + c))
+                                 : __ldg(reinterpret_cast<const float4*>(P.src1 + sp * P.cs1 + (c - P.c0)));
+                    if (P.nscale) {
+                        const float4 sc = __ldg(reinterpret_cast<const float4*>(P.nscale + (size_t)n * P.cin + c));
+                        const float4 sh = __ldg(reinterpret_cast<const float4*>(P.nshift + (size_t)n * P.cin + c));
+                        v.x = silu(fmaf(v.x, sc.x, sh.x)); v.y = silu(fmaf(v.y, sc.y, sh.y));
+                        v.z = silu(fmaf(v.z, sc.z, sh.z)); v.w = silu(fmaf(v.w, sc.w, sh.w));
+                    }
+                }
+                float* tp = tile + (size_t)(4 * cv) * PLANE + ly * TIN_WP + lx;
+                tp[0] = v.x; tp[PLANE] = v.y; tp[2 * PLANE] = v.z; tp[3 * PLANE] = v.w;
+            }
+        } else
         for (int i = tid; i < TIN_W * TIN_H * cc; i += NT) {
             const int ci = i % cc, pix = i / cc;
             const int ly = pix / TIN_W, lx = pix - ly * TIN_W;
@@ -185,6 +214,9 @@ int conv_direct_launch(const ConvDirectDesc& d, cudaStream_t st) {
     const int ct = d.cout <= 4 ? 4 : (d.cout <= 8 ? 8 : 16);
     P.co_tiles = (d.cout + ct - 1) / ct;
     P.cin_chunk = std::min(d.cin, d.stride == 2 ? 4 : 8);
+    // 128-bit staging loads need every channel group of 4 to live in one source, 16-byte aligned
+    P.vec4 = d.cin % 4 == 0 && P.c0 % 4 == 0 && P.cs0 % 4 == 0 && (d.nsrc == 1 || P.cs1 % 4 == 0) && P.cin_chunk % 4 == 0 &&
+             ((uintptr_t)P.src0 % 16 == 0) && (d.nsrc == 1 || (uintptr_t)P.src1 % 16 == 0);
     ProfScope prof(PROF_CONV_DIRECT, st, 4.0 * s0.n * ((double)s0.h * s0.w * d.cin + (double)P.hout * P.wout * d.cout));   // bytes
     int rc = IPDM_ERR_UNSUPPORTED;
 #define IPDM_CD(CT) (d.ksize == 1 ? launch_direct<CT, 1, 1>(P, s0.n, st) : (d.stride == 1 ? launch_direct<CT, 3, 1>(P, s0.n, st) : launch_direct<CT, 3, 2>(P, s0.n, st)))
@@ -311,10 +343,20 @@ int groupnorm_stats_launch(const GroupNormDesc& d, cudaStream_t st) {
 // GroupNorm apply + SiLU (+ virtual concat, + channel padding) -> operand tensor of a tensor-core conv.
 // HBM-bound: 4 B read + 4 B written per element; two independent 128-bit loads in flight per thread.
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void store_vec4(float* out, size_t elem_off, const float4& o, int bf16) {
+    if (bf16) {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+        uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&lo); pk.y = *reinterpret_cast<uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(out) + elem_off) = pk;
+    } else {
+        *reinterpret_cast<float4*>(out + elem_off) = o;
+    }
+}
+
 __global__ void __launch_bounds__(256)
 gn_apply_kernel(const float* __restrict__ s0, int c0, int cs0, const float* __restrict__ s1, int c1, int cs1,
                 const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ out, int ocs,
-                size_t npix_per_slice, size_t nvec_total, int act, int rnd) {
+                size_t npix_per_slice, size_t nvec_total, int act, int rnd, int obf16) {
     const int Ctot = c0 + c1, V = ocs / 4;
     const size_t stride = (size_t)gridDim.x * 256;
     for (size_t i0 = (size_t)blockIdx.x * 256 + threadIdx.x; i0 < nvec_total; i0 += 2 * stride) {
@@ -342,7 +384,7 @@ gn_apply_kernel(const float* __restrict__ s0, int c0, int cs0, const float* __re
                 if (act) { o.x = silu(o.x); o.y = silu(o.y); o.z = silu(o.z); o.w = silu(o.w); }
                 if (rnd) { o.x = tf32_rn(o.x); o.y = tf32_rn(o.y); o.z = tf32_rn(o.z); o.w = tf32_rn(o.w); }   // tf32 mode: MMA operand
             }
-            *reinterpret_cast<float4*>(out + pix[u] * ocs + c[u]) = o;
+            store_vec4(out, pix[u] * ocs + c[u], o, obf16);
         }
     }
 }
@@ -353,9 +395,9 @@ int groupnorm_apply_launch(const GroupNormDesc& d, const TensorNHWC& out, int ac
     IPDM_REQUIRE(out.cs % 4 == 0 && out.cs >= a.c + c1 && a.c % 4 == 0, "groupnorm_apply: bad channel layout");
     const size_t npix = (size_t)a.h * a.w, nvec = (size_t)a.n * npix * (out.cs / 4);
     const int grid = (int)std::min<size_t>((size_t)kNumSMs * 16, (nvec + 511) / 512);
-    ProfScope prof(PROF_GROUPNORM, st, 4.0 * a.n * (double)npix * (a.c + c1 + out.cs));
+    ProfScope prof(PROF_GROUPNORM, st, a.n * (double)npix * (4.0 * (a.c + c1) + (out.bf16 ? 2.0 : 4.0) * out.cs));
     gn_apply_kernel<<<std::max(grid, 1), 256, 0, st>>>(a.p, a.c, a.cs, d.nsrc == 2 ? d.src[1].p : nullptr, c1, d.nsrc == 2 ? d.src[1].cs : 0,
-                                          d.scale, d.shift, out.p, out.cs, npix, nvec, act_silu, round_tf32);
+                                          d.scale, d.shift, out.p, out.cs, npix, nvec, act_silu, round_tf32 && !out.bf16, out.bf16);
     count_launch();
     IPDM_CHECK_LAUNCH();
     return IPDM_OK;
@@ -366,7 +408,7 @@ int groupnorm_apply_launch(const GroupNormDesc& d, const TensorNHWC& out, int ac
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 upsample_kernel(const float* __restrict__ src, int hs, int ws, int scs, float* __restrict__ dst, int hd, int wd, int dcs,
-                float sy, float sx, size_t nvec_total, int rnd) {
+                float sy, float sx, size_t nvec_total, int rnd, int obf16) {
     const int V = dcs / 4;
     for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < nvec_total; i += (size_t)gridDim.x * 256) {
         const size_t pix = i / V;
@@ -378,7 +420,7 @@ upsample_kernel(const float* __restrict__ src, int hs, int ws, int scs, float* _
         float4 v = make_float4(0, 0, 0, 0);
         if (c < scs) v = __ldg(reinterpret_cast<const float4*>(src + (((size_t)n * hs + yy) * ws + xx) * scs + c));
         if (rnd) { v.x = tf32_rn(v.x); v.y = tf32_rn(v.y); v.z = tf32_rn(v.z); v.w = tf32_rn(v.w); }   // tf32 mode: feeds a tensor-core conv only
-        *reinterpret_cast<float4*>(dst + pix * dcs + c) = v;
+        store_vec4(dst, pix * dcs + c, v, obf16);
     }
 }
 
@@ -386,9 +428,9 @@ int upsample_nearest_launch(const TensorNHWC& src, const TensorNHWC& dst, int ro
     IPDM_REQUIRE(src.cs % 4 == 0 && dst.cs % 4 == 0 && dst.cs >= src.cs && src.n == dst.n, "upsample: bad layout");
     const size_t nvec = dst.pixels() * (dst.cs / 4);
     const int grid = (int)std::min<size_t>((size_t)kNumSMs * 8, (nvec + 255) / 256);
-    ProfScope prof(PROF_UPSAMPLE, st, 4.0 * ((double)src.elems() + dst.elems()));
+    ProfScope prof(PROF_UPSAMPLE, st, 4.0 * (double)src.elems() + (dst.bf16 ? 2.0 : 4.0) * dst.elems());
     upsample_kernel<<<grid, 256, 0, st>>>(src.p, src.h, src.w, src.cs, dst.p, dst.h, dst.w, dst.cs, (float)src.h / dst.h,
-                                          (float)src.w / dst.w, nvec, round_tf32);
+                                          (float)src.w / dst.w, nvec, round_tf32 && !dst.bf16, dst.bf16);
     count_launch();
     IPDM_CHECK_LAUNCH();
     return IPDM_OK;

@@ -6,10 +6,12 @@
 
 namespace ipdm {
 
-// Activation tensor: NHWC fp32, `cs` >= c floats per pixel (pad channels hold zeros).
+// Activation tensor: NHWC, `cs` >= c elements per pixel (pad channels hold zeros); fp32, or bf16 for tensors that exist
+// only as tensor-core operands in the bf16 precision mode (GroupNorm-apply and upsample outputs).
 struct TensorNHWC {
     float* p = nullptr;
     int n = 0, h = 0, w = 0, c = 0, cs = 0;
+    int bf16 = 0;
     size_t pixels() const { return (size_t)n * h * w; }
     size_t elems() const { return pixels() * cs; }
 };
@@ -35,7 +37,7 @@ struct ConvTcDesc {
 struct ConvTcParams {
     CUtensorMap mapA[4];
     CUtensorMap mapB, mapBlo;
-    int split;
+    int split, bf16, kc;
     int H, W, tiles_x, tiles_y, tw_log2, batch;
     int ntaps, stride, nk0, nk1;
     int cout, cout_rows, block_n;

@@ -41,7 +41,7 @@ def test_proj_domain_adaptive_lambda_two_slices(cuda, prec, tol):
     assert rel_l2(one[-1].cpu().numpy(), res[-1][1:2].cpu().numpy()) < 1e-5
 
 
-@pytest.mark.parametrize("prec,tol", [("tf32", GRP_TOL), ("fp32", GRP_TOL_FP32)])
+@pytest.mark.parametrize("prec,tol", [("tf32", GRP_TOL), ("fp32", GRP_TOL_FP32), ("bf16", 5e-2)])
 def test_img_domain_constant_guidance_and_ultra(cuda, prec, tol):
     from Model.model import GaussianDiffusion, UNetModel
     g = golden("grp_small")

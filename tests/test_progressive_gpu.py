@@ -73,8 +73,10 @@ def test_full_slice_matches_reference_golden(cuda, tmp_path, prec):
           f"(final image spans [{g['final'].min():.2f}, {g['final'].max():.2f}] mu with random-init weights)")
     # tf32 mode with RANDOM-INIT weights: the per-forward tf32 error (4e-3 at 2000x912, tests/test_unet_gpu.py) is re-fed
     # 45 times through an untrained, expansive network; DESIGN.md "Parity" reports these numbers and the fp32-mode ones.
-    assert max(perr) < (5e-2 if prec == "tf32" else 5e-3)
-    assert ferr < (0.2 if prec == "tf32" else 2e-2)
+    # Even the fp32 mode cannot beat the reference's OWN reproducibility here: torch-fp32-on-GPU vs torch-fp32-on-CPU differ by
+    # 1.6e-3 / 7.8e-3 / 1.8e-2 / 1.2e-2 on these four iterates (test_reference_own_noise_floor_full_size_proj_stage).
+    assert max(perr) < 5e-2
+    assert ferr < 0.2
 
 
 def test_batch_of_two_slices_equals_single_slices_philox(cuda, tmp_path):
@@ -116,7 +118,7 @@ def test_reference_own_noise_floor_full_size_proj_stage(cuda):
     assert max(err) < 5e-2
 
 
-@pytest.mark.parametrize("prec", ["fp32", "tf32"])
+@pytest.mark.parametrize("prec", ["fp32", "tf32", "bf16"])
 def test_image_stage_512_matches_reference_golden(cuda, tmp_path, prec):
     """Image-domain stage alone at the real size (60 forwards at 512x512, clip, constant guidance, ultra pass) from the
     reference's own sharpened FBP image; golden from the unmodified reference (oracle/make_golden.py img512)."""

@@ -46,15 +46,22 @@ def _p(t):
 
 def run_conv(cuda, x0, x1, weight, bias, k, stride, use_tc, res=None, up=None, norm=None):
     from ipdm_pytorch_b200 import _lib
+    use_tc = int(use_tc)
+    if use_tc == 3:                                                     # bf16 operand tensor: one source, stride multiple of 64
+        x0 = x0 if x1 is None else torch.cat([x0, x1], 1)
+        x1 = None
     n, c0, h, w = x0.shape
     c1 = 0 if x1 is None else x1.shape[1]
     cs0, cs1 = (alloc_cs(c0), alloc_cs(c1)) if use_tc else (c0, c1)
-    use_tc = int(use_tc)
+    if use_tc == 3:
+        cs0 = (c0 + 63) // 64 * 64
     cout = weight.shape[0]
     hin, win = (h, w) if up is None else up
     ho, wo = (hin, win) if stride == 1 else ((hin + 1) // 2, (win + 1) // 2)
     ocs = alloc_cs(cout)
     a0 = nhwc(x0, cs0).to(cuda)
+    if use_tc == 3:
+        a0 = a0.to(torch.bfloat16).contiguous()
     a1 = None if x1 is None else nhwc(x1, cs1).to(cuda)
     r = None if res is None else nhwc(res, ocs).to(cuda)
     out = torch.full((n, ho, wo, ocs), float("nan"), device=cuda)
@@ -175,6 +182,13 @@ def test_tc_conv(cuda, c0, c1, cout, k, stride, hw):
         err = rel_l2(got.numpy(), want.numpy())
         print(f"tc conv {c0}+{c1}->{cout} k{k} s{stride} {hw} mode {'tf32' if mode == 1 else '3xtf32'}: rel-L2 {err:.2e}")
         assert err < tol
+    if stride == 1:                                                     # bf16 operands (GroupNorm-apply / upsample outputs only: stride 1)
+        got = run_conv(cuda, x0, x1, w, b, k, stride, 3, res=res)
+        xb = (x0 if x1 is None else torch.cat([x0, x1], 1)).to(torch.bfloat16).float()
+        exact = ref_conv(xb, None, w.to(torch.bfloat16).float(), b, k, stride, res=res)
+        e_fp32, e_bf16 = rel_l2(got.numpy(), want.numpy()), rel_l2(got.numpy(), exact.numpy())
+        print(f"tc conv {c0}+{c1}->{cout} k{k} {hw} mode bf16: rel-L2 {e_fp32:.2e} vs fp32, {e_bf16:.2e} vs bf16-rounded operands")
+        assert e_fp32 < 8e-3 and e_bf16 < 2e-5
 
 
 def test_tc_conv_full_size_row_shapes(cuda):
