@@ -281,7 +281,8 @@ struct BuildVisitor : ArchVisitor {
     void attn(int c, int) override {
         net->attn.emplace_back(); AttnW& a = net->attn.back(); a.C = c;
         fail(read_gn(net, r, a.norm, c)); read_conv(r, a.qkv, c, 3 * c, 1, false); read_conv(r, a.proj, c, c, 1, true);
-        fail(pack_conv(net, a.qkv, c, 0, false)); fail(pack_conv(net, a.proj, c, 0, false));
+        fail(pack_conv(net, a.qkv, c, 0, false));        // reads the GroupNorm-apply output (operand tensor)
+        fail(pack_conv(net, a.proj, c, 0, true));         // reads the attention output (fp32 residual-stream layout)
         if (!a.qkv.tc || !a.proj.tc || c % (64 * net->heads) != 0 || c / net->heads != 64) {
             set_error("attention block with %d channels / %d heads is not supported (head_dim must be 64)", c, net->heads);
             fail(IPDM_ERR_UNSUPPORTED);
