@@ -70,6 +70,74 @@ constexpr int TC_THREADS = 128;
 constexpr int TC_KC = 32;                 // fp32 elements per 128-byte operand row (bf16 operands: 64, P.kc)
 constexpr int TC_A_BYTES = 128 * 128;
 
+// ---------------- epilogue of one 128-pixel sub-tile: TMEM -> registers -> (+bias, +residual) -> NHWC global ----------------
+// Row m of the accumulator (== TMEM lane) is pixel (y0 + (m >> tw_log2), x0 + (m & (2^tw_log2 - 1))); columns >= tw_valid of a
+// tile row are the padding columns of the halo kernel and are dropped.
+template <int BLOCK_N, bool SPLIT>
+__device__ __forceinline__ void tc_epilogue(const ConvTcParams& P, uint32_t tmem_acc, int warp, int lane, int b, int x0, int y0, int n0,
+                                            int tw_valid) {
+    const int m = warp * 32 + lane;
+    const int TW = 1 << P.tw_log2;
+    const float* bias = P.bias ? P.bias + (P.t_dev ? (size_t)(*P.t_dev) * P.bias_t_stride : 0) : nullptr;
+    constexpr int CHUNK = BLOCK_N < 32 ? 16 : 32;
+    const int py = y0 + (m >> P.tw_log2), px = x0 + (m & (TW - 1));
+    const bool valid = py < P.H && px < P.W && (m & (TW - 1)) < tw_valid;
+    const size_t pix = ((size_t)b * P.H + py) * P.W + px;
+#pragma unroll 1
+    for (int cc = 0; cc < BLOCK_N; cc += CHUNK) {
+        __syncwarp();
+        uint32_t r[32];
+        const uint32_t taddr = tmem_acc + ((uint32_t)(warp * 32) << 16) + (uint32_t)cc;
+        if constexpr (CHUNK == 32) tc::tmem_ld32(taddr, r);
+        else { uint32_t r16[16]; tc::tmem_ld16(taddr, r16);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) r[i] = r16[i]; }
+        tc::tmem_ld_wait();
+        const int n = n0 + cc;
+        if (!valid || n >= P.cout) continue;
+        float v[CHUNK];
+#pragma unroll
+        for (int i = 0; i < CHUNK; ++i) v[i] = __uint_as_float(r[i]) + (bias ? __ldg(bias + n + i) : 0.f);
+        if (P.res) {
+            const float4* rp = reinterpret_cast<const float4*>(P.res + pix * P.res_cs + n);
+#pragma unroll
+            for (int i = 0; i < CHUNK / 4; ++i) { const float4 t = __ldg(rp + i); v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w; }
+        }
+        if (P.qkv_mode && !SPLIT) {                  // q, k, v are operands of the attention MMAs: round to nearest tf32
+#pragma unroll
+            for (int i = 0; i < CHUNK; ++i) v[i] = tf32_rn(v[i]);
+        }
+        float lo[CHUNK];
+        if (P.qkv_mode && SPLIT) {                   // fp32 mode: hand q, k, v to the attention kernel as tf32 hi / lo pairs
+#pragma unroll
+            for (int i = 0; i < CHUNK; ++i) { const float h = tf32_rn(v[i]); lo[i] = tf32_rn(v[i] - h); v[i] = h; }
+        }
+        if (P.qkv_mode && ((n % (3 * P.head_dim)) >= 2 * P.head_dim)) {
+            // V of one head: write transposed, [b][head][d][t_pad] (token contiguous), so P.V^T is K-major for attention
+            const int head = n / (3 * P.head_dim), d0 = n % (3 * P.head_dim) - 2 * P.head_dim;
+            const size_t tok = (size_t)py * P.W + px;
+            const size_t vo = (((size_t)b * P.heads + head) * P.head_dim + d0) * P.t_pad + tok;
+#pragma unroll
+            for (int i = 0; i < CHUNK; ++i) P.vt[vo + (size_t)i * P.t_pad] = v[i];
+            if (SPLIT) {
+#pragma unroll
+                for (int i = 0; i < CHUNK; ++i) P.vt_lo[vo + (size_t)i * P.t_pad] = lo[i];
+            }
+        } else {
+            if (P.qkv_mode && SPLIT) {
+                float4* lp = reinterpret_cast<float4*>(P.out_lo + pix * P.out_cs + n);
+#pragma unroll
+                for (int i = 0; i < CHUNK / 4; ++i) lp[i] = make_float4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+            }
+            float4* op = reinterpret_cast<float4*>(P.out + pix * P.out_cs + n);
+#pragma unroll
+            for (int i = 0; i < CHUNK / 4; ++i) op[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        }
+    }
+    if (valid && !P.qkv_mode && blockIdx.y == gridDim.y - 1)     // keep the channel padding of the output at zero
+        for (int c = P.cout; c < P.out_cs; ++c) P.out[pix * P.out_cs + c] = 0.f;
+}
+
 // SPLIT = fp32-accurate "3xTF32" mode: every fp32 operand x is used as x_hi + x_lo (x_hi = rn_tf32(x), x_lo =
 // rn_tf32(x - x_hi)) and D += A_hi B_hi + A_hi B_lo + A_lo B_hi.  Weights are split on the host (two packed arrays, two
 // TMA loads); the activation tile is split in shared memory by warps 2-3 right after the TMA lands (the split is
@@ -200,68 +268,135 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams P) {
         }
     }
 
-    // ---------------- epilogue: TMEM -> registers -> (+bias, +residual) -> NHWC global ----------------
+    // ---------------- epilogue: all four warps ----------------
     tc::mbar_wait(accum, 0);
     tc::tc_fence_after();
-    const int m = warp * 32 + lane;                  // accumulator row == TMEM lane == pixel inside the tile
-    const int py = y0 + (m >> P.tw_log2), px = x0 + (m & (TW - 1));
-    const bool valid = py < P.H && px < P.W;
-    const size_t pix = ((size_t)b * P.H + py) * P.W + px;
-    const float* bias = P.bias ? P.bias + (P.t_dev ? (size_t)(*P.t_dev) * P.bias_t_stride : 0) : nullptr;
-    constexpr int CHUNK = BLOCK_N < 32 ? 16 : 32;
-#pragma unroll 1
-    for (int cc = 0; cc < BLOCK_N; cc += CHUNK) {
-        __syncwarp();
-        uint32_t r[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)cc;
-        if constexpr (CHUNK == 32) tc::tmem_ld32(taddr, r);
-        else { uint32_t r16[16]; tc::tmem_ld16(taddr, r16);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) r[i] = r16[i]; }
-        tc::tmem_ld_wait();
-        const int n = n0 + cc;
-        if (!valid || n >= P.cout) continue;
-        float v[CHUNK];
-#pragma unroll
-        for (int i = 0; i < CHUNK; ++i) v[i] = __uint_as_float(r[i]) + (bias ? __ldg(bias + n + i) : 0.f);
-        if (P.res) {
-            const float4* rp = reinterpret_cast<const float4*>(P.res + pix * P.res_cs + n);
-#pragma unroll
-            for (int i = 0; i < CHUNK / 4; ++i) { const float4 t = __ldg(rp + i); v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w; }
-        }
-        if (P.qkv_mode && !SPLIT) {                  // q, k, v are operands of the attention MMAs: round to nearest tf32
-#pragma unroll
-            for (int i = 0; i < CHUNK; ++i) v[i] = tf32_rn(v[i]);
-        }
-        float lo[CHUNK];
-        if (P.qkv_mode && SPLIT) {                   // fp32 mode: hand q, k, v to the attention kernel as tf32 hi / lo pairs
-#pragma unroll
-            for (int i = 0; i < CHUNK; ++i) { const float h = tf32_rn(v[i]); lo[i] = tf32_rn(v[i] - h); v[i] = h; }
-        }
-        if (P.qkv_mode && ((n % (3 * P.head_dim)) >= 2 * P.head_dim)) {
-            // V of one head: write transposed, [b][head][d][t_pad] (token contiguous), so P.V^T is K-major for attention
-            const int head = n / (3 * P.head_dim), d0 = n % (3 * P.head_dim) - 2 * P.head_dim;
-            const size_t tok = (size_t)py * P.W + px;
-            const size_t vo = (((size_t)b * P.heads + head) * P.head_dim + d0) * P.t_pad + tok;
-#pragma unroll
-            for (int i = 0; i < CHUNK; ++i) P.vt[vo + (size_t)i * P.t_pad] = v[i];
-            if (SPLIT) {
-#pragma unroll
-                for (int i = 0; i < CHUNK; ++i) P.vt_lo[vo + (size_t)i * P.t_pad] = lo[i];
-            }
-        } else {
-            if (P.qkv_mode && SPLIT) {
-                float4* lp = reinterpret_cast<float4*>(P.out_lo + pix * P.out_cs + n);
-#pragma unroll
-                for (int i = 0; i < CHUNK / 4; ++i) lp[i] = make_float4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
-            }
-            float4* op = reinterpret_cast<float4*>(P.out + pix * P.out_cs + n);
-#pragma unroll
-            for (int i = 0; i < CHUNK / 4; ++i) op[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-        }
+    tc_epilogue<BLOCK_N, SPLIT>(P, tmem_base, warp, lane, b, x0, y0, n0, TW);
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tc::tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+
+// ================================================================================================
+// Halo-reuse variant for stride-1 3x3 convolutions (the bulk of the FLOPs).
+//
+// The generic kernel above re-fetches a shifted 128-pixel activation tile for every tap: per 32-channel chunk it streams
+// 9 x (16 KB + 16 KB) through shared memory and is bound by the L2 -> SM operand stream (profiles/r01_*: 1440 cycles per
+// 256-cycle stage).  Here ONE halo tile [(8+2) rows x 32 pixels x 128 B] is loaded per chunk (one 4-D TMA box, OOB zero
+// fill = padding) and all nine taps read it in place: a K-major SWIZZLE_128B UMMA operand may start at ANY 128-byte row of
+// a TMA-written tile (the swizzle is a function of the absolute shared-memory address; verified on B200 by
+// tools/experiments/shifted_desc.cu), so tap (dy,dx) of output sub-tile mt is simply the descriptor at row
+// (4*mt + dy)*32 + dx.  Tile rows have a pitch of 32 pixels of which 30 are outputs (the two extra columns are computed and
+// dropped), a CTA owns 8 x 30 outputs = two 128-row MMAs that share every weight tile.
+// Operand bytes per chunk: 40 KB halo + 9 x 16 KB weights for 4608 MMA cycles = 40 B/cycle (generic kernel: 125 B/cycle).
+// ================================================================================================
+constexpr int HALO_RP = 32, HALO_TWV = 30, HALO_TH = 8;
+constexpr int HALO_A_BYTES = (HALO_TH + 2) * HALO_RP * 128;          // 40 KB TMA box
+constexpr int HALO_A_STRIDE = HALO_A_BYTES + 1024;                   // + the 2 pixels the last tap over-reads (garbage rows only)
+
+template <int BLOCK_N, int NB>
+struct HaloSmem {
+    static constexpr int B_BYTES = BLOCK_N * 128;
+    static constexpr int OFF_B = 2 * HALO_A_STRIDE;
+    static constexpr int BAR_OFF = OFF_B + NB * B_BYTES;
+    static constexpr int TOTAL = BAR_OFF + (2 * NB + 4 + 1) * 8 + 16 + 1024;
+};
+
+template <int BLOCK_N, int NB>
+__global__ void __launch_bounds__(TC_THREADS)
+conv_halo_kernel(const __grid_constant__ ConvTcParams P) {
+    using S = HaloSmem<BLOCK_N, NB>;
+    constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* a_full = (uint64_t*)(smem + S::BAR_OFF);
+    uint64_t* a_empty = a_full + 2;
+    uint64_t* b_full = a_empty + 2;
+    uint64_t* b_empty = b_full + NB;
+    uint64_t* accum = b_empty + NB;
+    uint32_t* tmem_slot = (uint32_t*)(accum + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_per_img = P.tiles_x * P.tiles_y;
+    const int b = blockIdx.x / tiles_per_img;
+    const int tr = blockIdx.x - b * tiles_per_img;
+    const int tyi = tr / P.tiles_x, txi = tr - tyi * P.tiles_x;
+    const int x0 = txi * HALO_TWV, y0 = tyi * HALO_TH;
+    const int n0 = blockIdx.y * BLOCK_N;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; ++i) { tc::mbar_init(&a_full[i], 1); tc::mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < NB; ++i) { tc::mbar_init(&b_full[i], 1); tc::mbar_init(&b_empty[i], 1); }
+        tc::mbar_init(accum, 1);
+        tc::fence_barrier_init();
     }
-    if (valid && !P.qkv_mode && blockIdx.y == gridDim.y - 1)     // keep the channel padding of the output at zero
-        for (int c = P.cout; c < P.out_cs; ++c) P.out[pix * P.out_cs + c] = 0.f;
+    if (warp == 2) tc::tmem_alloc(tmem_slot, TMEM_COLS);
+    if (warp == 0 && lane == 0) { tc::prefetch_tmap(&P.mapA[0]); tc::prefetch_tmap(&P.mapB); }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int nk = P.nk0 + P.nk1;
+
+    if (warp == 0) {
+        if (tc::elect_one()) {
+            int j = 0;
+            for (int kc = 0; kc < nk; ++kc) {
+                const int sa = kc & 1;
+                tc::mbar_wait(&a_empty[sa], (((uint32_t)kc >> 1) & 1u) ^ 1u);
+                tc::mbar_expect_tx(&a_full[sa], HALO_A_BYTES);
+                const bool first = kc < P.nk0;
+                tc::tma_load_4d(smem + sa * HALO_A_STRIDE, first ? &P.mapA[0] : &P.mapA[1], &a_full[sa], (first ? kc : kc - P.nk0) * P.kc,
+                                x0 - 1, y0 - 1, b);
+                for (int tap = 0; tap < 9; ++tap, ++j) {
+                    const int sb = j % NB;
+                    tc::mbar_wait(&b_empty[sb], ((uint32_t)(j / NB) & 1u) ^ 1u);
+                    tc::mbar_expect_tx(&b_full[sb], S::B_BYTES);
+                    tc::tma_load_2d(smem + S::OFF_B + sb * S::B_BYTES, &P.mapB, &b_full[sb], kc * P.kc, tap * P.cout_rows + n0);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (tc::elect_one()) {
+            const bool bf16 = P.bf16;
+            const uint32_t idesc = tc::make_idesc(bf16 ? tc::FMT_BF16 : tc::FMT_TF32, 128, BLOCK_N);
+            int j = 0;
+            for (int kc = 0; kc < nk; ++kc) {
+                const int sa = kc & 1;
+                tc::mbar_wait(&a_full[sa], ((uint32_t)kc >> 1) & 1u);
+                const uint32_t a_base = tc::smem_u32(smem + sa * HALO_A_STRIDE);
+                for (int tap = 0; tap < 9; ++tap, ++j) {
+                    const int sb = j % NB;
+                    tc::mbar_wait(&b_full[sb], (uint32_t)(j / NB) & 1u);
+                    tc::tc_fence_after();
+                    const int dy = tap / 3, dx = tap - dy * 3;
+                    const uint64_t bdesc = tc::smem_desc_k_sw128(tc::smem_u32(smem + S::OFF_B + sb * S::B_BYTES));
+#pragma unroll
+                    for (int mt = 0; mt < 2; ++mt) {
+                        const uint64_t adesc = tc::smem_desc_k_sw128(a_base + (uint32_t)(((4 * mt + dy) * HALO_RP + dx) * 128));
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint32_t acc = (uint32_t)((kc | tap | k) != 0);
+                            if (bf16) tc::umma_f16(tmem_base + mt * BLOCK_N, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, acc);
+                            else tc::umma_tf32(tmem_base + mt * BLOCK_N, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, acc);
+                        }
+                    }
+                    tc::umma_commit(&b_empty[sb]);
+                }
+                tc::umma_commit(&a_empty[sa]);
+            }
+            tc::umma_commit(accum);
+        }
+        __syncwarp();
+    }
+
+    tc::mbar_wait(accum, 0);
+    tc::tc_fence_after();
+#pragma unroll 1
+    for (int mt = 0; mt < 2; ++mt)
+        tc_epilogue<BLOCK_N, false>(P, tmem_base + mt * BLOCK_N, warp, lane, b, x0, y0 + 4 * mt, n0, HALO_TWV);
     tc::tc_fence_before();
     __syncthreads();
     if (warp == 2) tc::tmem_dealloc(tmem_base, TMEM_COLS);
@@ -288,10 +423,14 @@ int conv_tc_prepare(ConvTcParams& P, const ConvTcDesc& d) {
     const int Hin = d.src[0].h, Win = d.src[0].w;
     P.H = d.stride == 1 ? Hin : (Hin + 1) / 2;      // k=3, pad=1, stride 2 -> floor((H-1)/2)+1
     P.W = d.stride == 1 ? Win : (Win + 1) / 2;
-    P.tw_log2 = pick_tw_log2(P.H, P.W);
-    const int TW = 1 << P.tw_log2, TH = 128 >> P.tw_log2;
-    P.tiles_x = ceil_div(P.W, TW); P.tiles_y = ceil_div(P.H, TH);
     P.batch = d.src[0].n;
+    // halo-reuse kernel: stride-1 3x3, not the 3xTF32 split path, and enough 8x30 tiles to give every SM work
+    P.halo = d.stride == 1 && d.ntaps == 9 && !d.w_packed_lo && !d.qkv_mode && !d.force_generic &&
+             (long long)ceil_div(P.W, HALO_TWV) * ceil_div(P.H, HALO_TH) * P.batch >= kNumSMs / 2;
+    P.tw_log2 = P.halo ? 5 : pick_tw_log2(P.H, P.W);
+    const int TW = P.halo ? HALO_RP : 1 << P.tw_log2, TH = P.halo ? HALO_TH + 2 : 128 >> P.tw_log2;     // TMA box extent
+    P.tiles_x = P.halo ? ceil_div(P.W, HALO_TWV) : ceil_div(P.W, TW);
+    P.tiles_y = P.halo ? ceil_div(P.H, HALO_TH) : ceil_div(P.H, TH);
     P.ntaps = d.ntaps; P.stride = d.stride;
     P.cout = d.cout; P.block_n = d.cout >= 128 ? 128 : (d.cout >= 64 ? 64 : 16);
     IPDM_REQUIRE(d.cout % P.block_n == 0, "conv_tc: C_out %d not a multiple of the N tile %d", d.cout, P.block_n);
@@ -362,8 +501,31 @@ static int launch_tc(const ConvTcParams& P, cudaStream_t st) {
     return IPDM_OK;
 }
 
+template <int BN, int NB>
+static int launch_halo(const ConvTcParams& P, cudaStream_t st) {
+    static bool configured = false;
+    constexpr int smem = HaloSmem<BN, NB>::TOTAL;
+    static_assert(smem <= 227 * 1024, "halo ring does not fit in shared memory");
+    if (!configured) {
+        IPDM_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<BN, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    dim3 grid(P.tiles_x * P.tiles_y * P.batch, P.cout / BN);
+    conv_halo_kernel<BN, NB><<<grid, TC_THREADS, smem, st>>>(P);
+    count_launch();
+    IPDM_CHECK_LAUNCH();
+    return IPDM_OK;
+}
+
 int conv_tc_launch(const ConvTcParams& P, cudaStream_t st) {
     ProfScope prof(PROF_CONV_TC, st, conv_tc_flops(P));      // padded-K FLOPs actually issued to the tensor pipe
+    if (P.halo) {
+        switch (P.block_n) {
+            case 128: return launch_halo<128, 6>(P, st);
+            case 64: return launch_halo<64, 8>(P, st);
+            case 16: return launch_halo<16, 8>(P, st);
+        }
+    }
     if (P.split) {
         switch (P.block_n) {
             case 128: return launch_tc<128, 3, true>(P, st);

@@ -191,6 +191,23 @@ def test_tc_conv(cuda, c0, c1, cout, k, stride, hw):
         assert e_fp32 < 8e-3 and e_bf16 < 2e-5
 
 
+@pytest.mark.parametrize("c0,c1,cout,k,stride,hw", [(128, 0, 128, 3, 1, (176, 228)), (64, 0, 64, 3, 1, (256, 160)), (128, 16, 16, 3, 1, (260, 300)),
+                                                  (128, 0, 128, 3, 2, (353, 457))])
+def test_tc_conv_halo_reuse_variant(cuda, c0, c1, cout, k, stride, hw):
+    """Stride-1 3x3 layers with >= 74 tiles of 8x30 outputs take the halo-reuse kernel (nine taps read one staged halo tile
+    through shifted UMMA descriptors); ragged in both directions, concat, N = 16/64/128, tf32 and bf16 operands."""
+    x0 = rnd(2, c0, *hw, seed=1)
+    x1 = rnd(2, c1, *hw, seed=2) if c1 else None
+    w = rnd(cout, c0 + c1, k, k, seed=3, scale=(1.0 / ((c0 + c1) * k * k)) ** 0.5)
+    b = rnd(cout, seed=4)
+    want = ref_conv(x0, x1, w, b, k, stride)
+    got = run_conv(cuda, x0, x1, w, b, k, stride, 1)
+    assert rel_l2(got.numpy(), want.numpy()) < TF32_TOL
+    if stride == 1:
+        got = run_conv(cuda, x0, x1, w, b, k, stride, 3)
+        assert rel_l2(got.numpy(), want.numpy()) < 8e-3
+
+
 def test_tc_conv_full_size_row_shapes(cuda):
     """The proj net's real row widths (228, 114, 57, 29) at reduced height, batch 1."""
     for hw, c in (((24, 228), 128), ((20, 114), 128), ((16, 57), 256), ((9, 29), 256)):
