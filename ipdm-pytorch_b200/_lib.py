@@ -73,6 +73,7 @@ _SIGNATURES = {
     "ipdm_debug_conv": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                        vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, vp, ctypes.c_int,
                                        vp, ctypes.c_int, ctypes.c_int, vp]),
+    "ipdm_debug_conv_time": (ctypes.c_int, [ctypes.c_int] * 12 + [c_float_p, c_double_p]),
     "ipdm_debug_groupnorm": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                             ctypes.c_int, vp, vp, ctypes.c_int, vp, vp, vp, ctypes.c_int, vp]),
     "ipdm_debug_attention": (ctypes.c_int, [vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp]),

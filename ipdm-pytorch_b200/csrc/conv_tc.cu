@@ -21,6 +21,8 @@
 #include "tc.cuh"
 #include "unet_ops.cuh"
 
+#include <algorithm>
+#include <cstdlib>
 #include <mutex>
 
 namespace ipdm {
@@ -70,38 +72,63 @@ constexpr int TC_THREADS = 128;
 constexpr int TC_KC = 32;                 // fp32 elements per 128-byte operand row (bf16 operands: 64, P.kc)
 constexpr int TC_A_BYTES = 128 * 128;
 
+// bias (+ time-embedding row) of this CTA's output channels -> shared memory, once per CTA
+template <int BLOCK_N>
+__device__ __forceinline__ void stage_bias(const ConvTcParams& P, float* sbias, int n0) {
+    const float* bias = P.bias ? P.bias + (P.t_dev ? (size_t)(*P.t_dev) * P.bias_t_stride : 0) : nullptr;
+    for (int i = threadIdx.x; i < BLOCK_N; i += blockDim.x) sbias[i] = (bias && n0 + i < P.cout) ? __ldg(bias + n0 + i) : 0.f;
+}
+
 // ---------------- epilogue of one 128-pixel sub-tile: TMEM -> registers -> (+bias, +residual) -> NHWC global ----------------
 // Row m of the accumulator (== TMEM lane) is pixel (y0 + (m >> tw_log2), x0 + (m & (2^tw_log2 - 1))); columns >= tw_valid of a
 // tile row are the padding columns of the halo kernel and are dropped.
 template <int BLOCK_N, bool SPLIT>
-__device__ __forceinline__ void tc_epilogue(const ConvTcParams& P, uint32_t tmem_acc, int warp, int lane, int b, int x0, int y0, int n0,
-                                            int tw_valid) {
-    const int m = warp * 32 + lane;
+__device__ __forceinline__ void tc_epilogue(const ConvTcParams& P, uint32_t tmem_acc, int quarter, int lane, int b, int x0, int y0, int n0,
+                                            int tw_valid, const float* sbias) {
+    const int m = quarter * 32 + lane;               // accumulator row == TMEM lane (a warp may only touch its own lane quarter)
     const int TW = 1 << P.tw_log2;
-    const float* bias = P.bias ? P.bias + (P.t_dev ? (size_t)(*P.t_dev) * P.bias_t_stride : 0) : nullptr;
     constexpr int CHUNK = BLOCK_N < 32 ? 16 : 32;
     const int py = y0 + (m >> P.tw_log2), px = x0 + (m & (TW - 1));
     const bool valid = py < P.H && px < P.W && (m & (TW - 1)) < tw_valid;
     const size_t pix = ((size_t)b * P.H + py) * P.W + px;
+    const bool has_res = valid && P.res != nullptr;
+    // the residual of chunk c+1 is requested before chunk c is processed, so its latency hides behind the TMEM load + stores
+    float4 rnext[CHUNK / 4];
+    if (has_res) {
+        const float4* rp = reinterpret_cast<const float4*>(P.res + pix * P.res_cs + n0);
+#pragma unroll
+        for (int i = 0; i < CHUNK / 4; ++i) rnext[i] = __ldg(rp + i);
+    }
 #pragma unroll 1
     for (int cc = 0; cc < BLOCK_N; cc += CHUNK) {
         __syncwarp();
         uint32_t r[32];
-        const uint32_t taddr = tmem_acc + ((uint32_t)(warp * 32) << 16) + (uint32_t)cc;
+        const uint32_t taddr = tmem_acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)cc;
         if constexpr (CHUNK == 32) tc::tmem_ld32(taddr, r);
         else { uint32_t r16[16]; tc::tmem_ld16(taddr, r16);
 #pragma unroll
             for (int i = 0; i < 16; ++i) r[i] = r16[i]; }
+        float4 rcur[CHUNK / 4];
+#pragma unroll
+        for (int i = 0; i < CHUNK / 4; ++i) rcur[i] = rnext[i];
+        if (has_res && cc + CHUNK < BLOCK_N && n0 + cc + CHUNK < P.cout) {
+            const float4* rp = reinterpret_cast<const float4*>(P.res + pix * P.res_cs + n0 + cc + CHUNK);
+#pragma unroll
+            for (int i = 0; i < CHUNK / 4; ++i) rnext[i] = __ldg(rp + i);
+        }
         tc::tmem_ld_wait();
         const int n = n0 + cc;
         if (!valid || n >= P.cout) continue;
         float v[CHUNK];
 #pragma unroll
-        for (int i = 0; i < CHUNK; ++i) v[i] = __uint_as_float(r[i]) + (bias ? __ldg(bias + n + i) : 0.f);
-        if (P.res) {
-            const float4* rp = reinterpret_cast<const float4*>(P.res + pix * P.res_cs + n);
+        for (int i = 0; i < CHUNK / 4; ++i) {
+            const float4 bq = *reinterpret_cast<const float4*>(sbias + cc + 4 * i);
+            v[4 * i] = __uint_as_float(r[4 * i]) + bq.x; v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + bq.y;
+            v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + bq.z; v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + bq.w;
+        }
+        if (has_res) {
 #pragma unroll
-            for (int i = 0; i < CHUNK / 4; ++i) { const float4 t = __ldg(rp + i); v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w; }
+            for (int i = 0; i < CHUNK / 4; ++i) { v[4 * i] += rcur[i].x; v[4 * i + 1] += rcur[i].y; v[4 * i + 2] += rcur[i].z; v[4 * i + 3] += rcur[i].w; }
         }
         if (P.qkv_mode && !SPLIT) {                  // q, k, v are operands of the attention MMAs: round to nearest tf32
 #pragma unroll
@@ -138,6 +165,74 @@ __device__ __forceinline__ void tc_epilogue(const ConvTcParams& P, uint32_t tmem
         for (int c = P.cout; c < P.out_cs; ++c) P.out[pix * P.out_cs + c] = 0.f;
 }
 
+
+// ---------------- coalesced epilogue (persistent kernel) ----------------
+// tcgen05.ld hands every lane ONE pixel x 32 channels; writing that straight to NHWC makes each warp store touch 32
+// different 128-byte lines with 16 bytes each (measured: ~8.7 us per 128x128 tile, the bottleneck of bf16 layers).
+// Here each warp transposes its 32 x 32 block through a private shared-memory tile (pitch 36 floats, 128-bit accesses)
+// so that 8 lanes cover one pixel's 128 contiguous bytes: every global load (residual) and store is a full line.
+constexpr int EPI_PITCH = 36;
+constexpr int EPI_WARP_FLOATS = 32 * EPI_PITCH;
+template <int BLOCK_N>
+__device__ __forceinline__ void tc_epilogue_coalesced(const ConvTcParams& P, uint32_t tmem_acc, int quarter, int lane, int b, int x0, int y0,
+                                                      int n0, const float* sbias, float* stile) {
+    const int TW = 1 << P.tw_log2;
+    constexpr int CHUNK = BLOCK_N < 32 ? 16 : 32;
+    constexpr int LPP = CHUNK / 4;                    // lanes per pixel row segment (8 for 32 channels, 4 for 16)
+    constexpr int PPI = 32 / LPP;                     // pixels per warp instruction
+    const int c4 = (lane % LPP) * 4, psub = lane / LPP;
+    // per-row coordinates of the 32/PPI rows this lane touches in every chunk
+    constexpr int NJ = 32 / PPI;
+    size_t pixv[NJ]; bool okv[NJ];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+        const int m = quarter * 32 + j * PPI + psub;
+        const int py = y0 + (m >> P.tw_log2), px = x0 + (m & (TW - 1));
+        okv[j] = py < P.H && px < P.W;
+        pixv[j] = ((size_t)b * P.H + py) * P.W + px;
+    }
+#pragma unroll 1
+    for (int cc = 0; cc < BLOCK_N; cc += CHUNK) {
+        const int n = n0 + cc + c4;
+        const bool nok = n < P.cout;
+        uint32_t r[32];
+        const uint32_t taddr = tmem_acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)cc;
+        if constexpr (CHUNK == 32) tc::tmem_ld32(taddr, r);
+        else { uint32_t r16[16]; tc::tmem_ld16(taddr, r16);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) r[i] = r16[i]; }
+        float4 rres[NJ];                               // all residual lines of the chunk are requested before anything waits
+#pragma unroll
+        for (int j = 0; j < NJ; ++j)
+            rres[j] = (P.res && okv[j] && nok) ? __ldg(reinterpret_cast<const float4*>(P.res + pixv[j] * P.res_cs + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        tc::tmem_ld_wait();
+        __syncwarp();                                  // previous chunk's readers are done with the tile
+        float4* row = reinterpret_cast<float4*>(stile + lane * EPI_PITCH);
+#pragma unroll
+        for (int i = 0; i < CHUNK / 4; ++i)
+            row[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+        __syncwarp();
+        const float4 bq = *reinterpret_cast<const float4*>(sbias + cc + c4);
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            if (okv[j] && nok) {
+                float4 v = *reinterpret_cast<const float4*>(stile + (j * PPI + psub) * EPI_PITCH + c4);
+                v.x += bq.x + rres[j].x; v.y += bq.y + rres[j].y; v.z += bq.z + rres[j].z; v.w += bq.w + rres[j].w;
+                *reinterpret_cast<float4*>(P.out + pixv[j] * P.out_cs + n) = v;
+            }
+        }
+    }
+    // keep the channel padding of the output at zero (layers with C_out < channel stride: 16 -> 32)
+    if (P.out_cs > P.cout && n0 + BLOCK_N >= P.cout) {
+        const int m = quarter * 32 + lane;
+        const int py = y0 + (m >> P.tw_log2), px = x0 + (m & (TW - 1));
+        if (py < P.H && px < P.W) {
+            const size_t pix = ((size_t)b * P.H + py) * P.W + px;
+            for (int c = P.cout; c < P.out_cs; ++c) P.out[pix * P.out_cs + c] = 0.f;
+        }
+    }
+}
+
 // SPLIT = fp32-accurate "3xTF32" mode: every fp32 operand x is used as x_hi + x_lo (x_hi = rn_tf32(x), x_lo =
 // rn_tf32(x - x_hi)) and D += A_hi B_hi + A_hi B_lo + A_lo B_hi.  Weights are split on the host (two packed arrays, two
 // TMA loads); the activation tile is split in shared memory by warps 2-3 right after the TMA lands (the split is
@@ -151,7 +246,9 @@ struct TcSmem {
     static constexpr int STAGE_BYTES = OFF_B + (SPLIT ? 2 : 1) * B_BYTES;
     static constexpr int TX_BYTES = TC_A_BYTES + (SPLIT ? 2 : 1) * B_BYTES;
     static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
-    static constexpr int TOTAL = BAR_OFF + (3 * STAGES + 1) * 8 + 16 + 1024;   // + alignment slack
+    static constexpr int BIAS_OFF = BAR_OFF + 256;
+    static constexpr int TOTAL = BIAS_OFF + BLOCK_N * 4 + 16 + 1024;           // + alignment slack
+    static_assert((3 * STAGES + 1) * 8 + 16 <= 256, "barrier block");
 };
 constexpr int TC_SPLIT_THREADS = 64;
 
@@ -167,6 +264,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams P) {
     uint64_t* ready = empty + STAGES;
     uint64_t* accum = ready + STAGES;
     uint32_t* tmem_slot = (uint32_t*)(accum + 1);
+    float* sbias = (float*)(smem + S::BIAS_OFF);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_per_img = P.tiles_x * P.tiles_y;
@@ -176,6 +274,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams P) {
     const int TW = 1 << P.tw_log2, TH = 128 >> P.tw_log2;
     const int x0 = txi * TW, y0 = tyi * TH;
     const int n0 = blockIdx.y * BLOCK_N;
+    stage_bias<BLOCK_N>(P, sbias, n0);
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < STAGES; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); tc::mbar_init(&ready[i], TC_SPLIT_THREADS); }
@@ -271,7 +370,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcParams P) {
     // ---------------- epilogue: all four warps ----------------
     tc::mbar_wait(accum, 0);
     tc::tc_fence_after();
-    tc_epilogue<BLOCK_N, SPLIT>(P, tmem_base, warp, lane, b, x0, y0, n0, TW);
+    tc_epilogue<BLOCK_N, SPLIT>(P, tmem_base, warp, lane, b, x0, y0, n0, TW, sbias);
     tc::tc_fence_before();
     __syncthreads();
     if (warp == 2) tc::tmem_dealloc(tmem_base, TMEM_COLS);
@@ -300,11 +399,14 @@ struct HaloSmem {
     static constexpr int B_BYTES = BLOCK_N * 128;
     static constexpr int OFF_B = 2 * HALO_A_STRIDE;
     static constexpr int BAR_OFF = OFF_B + NB * B_BYTES;
-    static constexpr int TOTAL = BAR_OFF + (2 * NB + 4 + 1) * 8 + 16 + 1024;
+    static constexpr int BIAS_OFF = BAR_OFF + 256;
+    static constexpr int TOTAL = BIAS_OFF + BLOCK_N * 4 + 16 + 1024;
+    static_assert((2 * NB + 4 + 1) * 8 + 16 <= 256, "barrier block");
 };
+constexpr int HALO_THREADS = 256;                    // warps 0-3 / 4-7: epilogue of sub-tile 0 / 1 (warp % 4 = TMEM lane quarter)
 
 template <int BLOCK_N, int NB>
-__global__ void __launch_bounds__(TC_THREADS)
+__global__ void __launch_bounds__(HALO_THREADS)
 conv_halo_kernel(const __grid_constant__ ConvTcParams P) {
     using S = HaloSmem<BLOCK_N, NB>;
     constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
@@ -324,6 +426,8 @@ conv_halo_kernel(const __grid_constant__ ConvTcParams P) {
     const int tyi = tr / P.tiles_x, txi = tr - tyi * P.tiles_x;
     const int x0 = txi * HALO_TWV, y0 = tyi * HALO_TH;
     const int n0 = blockIdx.y * BLOCK_N;
+    float* sbias = (float*)(smem + S::BIAS_OFF);
+    stage_bias<BLOCK_N>(P, sbias, n0);
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; ++i) { tc::mbar_init(&a_full[i], 1); tc::mbar_init(&a_empty[i], 1); }
@@ -394,12 +498,170 @@ conv_halo_kernel(const __grid_constant__ ConvTcParams P) {
 
     tc::mbar_wait(accum, 0);
     tc::tc_fence_after();
-#pragma unroll 1
-    for (int mt = 0; mt < 2; ++mt)
-        tc_epilogue<BLOCK_N, false>(P, tmem_base + mt * BLOCK_N, warp, lane, b, x0, y0 + 4 * mt, n0, HALO_TWV);
+    {
+        const int mt = warp >> 2;                    // two warpgroups drain the two accumulators concurrently
+        tc_epilogue<BLOCK_N, false>(P, tmem_base + mt * BLOCK_N, warp & 3, lane, b, x0, y0 + 4 * mt, n0, HALO_TWV, sbias);
+    }
     tc::tc_fence_before();
     __syncthreads();
     if (warp == 2) tc::tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+
+// ================================================================================================
+// Persistent, warp-specialised variant of the per-tap kernel (the default for every non-split layer).
+//
+// Measured on B200 (tools/bench_conv.py): the one-tile-per-CTA kernel above sustains ~93 % tensor-pipe occupancy INSIDE its
+// main loop but pays ~14 us of prologue / pipeline fill / epilogue per 128x128 tile, i.e. about as much as the 36-stage main
+// loop of a 128-channel 3x3 layer.  Here one CTA per SM walks its tiles with
+//   warp 0      TMA producer, 6-stage ring that keeps running across tile boundaries
+//   warp 1      MMA issuer; accumulators alternate between two TMEM buffers
+//   warps 4-7   epilogue of tile i (TMEM -> +bias/+residual -> NHWC) while the main loop of tile i+1 runs
+// so the fixed costs are paid once per CTA and the epilogue is hidden.
+// ================================================================================================
+constexpr int PERS_THREADS = 256;
+template <int BLOCK_N, int STAGES>
+struct PersSmem {
+    static constexpr int B_BYTES = BLOCK_N * 128;
+    static constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
+    static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+    static constexpr int BIAS_OFF = BAR_OFF + 256;
+    static constexpr int MAX_COUT = 768;
+    static constexpr int EPI_OFF = BIAS_OFF + MAX_COUT * 4;
+    static constexpr int TOTAL = EPI_OFF + 4 * EPI_WARP_FLOATS * 4 + 16 + 1024;
+    static_assert((2 * STAGES + 4) * 8 + 16 <= 256, "barrier block");
+};
+
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(PERS_THREADS, 1)
+conv_tc_persistent_kernel(const __grid_constant__ ConvTcParams P) {
+    using S = PersSmem<BLOCK_N, STAGES>;
+    constexpr int ACC_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
+    constexpr int TMEM_COLS = 2 * ACC_COLS;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* full = (uint64_t*)(smem + S::BAR_OFF);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tfull = empty + STAGES;            // [2] accumulator ready for the epilogue
+    uint64_t* tempty = tfull + 2;                // [2] accumulator drained (128 arrivals)
+    uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
+    float* sbias = (float*)(smem + S::BIAS_OFF);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int TW = 1 << P.tw_log2, TH = 128 >> P.tw_log2;
+    const int tiles_per_img = P.tiles_x * P.tiles_y;
+    const int n_ntiles = P.cout / BLOCK_N;
+    const int total_tiles = tiles_per_img * P.batch * n_ntiles;
+    const int nk = P.nk0 + P.nk1;
+    const int iters_per_tile = P.ntaps * nk;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < STAGES; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { tc::mbar_init(&tfull[i], 1); tc::mbar_init(&tempty[i], 128); }
+        tc::fence_barrier_init();
+    }
+    if (warp == 2) tc::tmem_alloc(tmem_slot, TMEM_COLS);
+    if (warp == 0 && lane == 0) { tc::prefetch_tmap(&P.mapA[0]); tc::prefetch_tmap(&P.mapB); }
+    {   // all bias (+ time-embedding) values of the layer -> smem, once per CTA
+        const float* bias = P.bias ? P.bias + (P.t_dev ? (size_t)(*P.t_dev) * P.bias_t_stride : 0) : nullptr;
+        for (int i = threadIdx.x; i < P.cout; i += PERS_THREADS) sbias[i] = bias ? __ldg(bias + i) : 0.f;
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    auto decode = [&](int tile, int& b, int& x0, int& y0, int& n0) {
+        const int nt = tile % n_ntiles, mt = tile / n_ntiles;
+        b = mt / tiles_per_img;
+        const int tr = mt - b * tiles_per_img;
+        const int tyi = tr / P.tiles_x, txi = tr - tyi * P.tiles_x;
+        x0 = txi * TW; y0 = tyi * TH; n0 = nt * BLOCK_N;
+    };
+
+    if (warp == 0) {
+        if (tc::elect_one()) {
+            int it = 0;                                            // ring position, continuous across tiles
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                int b, x0, y0, n0; decode(tile, b, x0, y0, n0);
+                for (int i = 0; i < iters_per_tile; ++i, ++it) {
+                    const int s = it % STAGES;
+                    tc::mbar_wait(&empty[s], ((uint32_t)(it / STAGES) & 1u) ^ 1u);
+                    tc::mbar_expect_tx(&full[s], S::STAGE_BYTES);
+                    const int tap = i / nk, kc = i - tap * nk;
+                    const int dy = P.ntaps == 9 ? tap / 3 : 1, dx = P.ntaps == 9 ? tap - (tap / 3) * 3 : 1;
+                    uint8_t* sA = smem + s * S::STAGE_BYTES;
+                    if (P.stride == 1) {
+                        const bool first = kc < P.nk0;
+                        tc::tma_load_4d(sA, first ? &P.mapA[0] : &P.mapA[1], &full[s], (first ? kc : kc - P.nk0) * P.kc, x0 + dx - 1, y0 + dy - 1, b);
+                    } else {
+                        const int py = dy != 1, px = dx != 1;
+                        tc::tma_load_4d(sA, &P.mapA[py * 2 + px], &full[s], kc * P.kc, x0 + (dx == 0 ? -1 : 0), y0 + (dy == 0 ? -1 : 0), b);
+                    }
+                    tc::tma_load_2d(sA + TC_A_BYTES, &P.mapB, &full[s], kc * P.kc, tap * P.cout_rows + n0);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (tc::elect_one()) {
+            const bool bf16 = P.bf16;
+            const uint32_t idesc = tc::make_idesc(bf16 ? tc::FMT_BF16 : tc::FMT_TF32, 128, BLOCK_N);
+            int it = 0, tl = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
+                const int acc = tl & 1;
+                tc::mbar_wait(&tempty[acc], (((uint32_t)tl >> 1) & 1u) ^ 1u);     // epilogue has drained this accumulator
+                tc::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
+                for (int i = 0; i < iters_per_tile; ++i, ++it) {
+                    const int s = it % STAGES;
+                    tc::mbar_wait(&full[s], (uint32_t)(it / STAGES) & 1u);
+                    tc::tc_fence_after();
+                    const uint32_t sA = tc::smem_u32(smem + s * S::STAGE_BYTES);
+                    const uint64_t adesc = tc::smem_desc_k_sw128(sA), bdesc = tc::smem_desc_k_sw128(sA + TC_A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if (bf16) tc::umma_f16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (uint32_t)((i | k) != 0));
+                        else tc::umma_tf32(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (uint32_t)((i | k) != 0));
+                    }
+                    tc::umma_commit(&empty[s]);
+                }
+                tc::umma_commit(&tfull[acc]);
+            }
+        }
+        __syncwarp();
+    } else if (warp >= 4) {
+        int tl = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
+            const int acc = tl & 1;
+            int b, x0, y0, n0; decode(tile, b, x0, y0, n0);
+            tc::mbar_wait(&tfull[acc], ((uint32_t)tl >> 1) & 1u);
+            tc::tc_fence_after();
+            tc_epilogue_coalesced<BLOCK_N>(P, tmem_base + acc * ACC_COLS, warp & 3, lane, b, x0, y0, n0, sbias + n0,
+                                           (float*)(smem + S::EPI_OFF) + (warp & 3) * EPI_WARP_FLOATS);
+            tc::tc_fence_before();
+            tc::mbar_arrive(&tempty[acc]);                           // 128 arrivals: the accumulator may be overwritten
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tc::tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+template <int BN, int ST>
+static int launch_pers(const ConvTcParams& P, cudaStream_t st) {
+    static bool configured = false;
+    constexpr int smem = PersSmem<BN, ST>::TOTAL;
+    static_assert(smem <= 227 * 1024, "persistent ring does not fit in shared memory");
+    if (!configured) {
+        IPDM_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_persistent_kernel<BN, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    const int total = P.tiles_x * P.tiles_y * P.batch * (P.cout / BN);
+    conv_tc_persistent_kernel<BN, ST><<<std::min(total, kNumSMs), PERS_THREADS, smem, st>>>(P);
+    count_launch();
+    IPDM_CHECK_LAUNCH();
+    return IPDM_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -425,8 +687,15 @@ int conv_tc_prepare(ConvTcParams& P, const ConvTcDesc& d) {
     P.W = d.stride == 1 ? Win : (Win + 1) / 2;
     P.batch = d.src[0].n;
     // halo-reuse kernel: stride-1 3x3, not the 3xTF32 split path, and enough 8x30 tiles to give every SM work
-    P.halo = d.stride == 1 && d.ntaps == 9 && !d.w_packed_lo && !d.qkv_mode && !d.force_generic &&
+    // kernel choice (d.variant: 0 auto, 1 one-tile-per-CTA, 2 halo-reuse, 3 persistent).  auto = persistent unless the layer needs
+    // the 3xTF32 split or the qkv epilogue; the halo-reuse kernel measured ~8 % slower than per-tap (tools/bench_conv.py) and is
+    // kept as an explicit variant.
+    static const int env_variant = getenv("IPDM_CONV_VARIANT") ? atoi(getenv("IPDM_CONV_VARIANT")) : 0;
+    const int variant = d.variant ? d.variant : env_variant;
+    const bool plain = !d.w_packed_lo && !d.qkv_mode && d.cout <= 768;
+    P.halo = variant == 2 && plain && d.stride == 1 && d.ntaps == 9 &&
              (long long)ceil_div(P.W, HALO_TWV) * ceil_div(P.H, HALO_TH) * P.batch >= kNumSMs / 2;
+    P.persistent = !P.halo && plain && (variant == 0 || variant == 3);
     P.tw_log2 = P.halo ? 5 : pick_tw_log2(P.H, P.W);
     const int TW = P.halo ? HALO_RP : 1 << P.tw_log2, TH = P.halo ? HALO_TH + 2 : 128 >> P.tw_log2;     // TMA box extent
     P.tiles_x = P.halo ? ceil_div(P.W, HALO_TWV) : ceil_div(P.W, TW);
@@ -511,7 +780,7 @@ static int launch_halo(const ConvTcParams& P, cudaStream_t st) {
         configured = true;
     }
     dim3 grid(P.tiles_x * P.tiles_y * P.batch, P.cout / BN);
-    conv_halo_kernel<BN, NB><<<grid, TC_THREADS, smem, st>>>(P);
+    conv_halo_kernel<BN, NB><<<grid, HALO_THREADS, smem, st>>>(P);
     count_launch();
     IPDM_CHECK_LAUNCH();
     return IPDM_OK;
@@ -524,6 +793,13 @@ int conv_tc_launch(const ConvTcParams& P, cudaStream_t st) {
             case 128: return launch_halo<128, 6>(P, st);
             case 64: return launch_halo<64, 8>(P, st);
             case 16: return launch_halo<16, 8>(P, st);
+        }
+    }
+    if (P.persistent) {
+        switch (P.block_n) {
+            case 128: return launch_pers<128, 5>(P, st);
+            case 64: return launch_pers<64, 7>(P, st);
+            case 16: return launch_pers<16, 9>(P, st);
         }
     }
     if (P.split) {

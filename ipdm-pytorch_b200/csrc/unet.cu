@@ -683,6 +683,45 @@ extern "C" int ipdm_debug_conv(const float* src0, int c0, int cs0, const float* 
     return rc;
 }
 
+// times `iters` launches of one tensor-core conv (weights random, data whatever is in the buffers); ms_out = average per launch
+extern "C" int ipdm_debug_conv_time(int c0, int c1, int n, int h, int w, int cout, int k, int stride, int mode, int variant,
+                                    int with_res, int iters, float* ms_out, double* flops_out) {
+    ipdm_unet holder;
+    holder.precision = mode == 2 ? IPDM_PREC_FP32 : (mode == 3 ? IPDM_PREC_BF16 : IPDM_PREC_TF32);
+    ConvW cw; cw.cin = c0 + c1; cw.cout = cout; cw.k = k;
+    cw.w_host.assign((size_t)cout * cw.cin * k * k, 0.01f);
+    cw.b_host.assign(cout, 0.1f);
+    IPDM_CHECK(pack_conv(&holder, cw, c0, c1, true, 1, mode == 3));
+    const int eb = cw.bf16 ? 2 : 4;
+    const int ho = stride == 1 ? h : (h + 1) / 2, wo = stride == 1 ? w : (w + 1) / 2;
+    float *s0 = nullptr, *s1 = nullptr, *out = nullptr, *res = nullptr;
+    IPDM_CHECK_CUDA(cudaMalloc(&s0, (size_t)n * h * w * cw.cs0 * eb));
+    IPDM_CHECK_CUDA(cudaMemset(s0, 0, (size_t)n * h * w * cw.cs0 * eb));
+    if (cw.cs1) { IPDM_CHECK_CUDA(cudaMalloc(&s1, (size_t)n * h * w * cw.cs1 * 4)); IPDM_CHECK_CUDA(cudaMemset(s1, 0, (size_t)n * h * w * cw.cs1 * 4)); }
+    const int ocs = alloc_cs(cout);
+    IPDM_CHECK_CUDA(cudaMalloc(&out, (size_t)n * ho * wo * ocs * 4));
+    if (with_res) { IPDM_CHECK_CUDA(cudaMalloc(&res, (size_t)n * ho * wo * ocs * 4)); IPDM_CHECK_CUDA(cudaMemset(res, 0, (size_t)n * ho * wo * ocs * 4)); }
+    ConvTcDesc d; d.nsrc = cw.cs1 ? 2 : 1; d.src[0] = mk(s0, n, h, w, cw.c0, cw.cs0); d.src[0].bf16 = cw.bf16;
+    if (cw.cs1) d.src[1] = mk(s1, n, h, w, cw.c1, cw.cs1);
+    d.ntaps = k * k; d.stride = stride; d.cout = cout; d.w_packed = cw.w_dev; d.w_packed_lo = cw.w_dev_lo; d.w_k = cw.kpad; d.bias = cw.b_dev;
+    if (res) d.res = mk(res, n, ho, wo, cout, ocs);
+    d.out = mk(out, n, ho, wo, cout, ocs);
+    d.variant = variant;
+    ConvTcParams P;
+    IPDM_CHECK(conv_tc_prepare(P, d));
+    cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+    for (int i = 0; i < 3; ++i) IPDM_CHECK(conv_tc_launch(P, nullptr));
+    cudaEventRecord(a, nullptr);
+    for (int i = 0; i < iters; ++i) IPDM_CHECK(conv_tc_launch(P, nullptr));
+    cudaEventRecord(b, nullptr);
+    IPDM_CHECK_CUDA(cudaDeviceSynchronize());
+    float ms = 0; cudaEventElapsedTime(&ms, a, b);
+    *ms_out = ms / iters;
+    if (flops_out) *flops_out = 2.0 * n * ho * wo * (double)cw.cin * cout * k * k;
+    cudaFree(s0); cudaFree(s1); cudaFree(out); cudaFree(res); cudaEventDestroy(a); cudaEventDestroy(b);
+    return IPDM_OK;
+}
+
 extern "C" int ipdm_debug_groupnorm(const float* src0, int c0, int cs0, const float* src1, int c1, int cs1, int n, int h, int w,
                                     const float* gamma_host, const float* beta_host, int act_silu, float* scale_out,
                                     float* shift_out, float* out, int out_cs, void* stream) {

@@ -32,13 +32,13 @@ struct ConvTcDesc {
     TensorNHWC out;
     int qkv_mode = 0; float* vt = nullptr; int t_pad = 0, heads = 0, head_dim = 0;
     float* out_lo = nullptr; float* vt_lo = nullptr;   // qkv epilogue in fp32 mode: q,k,v are written as tf32 hi / lo pairs
-    int force_generic = 0;                             // tests: keep stride-1 3x3 layers on the per-tap kernel
+    int variant = 0;                                   // 0 auto, 1 one-tile-per-CTA, 2 halo-reuse, 3 persistent (tests / benchmarks)
 };
 
 struct ConvTcParams {
     CUtensorMap mapA[4];
     CUtensorMap mapB, mapBlo;
-    int split, bf16, kc, halo;
+    int split, bf16, kc, halo, persistent;
     int H, W, tiles_x, tiles_y, tw_log2, batch;
     int ntaps, stride, nk0, nk1;
     int cout, cout_rows, block_n;
