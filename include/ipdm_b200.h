@@ -206,7 +206,8 @@ int ipdm_guided_process(ipdm_unet* net, const ipdm_guided_params* p, const float
  *   conv        nn.Conv2d 3x3 / 1x1, stride 1 / 2, over a virtual concat of two sources
  *               (Model/model.py:101,113,117,142,143,165,180,306); use_tc: 0 CUDA-core path, 1 tcgen05 kind::tf32,
  *               2 tcgen05 3xTF32 (fp32-accurate), 3 tcgen05 kind::f16 with bf16 operands (src0 is then a bf16 NHWC tensor
- *               with a channel stride that is a multiple of 64, single source);
+ *               with a channel stride that is a multiple of 64, single source), 4 thin tcgen05 path (C_in <= 32, C_out 8 / 16,
+ *               src0 channel stride 8 / 16 / 32, single source, stride 1);
  *               the direct path can fuse GroupNorm+SiLU on load and a nearest upsample (:168).
  *   groupnorm   norm_layer(C) statistics -> per-(slice, channel) scale/shift (+ optional apply, +SiLU) (:82-90)
  *   attention   AttentionBlock core (:148-153) from q,k in NHWC [B,T,3C] and v transposed [B,heads,d,t_pad]

@@ -1,0 +1,229 @@
+// Thin convolutions (C_in <= 32, C_out in {8, 16}) of the full-resolution levels on the tensor cores.
+//
+// The projection UNet spends its first and last two levels (2000x912 and 1000x456) in layers with 4...24 channels
+// (Model/model.py channel_mult = [1/16, 1/8, 1/4, ...]).  On CUDA cores they were a third of the whole step
+// (profiles/r01_*: conv_direct), although each of them only moves 4*(C_in + C_out) bytes per pixel.  This kernel maps them
+// to tcgen05:  D[128 pixels, 16] += A_tap[128 pixels, K = C_in] * W_tap[16, K]^T  with
+//   * a pixel row of C_in in {8, 16, 32} fp32 channels = 32 / 64 / 128 bytes = one K-major operand row in the matching
+//     SWIZZLE_32B / 64B / 128B mode (TMA writes it, UMMA reads it; verified by tools/experiments/shifted_desc_narrow.cu),
+//   * ONE halo tile [(4+2) rows x 32 pixels] per output tile, read in place by all nine taps through descriptors that
+//     start at row dy*32 + dx (30 of the 32 columns are outputs),
+//   * all tap weights (<= 18 KB) resident in shared memory for the lifetime of the persistent CTA,
+//   * four TMEM accumulators (16 columns each) so that epilogues overlap the next tiles' MMAs.
+// Per tile the tensor pipe issues 9 * C_in/8 instructions of ~45 cycles; the layer becomes HBM / issue bound
+// (2000x912, 8 -> 8: 117 MB, ~25 us) instead of FP32-FMA bound (~160 us).
+#include "common.cuh"
+#include "tc.cuh"
+#include "unet_ops.cuh"
+
+#include <algorithm>
+
+namespace ipdm {
+
+constexpr int TH_RP = 32, TH_TWV = 30, TH_ROWS = 4;     // row pitch (pixels), valid columns, output rows per tile
+constexpr int TH_NACC = 4;
+constexpr int TH_THREADS = 256;                         // warp 0 producer, 1 MMA, 2 TMEM alloc, 4-7 epilogue
+constexpr int TH_W_BYTES = 19 * 1024;
+
+template <int RB> struct ThinCfg {                      // RB = bytes per pixel row of the operand tensor
+    static constexpr int BOX_BYTES = (TH_ROWS + 2) * TH_RP * RB;
+    static constexpr int SLOT = (BOX_BYTES + 2 * RB + 1023) / 1024 * 1024;   // + the 2 pixels the last tap over-reads
+    static constexpr int NSA = RB == 32 ? 12 : (RB == 64 ? 10 : 6);
+    static constexpr int LAYOUT = RB == 32 ? 6 : (RB == 64 ? 4 : 2);         // UMMA layout_type: SWIZZLE_32B / 64B / 128B
+    static constexpr int SBO = 8 * RB;
+    static constexpr int OFF_A = TH_W_BYTES;
+    static constexpr int BAR_OFF = OFF_A + NSA * SLOT;
+    static constexpr int TOTAL = BAR_OFF + 512 + 1024;
+};
+
+__device__ __forceinline__ uint64_t thin_desc(uint32_t saddr, int layout, int sbo) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(sbo >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)layout << 61;
+    return d;
+}
+
+template <int RB>
+__global__ void __launch_bounds__(TH_THREADS, 1)
+conv_thin_kernel(const __grid_constant__ ConvThinParams P) {
+    using C = ThinCfg<RB>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* a_full = (uint64_t*)(smem + C::BAR_OFF);
+    uint64_t* a_empty = a_full + C::NSA;
+    uint64_t* t_full = a_empty + C::NSA;
+    uint64_t* t_empty = t_full + TH_NACC;
+    uint64_t* w_full = t_empty + TH_NACC;
+    uint32_t* tmem_slot = (uint32_t*)(w_full + 1);
+    float* sbias = (float*)(tmem_slot + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_per_img = P.tiles_x * P.tiles_y;
+    const int total_tiles = tiles_per_img * P.batch;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < C::NSA; ++i) { tc::mbar_init(&a_full[i], 1); tc::mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < TH_NACC; ++i) { tc::mbar_init(&t_full[i], 1); tc::mbar_init(&t_empty[i], 128); }
+        tc::mbar_init(w_full, 1);
+        tc::fence_barrier_init();
+    }
+    if (warp == 2) tc::tmem_alloc(tmem_slot, 32 * TH_NACC);
+    if (threadIdx.x < 16) {
+        const float* bias = P.bias ? P.bias + (P.t_dev ? (size_t)(*P.t_dev) * P.bias_t_stride : 0) : nullptr;
+        sbias[threadIdx.x] = (bias && (int)threadIdx.x < P.cout) ? __ldg(bias + threadIdx.x) : 0.f;
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    auto decode = [&](int tile, int& b, int& x0, int& y0) {
+        b = tile / tiles_per_img;
+        const int tr = tile - b * tiles_per_img;
+        const int tyi = tr / P.tiles_x, txi = tr - tyi * P.tiles_x;
+        x0 = txi * TH_TWV; y0 = tyi * TH_ROWS;
+    };
+
+    if (warp == 0) {
+        if (tc::elect_one()) {
+            tc::mbar_expect_tx(w_full, P.ntaps * 16 * RB);
+            tc::tma_load_2d(smem, &P.mapW, w_full, 0, 0);
+            const int off = P.ntaps == 9 ? 1 : 0;                 // 1x1: the tile is its own halo
+            int it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+                int b, x0, y0; decode(tile, b, x0, y0);
+                const int s = it % C::NSA;
+                tc::mbar_wait(&a_empty[s], ((uint32_t)(it / C::NSA) & 1u) ^ 1u);
+                tc::mbar_expect_tx(&a_full[s], C::BOX_BYTES);
+                tc::tma_load_4d(smem + C::OFF_A + s * C::SLOT, &P.mapA, &a_full[s], 0, x0 - off, y0 - off, b);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (tc::elect_one()) {
+            const uint32_t idesc = tc::make_idesc(tc::FMT_TF32, 128, 16);
+            const uint32_t w_base = tc::smem_u32(smem);
+            tc::mbar_wait(w_full, 0);
+            int it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+                const int s = it % C::NSA, acc = it % TH_NACC;
+                tc::mbar_wait(&t_empty[acc], ((uint32_t)(it / TH_NACC) & 1u) ^ 1u);
+                tc::mbar_wait(&a_full[s], (uint32_t)(it / C::NSA) & 1u);
+                tc::tc_fence_after();
+                const uint32_t a_base = tc::smem_u32(smem + C::OFF_A + s * C::SLOT);
+                const uint32_t d_tmem = tmem_base + acc * 32;
+                for (int tap = 0; tap < P.ntaps; ++tap) {
+                    const int dy = P.ntaps == 9 ? tap / 3 : 0, dx = P.ntaps == 9 ? tap - (tap / 3) * 3 : 0;
+                    const uint64_t ad = thin_desc(a_base + (uint32_t)((dy * TH_RP + dx) * RB), C::LAYOUT, C::SBO);
+                    const uint64_t bd = thin_desc(w_base + (uint32_t)(tap * 16 * RB), C::LAYOUT, C::SBO);
+#pragma unroll
+                    for (int k = 0; k < RB / 32; ++k)
+                        tc::umma_tf32(d_tmem, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (uint32_t)((tap | k) != 0));
+                }
+                tc::umma_commit(&a_empty[s]);
+                tc::umma_commit(&t_full[acc]);
+            }
+        }
+        __syncwarp();
+    } else if (warp >= 4) {
+        const int q = warp & 3;                                  // TMEM lane quarter == output row of the tile
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const int acc = it % TH_NACC;
+            int b, x0, y0; decode(tile, b, x0, y0);
+            tc::mbar_wait(&t_full[acc], (uint32_t)(it / TH_NACC) & 1u);
+            tc::tc_fence_after();
+            uint32_t r[16];
+            tc::tmem_ld16(tmem_base + acc * 32 + ((uint32_t)(q * 32) << 16), r);
+            const int py = y0 + q, px = x0 + lane;
+            const bool valid = lane < TH_TWV && py < P.H && px < P.W;
+            const size_t pix = ((size_t)b * P.H + py) * P.W + px;
+            float4 rr[4];
+            if (valid && P.res) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (4 * i < P.cout) rr[i] = __ldg(reinterpret_cast<const float4*>(P.res + pix * P.res_cs) + i);
+            }
+            tc::tmem_ld_wait();
+            tc::tc_fence_before();
+            tc::mbar_arrive(&t_empty[acc]);                        // values are in registers: release the accumulator early
+            if (valid) {
+                float4* op = reinterpret_cast<float4*>(P.out + pix * P.out_cs);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if (4 * i < P.cout) {
+                        float4 v = make_float4(__uint_as_float(r[4 * i]) + sbias[4 * i], __uint_as_float(r[4 * i + 1]) + sbias[4 * i + 1],
+                                               __uint_as_float(r[4 * i + 2]) + sbias[4 * i + 2], __uint_as_float(r[4 * i + 3]) + sbias[4 * i + 3]);
+                        if (P.res) { v.x += rr[i].x; v.y += rr[i].y; v.z += rr[i].z; v.w += rr[i].w; }
+                        op[i] = v;
+                    } else if (4 * i < P.out_cs) {
+                        op[i] = make_float4(0.f, 0.f, 0.f, 0.f);   // channel padding of the output stays zero
+                    }
+                }
+                for (int c = 16; c < P.out_cs; c += 4) op[c / 4] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tc::tmem_dealloc(tmem_base, 32 * TH_NACC);
+}
+
+int conv_thin_prepare(ConvThinParams& P, const ConvThinDesc& d) {
+    memset(&P, 0, sizeof(P));
+    const TensorNHWC& t = d.src;
+    IPDM_REQUIRE(t.cs == 8 || t.cs == 16 || t.cs == 32, "conv_thin: operand channel stride %d must be 8, 16 or 32", t.cs);
+    IPDM_REQUIRE(d.cout == 8 || d.cout == 16, "conv_thin: C_out %d must be 8 or 16", d.cout);
+    IPDM_REQUIRE(d.ntaps == 1 || d.ntaps == 9, "conv_thin: 1x1 or 3x3");
+    IPDM_REQUIRE(!t.bf16 && ((uintptr_t)t.p % 16) == 0 && d.out.cs % 4 == 0 && d.out.cs >= d.cout, "conv_thin: bad tensor layout");
+    IPDM_REQUIRE(d.out.h == t.h && d.out.w == t.w && d.out.n == t.n, "conv_thin: output shape mismatch");
+    P.H = t.h; P.W = t.w; P.batch = t.n; P.ntaps = d.ntaps; P.cs = t.cs; P.cout = d.cout;
+    P.tiles_x = ceil_div(P.W, TH_TWV); P.tiles_y = ceil_div(P.H, TH_ROWS);
+    const CUtensorMapSwizzle sw = t.cs == 8 ? CU_TENSOR_MAP_SWIZZLE_32B : (t.cs == 16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
+    const uint64_t dims[4] = {(uint64_t)t.cs, (uint64_t)t.w, (uint64_t)t.h, (uint64_t)t.n};
+    const uint64_t str[3] = {(uint64_t)t.cs * 4, (uint64_t)t.w * t.cs * 4, (uint64_t)t.h * t.w * t.cs * 4};
+    const uint32_t box[4] = {(uint32_t)t.cs, TH_RP, TH_ROWS + 2, 1};
+    IPDM_CHECK(tmap_encode(&P.mapA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, t.p, dims, str, box, sw));
+    const uint64_t wd[2] = {(uint64_t)t.cs, (uint64_t)d.ntaps * 16};
+    const uint64_t ws[1] = {(uint64_t)t.cs * 4};
+    const uint32_t wb[2] = {(uint32_t)t.cs, (uint32_t)d.ntaps * 16};
+    IPDM_CHECK(tmap_encode(&P.mapW, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, d.w_packed, wd, ws, wb, sw));
+    P.out = d.out.p; P.out_cs = d.out.cs;
+    P.bias = d.bias; P.bias_t_stride = d.bias_t_stride; P.t_dev = d.t_dev;
+    P.res = d.res.p; P.res_cs = d.res.cs;
+    IPDM_REQUIRE(!P.res || P.res_cs % 4 == 0, "conv_thin: residual channel stride must be a multiple of 4");
+    return IPDM_OK;
+}
+
+template <int RB>
+static int launch_thin(const ConvThinParams& P, cudaStream_t st) {
+    static bool configured = false;
+    constexpr int smem = ThinCfg<RB>::TOTAL;
+    static_assert(smem <= 227 * 1024, "thin conv ring does not fit in shared memory");
+    static_assert((2 * ThinCfg<RB>::NSA + 2 * TH_NACC + 1) * 8 + 16 + 64 <= 512, "barrier block");
+    if (!configured) {
+        IPDM_CHECK_CUDA(cudaFuncSetAttribute(conv_thin_kernel<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    const int total = P.tiles_x * P.tiles_y * P.batch;
+    conv_thin_kernel<RB><<<std::min(total, kNumSMs), TH_THREADS, smem, st>>>(P);
+    count_launch();
+    IPDM_CHECK_LAUNCH();
+    return IPDM_OK;
+}
+
+int conv_thin_launch(const ConvThinParams& P, cudaStream_t st) {
+    ProfScope prof(PROF_CONV_DIRECT, st, 4.0 * P.batch * (double)P.H * P.W * (P.cs + P.cout));    // bytes (same family as the direct convs)
+    switch (P.cs) {
+        case 8: return launch_thin<32>(P, st);
+        case 16: return launch_thin<64>(P, st);
+        case 32: return launch_thin<128>(P, st);
+    }
+    set_error("conv_thin_launch: unsupported channel stride %d", P.cs);
+    return IPDM_ERR_UNSUPPORTED;
+}
+
+}  // namespace ipdm

@@ -40,6 +40,7 @@ struct ConvW {
     float* w_dev = nullptr; float* w_dev_lo = nullptr; float* b_dev = nullptr;
     bool tc = false; int c0 = 0, cs0 = 0, c1 = 0, cs1 = 0, kpad = 0;
     bool bf16 = false;                       // operands (activation tile and packed weights) are bf16
+    bool thin = false; int thin_cs = 0;      // thin tensor-core path (conv_thin.cu): operand channel stride 8 / 16 / 32
 };
 struct ResW { GNW gn1, gn2; ConvW conv1, conv2, shortcut; bool has_shortcut = false; std::vector<float> temb_w, temb_b; float* bias1_t = nullptr; int cin = 0, cout = 0; };
 struct AttnW { GNW norm; ConvW qkv, proj; int C = 0; };
@@ -49,13 +50,13 @@ typedef std::vector<LayerRef> Block;
 struct VTensor { int n = 0, h = 0, w = 0, c = 0, cs = 0; int def = -1, last = -1; size_t off = 0; bool external = false; int bf16 = 0; };
 
 struct Op {
-    enum Kind { GN_STATS, GN_APPLY, CONV_TC, CONV_DIRECT, UPSAMPLE, ATTN } kind;
+    enum Kind { GN_STATS, GN_APPLY, CONV_TC, CONV_DIRECT, CONV_THIN, UPSAMPLE, ATTN } kind;
     int src[2] = {-1, -1}; int nsrc = 0; int dst = -1, res = -1, aux = -1, aux2 = -1, aux3 = -1;
     const GNW* gn = nullptr; int norm_slot = -1; int act = 1;
     const ConvW* cw = nullptr; const float* bias = nullptr; int bias_t_stride = 0; bool use_t = false;
     int stride = 1, upsample = 0, qkv = 0;
     // materialised
-    ConvTcParams tcp; ConvDirectDesc cd; GroupNormDesc gd; TensorNHWC out_t, src_t; AttentionParams ap; AttentionDesc ad;
+    ConvTcParams tcp; ConvThinParams thp; ConvDirectDesc cd; GroupNormDesc gd; TensorNHWC out_t, src_t; AttentionParams ap; AttentionDesc ad;
     double flops = 0;
 };
 
@@ -124,6 +125,7 @@ static int read_gn(ipdm_unet* net, Reader& r, GNW& g, int C) {
     return IPDM_OK;
 }
 
+static int thin_cs_of(int c) { return c <= 8 ? 8 : (c <= 16 ? 16 : 32); }
 static bool wants_tc(int cin_total, int cout) { return cout % 16 == 0 && cin_total >= 16 && (cout >= 64 || cin_total >= 64); }
 
 // K layout of a tensor-core conv: channel c of the virtual concat -> column c (c < c0) or cs0 + (c - c0)
@@ -139,6 +141,22 @@ static int pack_conv(ipdm_unet* net, ConvW& c, int c0, int c1, bool raw_sources,
     const int kk = c.k * c.k;
     c.tc = force < 0 ? wants_tc(c.cin, c.cout) : force != 0;
     c.bf16 = c.tc && net->precision == IPDM_PREC_BF16 && (operand_tensor || !raw_sources);
+    // thin tensor-core path: not in the fp32 parity mode (the CUDA-core kernel is exact fp32), single operand tensor whose channel
+    // stride is 8 / 16 / 32 floats: a GroupNorm-apply or upsample output (stride chosen by the plan), or a raw tensor that already has one
+    c.thin = false;
+    if (!c.tc && force < 0 && net->precision != IPDM_PREC_FP32 && (c.cout == 8 || c.cout == 16) && c.cin <= 32 && c1 == 0) {
+        if (operand_tensor || !raw_sources) { c.thin = true; c.thin_cs = thin_cs_of(c.cin); }
+        else if (c.k == 1 && c0 >= 8 && (alloc_cs(c0) == 8 || alloc_cs(c0) == 16 || alloc_cs(c0) == 32)) { c.thin = true; c.thin_cs = alloc_cs(c0); }
+    }
+    if (c.thin) {
+        std::vector<float> p((size_t)kk * 16 * c.thin_cs, 0.f);
+        for (int co = 0; co < c.cout; ++co)
+            for (int ci = 0; ci < c.cin; ++ci)
+                for (int t = 0; t < kk; ++t) p[((size_t)t * 16 + co) * c.thin_cs + ci] = tf32_rn_host(c.w_host[((size_t)co * c.cin + ci) * kk + t]);
+        IPDM_CHECK(upload(net, p, &c.w_dev));
+        if (!c.b_host.empty()) IPDM_CHECK(upload(net, c.b_host, &c.b_dev));
+        return IPDM_OK;
+    }
     if (c.tc) {
         c.c0 = c0; c.c1 = c1;
         if (c.bf16) { c.c0 = c.cin; c.c1 = 0; c.cs0 = round_up(c.cin, 64); c.cs1 = 0; }
@@ -359,7 +377,13 @@ struct PlanBuilder {
         max_c = std::max(max_c, gn.C);
         push(st);
         const VTensor& s0 = pl->vt[src[0]];
-        if (cw.tc) {
+        if (cw.thin) {
+            const int a = new_tensor(pl->B, s0.h, s0.w, gn.C, cw.thin_cs);
+            Op ap; ap.kind = Op::GN_APPLY; ap.nsrc = nsrc; ap.src[0] = src[0]; ap.src[1] = st.src[1]; ap.gn = &gn; ap.norm_slot = st.norm_slot; ap.dst = a; ap.act = act_silu;
+            push(ap);
+            Op cv; cv.kind = Op::CONV_THIN; cv.nsrc = 1; cv.src[0] = a; cv.cw = &cw; cv.dst = dst; cv.res = res; cv.bias = bias; cv.bias_t_stride = bstride; cv.use_t = use_t;
+            push(cv);
+        } else if (cw.tc) {
             const int a = new_tensor(pl->B, s0.h, s0.w, gn.C, cw.bf16 ? round_up(gn.C, 64) : round_up(gn.C, 32));
             pl->vt[a].bf16 = cw.bf16;
             Op ap; ap.kind = Op::GN_APPLY; ap.nsrc = nsrc; ap.src[0] = src[0]; ap.src[1] = st.src[1]; ap.gn = &gn; ap.norm_slot = st.norm_slot; ap.dst = a; ap.act = act_silu;
@@ -373,7 +397,7 @@ struct PlanBuilder {
         }
     }
     void plain_conv(const int* src, int nsrc, const ConvW& cw, int dst, int res, int stride, int upsample) {
-        Op cv; cv.kind = cw.tc ? Op::CONV_TC : Op::CONV_DIRECT; cv.nsrc = nsrc; cv.src[0] = src[0]; cv.src[1] = nsrc > 1 ? src[1] : -1;
+        Op cv; cv.kind = cw.tc ? Op::CONV_TC : ((cw.thin && stride == 1 && !upsample && nsrc == 1 && pl->vt[src[0]].cs == cw.thin_cs) ? Op::CONV_THIN : Op::CONV_DIRECT); cv.nsrc = nsrc; cv.src[0] = src[0]; cv.src[1] = nsrc > 1 ? src[1] : -1;
         cv.cw = &cw; cv.dst = dst; cv.res = res; cv.bias = cw.b_dev; cv.stride = stride; cv.upsample = upsample;
         push(cv);
     }
@@ -419,8 +443,9 @@ struct PlanBuilder {
                 case LayerRef::UP: {
                     const ConvW& cw = net->convs[l.idx];
                     out = act(up_h, up_w, s0.c);
-                    if (cw.tc) {
-                        const int u = cw.bf16 ? new_tensor(pl->B, up_h, up_w, s0.c, round_up(s0.c, 64)) : act(up_h, up_w, s0.c);
+                    if (cw.tc || cw.thin) {
+                        const int u = cw.thin ? new_tensor(pl->B, up_h, up_w, s0.c, cw.thin_cs)
+                                              : (cw.bf16 ? new_tensor(pl->B, up_h, up_w, s0.c, round_up(s0.c, 64)) : act(up_h, up_w, s0.c));
                         pl->vt[u].bf16 = cw.bf16;
                         Op up; up.kind = Op::UPSAMPLE; up.nsrc = 1; up.src[0] = cur[0]; up.dst = u; push(up);
                         plain_conv(&u, 1, cw, out, -1, 1, 0);
@@ -533,6 +558,15 @@ static int build_plan(ipdm_unet* net, int B, int H, int W, Plan** out) {
                 IPDM_CHECK(conv_tc_prepare(o.tcp, d));
                 o.flops = 2.0 * B * o.tcp.H * o.tcp.W * (double)o.cw->cin * o.cw->cout * d.ntaps;
             } break;
+            case Op::CONV_THIN: {
+                ConvThinDesc d;
+                d.src = resolve(*pl, o.src[0]); d.ntaps = o.cw->k * o.cw->k; d.cout = o.cw->cout; d.w_packed = o.cw->w_dev;
+                d.bias = o.bias; d.bias_t_stride = o.bias_t_stride; d.t_dev = o.use_t ? net->t_dev : nullptr;
+                if (o.res >= 0) d.res = resolve(*pl, o.res);
+                d.out = resolve(*pl, o.dst);
+                IPDM_CHECK(conv_thin_prepare(o.thp, d));
+                o.flops = 2.0 * B * d.out.h * d.out.w * (double)o.cw->cin * o.cw->cout * d.ntaps;
+            } break;
             case Op::CONV_DIRECT: {
                 ConvDirectDesc& d = o.cd;
                 d.nsrc = o.nsrc; d.src[0] = resolve(*pl, o.src[0]); if (o.nsrc > 1) d.src[1] = resolve(*pl, o.src[1]);
@@ -572,6 +606,7 @@ static int run_plan(ipdm_unet* net, Plan* pl, const float* x, int t, float* eps,
             case Op::GN_STATS: IPDM_CHECK(groupnorm_stats_launch(o.gd, st)); break;
             case Op::GN_APPLY: IPDM_CHECK(groupnorm_apply_launch(o.gd, o.out_t, o.act, net->precision != IPDM_PREC_FP32, st)); break;
             case Op::CONV_TC: IPDM_CHECK(conv_tc_launch(o.tcp, st)); break;
+            case Op::CONV_THIN: IPDM_CHECK(conv_thin_launch(o.thp, st)); break;
             case Op::CONV_DIRECT: {
                 ConvDirectDesc d = o.cd;
                 if ((int)i == pl->first_op) d.src[0].p = const_cast<float*>(x);
@@ -655,6 +690,19 @@ extern "C" int ipdm_debug_conv(const float* src0, int c0, int cs0, const float* 
     ConvW cw; cw.cin = c0 + c1; cw.cout = cout; cw.k = k;
     cw.w_host.assign(w_host, w_host + (size_t)cout * cw.cin * k * k);
     if (bias_host) cw.b_host.assign(bias_host, bias_host + cout);
+    if (use_tc == 4) {                                   // thin tensor-core path: src0 is the operand tensor (channel stride cs0 in {8,16,32})
+        IPDM_REQUIRE(c1 == 0 && stride == 1 && upsample_h == 0 && !norm_scale, "ipdm_debug_conv: thin path takes one plain source");
+        IPDM_CHECK(pack_conv(&holder, cw, c0, 0, false));
+        IPDM_REQUIRE(cw.thin && cw.thin_cs == cs0, "ipdm_debug_conv: shape is not eligible for the thin path (stride %d expected)", cw.thin_cs);
+        ConvThinDesc d; d.src = mk(src0, n, h, w, c0, cs0); d.ntaps = k * k; d.cout = cout; d.w_packed = cw.w_dev; d.bias = cw.b_dev;
+        if (res) d.res = mk(res, n, h, w, cout, res_cs);
+        d.out = mk(out, n, h, w, cout, out_cs);
+        ConvThinParams TP;
+        IPDM_CHECK(conv_thin_prepare(TP, d));
+        int rc2 = conv_thin_launch(TP, (cudaStream_t)stream);
+        cudaStreamSynchronize((cudaStream_t)stream);
+        return rc2;
+    }
     IPDM_CHECK(pack_conv(&holder, cw, c0, c1, true, use_tc != 0, use_tc == 3));
     cudaStream_t st = (cudaStream_t)stream;
     const int hin = upsample_h > 0 ? upsample_h : h, win = upsample_w > 0 ? upsample_w : w;

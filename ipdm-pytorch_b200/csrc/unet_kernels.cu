@@ -407,7 +407,7 @@ int groupnorm_apply_launch(const GroupNormDesc& d, const TensorNHWC& out, int ac
 // nearest resize
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-upsample_kernel(const float* __restrict__ src, int hs, int ws, int scs, float* __restrict__ dst, int hd, int wd, int dcs,
+upsample_kernel(const float* __restrict__ src, int hs, int ws, int sc, int scs, float* __restrict__ dst, int hd, int wd, int dcs,
                 float sy, float sx, size_t nvec_total, int rnd, int obf16) {
     const int V = dcs / 4;
     for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < nvec_total; i += (size_t)gridDim.x * 256) {
@@ -418,18 +418,18 @@ upsample_kernel(const float* __restrict__ src, int hs, int ws, int scs, float* _
         const int y = (int)(r % hd), n = (int)(r / hd);
         const int yy = min((int)floorf((float)y * sy), hs - 1), xx = min((int)floorf((float)x * sx), ws - 1);
         float4 v = make_float4(0, 0, 0, 0);
-        if (c < scs) v = __ldg(reinterpret_cast<const float4*>(src + (((size_t)n * hs + yy) * ws + xx) * scs + c));
+        if (c < sc) v = __ldg(reinterpret_cast<const float4*>(src + (((size_t)n * hs + yy) * ws + xx) * scs + c));
         if (rnd) { v.x = tf32_rn(v.x); v.y = tf32_rn(v.y); v.z = tf32_rn(v.z); v.w = tf32_rn(v.w); }   // tf32 mode: feeds a tensor-core conv only
         store_vec4(dst, pix * dcs + c, v, obf16);
     }
 }
 
 int upsample_nearest_launch(const TensorNHWC& src, const TensorNHWC& dst, int round_tf32, cudaStream_t st) {
-    IPDM_REQUIRE(src.cs % 4 == 0 && dst.cs % 4 == 0 && dst.cs >= src.cs && src.n == dst.n, "upsample: bad layout");
+    IPDM_REQUIRE(src.cs % 4 == 0 && dst.cs % 4 == 0 && dst.cs >= src.c && src.c % 4 == 0 && src.n == dst.n, "upsample: bad layout");
     const size_t nvec = dst.pixels() * (dst.cs / 4);
     const int grid = (int)std::min<size_t>((size_t)kNumSMs * 8, (nvec + 255) / 256);
     ProfScope prof(PROF_UPSAMPLE, st, 4.0 * (double)src.elems() + (dst.bf16 ? 2.0 : 4.0) * dst.elems());
-    upsample_kernel<<<grid, 256, 0, st>>>(src.p, src.h, src.w, src.cs, dst.p, dst.h, dst.w, dst.cs, (float)src.h / dst.h,
+    upsample_kernel<<<grid, 256, 0, st>>>(src.p, src.h, src.w, src.c, src.cs, dst.p, dst.h, dst.w, dst.cs, (float)src.h / dst.h,
                                           (float)src.w / dst.w, nvec, round_tf32 && !dst.bf16, dst.bf16);
     count_launch();
     IPDM_CHECK_LAUNCH();

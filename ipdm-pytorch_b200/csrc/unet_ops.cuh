@@ -53,6 +53,24 @@ int conv_tc_prepare(ConvTcParams& P, const ConvTcDesc& d);
 int conv_tc_launch(const ConvTcParams& P, cudaStream_t st);
 double conv_tc_flops(const ConvTcParams& P);
 
+// ---- tensor-core convolution for thin layers: C_in <= 32, C_out in {8, 16}, 3x3 / 1x1 stride 1 (conv_thin.cu) ------
+struct ConvThinDesc {
+    TensorNHWC src;                    // fp32 operand tensor, channel stride 8, 16 or 32 (pad channels zero)
+    int ntaps = 9, cout = 0;
+    const float* w_packed = nullptr;   // [ntaps][16][src.cs], tf32-rounded, rows >= cout and columns >= C_in zero
+    const float* bias = nullptr; int bias_t_stride = 0; const int* t_dev = nullptr;
+    TensorNHWC res, out;
+};
+struct ConvThinParams {
+    CUtensorMap mapA, mapW;
+    int H, W, tiles_x, tiles_y, batch, ntaps, cs, cout;
+    float* out; int out_cs;
+    const float* bias; int bias_t_stride; const int* t_dev;
+    const float* res; int res_cs;
+};
+int conv_thin_prepare(ConvThinParams& P, const ConvThinDesc& d);
+int conv_thin_launch(const ConvThinParams& P, cudaStream_t st);
+
 // ---- direct (CUDA-core) convolution for thin layers (unet_kernels.cu) -------------------------------
 struct ConvDirectDesc {
     int nsrc = 1;

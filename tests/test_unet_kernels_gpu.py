@@ -208,6 +208,32 @@ def test_tc_conv_halo_reuse_variant(cuda, c0, c1, cout, k, stride, hw):
         assert rel_l2(got.numpy(), want.numpy()) < 8e-3
 
 
+@pytest.mark.parametrize("cin,cs,cout,k,hw,batch", [(8, 8, 8, 3, (40, 70), 2), (4, 8, 8, 3, (33, 65), 1), (8, 8, 16, 1, (21, 47), 2), (16, 16, 16, 3, (50, 38), 2),
+                                                    (12, 16, 8, 3, (25, 61), 1), (24, 32, 8, 3, (37, 95), 2), (32, 32, 16, 3, (64, 64), 1),
+                                                    (16, 32, 16, 1, (30, 31), 2), (8, 8, 8, 3, (300, 400), 2)])
+def test_thin_tc_conv(cuda, cin, cs, cout, k, hw, batch):
+    """Thin layers on tcgen05 with 32 / 64 / 128-byte swizzled operand rows, nine taps from one staged halo tile."""
+    from ipdm_pytorch_b200 import _lib
+    x = rnd(batch, cin, *hw, seed=1)
+    w = rnd(cout, cin, k, k, seed=3, scale=(1.0 / (cin * k * k)) ** 0.5)
+    b = rnd(cout, seed=4)
+    res = rnd(batch, cout, *hw, seed=5)
+    ocs = alloc_cs(cout)
+    a0 = nhwc(x, cs).to(cuda)
+    r = nhwc(res, ocs).to(cuda)
+    out = torch.full((batch, hw[0], hw[1], ocs), float("nan"), device=cuda)
+    rc = _lib.lib().ipdm_debug_conv(_p(a0), cin, cs, None, 0, 0, batch, hw[0], hw[1], _p(w.contiguous()), _p(b.contiguous()), cout, k, 1, 0, 0,
+                                    None, None, _p(r), ocs, _p(out), ocs, 4, None)
+    _lib.check(rc, "ipdm_debug_conv(thin)")
+    full = out.cpu()
+    assert torch.isfinite(full).all()
+    if ocs > cout:
+        assert float(full[..., cout:].abs().max()) == 0.0
+    err = rel_l2(nchw(full, cout).numpy(), ref_conv(x, None, w, b, k, 1, res=res).numpy())
+    print(f"thin conv {cin}({cs})->{cout} k{k} {hw}: rel-L2 {err:.2e}")
+    assert err < TF32_TOL
+
+
 def test_tc_conv_full_size_row_shapes(cuda):
     """The proj net's real row widths (228, 114, 57, 29) at reduced height, batch 1."""
     for hw, c in (((24, 228), 128), ((20, 114), 128), ((16, 57), 256), ((9, 29), 256)):
