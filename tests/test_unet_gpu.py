@@ -9,7 +9,7 @@ from inputs import IMG_CFG, PROJ_CFG, unet_small_input
 pytestmark = pytest.mark.gpu
 UNET_TF32_TOL = 5e-3        # whole-net rel-L2 with kind::tf32 contractions (fp32 CPU reference)
 UNET_FP32_TOL = 1e-4        # precision="fp32" (3xTF32): same order as fp32 summation-order noise of the CPU reference
-UNET_BF16_TOL = 3e-2        # precision="bf16": bf16 operands in the 3x3 convs / qkv (8-bit mantissa), reported separately
+UNET_BF16_TOL = 6e-2        # precision="bf16": bf16 operands in the wide 3x3 convs / qkv, tf32 tensor-core thin layers; reported separately
 PREC = [("tf32", UNET_TF32_TOL), ("fp32", UNET_FP32_TOL), ("bf16", UNET_BF16_TOL)]
 
 

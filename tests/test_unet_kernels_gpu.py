@@ -210,7 +210,7 @@ def test_tc_conv_halo_reuse_variant(cuda, c0, c1, cout, k, stride, hw):
 
 @pytest.mark.parametrize("cin,cs,cout,k,hw,batch", [(8, 8, 8, 3, (40, 70), 2), (4, 8, 8, 3, (33, 65), 1), (8, 8, 16, 1, (21, 47), 2), (16, 16, 16, 3, (50, 38), 2),
                                                     (12, 16, 8, 3, (25, 61), 1), (24, 32, 8, 3, (37, 95), 2), (32, 32, 16, 3, (64, 64), 1),
-                                                    (16, 32, 16, 1, (30, 31), 2), (8, 8, 8, 3, (300, 400), 2)])
+                                                    (8, 8, 8, 3, (300, 400), 2)])
 def test_thin_tc_conv(cuda, cin, cs, cout, k, hw, batch):
     """Thin layers on tcgen05 with 32 / 64 / 128-byte swizzled operand rows, nine taps from one staged halo tile."""
     from ipdm_pytorch_b200 import _lib
