@@ -134,19 +134,19 @@ conv_thin_kernel(const __grid_constant__ ConvThinParams P) {
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const int acc = it % TH_NACC;
             int b, x0, y0; decode(tile, b, x0, y0);
-            tc::mbar_wait(&t_full[acc], (uint32_t)(it / TH_NACC) & 1u);
-            tc::tc_fence_after();
-            uint32_t r[16];
-            tc::tmem_ld16(tmem_base + acc * 32 + ((uint32_t)(q * 32) << 16), r);
             const int py = y0 + q, px = x0 + lane;
             const bool valid = lane < TH_TWV && py < P.H && px < P.W;
             const size_t pix = ((size_t)b * P.H + py) * P.W + px;
             float4 rr[4];
-            if (valid && P.res) {
+            if (valid && P.res) {                                  // requested before the accumulator wait: the latencies overlap
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
                     if (4 * i < P.cout) rr[i] = __ldg(reinterpret_cast<const float4*>(P.res + pix * P.res_cs) + i);
             }
+            tc::mbar_wait(&t_full[acc], (uint32_t)(it / TH_NACC) & 1u);
+            tc::tc_fence_after();
+            uint32_t r[16];
+            tc::tmem_ld16(tmem_base + acc * 32 + ((uint32_t)(q * 32) << 16), r);
             tc::tmem_ld_wait();
             tc::tc_fence_before();
             tc::mbar_arrive(&t_empty[acc]);                        // values are in registers: release the accumulator early

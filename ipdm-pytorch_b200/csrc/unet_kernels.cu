@@ -358,11 +358,12 @@ gn_apply_kernel(const float* __restrict__ s0, int c0, int cs0, const float* __re
                 const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ out, int ocs,
                 size_t npix_per_slice, size_t nvec_total, int act, int rnd, int obf16) {
     const int Ctot = c0 + c1, V = ocs / 4;
+    constexpr int U = 4;                                         // independent 128-bit loads in flight per thread
     const size_t stride = (size_t)gridDim.x * 256;
-    for (size_t i0 = (size_t)blockIdx.x * 256 + threadIdx.x; i0 < nvec_total; i0 += 2 * stride) {
-        float4 v[2]; size_t pix[2]; int c[2]; bool live[2];
+    for (size_t i0 = (size_t)blockIdx.x * 256 + threadIdx.x; i0 < nvec_total; i0 += U * stride) {
+        float4 v[U]; size_t pix[U]; int c[U]; bool live[U];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
+        for (int u = 0; u < U; ++u) {
             const size_t i = i0 + u * stride;
             live[u] = i < nvec_total;
             pix[u] = live[u] ? i / V : 0;
@@ -373,7 +374,7 @@ gn_apply_kernel(const float* __restrict__ s0, int c0, int cs0, const float* __re
                                  : ld_stream(reinterpret_cast<const float4*>(s1 + pix[u] * cs1 + (c[u] - c0)));
         }
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
+        for (int u = 0; u < U; ++u) {
             if (!live[u]) continue;
             float4 o = make_float4(0, 0, 0, 0);
             if (c[u] < Ctot) {
@@ -394,7 +395,7 @@ int groupnorm_apply_launch(const GroupNormDesc& d, const TensorNHWC& out, int ac
     const int c1 = d.nsrc == 2 ? d.src[1].c : 0;
     IPDM_REQUIRE(out.cs % 4 == 0 && out.cs >= a.c + c1 && a.c % 4 == 0, "groupnorm_apply: bad channel layout");
     const size_t npix = (size_t)a.h * a.w, nvec = (size_t)a.n * npix * (out.cs / 4);
-    const int grid = (int)std::min<size_t>((size_t)kNumSMs * 16, (nvec + 511) / 512);
+    const int grid = (int)std::min<size_t>((size_t)kNumSMs * 8, (nvec + 1023) / 1024);
     ProfScope prof(PROF_GROUPNORM, st, a.n * (double)npix * (4.0 * (a.c + c1) + (out.bf16 ? 2.0 : 4.0) * out.cs));
     gn_apply_kernel<<<std::max(grid, 1), 256, 0, st>>>(a.p, a.c, a.cs, d.nsrc == 2 ? d.src[1].p : nullptr, c1, d.nsrc == 2 ? d.src[1].cs : 0,
                                           d.scale, d.shift, out.p, out.cs, npix, nvec, act_silu, round_tf32 && !out.bf16, out.bf16);
