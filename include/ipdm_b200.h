@@ -226,6 +226,9 @@ int ipdm_debug_groupnorm(const float* src0_dev, int c0, int cs0, const float* sr
 /* qk_lo_dev / vt_lo_dev: NULL (tf32 mode: qk, vt are used as they are) or the tf32 "lo" parts for the 3xTF32 fp32 mode */
 int ipdm_debug_attention(const float* qk_dev, const float* vt_dev, const float* qk_lo_dev, const float* vt_lo_dev, float* out_dev,
                          int batch, int T, int t_pad, int heads, int C, void* stream);
+/* the bf16 operand mode of the same kernel: qk_dev [B][T][3C] and vt_dev [B][heads][64][t_pad] hold bf16, t_pad % 8 == 0 */
+int ipdm_debug_attention_bf16(const void* qk_dev, const void* vt_dev, float* out_dev, int batch, int T, int t_pad, int heads, int C,
+                              void* stream);
 int ipdm_debug_upsample(const float* src_dev, int n, int hs, int ws, int cs, float* dst_dev, int hd, int wd, void* stream);
 
 #ifdef __cplusplus

@@ -13,6 +13,7 @@
 //                O accumulated in registers (O_blk = P.V is a fresh TMEM tile per key block).
 // S = QK^T: kind::tf32 M=128 N=64 K=8 x8;  O_blk = P V: M=128 N=64 K=8 x8.  Out-of-range keys are
 // zero-filled by TMA and masked to -inf; out-of-range query rows are computed and dropped.
+#include <cuda_bf16.h>
 #include "common.cuh"
 #include "tc.cuh"
 #include "unet_ops.cuh"
@@ -21,33 +22,42 @@ namespace ipdm {
 
 constexpr int AT_BQ = 128, AT_BKV = 64, AT_D = 64;
 constexpr int AT_THREADS = 192;
-constexpr int AT_Q_BYTES = 2 * AT_BQ * 128;          // 2 channel chunks x [128 rows x 128 B]
-constexpr int AT_K_BYTES = 2 * AT_BKV * 128;         // 2 channel chunks x [64 keys x 128 B]
-constexpr int AT_V_BYTES = 2 * AT_D * 128;           // 2 key chunks x [64 d-rows x 128 B]
-constexpr int AT_P_BYTES = 2 * AT_BQ * 128;          // 2 key chunks x [128 rows x 128 B]
-// SPLIT = fp32-accurate 3xTF32 mode: q, k, v arrive as tf32 hi/lo pairs (written by the qkv GEMM epilogue), the softmax
-// threads write P as hi/lo, and every product is hi*hi + hi*lo + lo*hi.  One K/V stage instead of two (192 KB of smem).
-template <bool SPLIT>
+constexpr int AT_TF32 = 0, AT_SPLIT = 1, AT_BF16 = 2;
+// MODE tf32 : q, k, v, P are fp32 words rounded to tf32; every operand tile is 2 chunks of 128-byte rows (32 elements each).
+// MODE split: fp32-accurate 3xTF32: q, k, v arrive as tf32 hi/lo pairs (written by the qkv GEMM epilogue), the softmax threads
+//             write P as hi/lo, and every product is hi*hi + hi*lo + lo*hi.  One K/V stage (192 KB of smem).
+// MODE bf16 : q, k, v, P are bf16 (kind::f16, fp32 accumulate); a 64-element row is ONE 128-byte swizzled row, so every tile is
+//             half the size, the MMA count halves, and three CTAs fit on an SM: one CTA's softmax hides behind the others' MMAs.
+template <int MODE>
 struct AtL {
+    static constexpr bool SPLIT = MODE == AT_SPLIT, BF = MODE == AT_BF16;
     static constexpr int M = SPLIT ? 2 : 1;                   // hi (+ lo) copies of every operand tile
+    static constexpr int NCH = BF ? 1 : 2;                    // 128-byte chunks per 64-element operand row
+    static constexpr int ELEMS = BF ? 64 : 32;                // elements per chunk row
+    static constexpr int Q_BYTES = NCH * AT_BQ * 128;
+    static constexpr int K_BYTES = NCH * AT_BKV * 128;
+    static constexpr int V_BYTES = NCH * AT_D * 128;
+    static constexpr int P_BYTES = NCH * AT_BQ * 128;
     static constexpr int NST = SPLIT ? 1 : 2;
-    static constexpr int STAGE = M * (AT_K_BYTES + AT_V_BYTES);
-    static constexpr int OFF_QLO = AT_Q_BYTES;
-    static constexpr int OFF_KV = M * AT_Q_BYTES;
-    static constexpr int OFF_KLO = AT_K_BYTES;                // inside a stage: K_hi [K_lo] V_hi [V_lo]
-    static constexpr int OFF_V = M * AT_K_BYTES;
-    static constexpr int OFF_VLO = OFF_V + AT_V_BYTES;
+    static constexpr int STAGE = M * (K_BYTES + V_BYTES);
+    static constexpr int OFF_QLO = Q_BYTES;
+    static constexpr int OFF_KV = M * Q_BYTES;
+    static constexpr int OFF_KLO = K_BYTES;                   // inside a stage: K_hi [K_lo] V_hi [V_lo]
+    static constexpr int OFF_V = M * K_BYTES;
+    static constexpr int OFF_VLO = OFF_V + V_BYTES;
     static constexpr int OFF_P = OFF_KV + NST * STAGE;
-    static constexpr int OFF_PLO = OFF_P + AT_P_BYTES;
-    static constexpr int OFF_BAR = OFF_P + M * AT_P_BYTES;
+    static constexpr int OFF_PLO = OFF_P + P_BYTES;
+    static constexpr int OFF_BAR = OFF_P + M * P_BYTES;
     static constexpr int SMEM = OFF_BAR + 16 * 8 + 1024;
+    static constexpr int MAX_REGS = BF ? 112 : 255;             // bf16: 3 CTAs x 192 threads x 112 registers = 63 K of the 64 K file
 };
 
-template <bool SPLIT>
-__global__ void __launch_bounds__(AT_THREADS)
+template <int MODE>
+__global__ void __launch_bounds__(AT_THREADS) __maxnreg__(AtL<MODE>::MAX_REGS)
 attention_kernel(const __grid_constant__ AttentionParams P) {
-    using L = AtL<SPLIT>;
-    constexpr int NST = L::NST;
+    using L = AtL<MODE>;
+    constexpr bool SPLIT = L::SPLIT, BF = L::BF;
+    constexpr int NST = L::NST, NCH = L::NCH;
     extern __shared__ uint8_t at_smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)at_smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = (uint64_t*)(smem + L::OFF_BAR);
@@ -78,8 +88,8 @@ attention_kernel(const __grid_constant__ AttentionParams P) {
 
     if (warp == 4) {
         if (tc::elect_one()) {
-            tc::mbar_expect_tx(q_full, L::M * AT_Q_BYTES);
-            for (int c = 0; c < 2; ++c) {
+            tc::mbar_expect_tx(q_full, L::M * L::Q_BYTES);
+            for (int c = 0; c < NCH; ++c) {
                 tc::tma_load_3d(smem + c * (AT_BQ * 128), &P.mapQ, q_full, head * 3 * AT_D + c * 32, q0, b);
                 if constexpr (SPLIT) tc::tma_load_3d(smem + L::OFF_QLO + c * (AT_BQ * 128), &P.mapQlo, q_full, head * 3 * AT_D + c * 32, q0, b);
             }
@@ -89,7 +99,7 @@ attention_kernel(const __grid_constant__ AttentionParams P) {
                 tc::mbar_expect_tx(&kv_full[s], L::STAGE);
                 uint8_t* sk = smem + L::OFF_KV + s * L::STAGE;
                 uint8_t* sv = sk + L::OFF_V;
-                for (int c = 0; c < 2; ++c) {
+                for (int c = 0; c < NCH; ++c) {
                     tc::tma_load_3d(sk + c * (AT_BKV * 128), &P.mapK, &kv_full[s], head * 3 * AT_D + AT_D + c * 32, j * AT_BKV, b);
                     tc::tma_load_3d(sv + c * (AT_D * 128), &P.mapV, &kv_full[s], j * AT_BKV + c * 32, head * AT_D, b);
                     if constexpr (SPLIT) {
@@ -102,7 +112,10 @@ attention_kernel(const __grid_constant__ AttentionParams P) {
         __syncwarp();
     } else if (warp == 5) {
         if (tc::elect_one()) {
-            constexpr uint32_t idesc = tc::make_idesc(tc::FMT_TF32, 128, 64);
+            constexpr uint32_t idesc = tc::make_idesc(BF ? tc::FMT_BF16 : tc::FMT_TF32, 128, 64);
+            auto mma = [&](uint32_t d, uint64_t a, uint64_t bb, uint32_t acc) {
+                if constexpr (BF) tc::umma_f16(d, a, bb, idesc, acc); else tc::umma_tf32(d, a, bb, idesc, acc);
+            };
             const uint32_t sQ = tc::smem_u32(smem), sP = tc::smem_u32(smem + L::OFF_P);
             auto issue_S = [&](int j) {
                 const int s = j % NST;
@@ -110,15 +123,15 @@ attention_kernel(const __grid_constant__ AttentionParams P) {
                 tc::tc_fence_after();
                 const uint32_t sK = tc::smem_u32(smem + L::OFF_KV + s * L::STAGE);
 #pragma unroll
-                for (int c = 0; c < 2; ++c)
+                for (int c = 0; c < NCH; ++c)
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
+                    for (int k = 0; k < 4; ++k) {                      // 32 bytes of K per instruction (8 tf32 / 16 bf16)
                         const uint64_t qd = tc::smem_desc_k_sw128(sQ + c * (AT_BQ * 128)) + (uint64_t)(k * 2);
                         const uint64_t kd = tc::smem_desc_k_sw128(sK + c * (AT_BKV * 128)) + (uint64_t)(k * 2);
-                        tc::umma_tf32(tmem_S, qd, kd, idesc, (uint32_t)((c | k) != 0));
+                        mma(tmem_S, qd, kd, (uint32_t)((c | k) != 0));
                         if constexpr (SPLIT) {
-                            tc::umma_tf32(tmem_S, qd, tc::smem_desc_k_sw128(sK + L::OFF_KLO + c * (AT_BKV * 128)) + (uint64_t)(k * 2), idesc, 1u);
-                            tc::umma_tf32(tmem_S, tc::smem_desc_k_sw128(sQ + L::OFF_QLO + c * (AT_BQ * 128)) + (uint64_t)(k * 2), kd, idesc, 1u);
+                            mma(tmem_S, qd, tc::smem_desc_k_sw128(sK + L::OFF_KLO + c * (AT_BKV * 128)) + (uint64_t)(k * 2), 1u);
+                            mma(tmem_S, tc::smem_desc_k_sw128(sQ + L::OFF_QLO + c * (AT_BQ * 128)) + (uint64_t)(k * 2), kd, 1u);
                         }
                     }
                 tc::umma_commit(s_full);
@@ -131,15 +144,15 @@ attention_kernel(const __grid_constant__ AttentionParams P) {
                 tc::tc_fence_after();
                 const uint32_t sV = tc::smem_u32(smem + L::OFF_KV + s * L::STAGE + L::OFF_V);
 #pragma unroll
-                for (int c = 0; c < 2; ++c)
+                for (int c = 0; c < NCH; ++c)
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const uint64_t pd = tc::smem_desc_k_sw128(sP + c * (AT_BQ * 128)) + (uint64_t)(k * 2);
                         const uint64_t vd = tc::smem_desc_k_sw128(sV + c * (AT_D * 128)) + (uint64_t)(k * 2);
-                        tc::umma_tf32(tmem_O, pd, vd, idesc, (uint32_t)((c | k) != 0));
+                        mma(tmem_O, pd, vd, (uint32_t)((c | k) != 0));
                         if constexpr (SPLIT) {
-                            tc::umma_tf32(tmem_O, pd, tc::smem_desc_k_sw128(sV + AT_V_BYTES + c * (AT_D * 128)) + (uint64_t)(k * 2), idesc, 1u);
-                            tc::umma_tf32(tmem_O, tc::smem_desc_k_sw128(sP + AT_P_BYTES + c * (AT_BQ * 128)) + (uint64_t)(k * 2), vd, idesc, 1u);
+                            mma(tmem_O, pd, tc::smem_desc_k_sw128(sV + L::V_BYTES + c * (AT_D * 128)) + (uint64_t)(k * 2), 1u);
+                            mma(tmem_O, tc::smem_desc_k_sw128(sP + L::P_BYTES + c * (AT_BQ * 128)) + (uint64_t)(k * 2), vd, 1u);
                         }
                     }
                 tc::umma_commit(o_full);
@@ -161,45 +174,89 @@ attention_kernel(const __grid_constant__ AttentionParams P) {
         for (int j = 0; j < nkv; ++j) {
             tc::mbar_wait(s_full, (uint32_t)j & 1u);
             tc::tc_fence_after();
-            uint32_t sr[2][32];
-            tc::tmem_ld32(tmem_S + lane_off, sr[0]);
-            tc::tmem_ld32(tmem_S + lane_off + 32, sr[1]);
-            tc::tmem_ld_wait();
             const int nvalid = P.T - j * AT_BKV;           // keys beyond T are masked
-            float mx = -INFINITY;
+            float rs = 0.f, alpha, m_new;
+            if constexpr (BF) {
+                // 32 score registers live at a time (three CTAs share the SM's register file): the first half is read once for the
+                // row maximum and again, after the second half has been exponentiated, for its own exponentials.
+                uint32_t sh[32];
+                auto load_half = [&](int h) {
+                    tc::tmem_ld32(tmem_S + lane_off + h * 32, sh);
+                    tc::tmem_ld_wait();
+                    if (nvalid < AT_BKV) {
 #pragma unroll
-            for (int h = 0; h < 2; ++h)
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    float v = __uint_as_float(sr[h][i]);
-                    v = (h * 32 + i < nvalid) ? v : -INFINITY;
-                    sr[h][i] = __float_as_uint(v);
-                    mx = fmaxf(mx, v);
-                }
-            const float m_new = fmaxf(m_run, mx);
-            const float alpha = exp2f((m_run - m_new) * P.scale_log2);
-            const float mb = m_new * P.scale_log2;
-            float rs = 0.f;
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    float4 pv;
-                    pv.x = exp2f(fmaf(__uint_as_float(sr[h][4 * u]), P.scale_log2, -mb));
-                    pv.y = exp2f(fmaf(__uint_as_float(sr[h][4 * u + 1]), P.scale_log2, -mb));
-                    pv.z = exp2f(fmaf(__uint_as_float(sr[h][4 * u + 2]), P.scale_log2, -mb));
-                    pv.w = exp2f(fmaf(__uint_as_float(sr[h][4 * u + 3]), P.scale_log2, -mb));
-                    float4 ph;
-                    ph.x = tf32_rn(pv.x); ph.y = tf32_rn(pv.y); ph.z = tf32_rn(pv.z); ph.w = tf32_rn(pv.w);   // P is an MMA operand
-                    if constexpr (SPLIT) {
-                        rs += (pv.x + pv.y) + (pv.z + pv.w);
-                        float4 pl;
-                        pl.x = tf32_rn(pv.x - ph.x); pl.y = tf32_rn(pv.y - ph.y); pl.z = tf32_rn(pv.z - ph.z); pl.w = tf32_rn(pv.w - ph.w);
-                        *reinterpret_cast<float4*>(prow + AT_P_BYTES + h * (AT_BQ * 128) + ((u ^ sw) << 4)) = pl;
-                    } else {
-                        rs += (ph.x + ph.y) + (ph.z + ph.w);
+                        for (int i = 0; i < 32; ++i)
+                            if (h * 32 + i >= nvalid) sh[i] = __float_as_uint(-INFINITY);
                     }
-                    *reinterpret_cast<float4*>(prow + h * (AT_BQ * 128) + ((u ^ sw) << 4)) = ph;
+                };
+                float mx = -INFINITY;
+                load_half(0);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(sh[i]));
+                load_half(1);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(sh[i]));
+                m_new = fmaxf(m_run, mx);
+                alpha = exp2f((m_run - m_new) * P.scale_log2);
+                const float mb = m_new * P.scale_log2;
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    const int h = 1 - hh;
+                    if (hh == 1) load_half(0);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {            // 8 keys = one 16-byte unit of the 128-byte row
+                        uint32_t w[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float a = exp2f(fmaf(__uint_as_float(sh[8 * u + 2 * i]), P.scale_log2, -mb));
+                            const float c = exp2f(fmaf(__uint_as_float(sh[8 * u + 2 * i + 1]), P.scale_log2, -mb));
+                            const __nv_bfloat162 pk = __floats2bfloat162_rn(a, c);
+                            const float2 back = __bfloat1622float2(pk);      // the denominator sums what the MMA multiplies
+                            rs += back.x + back.y;
+                            w[i] = *reinterpret_cast<const uint32_t*>(&pk);
+                        }
+                        *reinterpret_cast<uint4*>(prow + (((h * 4 + u) ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+                    }
+                }
+            } else {
+                uint32_t sr[2][32];
+                tc::tmem_ld32(tmem_S + lane_off, sr[0]);
+                tc::tmem_ld32(tmem_S + lane_off + 32, sr[1]);
+                tc::tmem_ld_wait();
+                float mx = -INFINITY;
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        float v = __uint_as_float(sr[h][i]);
+                        v = (h * 32 + i < nvalid) ? v : -INFINITY;
+                        sr[h][i] = __float_as_uint(v);
+                        mx = fmaxf(mx, v);
+                    }
+                m_new = fmaxf(m_run, mx);
+                alpha = exp2f((m_run - m_new) * P.scale_log2);
+                const float mb = m_new * P.scale_log2;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        float4 pv;
+                        pv.x = exp2f(fmaf(__uint_as_float(sr[h][4 * u]), P.scale_log2, -mb));
+                        pv.y = exp2f(fmaf(__uint_as_float(sr[h][4 * u + 1]), P.scale_log2, -mb));
+                        pv.z = exp2f(fmaf(__uint_as_float(sr[h][4 * u + 2]), P.scale_log2, -mb));
+                        pv.w = exp2f(fmaf(__uint_as_float(sr[h][4 * u + 3]), P.scale_log2, -mb));
+                        float4 ph;
+                        ph.x = tf32_rn(pv.x); ph.y = tf32_rn(pv.y); ph.z = tf32_rn(pv.z); ph.w = tf32_rn(pv.w);   // P is an MMA operand
+                        if constexpr (SPLIT) {
+                            rs += (pv.x + pv.y) + (pv.z + pv.w);
+                            float4 pl;
+                            pl.x = tf32_rn(pv.x - ph.x); pl.y = tf32_rn(pv.y - ph.y); pl.z = tf32_rn(pv.z - ph.z); pl.w = tf32_rn(pv.w - ph.w);
+                            *reinterpret_cast<float4*>(prow + L::P_BYTES + h * (AT_BQ * 128) + ((u ^ sw) << 4)) = pl;
+                        } else {
+                            rs += (ph.x + ph.y) + (ph.z + ph.w);
+                        }
+                        *reinterpret_cast<float4*>(prow + h * (AT_BQ * 128) + ((u ^ sw) << 4)) = ph;
+                    }
                 }
             }
             l_run = fmaf(l_run, alpha, rs);
@@ -226,7 +283,7 @@ attention_kernel(const __grid_constant__ AttentionParams P) {
             for (int i = 0; i < AT_D / 4; ++i)
                 op[i] = SPLIT ? make_float4(o_acc[4 * i] * inv, o_acc[4 * i + 1] * inv, o_acc[4 * i + 2] * inv, o_acc[4 * i + 3] * inv)
                               : make_float4(tf32_rn(o_acc[4 * i] * inv), tf32_rn(o_acc[4 * i + 1] * inv), tf32_rn(o_acc[4 * i + 2] * inv),
-                                            tf32_rn(o_acc[4 * i + 3] * inv));      // tf32 mode: operand of the proj 1x1 GEMM
+                                            tf32_rn(o_acc[4 * i + 3] * inv));      // tf32 / bf16 mode: operand of the proj 1x1 GEMM
         }
     }
     tc::tc_fence_before();
@@ -236,18 +293,23 @@ attention_kernel(const __grid_constant__ AttentionParams P) {
 
 int attention_prepare(AttentionParams& P, const AttentionDesc& d) {
     IPDM_REQUIRE(d.head_dim == AT_D && d.C == d.heads * AT_D, "attention: head_dim must be 64 (got %d)", d.head_dim);
-    IPDM_REQUIRE(d.t_pad % 4 == 0 && d.t_pad >= d.T, "attention: t_pad must be a multiple of 4");
+    IPDM_REQUIRE(d.t_pad % (d.bf16 ? 8 : 4) == 0 && d.t_pad >= d.T, "attention: t_pad must be a multiple of %d", d.bf16 ? 8 : 4);
+    IPDM_REQUIRE(!(d.bf16 && d.qk_lo), "attention: bf16 operands and the 3xTF32 split are exclusive");
     memset(&P, 0, sizeof(P));
+    const uint64_t eb = d.bf16 ? 2 : 4;                          // bytes per q/k/v element
+    const uint32_t row = d.bf16 ? 64 : 32;                        // elements per 128-byte operand row
+    const CUtensorMapDataType dt = d.bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
     const uint64_t dq[3] = {(uint64_t)3 * d.C, (uint64_t)d.T, (uint64_t)d.batch};
-    const uint64_t sq[2] = {(uint64_t)3 * d.C * 4, (uint64_t)d.T * 3 * d.C * 4};
-    const uint32_t bq[3] = {32, AT_BQ, 1}, bk[3] = {32, AT_BKV, 1};
-    IPDM_CHECK(tmap_encode(&P.mapQ, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, d.qk, dq, sq, bq, CU_TENSOR_MAP_SWIZZLE_128B));
-    IPDM_CHECK(tmap_encode(&P.mapK, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, d.qk, dq, sq, bk, CU_TENSOR_MAP_SWIZZLE_128B));
+    const uint64_t sq[2] = {(uint64_t)3 * d.C * eb, (uint64_t)d.T * 3 * d.C * eb};
+    const uint32_t bq[3] = {row, AT_BQ, 1}, bk[3] = {row, AT_BKV, 1};
+    IPDM_CHECK(tmap_encode(&P.mapQ, dt, 3, d.qk, dq, sq, bq, CU_TENSOR_MAP_SWIZZLE_128B));
+    IPDM_CHECK(tmap_encode(&P.mapK, dt, 3, d.qk, dq, sq, bk, CU_TENSOR_MAP_SWIZZLE_128B));
     const uint64_t dv[3] = {(uint64_t)d.T, (uint64_t)d.heads * AT_D, (uint64_t)d.batch};
-    const uint64_t sv[2] = {(uint64_t)d.t_pad * 4, (uint64_t)d.heads * AT_D * d.t_pad * 4};
-    const uint32_t bv[3] = {32, AT_D, 1};
-    IPDM_CHECK(tmap_encode(&P.mapV, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, d.vt, dv, sv, bv, CU_TENSOR_MAP_SWIZZLE_128B));
+    const uint64_t sv[2] = {(uint64_t)d.t_pad * eb, (uint64_t)d.heads * AT_D * d.t_pad * eb};
+    const uint32_t bv[3] = {row, AT_D, 1};
+    IPDM_CHECK(tmap_encode(&P.mapV, dt, 3, d.vt, dv, sv, bv, CU_TENSOR_MAP_SWIZZLE_128B));
     P.split = d.qk_lo != nullptr;
+    P.bf16 = d.bf16;
     if (P.split) {
         IPDM_REQUIRE(d.vt_lo != nullptr, "attention: fp32 mode needs both qk_lo and vt_lo");
         IPDM_CHECK(tmap_encode(&P.mapQlo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, d.qk_lo, dq, sq, bq, CU_TENSOR_MAP_SWIZZLE_128B));
@@ -261,16 +323,19 @@ int attention_prepare(AttentionParams& P, const AttentionDesc& d) {
 
 int attention_launch(const AttentionParams& P, cudaStream_t st) {
     static bool configured = false;
-    static_assert(AtL<true>::SMEM <= 227 * 1024, "fp32-mode attention tiles do not fit in shared memory");
+    static_assert(AtL<AT_SPLIT>::SMEM <= 227 * 1024, "fp32-mode attention tiles do not fit in shared memory");
+    static_assert(3 * (AtL<AT_BF16>::SMEM + 1024) <= 227 * 1024, "bf16 attention is sized for three CTAs per SM");
     if (!configured) {
-        IPDM_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AtL<false>::SMEM));
-        IPDM_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AtL<true>::SMEM));
+        IPDM_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<AT_TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, AtL<AT_TF32>::SMEM));
+        IPDM_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<AT_SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, AtL<AT_SPLIT>::SMEM));
+        IPDM_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<AT_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, AtL<AT_BF16>::SMEM));
         configured = true;
     }
     dim3 grid((P.T + AT_BQ - 1) / AT_BQ, P.heads, P.batch);
     ProfScope prof(PROF_ATTENTION, st, (P.split ? 3.0 : 1.0) * 4.0 * P.batch * P.heads * (double)P.T * P.T * AT_D);
-    if (P.split) attention_kernel<true><<<grid, AT_THREADS, AtL<true>::SMEM, st>>>(P);
-    else attention_kernel<false><<<grid, AT_THREADS, AtL<false>::SMEM, st>>>(P);
+    if (P.split) attention_kernel<AT_SPLIT><<<grid, AT_THREADS, AtL<AT_SPLIT>::SMEM, st>>>(P);
+    else if (P.bf16) attention_kernel<AT_BF16><<<grid, AT_THREADS, AtL<AT_BF16>::SMEM, st>>>(P);
+    else attention_kernel<AT_TF32><<<grid, AT_THREADS, AtL<AT_TF32>::SMEM, st>>>(P);
     count_launch();
     IPDM_CHECK_LAUNCH();
     return IPDM_OK;

@@ -17,6 +17,7 @@
 // warps run the epilogue: tcgen05.ld 32 lanes x 32 columns, + bias[t] (+ residual), 128-bit NHWC stores.
 // 3 stages x 32 KB of shared memory -> two CTAs per SM, so one CTA's epilogue overlaps the other's
 // main loop without a persistent scheduler.
+#include <cuda_bf16.h>
 #include "common.cuh"
 #include "tc.cuh"
 #include "unet_ops.cuh"
@@ -130,7 +131,7 @@ __device__ __forceinline__ void tc_epilogue(const ConvTcParams& P, uint32_t tmem
 #pragma unroll
             for (int i = 0; i < CHUNK / 4; ++i) { v[4 * i] += rcur[i].x; v[4 * i + 1] += rcur[i].y; v[4 * i + 2] += rcur[i].z; v[4 * i + 3] += rcur[i].w; }
         }
-        if (P.qkv_mode && !SPLIT) {                  // q, k, v are operands of the attention MMAs: round to nearest tf32
+        if (P.qkv_mode && !SPLIT && !P.qkv_bf16) {   // q, k, v are operands of the attention MMAs: round to nearest tf32
 #pragma unroll
             for (int i = 0; i < CHUNK; ++i) v[i] = tf32_rn(v[i]);
         }
@@ -138,6 +139,28 @@ __device__ __forceinline__ void tc_epilogue(const ConvTcParams& P, uint32_t tmem
         if (P.qkv_mode && SPLIT) {                   // fp32 mode: hand q, k, v to the attention kernel as tf32 hi / lo pairs
 #pragma unroll
             for (int i = 0; i < CHUNK; ++i) { const float h = tf32_rn(v[i]); lo[i] = tf32_rn(v[i] - h); v[i] = h; }
+        }
+        if (P.qkv_mode && P.qkv_bf16) {              // bf16 mode: q, k, v are bf16 operands of the attention MMAs
+            const bool is_v = (n % (3 * P.head_dim)) >= 2 * P.head_dim;
+            if (is_v) {
+                const int head = n / (3 * P.head_dim), d0 = n % (3 * P.head_dim) - 2 * P.head_dim;
+                __nv_bfloat16* vp = reinterpret_cast<__nv_bfloat16*>(P.vt) + (((size_t)b * P.heads + head) * P.head_dim + d0) * P.t_pad + ((size_t)py * P.W + px);
+#pragma unroll
+                for (int i = 0; i < CHUNK; ++i) vp[(size_t)i * P.t_pad] = __float2bfloat16_rn(v[i]);
+            } else {
+                uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(P.out) + pix * P.out_cs + n);
+#pragma unroll
+                for (int i = 0; i < CHUNK / 8; ++i) {
+                    uint32_t w[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const __nv_bfloat162 pk = __floats2bfloat162_rn(v[8 * i + 2 * k], v[8 * i + 2 * k + 1]);
+                        w[k] = *reinterpret_cast<const uint32_t*>(&pk);
+                    }
+                    op[i] = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+            }
+            continue;
         }
         if (P.qkv_mode && ((n % (3 * P.head_dim)) >= 2 * P.head_dim)) {
             // V of one head: write transposed, [b][head][d][t_pad] (token contiguous), so P.V^T is K-major for attention
@@ -749,7 +772,8 @@ int conv_tc_prepare(ConvTcParams& P, const ConvTcDesc& d) {
     P.bias = d.bias; P.bias_t_stride = d.bias_t_stride; P.t_dev = d.t_dev;
     P.res = d.res.p; P.res_cs = d.res.cs;
     P.qkv_mode = d.qkv_mode; P.vt = d.vt; P.t_pad = d.t_pad; P.heads = d.heads; P.head_dim = d.head_dim;
-    P.out_lo = d.out_lo; P.vt_lo = d.vt_lo;
+    P.out_lo = d.out_lo; P.vt_lo = d.vt_lo; P.qkv_bf16 = d.qkv_bf16;
+    IPDM_REQUIRE(!d.qkv_bf16 || (d.qkv_mode && !P.split && d.t_pad % 8 == 0 && d.out.cs % 8 == 0), "conv_tc: the bf16 qkv epilogue needs t_pad and the qk channel stride to be multiples of 8");
     IPDM_REQUIRE(!(d.qkv_mode && P.split) || (d.out_lo && d.vt_lo), "conv_tc: the fp32-mode qkv epilogue needs out_lo and vt_lo");
     return IPDM_OK;
 }

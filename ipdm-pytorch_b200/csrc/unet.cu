@@ -416,10 +416,12 @@ struct PlanBuilder {
     }
     int attn_block(const AttnW& a, int x) {
         const VTensor s = pl->vt[x];
-        const int T = s.h * s.w, tpad = round_up(T, 4);
+        const int T = s.h * s.w, tpad = round_up(T, 8);
         const bool split = net->precision == IPDM_PREC_FP32;
+        const bool bf = net->precision == IPDM_PREC_BF16;          // q, k, v^T stored as bf16, attention runs kind::f16
         const int qk = new_tensor(pl->B, s.h, s.w, 3 * a.C, 3 * a.C);
         const int vt = new_tensor(pl->B, 1, 1, a.C * tpad, a.C * tpad);
+        pl->vt[qk].bf16 = bf; pl->vt[vt].bf16 = bf;
         const int qk_lo = split ? new_tensor(pl->B, s.h, s.w, 3 * a.C, 3 * a.C) : -1;
         const int vt_lo = split ? new_tensor(pl->B, 1, 1, a.C * tpad, a.C * tpad) : -1;
         Op st; st.kind = Op::GN_STATS; st.nsrc = 1; st.src[0] = x; st.gn = &a.norm; st.norm_slot = norm_slots++; max_c = std::max(max_c, a.C); push(st);
@@ -557,6 +559,7 @@ static int build_plan(ipdm_unet* net, int B, int H, int W, Plan** out) {
                     const TensorNHWC v = resolve(*pl, o.aux);
                     d.qkv_mode = 1; d.vt = v.p; d.heads = net->heads; d.head_dim = o.cw->cin / net->heads; d.t_pad = v.c / o.cw->cin;
                     if (o.aux2 >= 0) { d.out_lo = resolve(*pl, o.aux2).p; d.vt_lo = resolve(*pl, o.aux3).p; }
+                    d.qkv_bf16 = v.bf16;
                 }
                 IPDM_CHECK(conv_tc_prepare(o.tcp, d));
                 o.flops = 2.0 * B * o.tcp.H * o.tcp.W * (double)o.cw->cin * o.cw->cout * d.ntaps;
@@ -585,7 +588,7 @@ static int build_plan(ipdm_unet* net, int B, int H, int W, Plan** out) {
                 const TensorNHWC qk = resolve(*pl, o.src[0]), v = resolve(*pl, o.aux), ot = resolve(*pl, o.dst);
                 AttentionDesc& a = o.ad;
                 a.qk = qk.p; a.vt = v.p; a.out = ot.p; a.batch = B; a.T = qk.h * qk.w; a.C = ot.c; a.heads = net->heads; a.head_dim = a.C / a.heads;
-                a.t_pad = v.c / a.C;
+                a.t_pad = v.c / a.C; a.bf16 = v.bf16;
                 if (o.aux2 >= 0) { a.qk_lo = resolve(*pl, o.aux2).p; a.vt_lo = resolve(*pl, o.aux3).p; }
                 IPDM_CHECK(attention_prepare(o.ap, a));
                 o.flops = attention_flops(a);
@@ -798,6 +801,14 @@ extern "C" int ipdm_debug_groupnorm(const float* src0, int c0, int cs0, const fl
 extern "C" int ipdm_debug_attention(const float* qk, const float* vt, const float* qk_lo, const float* vt_lo, float* out, int batch, int T,
                                     int t_pad, int heads, int C, void* stream) {
     AttentionDesc a; a.qk = qk; a.vt = vt; a.qk_lo = qk_lo; a.vt_lo = vt_lo; a.out = out; a.batch = batch; a.T = T; a.t_pad = t_pad; a.heads = heads; a.C = C; a.head_dim = C / heads;
+    AttentionParams P;
+    IPDM_CHECK(attention_prepare(P, a));
+    return attention_launch(P, (cudaStream_t)stream);
+}
+
+extern "C" int ipdm_debug_attention_bf16(const void* qk, const void* vt, float* out, int batch, int T, int t_pad, int heads, int C, void* stream) {
+    AttentionDesc a; a.qk = (const float*)qk; a.vt = (const float*)vt; a.out = out; a.batch = batch; a.T = T; a.t_pad = t_pad; a.heads = heads; a.C = C;
+    a.head_dim = C / heads; a.bf16 = 1;
     AttentionParams P;
     IPDM_CHECK(attention_prepare(P, a));
     return attention_launch(P, (cudaStream_t)stream);

@@ -32,6 +32,7 @@ struct ConvTcDesc {
     TensorNHWC out;
     int qkv_mode = 0; float* vt = nullptr; int t_pad = 0, heads = 0, head_dim = 0;
     float* out_lo = nullptr; float* vt_lo = nullptr;   // qkv epilogue in fp32 mode: q,k,v are written as tf32 hi / lo pairs
+    int qkv_bf16 = 0;                                  // qkv epilogue writes q,k (out) and v^T (vt) as bf16, t_pad % 8 == 0
     int variant = 0;                                   // 0 auto, 1 one-tile-per-CTA, 2 halo-reuse, 3 persistent (tests / benchmarks)
 };
 
@@ -46,7 +47,7 @@ struct ConvTcParams {
     const float* bias; int bias_t_stride; const int* t_dev;
     const float* res; int res_cs;
     int qkv_mode; float* vt; int t_pad, heads, head_dim;
-    float* out_lo; float* vt_lo;
+    float* out_lo; float* vt_lo; int qkv_bf16;
 };
 
 int conv_tc_prepare(ConvTcParams& P, const ConvTcDesc& d);
@@ -116,10 +117,11 @@ struct AttentionDesc {
     float* out = nullptr;       // NHWC [B][T][C], channel = h*d + dd
     const float* qk_lo = nullptr; const float* vt_lo = nullptr;   // fp32 (3xTF32) mode: tf32 lo parts, same layouts
     int batch = 0, T = 0, t_pad = 0, heads = 0, head_dim = 0, C = 0;
+    int bf16 = 0;               // qk and vt hold bf16 elements (same layouts, t_pad a multiple of 8)
 };
 struct AttentionParams {
     CUtensorMap mapQ, mapK, mapV, mapQlo, mapKlo, mapVlo;
-    int split;
+    int split, bf16;
     float* out; int batch, T, heads, C; float scale_log2;
 };
 int attention_prepare(AttentionParams& P, const AttentionDesc& d);

@@ -274,6 +274,19 @@ def test_attention(cuda, hw, batch):
         err = rel_l2(got.numpy(), want.numpy())
         print(f"attention T={T} {'3xtf32' if split else 'tf32'}: rel-L2 {err:.2e}")
         assert err < tol
+    # bf16 operand mode (kind::f16): q, k, v^T handed over as bf16, t_pad a multiple of 8
+    tpad8 = (T + 7) // 8 * 8
+    vt8 = torch.zeros(batch, heads, d, tpad8)
+    vt8[..., :T] = v.reshape(batch, heads, d, T)
+    out = torch.full((batch, hw[0], hw[1], C), float("nan"), device=cuda)
+    qk16, vt16 = qk_nhwc.to(torch.bfloat16).contiguous(), vt8.to(cuda).to(torch.bfloat16).contiguous()
+    _lib.check(_lib.lib().ipdm_debug_attention_bf16(_p(qk16), _p(vt16), _p(out), batch, T, tpad8, heads, C, None), "ipdm_debug_attention_bf16")
+    torch.cuda.synchronize()
+    got = nchw(out.cpu(), C)
+    assert torch.isfinite(got).all()
+    err = rel_l2(got.numpy(), want.numpy())
+    print(f"attention T={T} bf16: rel-L2 {err:.2e}")
+    assert err < 2e-2
 
 
 def test_upsample_nearest_index_rule(cuda):
