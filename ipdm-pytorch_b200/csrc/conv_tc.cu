@@ -716,7 +716,10 @@ int conv_tc_prepare(ConvTcParams& P, const ConvTcDesc& d) {
     static const int env_variant = getenv("IPDM_CONV_VARIANT") ? atoi(getenv("IPDM_CONV_VARIANT")) : 0;
     const int variant = d.variant ? d.variant : env_variant;
     const bool plain = !d.w_packed_lo && !d.qkv_mode && d.cout <= 768;
-    P.halo = variant == 2 && plain && d.stride == 1 && d.ntaps == 9 &&
+    // N = 16 layers (144 -> 16 at 1000x456) are bound by the L2 -> shared traffic of the A tiles, which the per-tap kernels fetch nine
+    // times: measured 2.96 ms per-tap at 16 slices; they take the halo-reuse kernel by default.
+    const bool narrow = d.cout < 64;
+    P.halo = (variant == 2 || (variant == 0 && narrow)) && plain && d.stride == 1 && d.ntaps == 9 &&
              (long long)ceil_div(P.W, HALO_TWV) * ceil_div(P.H, HALO_TH) * P.batch >= kNumSMs / 2;
     P.persistent = !P.halo && plain && (variant == 0 || variant == 3);
     P.tw_log2 = P.halo ? 5 : pick_tw_log2(P.H, P.W);

@@ -10,6 +10,8 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <map>
 #include <memory>
 #include <tuple>
@@ -18,7 +20,11 @@
 namespace ipdm {
 
 static int round_up(int a, int b) { return (a + b - 1) / b * b; }
-static int alloc_cs(int c) { return c >= 16 ? round_up(c, 32) : c; }
+// Channel stride of an activation tensor.  Thin tensors (<= 16 channels: the 2000x912 and 1000x456 levels, where a pad channel is
+// a full HBM stream) are stored dense; wider ones are padded to 32 floats = one 128-byte K chunk of the tf32 tensor-core path.
+// A 16-channel tensor that is read RAW by a tensor-core conv (1x1 shortcut over a concat) is widened to 32 by build_plan.
+static int alloc_cs(int c) { return c > 16 ? round_up(c, 32) : c; }
+static int tc_src_cs(int c) { return c >= 16 ? round_up(c, 32) : c; }      // stride a raw tcgen05 source must have
 
 static int gn_groups(int c) {           // norm_layer, model.py:82-90
     if (c % 32 == 0) return 32;
@@ -40,6 +46,7 @@ struct ConvW {
     float* w_dev = nullptr; float* w_dev_lo = nullptr; float* b_dev = nullptr;
     bool tc = false; int c0 = 0, cs0 = 0, c1 = 0, cs1 = 0, kpad = 0;
     bool bf16 = false;                       // operands (activation tile and packed weights) are bf16
+    float* w_dev_direct = nullptr;           // thin layers: the [tap][cin][cout] copy for the direct-kernel fallback
     bool thin = false; int thin_cs = 0;      // thin tensor-core path (conv_thin.cu): operand channel stride 8 / 16 / 32
 };
 struct ResW { GNW gn1, gn2; ConvW conv1, conv2, shortcut; bool has_shortcut = false; std::vector<float> temb_w, temb_b; float* bias1_t = nullptr; int cin = 0, cout = 0; };
@@ -157,13 +164,18 @@ static int pack_conv(ipdm_unet* net, ConvW& c, int c0, int c1, bool raw_sources,
             for (int ci = 0; ci < c.cin; ++ci)
                 for (int t = 0; t < kk; ++t) p[((size_t)t * 16 + co) * c.thin_cs + ci] = tf32_rn_host(c.w_host[((size_t)co * c.cin + ci) * kk + t]);
         IPDM_CHECK(upload(net, p, &c.w_dev));
+        std::vector<float> pd((size_t)kk * c.cin * c.cout);
+        for (int co = 0; co < c.cout; ++co)
+            for (int ci = 0; ci < c.cin; ++ci)
+                for (int t = 0; t < kk; ++t) pd[((size_t)t * c.cin + ci) * c.cout + co] = c.w_host[((size_t)co * c.cin + ci) * kk + t];
+        IPDM_CHECK(upload(net, pd, &c.w_dev_direct));
         if (!c.b_host.empty()) IPDM_CHECK(upload(net, c.b_host, &c.b_dev));
         return IPDM_OK;
     }
     if (c.tc) {
         c.c0 = c0; c.c1 = c1;
         if (c.bf16) { c.c0 = c.cin; c.c1 = 0; c.cs0 = round_up(c.cin, 64); c.cs1 = 0; }
-        else if (raw_sources) { c.cs0 = alloc_cs(c0); c.cs1 = c1 ? alloc_cs(c1) : 0; }
+        else if (raw_sources) { c.cs0 = tc_src_cs(c0); c.cs1 = c1 ? tc_src_cs(c1) : 0; }
         else { c.c0 = c.cin; c.c1 = 0; c.cs0 = round_up(c.cin, 32); c.cs1 = 0; }
         IPDM_REQUIRE(c.cs0 % 32 == 0 && c.cs1 % 32 == 0, "pack_conv: source strides %d/%d are not multiples of 32", c.cs0, c.cs1);
         c.kpad = c.cs0 + c.cs1;
@@ -492,6 +504,16 @@ static int build_plan(ipdm_unet* net, int B, int H, int W, Plan** out) {
     }
     pb.norm_conv(&h, 1, net->out_gn, net->convs[net->out_conv], pl->eps_id, -1, net->convs[net->out_conv].b_dev, 0, false, 1);
     pl->first_op = 0; pl->last_op = (int)pl->ops.size() - 1;
+    // raw fp32 sources of tensor-core convs are read in 128-byte K chunks: widen the (16-channel) tensors they touch, and send
+    // thin-path convs whose source no longer has the packed stride to the direct kernel
+    for (const Op& o : pl->ops)
+        if (o.kind == Op::CONV_TC)
+            for (int s = 0; s < o.nsrc; ++s) {
+                VTensor& t = pl->vt[o.src[s]];
+                if (!t.bf16 && !t.external && t.cs % 32 != 0) t.cs = round_up(t.c, 32);
+            }
+    for (Op& o : pl->ops)
+        if (o.kind == Op::CONV_THIN && pl->vt[o.src[0]].cs != o.cw->thin_cs) o.kind = Op::CONV_DIRECT;
     IPDM_REQUIRE(pl->ops[0].kind == Op::CONV_DIRECT && pl->ops.back().kind == Op::CONV_DIRECT,
                  "unet: first and last convolutions must be on the direct path (in/out channels too wide)");
 
@@ -577,7 +599,8 @@ static int build_plan(ipdm_unet* net, int B, int H, int W, Plan** out) {
                 ConvDirectDesc& d = o.cd;
                 d.nsrc = o.nsrc; d.src[0] = resolve(*pl, o.src[0]); if (o.nsrc > 1) d.src[1] = resolve(*pl, o.src[1]);
                 d.norm_scale = o.gn ? nscale : nullptr; d.norm_shift = o.gn ? nshift : nullptr;
-                d.ksize = o.cw->k; d.stride = o.stride; d.upsample = o.upsample; d.cin = o.cw->cin; d.cout = o.cw->cout; d.w = o.cw->w_dev;
+                d.ksize = o.cw->k; d.stride = o.stride; d.upsample = o.upsample; d.cin = o.cw->cin; d.cout = o.cw->cout;
+                d.w = o.cw->thin ? o.cw->w_dev_direct : o.cw->w_dev;
                 d.bias = o.bias; d.bias_t_stride = o.bias_t_stride; d.t_dev = o.use_t ? net->t_dev : nullptr;
                 if (o.res >= 0) d.res = resolve(*pl, o.res);
                 d.out = resolve(*pl, o.dst);
@@ -606,8 +629,17 @@ __global__ void set_int_kernel(int* p, int v) { *p = v; }
 static int run_plan(ipdm_unet* net, Plan* pl, const float* x, int t, float* eps, cudaStream_t st) {
     set_int_kernel<<<1, 1, 0, st>>>(net->t_dev, t);
     count_launch();
+    // IPDM_OP_TRACE=<file>: per-op CUDA-event timings of every forward, appended as text (tools/op_trace.py); not for timed runs
+    static const char* trace_path = getenv("IPDM_OP_TRACE");
+    std::vector<cudaEvent_t> ev;
+    if (trace_path) {
+        ev.resize(pl->ops.size() + 1);
+        for (auto& e : ev) cudaEventCreate(&e);
+        cudaEventRecord(ev[0], st);
+    }
     for (size_t i = 0; i < pl->ops.size(); ++i) {
         Op& o = pl->ops[i];
+        struct Rec { cudaEvent_t* e; cudaStream_t s; ~Rec() { if (e) cudaEventRecord(*e, s); } } rec{trace_path ? &ev[i + 1] : nullptr, st};
         switch (o.kind) {
             case Op::GN_STATS: IPDM_CHECK(groupnorm_stats_launch(o.gd, st)); break;
             case Op::GN_APPLY: IPDM_CHECK(groupnorm_apply_launch(o.gd, o.out_t, o.act, net->precision != IPDM_PREC_FP32, st)); break;
@@ -622,6 +654,23 @@ static int run_plan(ipdm_unet* net, Plan* pl, const float* x, int t, float* eps,
             case Op::UPSAMPLE: IPDM_CHECK(upsample_nearest_launch(o.src_t, o.out_t, net->precision != IPDM_PREC_FP32, st)); break;
             case Op::ATTN: IPDM_CHECK(attention_launch(o.ap, st)); break;
         }
+    }
+    if (trace_path) {
+        cudaStreamSynchronize(st);
+        if (FILE* f = fopen(trace_path, "a")) {
+            static const char* names[] = {"gn_stats", "gn_apply", "conv_tc", "conv_direct", "conv_thin", "upsample", "attention"};
+            fprintf(f, "# forward B=%d\n", pl->B);
+            for (size_t i = 0; i < pl->ops.size(); ++i) {
+                const Op& o = pl->ops[i];
+                float ms = 0.f; cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+                const VTensor& s0 = pl->vt[o.src[0]];
+                const VTensor* d = o.dst >= 0 ? &pl->vt[o.dst] : nullptr;
+                fprintf(f, "%s src %dx%dx%d(+%d) dst %dx%dx%d k%d s%d %.1f us\n", names[(int)o.kind], s0.h, s0.w, s0.c, o.nsrc > 1 ? pl->vt[o.src[1]].c : 0,
+                        d ? d->h : 0, d ? d->w : 0, d ? d->c : 0, o.cw ? o.cw->k : 0, o.stride, ms * 1e3f);
+            }
+            fclose(f);
+        }
+        for (auto& e : ev) cudaEventDestroy(e);
     }
     return IPDM_OK;
 }

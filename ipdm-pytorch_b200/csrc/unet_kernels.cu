@@ -159,20 +159,134 @@ conv_direct_kernel(const ConvDirectParams P) {
         const int ox = ox0 + threadIdx.x * CD_PX + p;
         if (ox >= P.wout) continue;
         const size_t op = ((size_t)n * P.hout + oy) * P.wout + ox;
+        float o[COUT_T];
 #pragma unroll
         for (int i = 0; i < COUT_T; ++i) {
             const int co = co_base + i;
+            float v = 0.f;                                          // pad channels of the output stay zero
             if (co < P.cout) {
-                float v = acc[p][i] + (bias ? __ldg(bias + co) : 0.f);
+                v = acc[p][i] + (bias ? __ldg(bias + co) : 0.f);
                 if (P.res) v += __ldg(P.res + op * P.res_cs + co);
-                P.out[op * P.out_cs + co] = v;
-            } else if (co < P.out_cs) {
-                P.out[op * P.out_cs + co] = 0.f;
             }
+            o[i] = v;
+        }
+        if ((P.out_cs & 3) == 0) {
+#pragma unroll
+            for (int q = 0; q < COUT_T / 4; ++q)
+                if (co_base + 4 * q < P.out_cs)
+                    *reinterpret_cast<float4*>(P.out + op * P.out_cs + co_base + 4 * q) = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < COUT_T; ++i)
+                if (co_base + i < P.out_cs) P.out[op * P.out_cs + co_base + i] = o[i];
         }
         if (co_base + COUT_T >= P.cout)
             for (int co = co_base + COUT_T; co < P.out_cs; ++co) P.out[op * P.out_cs + co] = 0.f;
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Small direct convolution without a staged tile: the 1x1 shortcuts over a virtual concat, the stride-2
+// Downsample convs of the thin levels and the 1 -> C stem convs.  These layers have no GroupNorm in
+// front, so nothing is amortised by staging; they are pure HBM streams (4*(C_in + C_out) B per pixel) and
+// the staged kernel above reaches only ~1.5 TB/s on them (two barriers per channel chunk).
+// A thread owns NP horizontally adjacent output pixels x 4 output channels; the C_out/4 channel groups of a
+// pixel sit in adjacent lanes, so a warp's 128-bit stores cover whole output pixels back to back (full
+// sectors) and its input loads are warp-broadcast 128-bit __ldg (neighbouring taps hit in L1).  Weights:
+// [tap][ci][C_out] in shared memory, one 128-bit load per (tap, ci).  A CTA walks image rows (grid-stride),
+// so the index arithmetic per item is a shift and a mask.
+// ------------------------------------------------------------------------------------------------
+template <int KS, int STRIDE, int NP, int VEC>
+__global__ void __launch_bounds__(256)
+conv_small_kernel(const ConvDirectParams P, int cog_log2, int nrows) {
+    extern __shared__ __align__(16) float cs_w[];                // [KS*KS][cin][ncog*4], zero beyond C_out
+    constexpr int PAD = KS / 2, NI = (NP - 1) * STRIDE + KS;
+    const int ncog = 1 << cog_log2, cpad = ncog * 4;
+    for (int i = threadIdx.x; i < KS * KS * P.cin * cpad; i += 256) {
+        const int co = i & (cpad - 1), rest = i >> (cog_log2 + 2);          // rest = tap * cin + ci
+        cs_w[i] = co < P.cout ? __ldg(P.w + (size_t)rest * P.cout + co) : 0.f;
+    }
+    __syncthreads();
+    const float* bias = P.bias ? P.bias + (P.t_dev ? (size_t)(*P.t_dev) * P.bias_t_stride : 0) : nullptr;
+    const int wq = (P.wout + NP - 1) / NP;
+    const int nv = P.cin / VEC;
+    const int row_items = wq << cog_log2;
+    for (int row = blockIdx.x; row < nrows; row += gridDim.x) {
+        const int n = row / P.hout, oy = row - n * P.hout;
+        for (int item = threadIdx.x; item < row_items; item += 256) {
+            const int cb = (item & (ncog - 1)) * 4;
+            const int ox0 = (item >> cog_log2) * NP, ixb = ox0 * STRIDE - PAD;
+            float acc[NP][4];
+#pragma unroll
+            for (int p = 0; p < NP; ++p) acc[p][0] = acc[p][1] = acc[p][2] = acc[p][3] = 0.f;
+#pragma unroll
+            for (int dy = 0; dy < KS; ++dy) {
+                const int iy = oy * STRIDE + dy - PAD;
+                if (iy < 0 || iy >= P.hin) continue;
+                const size_t rowp = ((size_t)n * P.hin + iy) * P.win;
+#pragma unroll 2
+                for (int v = 0; v < nv; ++v) {
+                    const int c = v * VEC;
+                    const float* sp; int scs;
+                    if (c < P.c0) { sp = P.src0 + c; scs = P.cs0; } else { sp = P.src1 + (c - P.c0); scs = P.cs1; }
+                    float in[NI][VEC];
+#pragma unroll
+                    for (int k = 0; k < NI; ++k) {
+                        const int ix = ixb + k;
+                        const bool ok = ix >= 0 && ix < P.win;
+                        if constexpr (VEC == 4) {
+                            const float4 t = ok ? __ldg(reinterpret_cast<const float4*>(sp + (rowp + ix) * scs)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            in[k][0] = t.x; in[k][1] = t.y; in[k][2] = t.z; in[k][3] = t.w;
+                        } else {
+                            in[k][0] = ok ? __ldg(sp + (rowp + ix) * scs) : 0.f;
+                        }
+                    }
+#pragma unroll
+                    for (int dx = 0; dx < KS; ++dx)
+#pragma unroll
+                        for (int e = 0; e < VEC; ++e) {
+                            const float4 w4 = *reinterpret_cast<const float4*>(cs_w + ((size_t)((dy * KS + dx) * P.cin + c + e)) * cpad + cb);
+#pragma unroll
+                            for (int p = 0; p < NP; ++p) {
+                                const float x = in[p * STRIDE + dx][e];
+                                acc[p][0] = fmaf(x, w4.x, acc[p][0]); acc[p][1] = fmaf(x, w4.y, acc[p][1]);
+                                acc[p][2] = fmaf(x, w4.z, acc[p][2]); acc[p][3] = fmaf(x, w4.w, acc[p][3]);
+                            }
+                        }
+                }
+            }
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+                const int ox = ox0 + p;
+                if (ox >= P.wout || cb >= P.out_cs) continue;
+                const size_t op = ((size_t)n * P.hout + oy) * P.wout + ox;
+                float o[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int co = cb + i;
+                    float v = 0.f;                                    // pad channels of the output stay zero
+                    if (co < P.cout) {
+                        v = acc[p][i] + (bias ? __ldg(bias + co) : 0.f);
+                        if (P.res) v += __ldg(P.res + op * P.res_cs + co);
+                    }
+                    o[i] = v;
+                }
+                *reinterpret_cast<float4*>(P.out + op * P.out_cs + cb) = make_float4(o[0], o[1], o[2], o[3]);
+            }
+        }
+    }
+}
+
+template <int KS, int STRIDE, int VEC>
+static int launch_small(const ConvDirectParams& P, int batch, cudaStream_t st) {
+    constexpr int NP = 2;
+    int cog_log2 = 0;
+    while ((4 << cog_log2) < std::max(P.cout, P.out_cs)) ++cog_log2;
+    const size_t smem = (size_t)KS * KS * P.cin * (4 << cog_log2) * sizeof(float);
+    IPDM_REQUIRE(smem <= 48 * 1024, "conv_small: weights (%zu B) do not fit in shared memory", smem);
+    const int nrows = batch * P.hout;
+    conv_small_kernel<KS, STRIDE, NP, VEC><<<std::min(nrows, 148 * 8), 256, smem, st>>>(P, cog_log2, nrows);
+    return IPDM_OK;
 }
 
 template <int COUT_T, int KS, int STRIDE>
@@ -219,6 +333,19 @@ int conv_direct_launch(const ConvDirectDesc& d, cudaStream_t st) {
              ((uintptr_t)P.src0 % 16 == 0) && (d.nsrc == 1 || (uintptr_t)P.src1 % 16 == 0);
     ProfScope prof(PROF_CONV_DIRECT, st, 4.0 * s0.n * ((double)s0.h * s0.w * d.cin + (double)P.hout * P.wout * d.cout));   // bytes
     int rc = IPDM_ERR_UNSUPPORTED;
+    // layers with nothing to amortise by staging (no fused GroupNorm / upsample): the streaming kernel
+    const bool small_ok = !d.norm_scale && !d.upsample && d.cin <= 64 && d.out.cs % 4 == 0 &&
+                          (size_t)d.ksize * d.ksize * d.cin * (size_t)(2 * std::max(d.cout, d.out.cs)) * 4 <= 48 * 1024;
+    int small_rc = 1;                                             // 1 = not a streaming-kernel layer
+    if (small_ok && P.vec4 && d.ksize == 1) small_rc = launch_small<1, 1, 4>(P, s0.n, st);                          // 1x1 shortcut over a concat
+    else if (small_ok && P.vec4 && d.ksize == 3 && d.stride == 2) small_rc = launch_small<3, 2, 4>(P, s0.n, st);    // Downsample
+    else if (small_ok && d.cin == 1 && d.nsrc == 1 && d.ksize == 3 && d.stride == 1) small_rc = launch_small<3, 1, 1>(P, s0.n, st);   // stem 1 -> C
+    if (small_rc <= 0) {
+        IPDM_CHECK(small_rc);
+        count_launch();
+        IPDM_CHECK_LAUNCH();
+        return IPDM_OK;
+    }
 #define IPDM_CD(CT) (d.ksize == 1 ? launch_direct<CT, 1, 1>(P, s0.n, st) : (d.stride == 1 ? launch_direct<CT, 3, 1>(P, s0.n, st) : launch_direct<CT, 3, 2>(P, s0.n, st)))
     rc = ct == 4 ? IPDM_CD(4) : (ct == 8 ? IPDM_CD(8) : IPDM_CD(16));
 #undef IPDM_CD

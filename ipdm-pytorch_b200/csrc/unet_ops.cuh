@@ -68,6 +68,7 @@ struct ConvThinParams {
     float* out; int out_cs;
     const float* bias; int bias_t_stride; const int* t_dev;
     const float* res; int res_cs;
+    int dbg;                           // IPDM_THIN_DBG experiments (tools only): 1 no stores, 2 no residual loads, 4 no MMAs
 };
 int conv_thin_prepare(ConvThinParams& P, const ConvThinDesc& d);
 int conv_thin_launch(const ConvThinParams& P, cudaStream_t st);

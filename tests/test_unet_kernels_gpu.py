@@ -100,6 +100,7 @@ def rnd(*shape, seed=0, scale=1.0):
     (1, 0, 4, 3, 1, (40, 70)), (4, 0, 8, 3, 1, (33, 65)), (4, 0, 8, 1, 1, (33, 65)), (8, 0, 8, 3, 2, (25, 57)),
     (16, 8, 16, 3, 1, (21, 47)), (8, 4, 8, 1, 1, (21, 47)), (8, 0, 1, 3, 1, (40, 70)), (16, 0, 16, 3, 2, (50, 38)),
     (1, 0, 64, 3, 1, (32, 32)), (64, 0, 1, 3, 1, (24, 40)),
+    (16, 8, 8, 1, 1, (37, 95)), (16, 16, 16, 1, 1, (21, 47)), (8, 0, 16, 1, 1, (64, 31)), (8, 0, 8, 3, 2, (64, 96)), (1, 0, 64, 3, 1, (47, 53)),
 ])
 def test_direct_conv(cuda, c0, c1, cout, k, stride, hw):
     x0 = rnd(2, c0, *hw, seed=1)
