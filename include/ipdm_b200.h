@@ -217,7 +217,7 @@ int ipdm_debug_conv(const float* src0_dev, int c0, int cs0, const float* src1_de
                     const float* norm_scale_dev, const float* norm_shift_dev, const float* res_dev, int res_cs, float* out_dev,
                     int out_cs, int use_tc, void* stream);
 /* average milliseconds of one tensor-core conv launch at the given shape (mode as use_tc above; variant: 0 auto,
- * 1 one-tile-per-CTA, 2 halo-reuse, 3 persistent); buffers are allocated and freed inside */
+ * 1 one-tile-per-CTA, 2 halo-reuse, 3 persistent, 4 persistent halo-reuse); buffers are allocated and freed inside */
 int ipdm_debug_conv_time(int c0, int c1, int n, int h, int w, int cout, int k, int stride, int mode, int variant, int with_res,
                          int iters, float* ms_out, double* flops_out);
 int ipdm_debug_groupnorm(const float* src0_dev, int c0, int cs0, const float* src1_dev, int c1, int cs1, int n, int h, int w,

@@ -738,8 +738,9 @@ static TensorNHWC mk(const float* p, int n, int h, int w, int c, int cs) {
 extern "C" int ipdm_debug_conv(const float* src0, int c0, int cs0, const float* src1, int c1, int cs1, int n, int h, int w,
                                const float* w_host, const float* bias_host, int cout, int k, int stride, int upsample_h,
                                int upsample_w, const float* norm_scale, const float* norm_shift, const float* res, int res_cs,
-                               float* out, int out_cs, int use_tc, void* stream) {
+                               float* out, int out_cs, int use_tc_arg, void* stream) {
     IPDM_REQUIRE(src0 && w_host && out, "ipdm_debug_conv: null argument");
+    const int use_tc = use_tc_arg & 0xff, variant = use_tc_arg >> 8;      // bits 8..: kernel variant of the tensor-core path (0 auto)
     ipdm_unet holder;
     holder.precision = use_tc == 2 ? IPDM_PREC_FP32 : (use_tc == 3 ? IPDM_PREC_BF16 : IPDM_PREC_TF32);
     ConvW cw; cw.cin = c0 + c1; cw.cout = cout; cw.k = k;
@@ -772,6 +773,7 @@ extern "C" int ipdm_debug_conv(const float* src0, int c0, int cs0, const float* 
         d.ntaps = k * k; d.stride = stride; d.cout = cout; d.w_packed = cw.w_dev; d.w_packed_lo = cw.w_dev_lo; d.w_k = cw.kpad; d.bias = cw.b_dev;
         if (res) d.res = mk(res, n, ho, wo, cout, res_cs);
         d.out = mk(out, n, ho, wo, cout, out_cs);
+        d.variant = variant;
         ConvTcParams P;
         IPDM_CHECK(conv_tc_prepare(P, d));
         rc = conv_tc_launch(P, st);

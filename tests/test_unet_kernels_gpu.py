@@ -47,6 +47,7 @@ def _p(t):
 def run_conv(cuda, x0, x1, weight, bias, k, stride, use_tc, res=None, up=None, norm=None):
     from ipdm_pytorch_b200 import _lib
     use_tc = int(use_tc)
+    variant, use_tc = use_tc >> 8, use_tc & 0xFF                       # bits 8..: tensor-core kernel variant (0 auto)
     if use_tc == 3:                                                     # bf16 operand tensor: one source, stride multiple of 64
         x0 = x0 if x1 is None else torch.cat([x0, x1], 1)
         x1 = None
@@ -72,7 +73,7 @@ def run_conv(cuda, x0, x1, weight, bias, k, stride, use_tc, res=None, up=None, n
         sc, sh = [t.to(cuda).contiguous() for t in norm]
     rc = _lib.lib().ipdm_debug_conv(_p(a0), c0, cs0, _p(a1), c1, cs1, n, h, w, _p(wh), _p(bh), cout, k, stride,
                                     0 if up is None else up[0], 0 if up is None else up[1], _p(sc), _p(sh), _p(r), ocs, _p(out), ocs,
-                                    int(use_tc), None)
+                                    int(use_tc) | (variant << 8), None)
     _lib.check(rc, "ipdm_debug_conv")
     torch.cuda.synchronize()
     full = out.cpu()
@@ -193,20 +194,23 @@ def test_tc_conv(cuda, c0, c1, cout, k, stride, hw):
 
 
 @pytest.mark.parametrize("c0,c1,cout,k,stride,hw", [(128, 0, 128, 3, 1, (176, 228)), (64, 0, 64, 3, 1, (256, 160)), (128, 16, 16, 3, 1, (260, 300)),
-                                                  (128, 0, 128, 3, 2, (353, 457))])
+                                                  (128, 0, 128, 3, 2, (353, 457)), (128, 128, 256, 3, 1, (203, 331)), (256, 0, 128, 3, 1, (500, 228))])
 def test_tc_conv_halo_reuse_variant(cuda, c0, c1, cout, k, stride, hw):
-    """Stride-1 3x3 layers with >= 74 tiles of 8x30 outputs take the halo-reuse kernel (nine taps read one staged halo tile
-    through shifted UMMA descriptors); ragged in both directions, concat, N = 16/64/128, tf32 and bf16 operands."""
+    """Halo-reuse kernels (nine taps read one staged halo tile through shifted UMMA descriptors): variant 2 one tile per CTA,
+    variant 4 persistent with double-buffered accumulator pairs; ragged in both directions, concat, N = 16/64/128, tf32 and bf16
+    operands.  The stride-2 case checks that an ineligible layer falls back to the per-tap kernels."""
     x0 = rnd(2, c0, *hw, seed=1)
     x1 = rnd(2, c1, *hw, seed=2) if c1 else None
     w = rnd(cout, c0 + c1, k, k, seed=3, scale=(1.0 / ((c0 + c1) * k * k)) ** 0.5)
     b = rnd(cout, seed=4)
-    want = ref_conv(x0, x1, w, b, k, stride)
-    got = run_conv(cuda, x0, x1, w, b, k, stride, 1)
-    assert rel_l2(got.numpy(), want.numpy()) < TF32_TOL
-    if stride == 1:
-        got = run_conv(cuda, x0, x1, w, b, k, stride, 3)
-        assert rel_l2(got.numpy(), want.numpy()) < 8e-3
+    res = rnd(2, cout, *hw, seed=5) if stride == 1 else None
+    want = ref_conv(x0, x1, w, b, k, stride, res=res)
+    for variant in (2, 4):
+        got = run_conv(cuda, x0, x1, w, b, k, stride, 1 | (variant << 8), res=res)
+        assert rel_l2(got.numpy(), want.numpy()) < TF32_TOL, variant
+        if stride == 1:
+            got = run_conv(cuda, x0, x1, w, b, k, stride, 3 | (variant << 8), res=res)
+            assert rel_l2(got.numpy(), want.numpy()) < 8e-3, variant
 
 
 @pytest.mark.parametrize("cin,cs,cout,k,hw,batch", [(8, 8, 8, 3, (40, 70), 2), (4, 8, 8, 3, (33, 65), 1), (8, 8, 16, 1, (21, 47), 2), (16, 16, 16, 3, (50, 38), 2),

@@ -1,4 +1,4 @@
-"""Per-shape timing of the tensor-core conv kernels: python tools/bench_conv.py  (prints a markdown table)."""
+"""Per-shape timing of the tensor-core conv kernels: python tools/bench_conv.py [batch]  (prints a markdown table)."""
 import ctypes
 import os
 import sys
@@ -8,19 +8,20 @@ import torch
 from ipdm_pytorch_b200 import _lib
 L = _lib.lib()
 torch.zeros(1, device="cuda")
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 4
 SHAPES = [  # c0, c1, n, h, w, cout, k, stride
-    (128, 0, 4, 500, 228, 128, 3, 1), (128, 128, 4, 500, 228, 128, 3, 1), (128, 0, 1, 1000, 456, 128, 3, 1), (128, 0, 1, 500, 228, 128, 3, 1),
-    (128, 0, 4, 250, 114, 128, 3, 1), (256, 0, 4, 125, 57, 256, 3, 1), (256, 0, 4, 63, 29, 256, 3, 1), (64, 0, 4, 512, 512, 64, 3, 1),
-    (128, 0, 4, 256, 256, 128, 3, 1), (256, 0, 4, 64, 64, 256, 3, 1), (128, 0, 4, 500, 228, 128, 3, 2), (256, 0, 4, 125, 57, 768, 1, 1),
+    (128, 0, B, 500, 228, 128, 3, 1), (256, 0, B, 500, 228, 128, 3, 1), (128, 0, B, 1000, 456, 128, 3, 1), (144, 0, B, 1000, 456, 16, 3, 1),
+    (128, 0, B, 250, 114, 128, 3, 1), (256, 0, B, 125, 57, 256, 3, 1), (256, 0, B, 63, 29, 256, 3, 1), (64, 0, B, 512, 512, 64, 3, 1),
+    (128, 0, B, 512, 512, 64, 3, 1), (128, 0, B, 512, 512, 128, 3, 1), (128, 0, B, 256, 256, 128, 3, 1), (256, 0, B, 64, 64, 256, 3, 1),
+    (256, 0, B, 32, 32, 256, 3, 1),
 ]
+NAMES = {1: "one-tile", 2: "halo", 3: "persistent", 4: "halo-persistent"}
 print("| shape | mode | kernel | ms | TFLOP/s |\n|---|---|---|---:|---:|")
 for sh in SHAPES:
     c0, c1, n, h, w, cout, k, stride = sh
     for mode, mname in ((1, "tf32"), (3, "bf16")):
-        if mode == 3 and stride != 1:
-            continue
-        for fg in (1, 3):
+        for fg in (3, 4):
             ms, fl = ctypes.c_float(), ctypes.c_double()
-            rc = L.ipdm_debug_conv_time(c0, c1, n, h, w, cout, k, stride, mode, fg, 1, 20, ctypes.byref(ms), ctypes.byref(fl))
+            rc = L.ipdm_debug_conv_time(c0, c1, n, h, w, cout, k, stride, mode, fg, 1, 10, ctypes.byref(ms), ctypes.byref(fl))
             _lib.check(rc, "conv_time")
-            print(f"| {c0}+{c1}->{cout} k{k} s{stride} {n}x{h}x{w} | {mname} | { {1: 'one-tile', 2: 'halo', 3: 'persistent'}[fg] } | {ms.value:.3f} | {fl.value / ms.value / 1e9:.0f} |")
+            print(f"| {c0}+{c1}->{cout} k{k} s{stride} {n}x{h}x{w} | {mname} | {NAMES[fg]} | {ms.value:.3f} | {fl.value / ms.value / 1e9:.0f} |")
