@@ -480,52 +480,62 @@ __device__ __forceinline__ void store_vec4(float* out, size_t elem_off, const fl
     }
 }
 
+// grid (nblk, slices).  Thread t always handles the same 4-channel vector (t % V) of pixel rows t / V, t / V + R, ...: its
+// scale / shift / source pointer live in registers, the loop body is U independent 128-bit loads, the affine + SiLU, and U
+// stores -- no index arithmetic (the flat-index version spent two 64-bit divisions per vector and reached 3.7-4.6 TB/s).
 __global__ void __launch_bounds__(256)
 gn_apply_kernel(const float* __restrict__ s0, int c0, int cs0, const float* __restrict__ s1, int c1, int cs1,
                 const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ out, int ocs,
-                size_t npix_per_slice, size_t nvec_total, int act, int rnd, int obf16) {
+                size_t npix, int act, int rnd, int obf16) {
     const int Ctot = c0 + c1, V = ocs / 4;
+    const int R = 256 / V > 0 ? 256 / V : 1;
     constexpr int U = 4;                                         // independent 128-bit loads in flight per thread
-    const size_t stride = (size_t)gridDim.x * 256;
-    for (size_t i0 = (size_t)blockIdx.x * 256 + threadIdx.x; i0 < nvec_total; i0 += U * stride) {
-        float4 v[U]; size_t pix[U]; int c[U]; bool live[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const size_t i = i0 + u * stride;
-            live[u] = i < nvec_total;
-            pix[u] = live[u] ? i / V : 0;
-            c[u] = live[u] ? (int)(i - pix[u] * V) * 4 : 0;
-            v[u] = make_float4(0, 0, 0, 0);
-            if (live[u] && c[u] < Ctot)
-                v[u] = c[u] < c0 ? ld_stream(reinterpret_cast<const float4*>(s0 + pix[u] * cs0 + c[u]))
-                                 : ld_stream(reinterpret_cast<const float4*>(s1 + pix[u] * cs1 + (c[u] - c0)));
+    const int n = blockIdx.y;
+    for (int t = threadIdx.x; t < R * V; t += 256) {             // one pass unless V > 256
+        const int cv = t % V, prow = t / V, c = 4 * cv;
+        const bool real = c < Ctot;                              // pad channels of the operand tensor are written as zeros
+        float4 sc = make_float4(0, 0, 0, 0), sh = sc;
+        const float* src = nullptr; int scs = 0;
+        if (real) {
+            sc = __ldg(reinterpret_cast<const float4*>(scale + (size_t)n * Ctot + c));
+            sh = __ldg(reinterpret_cast<const float4*>(shift + (size_t)n * Ctot + c));
+            if (c < c0) { src = s0 + (size_t)n * npix * cs0 + c; scs = cs0; } else { src = s1 + (size_t)n * npix * cs1 + (c - c0); scs = cs1; }
         }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            if (!live[u]) continue;
+        const size_t obase = (size_t)n * npix * ocs + c;
+        const size_t stride = (size_t)gridDim.x * R;
+        auto finish = [&](float4 v, size_t pix) {
             float4 o = make_float4(0, 0, 0, 0);
-            if (c[u] < Ctot) {
-                const int n = (int)(pix[u] / npix_per_slice);
-                const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + (size_t)n * Ctot + c[u]));
-                const float4 sh = __ldg(reinterpret_cast<const float4*>(shift + (size_t)n * Ctot + c[u]));
-                o.x = fmaf(v[u].x, sc.x, sh.x); o.y = fmaf(v[u].y, sc.y, sh.y); o.z = fmaf(v[u].z, sc.z, sh.z); o.w = fmaf(v[u].w, sc.w, sh.w);
+            if (real) {
+                o.x = fmaf(v.x, sc.x, sh.x); o.y = fmaf(v.y, sc.y, sh.y); o.z = fmaf(v.z, sc.z, sh.z); o.w = fmaf(v.w, sc.w, sh.w);
                 if (act) { o.x = silu(o.x); o.y = silu(o.y); o.z = silu(o.z); o.w = silu(o.w); }
                 if (rnd) { o.x = tf32_rn(o.x); o.y = tf32_rn(o.y); o.z = tf32_rn(o.z); o.w = tf32_rn(o.w); }   // tf32 mode: MMA operand
             }
-            store_vec4(out, pix[u] * ocs + c[u], o, obf16);
+            store_vec4(out, obase + pix * ocs, o, obf16);
+        };
+        size_t pix = (size_t)blockIdx.x * R + prow;
+        for (; pix + (U - 1) * stride < npix; pix += U * stride) {
+            float4 v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) v[u] = real ? ld_stream(reinterpret_cast<const float4*>(src + (pix + u * stride) * scs)) : make_float4(0, 0, 0, 0);
+#pragma unroll
+            for (int u = 0; u < U; ++u) finish(v[u], pix + u * stride);
         }
+        for (; pix < npix; pix += stride)
+            finish(real ? ld_stream(reinterpret_cast<const float4*>(src + pix * scs)) : make_float4(0, 0, 0, 0), pix);
     }
 }
 
 int groupnorm_apply_launch(const GroupNormDesc& d, const TensorNHWC& out, int act_silu, int round_tf32, cudaStream_t st) {
     const TensorNHWC& a = d.src[0];
     const int c1 = d.nsrc == 2 ? d.src[1].c : 0;
-    IPDM_REQUIRE(out.cs % 4 == 0 && out.cs >= a.c + c1 && a.c % 4 == 0, "groupnorm_apply: bad channel layout");
-    const size_t npix = (size_t)a.h * a.w, nvec = (size_t)a.n * npix * (out.cs / 4);
-    const int grid = (int)std::min<size_t>((size_t)kNumSMs * 8, (nvec + 1023) / 1024);
+    IPDM_REQUIRE(out.cs % 4 == 0 && out.cs >= a.c + c1 && a.c % 4 == 0 && out.cs <= 1024, "groupnorm_apply: bad channel layout");
+    const size_t npix = (size_t)a.h * a.w;
+    const int V = out.cs / 4, R = std::max(256 / V, 1);
+    // ~8 CTAs per SM over the whole batch, at least 4 row-iterations per thread
+    const int nblk = (int)std::max<size_t>(1, std::min<size_t>((size_t)ceil_div(kNumSMs * 8, a.n), (npix + (size_t)R * 4 - 1) / ((size_t)R * 4)));
     ProfScope prof(PROF_GROUPNORM, st, a.n * (double)npix * (4.0 * (a.c + c1) + (out.bf16 ? 2.0 : 4.0) * out.cs));
-    gn_apply_kernel<<<std::max(grid, 1), 256, 0, st>>>(a.p, a.c, a.cs, d.nsrc == 2 ? d.src[1].p : nullptr, c1, d.nsrc == 2 ? d.src[1].cs : 0,
-                                          d.scale, d.shift, out.p, out.cs, npix, nvec, act_silu, round_tf32 && !out.bf16, out.bf16);
+    gn_apply_kernel<<<dim3(nblk, a.n), 256, 0, st>>>(a.p, a.c, a.cs, d.nsrc == 2 ? d.src[1].p : nullptr, c1, d.nsrc == 2 ? d.src[1].cs : 0,
+                                                     d.scale, d.shift, out.p, out.cs, npix, act_silu, round_tf32 && !out.bf16, out.bf16);
     count_launch();
     IPDM_CHECK_LAUNCH();
     return IPDM_OK;
@@ -534,31 +544,38 @@ int groupnorm_apply_launch(const GroupNormDesc& d, const TensorNHWC& out, int ac
 // ------------------------------------------------------------------------------------------------
 // nearest resize
 // ------------------------------------------------------------------------------------------------
+// grid (nblk, slices); thread t owns the 4-channel vector t % V (as gn_apply), 32-bit index arithmetic per pixel
 __global__ void __launch_bounds__(256)
 upsample_kernel(const float* __restrict__ src, int hs, int ws, int sc, int scs, float* __restrict__ dst, int hd, int wd, int dcs,
-                float sy, float sx, size_t nvec_total, int rnd, int obf16) {
-    const int V = dcs / 4;
-    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < nvec_total; i += (size_t)gridDim.x * 256) {
-        const size_t pix = i / V;
-        const int c = (int)(i - pix * V) * 4;
-        const int x = (int)(pix % wd);
-        const size_t r = pix / wd;
-        const int y = (int)(r % hd), n = (int)(r / hd);
-        const int yy = min((int)floorf((float)y * sy), hs - 1), xx = min((int)floorf((float)x * sx), ws - 1);
-        float4 v = make_float4(0, 0, 0, 0);
-        if (c < sc) v = __ldg(reinterpret_cast<const float4*>(src + (((size_t)n * hs + yy) * ws + xx) * scs + c));
-        if (rnd) { v.x = tf32_rn(v.x); v.y = tf32_rn(v.y); v.z = tf32_rn(v.z); v.w = tf32_rn(v.w); }   // tf32 mode: feeds a tensor-core conv only
-        store_vec4(dst, pix * dcs + c, v, obf16);
+                float sy, float sx, int rnd, int obf16) {
+    const int V = dcs / 4, R = 256 / V > 0 ? 256 / V : 1;
+    const int n = blockIdx.y;
+    const unsigned npix = (unsigned)hd * (unsigned)wd;
+    for (int t = threadIdx.x; t < R * V; t += 256) {
+        const int cv = t % V, c = 4 * cv;
+        const bool real = c < sc;
+        const float* sp = src + (size_t)n * hs * ws * scs + c;
+        const size_t obase = (size_t)n * npix * dcs + c;
+        for (unsigned pix = blockIdx.x * R + t / V; pix < npix; pix += gridDim.x * R) {
+            const unsigned y = pix / (unsigned)wd, x = pix - y * (unsigned)wd;
+            const int yy = min((int)floorf((float)y * sy), hs - 1), xx = min((int)floorf((float)x * sx), ws - 1);
+            float4 v = make_float4(0, 0, 0, 0);
+            if (real) v = __ldg(reinterpret_cast<const float4*>(sp + ((size_t)yy * ws + xx) * scs));
+            if (rnd) { v.x = tf32_rn(v.x); v.y = tf32_rn(v.y); v.z = tf32_rn(v.z); v.w = tf32_rn(v.w); }   // tf32 mode: feeds a tensor-core conv only
+            store_vec4(dst, obase + (size_t)pix * dcs, v, obf16);
+        }
     }
 }
 
 int upsample_nearest_launch(const TensorNHWC& src, const TensorNHWC& dst, int round_tf32, cudaStream_t st) {
-    IPDM_REQUIRE(src.cs % 4 == 0 && dst.cs % 4 == 0 && dst.cs >= src.c && src.c % 4 == 0 && src.n == dst.n, "upsample: bad layout");
-    const size_t nvec = dst.pixels() * (dst.cs / 4);
-    const int grid = (int)std::min<size_t>((size_t)kNumSMs * 8, (nvec + 255) / 256);
+    IPDM_REQUIRE(src.cs % 4 == 0 && dst.cs % 4 == 0 && dst.cs >= src.c && src.c % 4 == 0 && src.n == dst.n && dst.cs <= 1024, "upsample: bad layout");
+    const size_t npix = (size_t)dst.h * dst.w;
+    IPDM_REQUIRE(npix < (1u << 31), "upsample: image too large");
+    const int V = dst.cs / 4, R = std::max(256 / V, 1);
+    const int nblk = (int)std::max<size_t>(1, std::min<size_t>((size_t)ceil_div(kNumSMs * 8, dst.n), (npix + (size_t)R * 4 - 1) / ((size_t)R * 4)));
     ProfScope prof(PROF_UPSAMPLE, st, 4.0 * (double)src.elems() + (dst.bf16 ? 2.0 : 4.0) * dst.elems());
-    upsample_kernel<<<grid, 256, 0, st>>>(src.p, src.h, src.w, src.c, src.cs, dst.p, dst.h, dst.w, dst.cs, (float)src.h / dst.h,
-                                          (float)src.w / dst.w, nvec, round_tf32 && !dst.bf16, dst.bf16);
+    upsample_kernel<<<dim3(nblk, dst.n), 256, 0, st>>>(src.p, src.h, src.w, src.c, src.cs, dst.p, dst.h, dst.w, dst.cs, (float)src.h / dst.h,
+                                                        (float)src.w / dst.w, round_tf32 && !dst.bf16, dst.bf16);
     count_launch();
     IPDM_CHECK_LAUNCH();
     return IPDM_OK;
