@@ -28,6 +28,11 @@ for p in (REPO, PKG):
         sys.path.insert(0, p)
 
 HBM_FALLBACK_GBS, TENSOR_FALLBACK_TFLOPS = 6650.0, 1590.0        # /opt/skills/guides/B200_PROFILING.md
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel from an `ncu --set full` capture
+CONV_TC_NCU_TRAFFIC = dict(bytes_per_launch=2.297e9,
+                           note="profiles/r01_conv_halo_persistent_ncu_full.md: conv_halo_persistent_kernel<128,6>, bf16, 16 x 500x228, 128->128 3x3 "
+                                "+residual: 1.401 GB read + 0.896 GB written per launch; algorithmic bytes of that layer 2.33 GB (bf16 operand 0.47 + fp32 "
+                                "residual 0.93 + fp32 output 0.93)")
 
 
 def parse():
@@ -36,8 +41,9 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=4, help="slices per GPU per step")
-    ap.add_argument("--precision", default="tf32")
+    ap.add_argument("--batch", type=int, default=16, help="slices per GPU per step (BASELINE.json configs[2]: batch 16 on one B200)")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32", "fp32"],
+                    help="UNet operand precision (configs[2]: bf16 UNet, fp32 sampler state); tf32 / fp32 are the parity modes")
     ap.add_argument("--t_start_proj", type=int, nargs="+", default=[15, 15, 15])
     ap.add_argument("--t_start_img", type=int, nargs="+", default=[15, 15, 15])
     ap.add_argument("--skip_cpu_baseline", action="store_true")
@@ -229,10 +235,13 @@ def run_b200(args, rank, world, local_rank):
     pk = peaks()
     tc_ms, tc_flops, tc_n = prof["conv_tc"]
     total_prof_ms = sum(v[0] for v in prof.values())
-    roof = dict(bound="tensor", kernel="conv_tc_kernel (tcgen05 kind::tf32 implicit-GEMM conv)", achieved=tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms else None,
-                peak=pk["tensor"], unit="TFLOP/s", traffic=None, peak_source=pk["which"],
-                note="achieved = FLOPs issued by all conv_tc launches of one step / their summed CUDA-event time; peak is dense bf16 "
-                     "(a kind::tf32 MMA runs at half that rate, so 0.5 is this kernel's ceiling in tf32 mode)",
+    kind = {"bf16": "kind::f16 (bf16 operands, fp32 accumulate)", "tf32": "kind::tf32", "fp32": "kind::tf32 x3 (3xTF32 split)"}[args.precision]
+    roof = dict(bound="tensor", kernel=f"conv_tc family: conv_halo_persistent_kernel / conv_tc_persistent_kernel (tcgen05 {kind} implicit-GEMM conv)",
+                achieved=tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms else None,
+                peak=pk["tensor"], unit="TFLOP/s", traffic=CONV_TC_NCU_TRAFFIC["bytes_per_launch"] if args.precision == "bf16" else None,
+                traffic_note=CONV_TC_NCU_TRAFFIC["note"], peak_source=pk["which"],
+                note="achieved = FLOPs issued by all conv_tc launches of one step / their summed CUDA-event time (launching stream); peak is "
+                     "dense bf16 (a kind::tf32 MMA runs at half that rate, so 0.5 is the ceiling of this family in tf32 mode)",
                 share_of_step=tc_ms / total_prof_ms if total_prof_ms else None, launches_per_step=tc_n)
     roof["frac"] = roof["achieved"] / roof["peak"] if roof["achieved"] else None
     families = {}
@@ -255,10 +264,37 @@ def run_b200(args, rank, world, local_rank):
                          ms_per_step=ms_e2e / args.steps),
                 gpu_launches=int(launches), clocks=clocks, roofline=roof, kernel_families=families,
                 unet_effective_tflops=step_flops * args.steps / (ms * 1e-3) / 1e12)
+    line["fbp_batch64"] = fbp_batch64(dev, pk)
     if not args.skip_cpu_baseline:
         c = cpu_reference_sample(args.t_start_proj, args.t_start_img)
         line["cpu_baseline"] = dict(value=1.0 / c["per_slice_s"], unit="slices/s", cores=c["cores"], kind="port", sample=c["sample"])
     print(json.dumps(line))
+
+
+def fbp_batch64(dev, pk):
+    """BASELINE.json configs[1]: the FBP convertor alone on 64 sinograms (fan-beam weight + ramp filter + pixel-driven backprojection).
+    Algorithmic HBM bytes per slice: sinogram read + filtered write + filtered read + image write; the backprojection itself is bound
+    by the 2000 x 512 x 512 pixel-view updates per slice (gather + interpolate from L1/shared), not by HBM."""
+    import torch
+    from ipdm_pytorch_b200 import engine, synthetic
+    n = 64
+    sino = torch.from_numpy(synthetic.cheap_sinogram(4, seed=7)).to(dev).repeat(n // 4, 1, 1).contiguous()
+    plan = engine.FBPPlan(max_batch=n)
+    out = torch.empty(n, 512, 512, device=dev)
+    for _ in range(2):
+        plan.forward(sino, out=out)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(5):
+        plan.forward(sino, out=out)
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / 5
+    bytes_alg = n * (3 * 2000 * 912 * 4 + 512 * 512 * 4)
+    return dict(workload="FBP convertor alone, 64 sinograms 2000x912 -> 512x512", ms=round(ms, 3), slices_per_s=round(n / (ms * 1e-3), 1),
+                algorithmic_gb_s=round(bytes_alg / (ms * 1e-3) / 1e9, 1), frac_of_hbm=round(bytes_alg / (ms * 1e-3) / 1e9 / pk["hbm"], 4),
+                pixel_view_updates_per_s=round(n * 2000 * 512 * 512 / (ms * 1e-3) / 1e9, 1), updates_unit="G/s")
 
 
 def main():
