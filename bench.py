@@ -100,6 +100,7 @@ def cpu_reference_sample(t_start_proj, t_start_img):
     import numpy as np
     import torch
     from oracle import ipdm_oracle as O
+    torch.set_num_threads(len(os.sched_getaffinity(0)))
     torch.manual_seed(0)
     pnet, inet = O.UNetOracle(**O.PROJ_UNET).eval(), O.UNetOracle(**O.IMG_UNET).eval()
     g = torch.Generator().manual_seed(0)
@@ -265,7 +266,7 @@ def run_b200(args, rank, world, local_rank):
                 gpu_launches=int(launches), clocks=clocks, roofline=roof, kernel_families=families,
                 unet_effective_tflops=step_flops * args.steps / (ms * 1e-3) / 1e12)
     line["fbp_batch64"] = fbp_batch64(dev, pk)
-    if not args.skip_cpu_baseline:
+    if not args.skip_cpu_baseline and world == 1:             # rank 0 at N=1 only
         c = cpu_reference_sample(args.t_start_proj, args.t_start_img)
         line["cpu_baseline"] = dict(value=1.0 / c["per_slice_s"], unit="slices/s", cores=c["cores"], kind="port", sample=c["sample"])
     print(json.dumps(line))
@@ -303,7 +304,10 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        if rank == 0:
+            # torchrun exports OMP_NUM_THREADS=1; the reference arm uses every host core it is allowed to run on
+            os.environ["OMP_NUM_THREADS"] = str(len(os.sched_getaffinity(0)))
+            run_reference(args, rank, world)
         return
     import torch
     import torch.distributed as dist
