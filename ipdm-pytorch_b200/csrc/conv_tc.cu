@@ -198,7 +198,7 @@ constexpr int EPI_PITCH = 36;
 constexpr int EPI_WARP_FLOATS = 32 * EPI_PITCH;
 template <int BLOCK_N>
 __device__ __forceinline__ void tc_epilogue_coalesced(const ConvTcParams& P, uint32_t tmem_acc, int quarter, int lane, int b, int x0, int y0,
-                                                      int n0, const float* sbias, float* stile, int tw_valid) {
+                                                      int n0, const float* sbias, float* stile, int tw_valid, float* stats_row) {
     const int TW = 1 << P.tw_log2;                    // tile row pitch; only the first tw_valid columns are outputs
     constexpr int CHUNK = BLOCK_N < 32 ? 16 : 32;
     constexpr int LPP = CHUNK / 4;                    // lanes per pixel row segment (8 for 32 channels, 4 for 16)
@@ -236,12 +236,30 @@ __device__ __forceinline__ void tc_epilogue_coalesced(const ConvTcParams& P, uin
             row[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
         __syncwarp();
         const float4 bq = *reinterpret_cast<const float4*>(sbias + cc + c4);
+        float4 ss = make_float4(0.f, 0.f, 0.f, 0.f), sq = ss;          // GroupNorm partials of this lane's 4 channels
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
             if (okv[j] && nok) {
                 float4 v = *reinterpret_cast<const float4*>(stile + (j * PPI + psub) * EPI_PITCH + c4);
                 v.x += bq.x + rres[j].x; v.y += bq.y + rres[j].y; v.z += bq.z + rres[j].z; v.w += bq.w + rres[j].w;
                 *reinterpret_cast<float4*>(P.out + pixv[j] * P.out_cs + n) = v;
+                ss.x += v.x; ss.y += v.y; ss.z += v.z; ss.w += v.w;
+                sq.x = fmaf(v.x, v.x, sq.x); sq.y = fmaf(v.y, v.y, sq.y); sq.z = fmaf(v.z, v.z, sq.z); sq.w = fmaf(v.w, v.w, sq.w);
+            }
+        }
+        if (stats_row) {
+            // statistics of the values just written, for the GroupNorm that reads this tensor next: sum over the warp's 32 pixels
+            // (lanes with equal lane % LPP hold the same channels), one [2][cout] row per warp, fixed order => deterministic
+#pragma unroll
+            for (int o = LPP; o < 32; o <<= 1) {
+                ss.x += __shfl_xor_sync(0xffffffffu, ss.x, o); ss.y += __shfl_xor_sync(0xffffffffu, ss.y, o);
+                ss.z += __shfl_xor_sync(0xffffffffu, ss.z, o); ss.w += __shfl_xor_sync(0xffffffffu, ss.w, o);
+                sq.x += __shfl_xor_sync(0xffffffffu, sq.x, o); sq.y += __shfl_xor_sync(0xffffffffu, sq.y, o);
+                sq.z += __shfl_xor_sync(0xffffffffu, sq.z, o); sq.w += __shfl_xor_sync(0xffffffffu, sq.w, o);
+            }
+            if (lane < LPP && nok) {
+                *reinterpret_cast<float4*>(stats_row + n) = ss;
+                *reinterpret_cast<float4*>(stats_row + P.cout + n) = sq;
             }
         }
     }
@@ -660,8 +678,13 @@ conv_tc_persistent_kernel(const __grid_constant__ ConvTcParams P) {
             int b, x0, y0, n0; decode(tile, b, x0, y0, n0);
             tc::mbar_wait(&tfull[acc], ((uint32_t)tl >> 1) & 1u);
             tc::tc_fence_after();
+            float* srow = nullptr;
+            if (P.stats_out) {
+                const int tr = tile / n_ntiles - b * tiles_per_img;                      // tile index inside the slice
+                srow = P.stats_out + ((size_t)b * P.stats_rows + tr * 4 + (warp & 3)) * 2 * P.cout;
+            }
             tc_epilogue_coalesced<BLOCK_N>(P, tmem_base + acc * ACC_COLS, warp & 3, lane, b, x0, y0, n0, sbias + n0,
-                                           (float*)(smem + S::EPI_OFF) + (warp & 3) * EPI_WARP_FLOATS, 1 << P.tw_log2);
+                                           (float*)(smem + S::EPI_OFF) + (warp & 3) * EPI_WARP_FLOATS, 1 << P.tw_log2, srow);
             tc::tc_fence_before();
             tc::mbar_arrive(&tempty[acc]);                           // 128 arrivals: the accumulator may be overwritten
         }
@@ -814,8 +837,13 @@ conv_halo_persistent_kernel(const __grid_constant__ ConvTcParams P) {
             int b, x0, y0, n0; decode(tile, b, x0, y0, n0);
             tc::mbar_wait(&tfull[buf], ((uint32_t)tl >> 1) & 1u);
             tc::tc_fence_after();
+            float* srow = nullptr;
+            if (P.stats_out) {
+                const int tr = tile / n_ntiles - b * tiles_per_img;
+                srow = P.stats_out + ((size_t)b * P.stats_rows + (tr * 2 + mt) * 4 + (warp & 3)) * 2 * P.cout;
+            }
             tc_epilogue_coalesced<BLOCK_N>(P, tmem_base + (buf * 2 + mt) * ACC_COLS, warp & 3, lane, b, x0, y0 + 4 * mt, n0, sbias + n0, stile,
-                                           HALO_TWV);
+                                           HALO_TWV, srow);
             tc::tc_fence_before();
             tc::mbar_arrive(&tempty[buf]);
         }
@@ -868,6 +896,11 @@ static int pick_tw_log2(int H, int W) {
         if (best_area < 0 || area < best_area || (area == best_area && l > best)) { best = l; best_area = area; }
     }
     return best;
+}
+
+int conv_tc_stats_rows_bound(int h, int w) {
+    const int halo = ceil_div(w, HALO_TWV) * ceil_div(h, HALO_TH) * 2, tap = ceil_div(w, 8) * ceil_div(h, 16);   // pick_tw_log2 never does worse than 8x16
+    return 4 * std::max(halo, tap);
 }
 
 int conv_tc_prepare(ConvTcParams& P, const ConvTcDesc& d) {
@@ -948,6 +981,9 @@ int conv_tc_prepare(ConvTcParams& P, const ConvTcDesc& d) {
     P.res = d.res.p; P.res_cs = d.res.cs;
     P.qkv_mode = d.qkv_mode; P.vt = d.vt; P.t_pad = d.t_pad; P.heads = d.heads; P.head_dim = d.head_dim;
     P.out_lo = d.out_lo; P.vt_lo = d.vt_lo; P.qkv_bf16 = d.qkv_bf16;
+    P.stats_out = P.persistent ? d.stats_out : nullptr;              // only the persistent kernels' epilogue produces statistics
+    P.stats_rows = P.stats_out ? P.tiles_x * P.tiles_y * (P.halo ? 2 : 1) * 4 : 0;
+    IPDM_REQUIRE(!P.stats_out || (d.cout % 4 == 0 && P.stats_rows <= conv_tc_stats_rows_bound(P.H, P.W)), "conv_tc: statistics rows %d exceed the bound", P.stats_rows);
     IPDM_REQUIRE(!d.qkv_bf16 || (d.qkv_mode && !P.split && d.t_pad % 8 == 0 && d.out.cs % 8 == 0), "conv_tc: the bf16 qkv epilogue needs t_pad and the qk channel stride to be multiples of 8");
     IPDM_REQUIRE(!(d.qkv_mode && P.split) || (d.out_lo && d.vt_lo), "conv_tc: the fp32-mode qkv epilogue needs out_lo and vt_lo");
     return IPDM_OK;

@@ -54,7 +54,8 @@ struct AttnW { GNW norm; ConvW qkv, proj; int C = 0; };
 struct LayerRef { enum Kind { CONV_IN, RES, ATTN, DOWN, UP } kind; int idx; };
 typedef std::vector<LayerRef> Block;
 
-struct VTensor { int n = 0, h = 0, w = 0, c = 0, cs = 0; int def = -1, last = -1; size_t off = 0; bool external = false; int bf16 = 0; };
+struct VTensor { int n = 0, h = 0, w = 0, c = 0, cs = 0; int def = -1, last = -1; size_t off = 0; bool external = false; int bf16 = 0;
+                 int stats_t = -1, stats_rows = 0; };   // companion tensor with the producer's GroupNorm partials (conv_tc epilogue), rows per slice
 
 struct Op {
     enum Kind { GN_STATS, GN_APPLY, CONV_TC, CONV_DIRECT, CONV_THIN, UPSAMPLE, ATTN } kind;
@@ -62,6 +63,7 @@ struct Op {
     const GNW* gn = nullptr; int norm_slot = -1; int act = 1;
     const ConvW* cw = nullptr; const float* bias = nullptr; int bias_t_stride = 0; bool use_t = false;
     int stride = 1, upsample = 0, qkv = 0;
+    int stats = -1;                            // CONV_TC: tensor that receives the GroupNorm partials of the output
     // materialised
     ConvTcParams tcp; ConvThinParams thp; ConvDirectDesc cd; GroupNormDesc gd; TensorNHWC out_t, src_t; AttentionParams ap; AttentionDesc ad;
     double flops = 0;
@@ -514,6 +516,31 @@ static int build_plan(ipdm_unet* net, int B, int H, int W, Plan** out) {
             }
     for (Op& o : pl->ops)
         if (o.kind == Op::CONV_THIN && pl->vt[o.src[0]].cs != o.cw->thin_cs) o.kind = Op::CONV_DIRECT;
+    // GroupNorm statistics come from the epilogue of the conv that writes the tensor when that conv runs a persistent tensor-core
+    // kernel (decided in conv_tc_prepare; the 3xTF32 and qkv kernels do not): a companion tensor holds the per-warp-row partials
+    // from the producer to the last GroupNorm that reads the tensor, and that GroupNorm skips its own read of the tensor.
+    if (net->precision != IPDM_PREC_FP32) {
+        std::vector<int> producer(pl->vt.size(), -1);
+        for (int i = 0; i < (int)pl->ops.size(); ++i) if (pl->ops[i].dst >= 0) producer[pl->ops[i].dst] = i;
+        for (int gi = 0; gi < (int)pl->ops.size(); ++gi) {
+            if (pl->ops[gi].kind != Op::GN_STATS) continue;
+            for (int sidx = 0; sidx < pl->ops[gi].nsrc; ++sidx) {
+                const int t = pl->ops[gi].src[sidx];
+                const int pi = t < (int)producer.size() ? producer[t] : -1;
+                // (the thin kernel's epilogue is its bottleneck: statistics there cost more than the separate read, measured)
+                if (pi < 0 || pl->ops[pi].kind != Op::CONV_TC || pl->ops[pi].qkv || pl->vt[t].c % 4 != 0) continue;
+                if (pl->vt[t].stats_t < 0) {
+                    const int rows = conv_tc_stats_rows_bound(pl->vt[t].h, pl->vt[t].w);
+                    const int len = rows * 2 * pl->vt[t].c;
+                    const int id = pb.new_tensor(B, 1, 1, len, len);
+                    pl->vt[id].def = pi; pl->vt[id].last = gi;
+                    pl->vt[t].stats_t = id; pl->ops[pi].stats = id;
+                } else {
+                    pl->vt[pl->vt[t].stats_t].last = std::max(pl->vt[pl->vt[t].stats_t].last, gi);
+                }
+            }
+        }
+    }
     IPDM_REQUIRE(pl->ops[0].kind == Op::CONV_DIRECT && pl->ops.back().kind == Op::CONV_DIRECT,
                  "unet: first and last convolutions must be on the direct path (in/out channels too wide)");
 
@@ -567,6 +594,10 @@ static int build_plan(ipdm_unet* net, int B, int H, int W, Plan** out) {
                 GroupNormDesc& g = o.gd;
                 g.nsrc = o.nsrc; g.src[0] = resolve(*pl, o.src[0]); if (o.nsrc > 1) g.src[1] = resolve(*pl, o.src[1]);
                 g.groups = o.gn->groups; g.gamma = o.gn->gamma; g.beta = o.gn->beta; g.scale = nscale; g.shift = nshift; g.partials = pl->gn_partials;
+                for (int sidx = 0; sidx < o.nsrc; ++sidx) {
+                    const VTensor& v = pl->vt[o.src[sidx]];
+                    if (v.stats_t >= 0 && v.stats_rows > 0) { g.tile_stats[sidx] = resolve(*pl, v.stats_t).p; g.tile_rows[sidx] = v.stats_rows; }
+                }
                 if (o.kind == Op::GN_APPLY) o.out_t = resolve(*pl, o.dst);
             } break;
             case Op::CONV_TC: {
@@ -583,7 +614,9 @@ static int build_plan(ipdm_unet* net, int B, int H, int W, Plan** out) {
                     if (o.aux2 >= 0) { d.out_lo = resolve(*pl, o.aux2).p; d.vt_lo = resolve(*pl, o.aux3).p; }
                     d.qkv_bf16 = v.bf16;
                 }
+                if (o.stats >= 0) d.stats_out = resolve(*pl, o.stats).p;
                 IPDM_CHECK(conv_tc_prepare(o.tcp, d));
+                pl->vt[o.dst].stats_rows = o.tcp.stats_out ? o.tcp.stats_rows : 0;
                 o.flops = 2.0 * B * o.tcp.H * o.tcp.W * (double)o.cw->cin * o.cw->cout * d.ntaps;
             } break;
             case Op::CONV_THIN: {

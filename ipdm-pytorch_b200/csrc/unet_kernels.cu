@@ -410,6 +410,35 @@ gn_partial_kernel(const float* __restrict__ src, int C, int cs, size_t npix, dou
     }
 }
 
+// A source whose producer conv already wrote per-warp-row statistics (ConvTcDesc::stats_out: [slice][rows][2][C] fp32) is not read
+// again: this kernel folds those rows (a few % of the tensor's bytes, coalesced) into the same fp64 partials gn_partial_kernel writes.
+// grid (nblk, slices); thread t owns the 4-float vector t % V of a row (V = 2C/4), rows t / V, t / V + R, ...
+__global__ void __launch_bounds__(256)
+gn_tile_reduce_kernel(const float* __restrict__ tile, int rows, int C, double* __restrict__ partials, int c_off, int Ctot) {
+    __shared__ double red[256][4];
+    const int n = blockIdx.y, V = 2 * C / 4;
+    const int R = 256 / V > 0 ? 256 / V : 1;
+    const int t = threadIdx.x;
+    double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+    if (t < R * V) {
+        const int cv = t % V;
+        const float* base = tile + (size_t)n * rows * 2 * C + 4 * cv;
+        for (int r = blockIdx.x * R + t / V; r < rows; r += gridDim.x * R) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(base + (size_t)r * 2 * C));
+            a0 += v.x; a1 += v.y; a2 += v.z; a3 += v.w;
+        }
+    }
+    red[t][0] = a0; red[t][1] = a1; red[t][2] = a2; red[t][3] = a3;
+    __syncthreads();
+    for (int i = t; i < 2 * C; i += 256) {                        // i indexes the [2][C] row: half = sum / sum of squares
+        const int cv = i / 4, comp = i % 4;
+        double a = 0;
+        for (int r = 0; r < R; ++r) a += red[r * V + cv][comp];
+        const int half = i / C, ch = i - half * C;
+        partials[(((size_t)n * gridDim.x + blockIdx.x) * Ctot + c_off + ch) * 2 + half] = a;
+    }
+}
+
 __global__ void __launch_bounds__(128)
 gn_finalize_kernel(const double* __restrict__ partials, int nblk, int Ctot, int groups, double count,
                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
@@ -446,7 +475,9 @@ int groupnorm_stats_launch(const GroupNormDesc& d, cudaStream_t st) {
     IPDM_REQUIRE(Ctot % d.groups == 0, "groupnorm: %d channels not divisible by %d groups", Ctot, d.groups);
     const TensorNHWC& s0 = d.src[0];
     const size_t npix = (size_t)s0.h * s0.w;
-    ProfScope prof(PROF_GROUPNORM, st, 4.0 * s0.n * (double)npix * Ctot);
+    double read_c = 0;
+    for (int s = 0; s < d.nsrc; ++s) if (!d.tile_stats[s]) read_c += d.src[s].c;
+    ProfScope prof(PROF_GROUPNORM, st, 4.0 * s0.n * (double)npix * read_c);
     const int R0 = std::max(1, 256 / (s0.c / 4));
     // one partial grid for all sources: enough CTAs to cover the machine a few times, at least 2 unrolled trips each
     int nblk = (int)std::min<size_t>(GN_MAX_BLOCKS, (npix + (size_t)R0 * 2 * GN_UNROLL - 1) / ((size_t)R0 * 2 * GN_UNROLL));
@@ -455,7 +486,12 @@ int groupnorm_stats_launch(const GroupNormDesc& d, cudaStream_t st) {
     for (int s = 0; s < d.nsrc; ++s) {
         const TensorNHWC& t = d.src[s];
         IPDM_REQUIRE(t.c % 4 == 0 && t.cs % 4 == 0 && t.c <= 1024, "groupnorm: channel count %d must be a multiple of 4", t.c);
-        gn_partial_kernel<<<dim3(nblk, s0.n), 256, 0, st>>>(t.p, t.c, t.cs, npix, d.partials, c_off, Ctot);
+        if (d.tile_stats[s]) {                                    // statistics from the producer's epilogue: fold its partial rows
+            IPDM_REQUIRE(t.c <= 512, "groupnorm: producer statistics support at most 512 channels per source");
+            gn_tile_reduce_kernel<<<dim3(nblk, s0.n), 256, 0, st>>>(d.tile_stats[s], d.tile_rows[s], t.c, d.partials, c_off, Ctot);
+        } else {                                                  // one read of the tensor
+            gn_partial_kernel<<<dim3(nblk, s0.n), 256, 0, st>>>(t.p, t.c, t.cs, npix, d.partials, c_off, Ctot);
+        }
         count_launch();
         c_off += t.c;
     }

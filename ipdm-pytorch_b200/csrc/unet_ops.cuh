@@ -33,8 +33,12 @@ struct ConvTcDesc {
     int qkv_mode = 0; float* vt = nullptr; int t_pad = 0, heads = 0, head_dim = 0;
     float* out_lo = nullptr; float* vt_lo = nullptr;   // qkv epilogue in fp32 mode: q,k,v are written as tf32 hi / lo pairs
     int qkv_bf16 = 0;                                  // qkv epilogue writes q,k (out) and v^T (vt) as bf16, t_pad % 8 == 0
-    int variant = 0;                                   // 0 auto, 1 one-tile-per-CTA, 2 halo-reuse, 3 persistent (tests / benchmarks)
+    int variant = 0;                                   // 0 auto, 1 one-tile-per-CTA, 2 halo-reuse, 3 persistent, 4 persistent halo (tests / benchmarks)
+    // GroupNorm statistics of the OUTPUT, fused into the persistent kernels' epilogue: per (slice, 32-pixel warp row) partial sums
+    // [batch][stats_rows][2][cout] (sum, sum of squares; fp32 over 32 pixels, reduced in fp64 by gn_finalize).  nullptr: off.
+    float* stats_out = nullptr;
 };
+int conv_tc_stats_rows_bound(int h, int w);            // upper bound of stats_rows for an h x w output, any kernel variant
 
 struct ConvTcParams {
     CUtensorMap mapA[4];
@@ -48,6 +52,7 @@ struct ConvTcParams {
     const float* res; int res_cs;
     int qkv_mode; float* vt; int t_pad, heads, head_dim;
     float* out_lo; float* vt_lo; int qkv_bf16;
+    float* stats_out; int stats_rows;                  // set by prepare only for the persistent kernels (else nullptr / 0)
 };
 
 int conv_tc_prepare(ConvTcParams& P, const ConvTcDesc& d);
@@ -102,6 +107,10 @@ struct GroupNormDesc {
     float* scale = nullptr;            // [batch][C] out
     float* shift = nullptr;
     double* partials = nullptr;        // workspace [batch][GN_MAX_BLOCKS][C][2]
+    // per source: statistics already produced by the conv that wrote the tensor (ConvTcDesc::stats_out), [batch][rows][2][c];
+    // such a source is not read again
+    const float* tile_stats[2] = {nullptr, nullptr};
+    int tile_rows[2] = {0, 0};
 };
 constexpr int GN_MAX_BLOCKS = 888;        // 6 CTAs per SM
 int groupnorm_stats_launch(const GroupNormDesc& d, cudaStream_t st);
