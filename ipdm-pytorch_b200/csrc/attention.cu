@@ -14,6 +14,7 @@
 // S = QK^T: kind::tf32 M=128 N=64 K=8 x8;  O_blk = P V: M=128 N=64 K=8 x8.  Out-of-range keys are
 // zero-filled by TMA and masked to -inf; out-of-range query rows are computed and dropped.
 #include <cuda_bf16.h>
+#include <cstdlib>
 #include "common.cuh"
 #include "tc.cuh"
 #include "unet_ops.cuh"
@@ -291,6 +292,230 @@ attention_kernel(const __grid_constant__ AttentionParams P) {
     if (warp == 5) tc::tmem_dealloc(tmem_base, 128);
 }
 
+// ------------------------------------------------------------------------------------------------------------------------
+// Pipelined schedule (tf32 and bf16 modes).  In the kernel above a key block is one serial chain
+//   S MMA -> softmax -> P -> PV MMA -> O read, and only co-resident CTAs overlap MMAs with softmax (measured 380 TFLOP/s in
+// bf16, ~1500 cycles per block and SM against 600 cycles of MMA).  Here S, P and O are double-buffered (TMEM: S0 S1 O0 O1 =
+// 256 columns; two P tiles in shared memory; three K/V stages), the MMA warp runs S two blocks ahead, and a softmax thread folds
+// O_blk(j-1) into its accumulator AFTER it has handed P(j) to the tensor core:
+//   MMA warp      : S(0) S(1) | wait P(j) -> PV(j) -> S(j+2)
+//   softmax thread: wait S(j) -> exp -> P(j) -> arrive | wait O(j-1) -> o = o*alpha(j-1) + O_blk(j-1)
+// so neither side waits for the other's latency.  Buffer reuse is ordered by the same barriers: P(j) is written after
+// O(j-2) was consumed (PV(j-2) done reading P[j&1]); PV(j) is issued after P(j) arrived, i.e. after O(j-2) was read from
+// O[j&1]; S(j+2) overwrites S[j&1] after P(j) arrived, i.e. after S(j) was read.
+// ------------------------------------------------------------------------------------------------------------------------
+template <int MODE>
+struct AtP {
+    static constexpr bool BF = MODE == AT_BF16;
+    static constexpr int NCH = BF ? 1 : 2;
+    static constexpr int Q_BYTES = NCH * AT_BQ * 128;
+    static constexpr int K_BYTES = NCH * AT_BKV * 128;
+    static constexpr int V_BYTES = NCH * AT_D * 128;
+    static constexpr int P_BYTES = NCH * AT_BQ * 128;
+    static constexpr int NST = 3;
+    static constexpr int STAGE = K_BYTES + V_BYTES;
+    static constexpr int OFF_KV = Q_BYTES;
+    static constexpr int OFF_P = OFF_KV + NST * STAGE;
+    static constexpr int OFF_BAR = OFF_P + 2 * P_BYTES;
+    static constexpr int SMEM = OFF_BAR + 16 * 8 + 1024;
+    static constexpr int MAX_REGS = BF ? 168 : 255;             // bf16: 2 CTAs x 192 threads x 168 registers
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(AT_THREADS) __maxnreg__(AtP<MODE>::MAX_REGS)
+attention_pipe_kernel(const __grid_constant__ AttentionParams P) {
+    using L = AtP<MODE>;
+    constexpr bool BF = L::BF;
+    constexpr int NST = L::NST, NCH = L::NCH;
+    extern __shared__ uint8_t at_smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)at_smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = (uint64_t*)(smem + L::OFF_BAR);
+    uint64_t* q_full = bars;            // 1
+    uint64_t* kv_full = bars + 1;       // 3
+    uint64_t* kv_empty = bars + 4;      // 3
+    uint64_t* s_full = bars + 7;        // 2
+    uint64_t* p_full = bars + 9;        // 2, 128 arrivals each
+    uint64_t* o_full = bars + 11;       // 2
+    uint32_t* tmem_slot = (uint32_t*)(bars + 13);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * AT_BQ, head = blockIdx.y, b = blockIdx.z;
+    const int nkv = (P.T + AT_BKV - 1) / AT_BKV;
+
+    if (threadIdx.x == 0) {
+        tc::mbar_init(q_full, 1);
+        for (int i = 0; i < NST; ++i) { tc::mbar_init(&kv_full[i], 1); tc::mbar_init(&kv_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { tc::mbar_init(&s_full[i], 1); tc::mbar_init(&p_full[i], 128); tc::mbar_init(&o_full[i], 1); }
+        tc::fence_barrier_init();
+    }
+    if (warp == 5) tc::tmem_alloc(tmem_slot, 256);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;                     // S0 | S1 | O0 | O1, 64 columns each
+
+    if (warp == 4) {
+        if (tc::elect_one()) {
+            tc::mbar_expect_tx(q_full, L::Q_BYTES);
+            for (int c = 0; c < NCH; ++c) tc::tma_load_3d(smem + c * (AT_BQ * 128), &P.mapQ, q_full, head * 3 * AT_D + c * 32, q0, b);
+            for (int j = 0; j < nkv; ++j) {
+                const int s = j % NST;
+                tc::mbar_wait(&kv_empty[s], ((uint32_t)(j / NST) & 1u) ^ 1u);
+                tc::mbar_expect_tx(&kv_full[s], L::STAGE);
+                uint8_t* sk = smem + L::OFF_KV + s * L::STAGE;
+                uint8_t* sv = sk + L::K_BYTES;
+                for (int c = 0; c < NCH; ++c) {
+                    tc::tma_load_3d(sk + c * (AT_BKV * 128), &P.mapK, &kv_full[s], head * 3 * AT_D + AT_D + c * 32, j * AT_BKV, b);
+                    tc::tma_load_3d(sv + c * (AT_D * 128), &P.mapV, &kv_full[s], j * AT_BKV + c * 32, head * AT_D, b);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 5) {
+        if (tc::elect_one()) {
+            constexpr uint32_t idesc = tc::make_idesc(BF ? tc::FMT_BF16 : tc::FMT_TF32, 128, 64);
+            auto mma = [&](uint32_t d, uint64_t a, uint64_t bb, uint32_t acc) {
+                if constexpr (BF) tc::umma_f16(d, a, bb, idesc, acc); else tc::umma_tf32(d, a, bb, idesc, acc);
+            };
+            const uint32_t sQ = tc::smem_u32(smem);
+            auto issue_S = [&](int j) {
+                const int s = j % NST;
+                tc::mbar_wait(&kv_full[s], (uint32_t)(j / NST) & 1u);
+                tc::tc_fence_after();
+                const uint32_t sK = tc::smem_u32(smem + L::OFF_KV + s * L::STAGE);
+#pragma unroll
+                for (int c = 0; c < NCH; ++c)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        mma(tmem_base + (j & 1) * 64, tc::smem_desc_k_sw128(sQ + c * (AT_BQ * 128)) + (uint64_t)(k * 2),
+                            tc::smem_desc_k_sw128(sK + c * (AT_BKV * 128)) + (uint64_t)(k * 2), (uint32_t)((c | k) != 0));
+                tc::umma_commit(&s_full[j & 1]);
+            };
+            tc::mbar_wait(q_full, 0);
+            issue_S(0);
+            if (nkv > 1) issue_S(1);
+            for (int j = 0; j < nkv; ++j) {
+                const int s = j % NST, bsel = j & 1;
+                tc::mbar_wait(&p_full[bsel], ((uint32_t)j >> 1) & 1u);
+                tc::tc_fence_after();
+                const uint32_t sV = tc::smem_u32(smem + L::OFF_KV + s * L::STAGE + L::K_BYTES);
+                const uint32_t sP = tc::smem_u32(smem + L::OFF_P + bsel * L::P_BYTES);
+#pragma unroll
+                for (int c = 0; c < NCH; ++c)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        mma(tmem_base + 128 + bsel * 64, tc::smem_desc_k_sw128(sP + c * (AT_BQ * 128)) + (uint64_t)(k * 2),
+                            tc::smem_desc_k_sw128(sV + c * (AT_D * 128)) + (uint64_t)(k * 2), (uint32_t)((c | k) != 0));
+                tc::umma_commit(&o_full[bsel]);
+                tc::umma_commit(&kv_empty[s]);
+                if (j + 2 < nkv) issue_S(j + 2);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ---------------- softmax / accumulate: one query row per thread ----------------
+        const int r = warp * 32 + lane;
+        const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+        float m_run = -INFINITY, l_run = 0.f, alpha_pend = 0.f;
+        float o_acc[AT_D];
+#pragma unroll
+        for (int i = 0; i < AT_D; ++i) o_acc[i] = 0.f;
+        const int sw = r & 7;
+        auto fold_O = [&](int j) {                               // o = o * alpha(j) + O_blk(j)
+            tc::mbar_wait(&o_full[j & 1], ((uint32_t)j >> 1) & 1u);
+            tc::tc_fence_after();
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                uint32_t orr[32];
+                tc::tmem_ld32(tmem_base + 128 + (j & 1) * 64 + lane_off + h * 32, orr);
+                tc::tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) o_acc[h * 32 + i] = fmaf(o_acc[h * 32 + i], alpha_pend, __uint_as_float(orr[i]));
+            }
+        };
+        for (int j = 0; j < nkv; ++j) {
+            const int bsel = j & 1;
+            const uint32_t tS = tmem_base + bsel * 64 + lane_off;
+            uint8_t* prow = smem + L::OFF_P + bsel * L::P_BYTES + (r >> 3) * 1024 + (r & 7) * 128;
+            tc::mbar_wait(&s_full[bsel], ((uint32_t)j >> 1) & 1u);
+            tc::tc_fence_after();
+            const int nvalid = P.T - j * AT_BKV;           // keys beyond T are masked
+            uint32_t sr[2][32];
+            tc::tmem_ld32(tS, sr[0]);
+            tc::tmem_ld32(tS + 32, sr[1]);
+            tc::tmem_ld_wait();
+            if (nvalid < AT_BKV) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (h * 32 + i >= nvalid) sr[h][i] = __float_as_uint(-INFINITY);
+            }
+            float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;      // four chains instead of one of 64
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    mx0 = fmaxf(mx0, __uint_as_float(sr[h][i])); mx1 = fmaxf(mx1, __uint_as_float(sr[h][i + 1]));
+                    mx2 = fmaxf(mx2, __uint_as_float(sr[h][i + 2])); mx3 = fmaxf(mx3, __uint_as_float(sr[h][i + 3]));
+                }
+            const float m_new = fmaxf(m_run, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)));
+            const float alpha = ex2_approx((m_run - m_new) * P.scale_log2);
+            const float mb = m_new * P.scale_log2;
+            float rs0 = 0.f, rs1 = 0.f;
+            if constexpr (BF) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {                // 8 keys = one 16-byte unit of the 128-byte row
+                    const uint32_t* sp = &sr[u >> 2][(u & 3) * 8];
+                    uint32_t w[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float a = ex2_approx(fmaf(__uint_as_float(sp[2 * i]), P.scale_log2, -mb));
+                        const float c = ex2_approx(fmaf(__uint_as_float(sp[2 * i + 1]), P.scale_log2, -mb));
+                        const __nv_bfloat162 pk = __floats2bfloat162_rn(a, c);
+                        rs0 += a; rs1 += c;                  // unrounded: the bf16 rounding of P is zero-mean over 64 keys
+                        w[i] = *reinterpret_cast<const uint32_t*>(&pk);
+                    }
+                    *reinterpret_cast<uint4*>(prow + ((u ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+            } else {
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        float4 ph;
+                        ph.x = tf32_rn(ex2_approx(fmaf(__uint_as_float(sr[h][4 * u]), P.scale_log2, -mb)));
+                        ph.y = tf32_rn(ex2_approx(fmaf(__uint_as_float(sr[h][4 * u + 1]), P.scale_log2, -mb)));
+                        ph.z = tf32_rn(ex2_approx(fmaf(__uint_as_float(sr[h][4 * u + 2]), P.scale_log2, -mb)));
+                        ph.w = tf32_rn(ex2_approx(fmaf(__uint_as_float(sr[h][4 * u + 3]), P.scale_log2, -mb)));      // P is an MMA operand
+                        rs0 += ph.x + ph.z; rs1 += ph.y + ph.w;
+                        *reinterpret_cast<float4*>(prow + h * (AT_BQ * 128) + ((u ^ sw) << 4)) = ph;
+                    }
+            }
+            l_run = fmaf(l_run, alpha, rs0 + rs1);
+            m_run = m_new;
+            tc::fence_proxy_async();                         // generic-proxy smem writes -> visible to the MMA (async proxy)
+            tc::tc_fence_before();
+            tc::mbar_arrive(&p_full[bsel]);
+            if (j >= 1) fold_O(j - 1);                       // the previous block's P.V, with the previous block's rescale factor
+            alpha_pend = alpha;
+        }
+        fold_O(nkv - 1);
+        const int t = q0 + r;
+        if (t < P.T) {
+            const float inv = 1.0f / l_run;
+            float4* op = reinterpret_cast<float4*>(P.out + ((size_t)b * P.T + t) * P.C + head * AT_D);
+#pragma unroll
+            for (int i = 0; i < AT_D / 4; ++i)
+                op[i] = make_float4(tf32_rn(o_acc[4 * i] * inv), tf32_rn(o_acc[4 * i + 1] * inv), tf32_rn(o_acc[4 * i + 2] * inv),
+                                    tf32_rn(o_acc[4 * i + 3] * inv));              // operand of the proj 1x1 GEMM
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 5) tc::tmem_dealloc(tmem_base, 256);
+}
+
 int attention_prepare(AttentionParams& P, const AttentionDesc& d) {
     IPDM_REQUIRE(d.head_dim == AT_D && d.C == d.heads * AT_D, "attention: head_dim must be 64 (got %d)", d.head_dim);
     IPDM_REQUIRE(d.t_pad % (d.bf16 ? 8 : 4) == 0 && d.t_pad >= d.T, "attention: t_pad must be a multiple of %d", d.bf16 ? 8 : 4);
@@ -329,11 +554,17 @@ int attention_launch(const AttentionParams& P, cudaStream_t st) {
         IPDM_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<AT_TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, AtL<AT_TF32>::SMEM));
         IPDM_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<AT_SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, AtL<AT_SPLIT>::SMEM));
         IPDM_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<AT_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, AtL<AT_BF16>::SMEM));
+        static_assert(AtP<AT_TF32>::SMEM <= 227 * 1024 && 2 * (AtP<AT_BF16>::SMEM + 1024) <= 227 * 1024, "pipelined attention tiles do not fit");
+        IPDM_CHECK_CUDA(cudaFuncSetAttribute(attention_pipe_kernel<AT_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, AtP<AT_BF16>::SMEM));
+        IPDM_CHECK_CUDA(cudaFuncSetAttribute(attention_pipe_kernel<AT_TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, AtP<AT_TF32>::SMEM));
         configured = true;
     }
     dim3 grid((P.T + AT_BQ - 1) / AT_BQ, P.heads, P.batch);
     ProfScope prof(PROF_ATTENTION, st, (P.split ? 3.0 : 1.0) * 4.0 * P.batch * P.heads * (double)P.T * P.T * AT_D);
+    static const bool pipe = !(getenv("IPDM_ATTN_PIPE") && atoi(getenv("IPDM_ATTN_PIPE")) == 0);      // 0: the serial schedule (experiments)
     if (P.split) attention_kernel<AT_SPLIT><<<grid, AT_THREADS, AtL<AT_SPLIT>::SMEM, st>>>(P);
+    else if (P.bf16 && pipe) attention_pipe_kernel<AT_BF16><<<grid, AT_THREADS, AtP<AT_BF16>::SMEM, st>>>(P);
+    else if (pipe) attention_pipe_kernel<AT_TF32><<<grid, AT_THREADS, AtP<AT_TF32>::SMEM, st>>>(P);
     else if (P.bf16) attention_kernel<AT_BF16><<<grid, AT_THREADS, AtL<AT_BF16>::SMEM, st>>>(P);
     else attention_kernel<AT_TF32><<<grid, AT_THREADS, AtL<AT_TF32>::SMEM, st>>>(P);
     count_launch();

@@ -87,6 +87,9 @@ __device__ __forceinline__ float silu(float x) { return __fdividef(x, 1.0f + __e
 // Round to the nearest TF32 value (10-bit mantissa).  The tensor core only reads the upper 19 bits of an
 // fp32 operand, i.e. it TRUNCATES; truncation shrinks every product coherently (measured: 4.3e-4 rel-L2 on a
 // K=1152 conv), whereas pre-rounded operands leave only zero-mean noise.  Operand producers call this.
+// 2^x in one MUFU instruction (exp2f adds a range fix-up of three more per call); arguments here are <= 0, underflow flushes to 0
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
 __device__ __forceinline__ float tf32_rn(float x) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
