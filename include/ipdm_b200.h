@@ -46,10 +46,11 @@ unsigned long long ipdm_launch_count(void);
 void ipdm_launch_count_reset(void);
 
 /* Per-kernel-family profiler for bench.py: when enabled, every launch is bracketed by CUDA events on its
- * stream.  Families (index): 0 conv_tc (work = FLOPs issued), 1 attention (FLOPs), 2 conv_direct (bytes),
+ * stream.  Families (index): 0 conv_tc other than family 8 (work = FLOPs issued), 1 attention (FLOPs), 2 conv_direct (bytes),
  * 3 groupnorm (bytes), 4 upsample (bytes), 5 fbp_filter (bytes), 6 fbp_backproject (compulsory bytes),
- * 7 sampler step (algorithmic bytes).  collect() synchronises the device and sums per family. */
-#define IPDM_PROF_KINDS 8
+ * 7 sampler step (algorithmic bytes), 8 conv_halo_persistent_kernel, the dominant kernel (FLOPs issued).
+ * collect() synchronises the device and sums per family. */
+#define IPDM_PROF_KINDS 9
 void ipdm_profile_enable(int on);
 int ipdm_profile_collect(double ms_out[IPDM_PROF_KINDS], double work_out[IPDM_PROF_KINDS], long long launches_out[IPDM_PROF_KINDS]);
 

@@ -49,7 +49,7 @@ inline void count_launch(int n = 1) { g_launch_count += (unsigned long long)n; }
 
 // per-kernel-family profiler (off by default): CUDA events around every launch, summed by family.
 enum ProfKind { PROF_CONV_TC = 0, PROF_ATTENTION, PROF_CONV_DIRECT, PROF_GROUPNORM, PROF_UPSAMPLE, PROF_FBP_FILTER,
-                PROF_FBP_BACKPROJECT, PROF_SAMPLER, PROF_KINDS };
+                PROF_FBP_BACKPROJECT, PROF_SAMPLER, PROF_CONV_HALO_PERS, PROF_KINDS };
 extern bool g_prof_on;
 void prof_begin(int kind, cudaStream_t st);
 void prof_end(int kind, cudaStream_t st, double work);

@@ -1022,7 +1022,8 @@ static int launch_halo(const ConvTcParams& P, cudaStream_t st) {
 }
 
 int conv_tc_launch(const ConvTcParams& P, cudaStream_t st) {
-    ProfScope prof(PROF_CONV_TC, st, conv_tc_flops(P));      // padded-K FLOPs actually issued to the tensor pipe
+    // padded-K FLOPs actually issued to the tensor pipe; the persistent halo kernel (the dominant kernel of the step) is its own family
+    ProfScope prof(P.halo && P.persistent ? PROF_CONV_HALO_PERS : PROF_CONV_TC, st, conv_tc_flops(P));
     if (P.halo && P.persistent) {
         switch (P.block_n) {
             case 128: return launch_halo_pers<128, 6>(P, st);

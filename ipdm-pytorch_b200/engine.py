@@ -44,7 +44,8 @@ def launch_count_reset():
     _lib.lib().ipdm_launch_count_reset()
 
 
-PROF_FAMILIES = ("conv_tc", "attention", "conv_direct", "groupnorm", "upsample", "fbp_filter", "fbp_backproject", "sampler")
+PROF_FAMILIES = ("conv_tc", "attention", "conv_direct", "groupnorm", "upsample", "fbp_filter", "fbp_backproject", "sampler",
+                 "conv_halo_persistent")
 
 
 def profile_enable(on=True):
@@ -52,8 +53,9 @@ def profile_enable(on=True):
 
 
 def profile_collect():
-    """{family: (milliseconds, work, launches)}; work is FLOPs for conv_tc / attention, bytes otherwise."""
-    ms, work, n = (ctypes.c_double * 8)(), (ctypes.c_double * 8)(), (ctypes.c_longlong * 8)()
+    """{family: (milliseconds, work, launches)}; work is FLOPs for conv_tc / conv_halo_persistent / attention, bytes otherwise."""
+    k = len(PROF_FAMILIES)
+    ms, work, n = (ctypes.c_double * k)(), (ctypes.c_double * k)(), (ctypes.c_longlong * k)()
     check(_lib.lib().ipdm_profile_collect(ms, work, n), "ipdm_profile_collect")
     return {f: (ms[i], work[i], int(n[i])) for i, f in enumerate(PROF_FAMILIES)}
 
