@@ -44,7 +44,7 @@ def _p(t):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
 
-def run_conv(cuda, x0, x1, weight, bias, k, stride, use_tc, res=None, up=None, norm=None):
+def run_conv(cuda, x0, x1, weight, bias, k, stride, use_tc, res=None, up=None, norm=None, dense_out=False):
     from ipdm_pytorch_b200 import _lib
     use_tc = int(use_tc)
     variant, use_tc = use_tc >> 8, use_tc & 0xFF                       # bits 8..: tensor-core kernel variant (0 auto)
@@ -59,7 +59,7 @@ def run_conv(cuda, x0, x1, weight, bias, k, stride, use_tc, res=None, up=None, n
     cout = weight.shape[0]
     hin, win = (h, w) if up is None else up
     ho, wo = (hin, win) if stride == 1 else ((hin + 1) // 2, (win + 1) // 2)
-    ocs = alloc_cs(cout)
+    ocs = cout if dense_out else alloc_cs(cout)                      # the planner stores <= 16-channel activations dense
     a0 = nhwc(x0, cs0).to(cuda)
     if use_tc == 3:
         a0 = a0.to(torch.bfloat16).contiguous()
@@ -112,6 +112,10 @@ def test_direct_conv(cuda, c0, c1, cout, k, stride, hw):
     res = rnd(2, cout, ho, wo, seed=5) if (stride == 1 and k == 3) else None
     got = run_conv(cuda, x0, x1, w, b, k, stride, False, res=res)
     assert rel_l2(got.numpy(), ref_conv(x0, x1, w, b, k, stride, res=res).numpy()) < FP32_TOL
+    if cout % 4 == 0:                                                   # dense output rows: the fully unrolled streaming kernels
+        res2 = rnd(2, cout, ho, wo, seed=6) if k == 1 else None
+        got = run_conv(cuda, x0, x1, w, b, k, stride, False, res=res2, dense_out=True)
+        assert rel_l2(got.numpy(), ref_conv(x0, x1, w, b, k, stride, res=res2).numpy()) < FP32_TOL
 
 
 def test_direct_conv_fused_norm_and_upsample(cuda):
