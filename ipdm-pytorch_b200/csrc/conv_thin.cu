@@ -65,7 +65,8 @@ conv_thin_kernel(const __grid_constant__ ConvThinParams P) {
     uint64_t* t_full = a_empty + C::NSA;
     uint64_t* t_empty = t_full + TH_NACC;
     uint64_t* w_full = t_empty + TH_NACC;
-    uint32_t* tmem_slot = (uint32_t*)(w_full + 1);
+    uint64_t* a_ready = w_full + 1;                          // fused GroupNorm: tile normalised in place (64 arrivals)
+    uint32_t* tmem_slot = (uint32_t*)(a_ready + C::NSA);
     float* sbias = (float*)(smem + C::BAR_OFF + 384);     // 16-byte aligned: the epilogue reads it as float4
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -73,7 +74,7 @@ conv_thin_kernel(const __grid_constant__ ConvThinParams P) {
     const int total_tiles = tiles_per_img * P.batch;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < C::NSA; ++i) { tc::mbar_init(&a_full[i], 1); tc::mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < C::NSA; ++i) { tc::mbar_init(&a_full[i], 1); tc::mbar_init(&a_empty[i], 1); tc::mbar_init(&a_ready[i], 64); }
         for (int i = 0; i < TH_NACC; ++i) { tc::mbar_init(&t_full[i], 1); tc::mbar_init(&t_empty[i], 128); }
         tc::mbar_init(w_full, 1);
         tc::fence_barrier_init();
@@ -119,7 +120,7 @@ conv_thin_kernel(const __grid_constant__ ConvThinParams P) {
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
                 const int s = it % C::NSA, acc = it % TH_NACC;
                 tc::mbar_wait(&t_empty[acc], ((uint32_t)(it / TH_NACC) & 1u) ^ 1u);
-                tc::mbar_wait(&a_full[s], (uint32_t)(it / C::NSA) & 1u);
+                tc::mbar_wait(P.norm_scale ? &a_ready[s] : &a_full[s], (uint32_t)(it / C::NSA) & 1u);
                 tc::tc_fence_after();
                 const uint32_t a_base = tc::smem_u32(smem + C::OFF_A + s * C::SLOT);
                 const uint32_t d_tmem = tmem_base + acc * 32;
@@ -136,7 +137,59 @@ conv_thin_kernel(const __grid_constant__ ConvThinParams P) {
             }
         }
         __syncwarp();
-    } else if (warp >= 4) {
+    } else if (warp < 4) {
+        // warps 2-3, fused GroupNorm(+SiLU): normalise the landed halo tile in place.  The transform is elementwise, so the swizzle
+        // only matters for finding the channel of a 16-byte unit: physical unit = logical ^ f(row) with f = (row>>2)&1 / (row>>1)&3 /
+        // row&7 for 32 / 64 / 128-byte rows.  Pixels outside the image stay 0 (the conv pads the NORMALISED tensor with zeros).
+        if (P.norm_scale) {
+            constexpr int UPR = RB / 16, NU = (TH_ROWS + 2) * TH_RP * UPR;
+            const int t2 = (warp - 2) * 32 + lane;
+            const int off = P.ntaps == 9 ? 1 : 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+                int b, x0, y0; decode(tile, b, x0, y0);
+                const int s = it % C::NSA;
+                tc::mbar_wait(&a_full[s], (uint32_t)(it / C::NSA) & 1u);
+                uint8_t* base = smem + C::OFF_A + s * C::SLOT;
+                // this slice's scale / shift for all C_in channels in registers (one load per tile, not per unit)
+                float4 scv[UPR], shv[UPR];
+#pragma unroll
+                for (int i = 0; i < UPR; ++i) {
+                    scv[i] = __ldg(reinterpret_cast<const float4*>(P.norm_scale + (size_t)b * P.cs) + i);
+                    shv[i] = __ldg(reinterpret_cast<const float4*>(P.norm_shift + (size_t)b * P.cs) + i);
+                }
+                constexpr int BATCH = 6;                       // NU / 64 = 6, 12, 24 units per thread: batches of 6 loads in flight
+#pragma unroll 1
+                for (int u0 = t2; u0 < NU; u0 += 64 * BATCH) {
+                    float4 v[BATCH]; bool in[BATCH];
+#pragma unroll
+                    for (int k = 0; k < BATCH; ++k) {
+                        const int u = u0 + 64 * k, row = u / UPR;
+                        const int gy = y0 - off + (row >> 5), gx = x0 - off + (row & 31);
+                        in[k] = gy >= 0 && gy < P.H && gx >= 0 && gx < P.W;
+                        v[k] = *reinterpret_cast<const float4*>(base + u * 16);
+                    }
+#pragma unroll
+                    for (int k = 0; k < BATCH; ++k) {
+                        if (!in[k]) continue;
+                        const int u = u0 + 64 * k, row = u / UPR, up = u - row * UPR;
+                        const int swz = RB == 32 ? (row >> 2) & 1 : (RB == 64 ? (row >> 1) & 3 : row & 7);
+                        const int lu = (up ^ swz) & (UPR - 1);
+                        float4 a = scv[0], d = shv[0];
+#pragma unroll
+                        for (int i = 1; i < UPR; ++i) if (lu == i) { a = scv[i]; d = shv[i]; }
+                        float4 w = v[k];
+                        w.x = fmaf(w.x, a.x, d.x); w.y = fmaf(w.y, a.y, d.y); w.z = fmaf(w.z, a.z, d.z); w.w = fmaf(w.w, a.w, d.w);
+                        if (P.act_silu) { w.x = silu(w.x); w.y = silu(w.y); w.z = silu(w.z); w.w = silu(w.w); }
+                        w.x = tf32_rn(w.x); w.y = tf32_rn(w.y); w.z = tf32_rn(w.z); w.w = tf32_rn(w.w);
+                        *reinterpret_cast<float4*>(base + u * 16) = w;
+                    }
+                }
+                tc::fence_proxy_async();                       // generic-proxy writes -> visible to the tensor core's async-proxy reads
+                tc::mbar_arrive(&a_ready[s]);
+            }
+        }
+    } else {
         const int q = warp & 3;                                  // TMEM lane quarter == output row of the tile
         // Coalesced path (the output and residual rows are exactly C_out floats wide, the normal case): a warp's 30 pixels are one
         // contiguous run of 30*C_out floats.  Each lane parks its pixel in a padded shared-memory tile and the warp then moves
@@ -252,6 +305,8 @@ int conv_thin_prepare(ConvThinParams& P, const ConvThinDesc& d) {
     P.out = d.out.p; P.out_cs = d.out.cs;
     P.bias = d.bias; P.bias_t_stride = d.bias_t_stride; P.t_dev = d.t_dev;
     P.res = d.res.p; P.res_cs = d.res.cs;
+    P.norm_scale = d.norm_scale; P.norm_shift = d.norm_shift; P.act_silu = d.act_silu;
+    IPDM_REQUIRE(!d.norm_scale || (d.norm_shift && t.c == t.cs), "conv_thin: the fused GroupNorm needs a dense source (C_in == channel stride)");
     static const int env_dbg = getenv("IPDM_THIN_DBG") ? atoi(getenv("IPDM_THIN_DBG")) : 0;
     P.dbg = env_dbg;
     if (P.dbg & 2) P.res = nullptr;
@@ -264,7 +319,7 @@ static int launch_thin(const ConvThinParams& P, cudaStream_t st) {
     static bool configured = false;
     constexpr int smem = ThinCfg<RB>::TOTAL;
     static_assert(ThinCfg<RB>::CTAS * (smem + 1024) <= 227 * 1024, "thin conv: operand rings of the co-resident CTAs do not fit in shared memory");
-    static_assert((2 * ThinCfg<RB>::NSA + 2 * TH_NACC + 1) * 8 + 16 <= 384, "barrier block");
+    static_assert((3 * ThinCfg<RB>::NSA + 2 * TH_NACC + 1) * 8 + 16 <= 384, "barrier block");
     if (!configured) {
         IPDM_CHECK_CUDA(cudaFuncSetAttribute(conv_thin_kernel<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;

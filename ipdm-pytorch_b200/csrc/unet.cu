@@ -394,7 +394,16 @@ struct PlanBuilder {
         max_c = std::max(max_c, gn.C);
         push(st);
         const VTensor& s0 = pl->vt[src[0]];
-        if (cw.thin) {
+        // IPDM_THIN_FUSE=1: the thin kernel normalises the TMA-landed tile itself (bit-identical results).  Off by default: with only
+        // the two spare warps per CTA doing the transform it is SLOWER than the separate apply pass (measured at 16 slices: 8 -> 8 at
+        // 2000x912 1025 us fused vs 600 + 311 us; 16 -> 16 at 1000x456 526 vs 283 + 155 us).
+        static const bool thin_fuse = getenv("IPDM_THIN_FUSE") && atoi(getenv("IPDM_THIN_FUSE")) == 1;
+        if (cw.thin && thin_fuse && nsrc == 1 && s0.c == cw.thin_cs && s0.cs == cw.thin_cs && !s0.bf16) {
+            // single dense source: the thin kernel normalises the TMA-landed tile itself, no operand tensor and no apply pass
+            Op cv; cv.kind = Op::CONV_THIN; cv.nsrc = 1; cv.src[0] = src[0]; cv.cw = &cw; cv.dst = dst; cv.res = res; cv.bias = bias; cv.bias_t_stride = bstride; cv.use_t = use_t;
+            cv.norm_slot = st.norm_slot; cv.gn = &gn; cv.act = act_silu;
+            push(cv);
+        } else if (cw.thin) {
             const int a = new_tensor(pl->B, s0.h, s0.w, gn.C, cw.thin_cs);
             Op ap; ap.kind = Op::GN_APPLY; ap.nsrc = nsrc; ap.src[0] = src[0]; ap.src[1] = st.src[1]; ap.gn = &gn; ap.norm_slot = st.norm_slot; ap.dst = a; ap.act = act_silu;
             push(ap);
@@ -625,6 +634,7 @@ static int build_plan(ipdm_unet* net, int B, int H, int W, Plan** out) {
                 d.bias = o.bias; d.bias_t_stride = o.bias_t_stride; d.t_dev = o.use_t ? net->t_dev : nullptr;
                 if (o.res >= 0) d.res = resolve(*pl, o.res);
                 d.out = resolve(*pl, o.dst);
+                if (o.gn) { d.norm_scale = nscale; d.norm_shift = nshift; d.act_silu = o.act; }
                 IPDM_CHECK(conv_thin_prepare(o.thp, d));
                 o.flops = 2.0 * B * d.out.h * d.out.w * (double)o.cw->cin * o.cw->cout * d.ntaps;
             } break;

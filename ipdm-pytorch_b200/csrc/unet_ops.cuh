@@ -66,6 +66,9 @@ struct ConvThinDesc {
     const float* w_packed = nullptr;   // [ntaps][16][src.cs], tf32-rounded, rows >= cout and columns >= C_in zero
     const float* bias = nullptr; int bias_t_stride = 0; const int* t_dev = nullptr;
     TensorNHWC res, out;
+    // optional fused GroupNorm(+SiLU) of the source: y = act(x*scale[n][c] + shift[n][c]), rounded to TF32, applied to the TMA-landed
+    // tile in shared memory by two helper warps (src is then the RAW activation tensor, dense: cs == C_in)
+    const float* norm_scale = nullptr; const float* norm_shift = nullptr; int act_silu = 1;
 };
 struct ConvThinParams {
     CUtensorMap mapA, mapW;
@@ -73,6 +76,7 @@ struct ConvThinParams {
     float* out; int out_cs;
     const float* bias; int bias_t_stride; const int* t_dev;
     const float* res; int res_cs;
+    const float* norm_scale; const float* norm_shift; int act_silu;
     int dbg;                           // IPDM_THIN_DBG experiments (tools only): 1 no stores, 2 no residual loads, 4 no MMAs
 };
 int conv_thin_prepare(ConvThinParams& P, const ConvThinDesc& d);

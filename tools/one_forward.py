@@ -18,7 +18,7 @@ if which in ("proj", "both"):
     for i in range(n):
         y = net(x, torch.full((1,), 7, device="cuda"))
     torch.cuda.synchronize()
-    print("proj ok", float(y.std()))
+    print("proj ok", float(y.std()), float(y.double().abs().sum()))
 if which in ("img", "both"):
     net = UNetModel(in_channels=1, model_channels=64, out_channels=1, attention_resolutions=[8, 16], channel_mult=[1, 1, 2, 2, 4, 4]).cuda().eval()
     net.set_precision(prec)
@@ -26,4 +26,4 @@ if which in ("img", "both"):
     for i in range(n):
         y = net(x, torch.full((1,), 7, device="cuda"))
     torch.cuda.synchronize()
-    print("img ok", float(y.std()))
+    print("img ok", float(y.std()), float(y.double().abs().sum()))
