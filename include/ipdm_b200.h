@@ -55,6 +55,19 @@ void ipdm_profile_enable(int on);
 int ipdm_profile_collect(double ms_out[IPDM_PROF_KINDS], double work_out[IPDM_PROF_KINDS], long long launches_out[IPDM_PROF_KINDS]);
 
 /* ------------------------------------------------------------------------------------------
+ * Image-quality metrics on the device.  Replaces the skimage calls of
+ * progressive_domain_denoiser.metric_calculate, Utils/train_test_utils.py:789-799
+ * (compare_psnr(fdct, ld, data_range=1), compare_ssim(fdct, ld, win_size=11, data_range=1)) and the
+ * unit conversion miu2pixel, Dataset/npz_data_loader.py:20-36.  Images are [batch][h][w] f32 in
+ * "pixel" units; NaNs of the test image count as 0.5 (:792).  out_dev[b] = {PSNR dB, SSIM} (f64).
+ * ---------------------------------------------------------------------------------------- */
+size_t ipdm_metrics_workspace_bytes(int batch, int h, int w);
+int ipdm_psnr_ssim(const float* test_dev, const float* ref_dev, int batch, int h, int w, int win_size, double* out_dev,
+                   void* workspace_dev, void* stream);
+/* pix = clip((HU(mu) - hu_lo) / (hu_hi - hu_lo), 0, 1), HU(mu) = (mu - 0.183) * 1e3 / 0.183 - 24; NaN -> 0.5 */
+int ipdm_miu2pixel(const float* mu_dev, float* pix_dev, size_t n, float hu_lo, float hu_hi, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * FBP convertor.  Replaces Recon/FBP_kernel.py: FBP.__init__ :27-67 (tables), FBP.convert
  * :86-122, conv_pj/conv_kernel :125-143 (ramp filter), fbp_cpu/fbp_kernel :146-184
  * (pixel-driven fan-beam backprojection).  Call site: Utils/train_test_utils.py:229, :465, :475.

@@ -393,16 +393,38 @@ class progressive_domain_denoiser:
             f.write(json.dumps(self.metric_instance, sort_keys=False, indent=4, separators=(',', ': ')))
 
     def result_figure_save(self, mode="progressive", display=True, only_metric=False):
-        """Figures need matplotlib and the skimage/piq metrics (reference :596-763): reporting only, out of scope.
-        PSNR against `fdct` is recorded when a full-dose slice was loaded."""
+        """Metric part of the reference's result_figure_save (:596-763): LDCT at it=0 and every stored iterate of the stage, in the
+        reference's order and key names.  The matplotlib figures themselves are reporting and out of scope."""
         if self.fdct is None:
             return
         store = {"progressive": (self.progressive_denoise_result, "deProg"), "dimg": (self.img_denoise_result, "deImg"),
                  "dproj2img": (self.proj_denoise_convert2img_result, "deProj2img")}[mode]
-        for k in range(1, len(store[0]) + 1):
-            img = miu2pixel(np.array(store[0][k]).squeeze())
-            mse = float(np.mean((np.asarray(self.fdct, dtype=np.float64) - img) ** 2))
-            self.metric_instance[store[1]][f"psnr_iter_{k}"] = 10 * np.log10(1.0 / mse) if mse > 0 else float("inf")
+        if self.ldct_np is not None:
+            self.metric_calculate(mode="LDCT", it=0, denoise_result=self.ldct_np)
+        n_it = len([k for k in store[0] if isinstance(k, str) and k.startswith("iter_")]) or len(store[0])
+        for i in range(1, n_it + 1):
+            r_it = n_it + 1 - i
+            key = f"iter_{r_it}" if f"iter_{r_it}" in store[0] else r_it
+            self.metric_calculate(mode=store[1], it=r_it, denoise_result=miu2pixel(np.array(store[0][key]).squeeze()))
+
+    def metric_calculate(self, mode="LDCT", **kwargs):
+        """PSNR / SSIM of `denoise_result` (pixel units, [H,W] or [B,H,W]) against the full-dose image, on the device with the
+        reference's definitions (:789-799: skimage compare_psnr(data_range=1), compare_ssim(win_size=11, data_range=1), NaN -> 0.5).
+        fsim / vif / nqm are piq / NQM reporting metrics outside this path and are skipped."""
+        from ipdm_pytorch_b200 import engine
+        i = kwargs["it"]
+        ld = kwargs["denoise_result"]
+        ld = ld if isinstance(ld, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(ld, dtype=np.float32))
+        fd = torch.from_numpy(np.ascontiguousarray(self.fdct, dtype=np.float32))
+        ld, fd = ld.reshape(-1, *ld.shape[-2:]), fd.reshape(-1, *fd.shape[-2:])
+        if fd.shape[0] == 1 and ld.shape[0] > 1:
+            fd = fd.expand_as(ld)
+        vals = engine.psnr_ssim(ld.to(self.opt.device).float().contiguous(), fd.to(self.opt.device).contiguous(), win_size=11).cpu().numpy()
+        grp = self.metric_instance.setdefault(mode, DotDict()) if hasattr(self.metric_instance, "setdefault") else self.metric_instance[mode]
+        if 'psnr' in self.opt.metrics:
+            grp["psnr_iter_{}".format(i)] = float(vals[:, 0].mean())
+        if 'ssim' in self.opt.metrics:
+            grp["ssim_iter_{}".format(i)] = float(vals[:, 1].mean())
 
     def metric_update(self):
         self.metric_each_sample.append(self.metric_instance)

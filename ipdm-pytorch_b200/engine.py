@@ -228,6 +228,34 @@ def sharpen3x3(img, N):
 # ---------------------------------------------------------------------------------------------
 # UNet
 # ---------------------------------------------------------------------------------------------
+# ---------------------------------------------------------------------------------------------
+# image-quality metrics (reference: metric_calculate, Utils/train_test_utils.py:789-799)
+# ---------------------------------------------------------------------------------------------
+def miu2pixel(mu, hu_range=(-1024.0, 3072.0), out=None):
+    """Dataset/npz_data_loader.py:20-36 on the device: mu -> HU -> [hu_lo, hu_hi] window mapped to [0,1], clipped; NaN -> 0.5."""
+    _require_cuda()
+    out = torch.empty_like(mu) if out is None else out
+    check(_lib.lib().ipdm_miu2pixel(_dev(mu, "mu"), _dev(out, "out"), mu.numel(), float(hu_range[0]), float(hu_range[1]), _stream()), "ipdm_miu2pixel")
+    return out
+
+
+def psnr_ssim(test, ref, win_size=11):
+    """[B,H,W] (or [B,1,H,W]) images in pixel units -> float64 CUDA tensor [B,2] = (PSNR dB, SSIM) with skimage's definitions
+    for data_range=1, win_size=11 (uniform window, K1=.01, K2=.03, sample covariance, map cropped by win//2)."""
+    _require_cuda()
+    if test.dim() == 4:
+        test, ref = test[:, 0], ref[:, 0]
+    if test.dim() != 3 or test.shape != ref.shape:
+        raise ValueError(f"psnr_ssim: shapes {tuple(test.shape)} / {tuple(ref.shape)} must be equal [B,H,W]")
+    test, ref = test.contiguous(), ref.contiguous()
+    b, h, w = test.shape
+    out = torch.empty(b, 2, device=test.device, dtype=torch.float64)
+    ws = _workspace(int(_lib.lib().ipdm_metrics_workspace_bytes(b, h, w)), test.device)
+    check(_lib.lib().ipdm_psnr_ssim(_dev(test, "test"), _dev(ref, "ref"), b, h, w, int(win_size), ctypes.c_void_p(out.data_ptr()),
+                                    ctypes.c_void_p(ws.data_ptr()), _stream()), "ipdm_psnr_ssim")
+    return out
+
+
 def unet_config(in_channels, model_channels, out_channels, num_res_blocks, attention_resolutions, channel_mult, num_heads,
                 precision="tf32", max_t=64):
     cfg = UNetConfig()

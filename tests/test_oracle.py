@@ -106,3 +106,32 @@ def test_sharpen_and_conversions():
     mu = torch.tensor([0.0, 0.183, 0.5, 1.0])
     pix = O.miu2pixel(mu)
     assert pix[0] == 0 and abs(float(pix[1]) - (1024 - 24) / 4096) < 1e-6 and pix[3] == 1
+
+
+# ---- N1: image-quality metrics (published skimage definitions; skimage itself is not installable here) --------------------
+def test_metrics_oracle_matches_the_definition_and_its_properties():
+    from oracle import metrics_oracle as M
+    rng = np.random.default_rng(0)
+    ref = rng.random((40, 37)).astype(np.float32)
+    test = (ref + 0.05 * rng.standard_normal(ref.shape)).astype(np.float32)
+    assert M.ssim(ref, ref) == pytest.approx(1.0, abs=1e-12)
+    assert M.psnr(ref, test) == pytest.approx(10 * np.log10(1.0 / np.mean((ref.astype(np.float64) - test) ** 2)), abs=1e-12)
+    # brute-force SSIM straight from the formula (explicit 11x11 windows over the cropped interior)
+    win, n = 11, 121
+    acc = []
+    x, y = test.astype(np.float64), ref.astype(np.float64)
+    for i in range(5, 40 - 5):
+        for j in range(5, 37 - 5):
+            a, b = x[i - 5:i + 6, j - 5:j + 6], y[i - 5:i + 6, j - 5:j + 6]
+            ux, uy = a.mean(), b.mean()
+            vx, vy, vxy = ((a - ux) ** 2).sum() / (n - 1), ((b - uy) ** 2).sum() / (n - 1), ((a - ux) * (b - uy)).sum() / (n - 1)
+            acc.append((2 * ux * uy + 1e-4) * (2 * vxy + 9e-4) / ((ux * ux + uy * uy + 1e-4) * (vx + vy + 9e-4)))
+    assert M.ssim(ref, test, win_size=win) == pytest.approx(np.mean(acc), abs=1e-10)
+    # NaNs of the test image count as 0.5 (metric_calculate :792)
+    t2 = test.copy(); t2[3, 4] = np.nan
+    t3 = test.copy(); t3[3, 4] = 0.5
+    assert M.psnr(ref, t2) == M.psnr(ref, t3) and M.ssim(ref, t2) == M.ssim(ref, t3)
+    # unit conversion agrees with the host mirror of Dataset/npz_data_loader.py
+    from Dataset.npz_data_loader import miu2pixel
+    mu = (0.25 * rng.random((8, 9))).astype(np.float32)
+    np.testing.assert_array_equal(M.miu2pixel(mu), miu2pixel(mu.copy()))

@@ -14,28 +14,6 @@ pytestmark = pytest.mark.gpu
 HU_PER_MU = 1e3 / 0.183
 
 
-def _psnr(img, ref):
-    """skimage.metrics.peak_signal_noise_ratio with data_range = the reference's range."""
-    rng = float(ref.max() - ref.min())
-    return 10.0 * np.log10(rng * rng / np.mean((img - ref) ** 2))
-
-
-def _ssim(img, ref, win=7):
-    """skimage.metrics.structural_similarity defaults: uniform 7x7 window, K1 = 0.01, K2 = 0.03, sample covariance, mean over
-    the valid interior."""
-    rng = float(ref.max() - ref.min())
-    c1, c2 = (0.01 * rng) ** 2, (0.03 * rng) ** 2
-
-    def box(a):
-        c = np.cumsum(np.cumsum(np.pad(a, ((1, 0), (1, 0))), axis=0), axis=1)
-        return (c[win:, win:] - c[:-win, win:] - c[win:, :-win] + c[:-win, :-win]) / (win * win)
-    ux, uy = box(img), box(ref)
-    n = win * win
-    cov = n / (n - 1.0)
-    vx, vy, vxy = cov * (box(img * img) - ux * ux), cov * (box(ref * ref) - uy * uy), cov * (box(img * ref) - ux * uy)
-    return float(np.mean(((2 * ux * uy + c1) * (2 * vxy + c2)) / ((ux * ux + uy * uy + c1) * (vx + vy + c2))))
-
-
 def _model(tmp_path, extra=None):
     from Config.default_config import default_cfg
     from Utils.train_test_utils import progressive_domain_denoiser
@@ -152,12 +130,16 @@ def test_image_stage_512_matches_reference_golden(cuda, tmp_path, prec):
     out = model.img_denoiser(x, noise_strength=None, save_state=True, noise=tape)
     err = [rel_l2(model.progressive_denoise_result[f"iter_{k}"][0, 0][1::4, 2::4], g[f"iter{k}_sub"]) for k in range(1, 9)]
     rmse_hu = float(np.sqrt(np.mean((out[0, 0].cpu().numpy().astype(np.float64) - g["final"]) ** 2))) * HU_PER_MU
-    # image-quality metrics against the normal-dose phantom (the reference reports skimage PSNR / SSIM vs NDCT; same definitions here)
+    # image-quality metrics against the normal-dose phantom with the reference's definitions (metric_calculate :789-799):
+    # both images through miu2pixel, PSNR data_range=1, SSIM win_size=11; ours computed ON THE DEVICE, the reference's by the oracle
     import ipdm_pytorch_b200.synthetic as S
-    ndct = S.rasterize(S.phantom_ellipses(0)).astype(np.float64)
-    ours, ref = out[0, 0].cpu().numpy().astype(np.float64), g["final"].astype(np.float64)
-    d_psnr = _psnr(ours, ndct) - _psnr(ref, ndct)
-    d_ssim = _ssim(ours, ndct) - _ssim(ref, ndct)
+    from ipdm_pytorch_b200 import engine
+    from oracle import metrics_oracle as M
+    ndct = M.miu2pixel(S.rasterize(S.phantom_ellipses(0)))
+    ref_pix = M.miu2pixel(g["final"])
+    ours = engine.psnr_ssim(engine.miu2pixel(out[:, 0].contiguous()), torch.from_numpy(ndct)[None].to(cuda)).cpu().numpy()[0]
+    d_psnr = float(ours[0]) - M.psnr(ndct, ref_pix)
+    d_ssim = float(ours[1]) - M.ssim(ndct, ref_pix, win_size=11)
     print(f"image stage 512^2 ({prec}): rel-L2 per iterate {['%.2e' % e for e in err]}; final RMSE {rmse_hu:.3f} HU; "
           f"vs NDCT: dPSNR {d_psnr:+.4f} dB, dSSIM {d_ssim:+.5f}")
     if prec == "fp32":
