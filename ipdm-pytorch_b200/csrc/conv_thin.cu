@@ -106,6 +106,7 @@ conv_thin_kernel(const __grid_constant__ ConvThinParams P) {
                 int b, x0, y0; decode(tile, b, x0, y0);
                 const int s = it % C::NSA;
                 tc::mbar_wait(&a_empty[s], ((uint32_t)(it / C::NSA) & 1u) ^ 1u);
+                if (P.dbg & 8) { tc::mbar_arrive(&a_full[s]); continue; }          // experiment: no operand loads at all
                 tc::mbar_expect_tx(&a_full[s], C::BOX_BYTES);
                 tc::tma_load_4d(smem + C::OFF_A + s * C::SLOT, &P.mapA, &a_full[s], 0, x0 - off, y0 - off, b);
             }

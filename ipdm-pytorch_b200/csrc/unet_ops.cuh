@@ -77,7 +77,7 @@ struct ConvThinParams {
     const float* bias; int bias_t_stride; const int* t_dev;
     const float* res; int res_cs;
     const float* norm_scale; const float* norm_shift; int act_silu;
-    int dbg;                           // IPDM_THIN_DBG experiments (tools only): 1 no stores, 2 no residual loads, 4 no MMAs
+    int dbg;                           // IPDM_THIN_DBG experiments (tools only): 1 no stores, 2 no residual loads, 4 no MMAs, 8 no operand loads
 };
 int conv_thin_prepare(ConvThinParams& P, const ConvThinDesc& d);
 int conv_thin_launch(const ConvThinParams& P, cudaStream_t st);
