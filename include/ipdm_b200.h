@@ -126,6 +126,15 @@ int ipdm_sampler_step(const float* x_t_dev, const float* x0c_dev, const float* e
                       float* x_out_dev, int batch, int h, int w, const float coef7[7], float lam_scalar,
                       const float* lam_map_dev, int ks, int clip, int t_nonzero, uint64_t seed, uint64_t call_id,
                       void* workspace_dev, void* stream);
+/*
+ * One guided DDIM step (sparse sampler, Model/model.py ddim_sample :654-720) with the same e~ and x0 as above:
+ *   x_out = coef1*x0 + coef_e*e~ + (with_noise ? sigma*noise : 0)
+ * coef8 = {sa, s1ma, srec, srecm1, coef1 = sqrt(abar_prev), coef2 = 0, sigma = ddim_eta*posterior_variance[t],
+ *          coef_e = sqrt(1 - abar_prev - sigma_t(eta)^2)}; lam is the scalar condition_lambda of the iteration.
+ */
+int ipdm_sampler_step_ddim(const float* x_t_dev, const float* x0c_dev, const float* eps_dev, const float* noise_dev,
+                           float* x_out_dev, int batch, int h, int w, const float coef8[8], float lam_scalar, int clip,
+                           int with_noise, uint64_t seed, uint64_t call_id, void* workspace_dev, void* stream);
 /* Device-resident half of the Philox key (default 0).  CUDA-graph replays reuse frozen kernel arguments, so callers
  * bump this epoch between replays to get fresh noise; it is an ordinary stream-ordered update. */
 int ipdm_set_noise_epoch(uint64_t epoch, void* stream);

@@ -226,8 +226,57 @@ class GaussianDiffusion:
         out = _eng.guided_process(model.cuda_handle(), p, img, None if ldct is None else ldct.contiguous().float(), noise)
         return [out[k] for k in range(out.shape[0])], [], None
 
-    def sparse_guided_reverse_process(self, *a, **k):
-        raise NotImplementedError("sample_method='sparse' (DDIM, model.py:654-759) is outside the B200 hot path (SURVEY N3)")
+    @torch.no_grad()
+    def ddim_sample(self, sample_img, model, condition, t_start, condition_lambda=0.5, batch_size=1, ddim_timesteps=2,
+                    ddim_discr_method="uniform", ddim_eta=0.0, clip_denoised=True, noise=None, seed=0, call_base=0):
+        """Guided DDIM sub-sequence of the sparse sampler (reference model.py:654-720): the timestep sequence and the prediction /
+        guidance / x_{t-1} algebra of the reference, each step = one UNet forward + one fused `ipdm_sampler_step_ddim`.
+        `noise`: optional list of tensors, one per step (the reference draws randn_like every step even when ddim_eta = 0)."""
+        if ddim_discr_method == 'uniform':
+            seq = np.linspace(t_start - 1, 0, ddim_timesteps + 1).astype(int)[0:-1]
+        elif ddim_discr_method == 'quad':
+            seq = ((np.linspace(0, np.sqrt(self.timesteps * .8), ddim_timesteps)) ** 2).astype(int)
+        else:
+            raise NotImplementedError(f'There is no ddim discretization method called "{ddim_discr_method}"')
+        prev = np.append(seq[1:], np.array([0]))
+        f32 = lambda v: v.float()                                                   # _extract(...).float()
+        for i in range(ddim_timesteps):
+            t, tp = int(seq[i]), int(prev[i])
+            a_t, a_p = f32(self.alphas_cumprod[t]), f32(self.alphas_cumprod[tp])
+            sig_dir = ddim_eta * torch.sqrt((1 - a_p) / (1 - a_t) * (1 - a_t / a_p))
+            coef8 = [f32(self.sqrt_alphas_cumprod[t]), f32(self.sqrt_one_minus_alphas_cumprod[t]), 1.0 / torch.sqrt(a_t),
+                     torch.sqrt(1. - a_t) / torch.sqrt(a_t), torch.sqrt(a_p), 0.0, ddim_eta * f32(self.posterior_variance[t]),
+                     torch.sqrt(1 - a_p - sig_dir ** 2)]
+            eps = model(sample_img, torch.full((1,), t, device=sample_img.device, dtype=torch.long))
+            sample_img = _eng.sampler_step_ddim(sample_img.contiguous(), condition.contiguous(), eps.contiguous(), [float(c) for c in coef8],
+                                                float(condition_lambda), noise=None if noise is None else noise[i].contiguous(),
+                                                clip=clip_denoised, with_noise=ddim_eta != 0.0, seed=seed, call_id=call_base + i)
+        return sample_img
+
+    @torch.no_grad()
+    def sparse_guided_reverse_process(self, model, condition, t_start, condition_lambda_max=0.5, condition_lambda_min=0.25,
+                                      batch_size=1, ddim_timesteps=[2], ddim_discr_method="uniform", ddim_eta=0.0, eta=0.5,
+                                      clip_denoised=True, noise=None, seed=0):
+        """Sparse (DDIM) guided sampler, reference model.py:726-759.  `noise`: optional tape in the reference's randn order:
+        [q_sample, then one tensor per DDIM step]."""
+        condition = condition.contiguous().float()
+        ts0 = int(t_start[0])
+        sample_img = _eng.q_sample(condition, float(self.sqrt_alphas_cumprod[ts0].float()), float(self.sqrt_one_minus_alphas_cumprod[ts0].float()),
+                                   noise=None if noise is None else noise[0].contiguous(), seed=seed, call_id=0)
+        condition_ = condition.clone()
+        step = (condition_lambda_max - condition_lambda_min) / len(t_start)
+        condition_lambda = np.arange(condition_lambda_max, condition_lambda_min - step, -step)
+        result, used = [], 1
+        for i, t in enumerate(t_start):
+            n_i = None if noise is None else [noise[used + k] for k in range(ddim_timesteps[i])]
+            sample_img = self.ddim_sample(sample_img=sample_img, model=model, condition=condition, t_start=t,
+                                          condition_lambda=condition_lambda[i], batch_size=batch_size, ddim_timesteps=ddim_timesteps[i],
+                                          ddim_discr_method=ddim_discr_method, ddim_eta=ddim_eta, clip_denoised=clip_denoised,
+                                          noise=n_i, seed=seed, call_base=1 + used)
+            used += ddim_timesteps[i]
+            condition = _eng.lincomb(eta, sample_img, 1 - eta, condition_)
+            result.append(sample_img.clone())
+        return result
 
 
 def yeo_johnson_transform(img_tensor):

@@ -216,8 +216,11 @@ class progressive_domain_denoiser:
     # ---- stages (device resident) ------------------------------------------------------------
     def _proj_stage(self, x, noise=None):
         o = self.opt
-        if o.sample_method_proj != "dense":
-            raise NotImplementedError("sample_method_proj='sparse' is outside the B200 hot path (SURVEY N3)")
+        if o.sample_method_proj == "sparse":                                   # reference :445-453
+            return self.proj_gaussian_diffusion.sparse_guided_reverse_process(
+                model=self.proj_model, condition=x.type(self.proj_dtype), t_start=o.t_start_proj, condition_lambda_max=0.49,
+                condition_lambda_min=0.35, clip_denoised=o.clip_proj, ddim_timesteps=o.ddim_timesteps_proj, eta=o.eta_proj,
+                noise=noise, seed=getattr(o, "noise_seed", 0))
         res, _, ns = self.proj_gaussian_diffusion.guided_reverse_process(
             model=self.proj_model, img=x.type(self.proj_dtype), t_start=o.t_start_proj, clip=o.clip_proj,
             lambda_ratio=o.lambda_ratio_proj, eta=o.eta_proj, lambda_curve=self.proj_lambda_curve, mode="proj",
@@ -237,19 +240,24 @@ class progressive_domain_denoiser:
 
     def _img_stage(self, x, noise=None, noise_strength=None):
         o = self.opt
-        if o.sample_method_img != "dense":
-            raise NotImplementedError("sample_method_img='sparse' is outside the B200 hot path (SURVEY N3)")
         x = x.type(self.img_dtype).to(self.img_device).contiguous()
         common = dict(model=self.img_model, clip=o.clip_img, lambda_ratio=o.lambda_ratio_img, save_states=o.save_states_img,
                       lambda_curve=self.img_lambda_curve, noise_strength=noise_strength, ldct=x, kernel_size_img=o.kernel_size_img,
                       amplitude_img=o.amplitude_img, only_convertor=o.benchmark_test, normal=o.normal, transformer=self.trans_ldimg,
                       mode="img")
-        n_main = None if noise is None else noise[:sum(o.t_start_img) + len(o.t_start_img)]
-        result, _, _ = self.img_gaussian_diffusion.guided_reverse_process(
-            img=x, t_start=o.t_start_img, eta=o.eta_img, constant_guidance=o.constant_guidance_img, noise=n_main,
-            seed=getattr(o, "noise_seed", 0) + 1, **common)
+        if o.sample_method_img == "sparse":                                    # reference :505-514
+            n_count = 1 + sum(o.ddim_timesteps_img[:len(o.t_start_img)])
+            result = self.img_gaussian_diffusion.sparse_guided_reverse_process(
+                model=self.img_model, condition=x, t_start=o.t_start_img, condition_lambda_max=0.5, condition_lambda_min=0.3,
+                clip_denoised=True, ddim_timesteps=o.ddim_timesteps_img, eta=o.eta_img,
+                noise=None if noise is None else noise[:n_count], seed=getattr(o, "noise_seed", 0) + 1)
+        else:
+            n_count = sum(o.t_start_img) + len(o.t_start_img)
+            result, _, _ = self.img_gaussian_diffusion.guided_reverse_process(
+                img=x, t_start=o.t_start_img, eta=o.eta_img, constant_guidance=o.constant_guidance_img,
+                noise=None if noise is None else noise[:n_count], seed=getattr(o, "noise_seed", 0) + 1, **common)
         if o.ultra_img_denoise:
-            n_ultra = None if noise is None else noise[sum(o.t_start_img) + len(o.t_start_img):]
+            n_ultra = None if noise is None else noise[n_count:]
             extra, _, _ = self.img_gaussian_diffusion.guided_reverse_process(
                 img=result[-1], t_start=[5, 5, 5], eta=0.6, constant_guidance=0.6, noise=n_ultra,
                 seed=getattr(o, "noise_seed", 0) + 2, **common)

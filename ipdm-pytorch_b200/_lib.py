@@ -53,6 +53,8 @@ _SIGNATURES = {
     "ipdm_sampler_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "ipdm_sampler_step": (ctypes.c_int, [vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_float_p, ctypes.c_float,
                                          vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_uint64, ctypes.c_uint64, vp, vp]),
+    "ipdm_sampler_step_ddim": (ctypes.c_int, [vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_float_p, ctypes.c_float,
+                                              ctypes.c_int, ctypes.c_int, ctypes.c_uint64, ctypes.c_uint64, vp, vp]),
     "ipdm_set_noise_epoch": (ctypes.c_int, [ctypes.c_uint64, vp]),
     "ipdm_q_sample": (ctypes.c_int, [vp, vp, vp, ctypes.c_float, ctypes.c_float, ctypes.c_size_t, ctypes.c_int, ctypes.c_uint64,
                                      ctypes.c_uint64, vp]),

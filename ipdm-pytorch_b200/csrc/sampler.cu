@@ -171,11 +171,12 @@ __global__ void finalize2_kernel(const double* __restrict__ partials, SliceStats
 // ------------------------------------------------------------------------------------------------
 // apply
 // ------------------------------------------------------------------------------------------------
-struct StepCoef { float sa, s1ma, srec, srecm1, c1, c2, sigma; };
+struct StepCoef { float sa, s1ma, srec, srecm1, c1, c2, sigma, ce; };      // ce: coefficient of e~ itself (DDIM direction term; 0 for DDPM)
 
 __device__ __forceinline__ float step_one(float x, float etil, const StepCoef& k, int clip, float nz) {
     float x0 = k.srec * x - k.srecm1 * etil;
     if (clip) x0 = fminf(fmaxf(x0, -1.0f), 1.0f);
+    if (k.ce != 0.0f) return k.c1 * x0 + k.c2 * x + k.ce * etil + nz;          // DDIM: sqrt(abar_prev) x0 + dir * e~ (+ sigma * noise)
     return k.c1 * x0 + k.c2 * x + nz;
 }
 
@@ -484,10 +485,10 @@ Ws carve(void* ws, int batch) {
 }
 }  // namespace
 
-extern "C" int ipdm_sampler_step(const float* x_t, const float* x0c, const float* eps, const float* noise, float* x_out,
-                                 int batch, int h, int w, const float coef7[7], float lam_scalar, const float* lam_map,
-                                 int ks, int clip, int t_nonzero, uint64_t seed, uint64_t call_id, void* workspace,
-                                 void* stream) {
+static int sampler_step_impl(const float* x_t, const float* x0c, const float* eps, const float* noise, float* x_out,
+                             int batch, int h, int w, const float coef7[7], float coef_e, float lam_scalar, const float* lam_map,
+                             int ks, int clip, int t_nonzero, uint64_t seed, uint64_t call_id, void* workspace,
+                             void* stream) {
     IPDM_REQUIRE(x_t && x0c && eps && x_out && coef7 && workspace && batch > 0 && h > 0 && w > 0, "ipdm_sampler_step: bad arguments");
     IPDM_REQUIRE(((uintptr_t)x_t | (uintptr_t)x0c | (uintptr_t)eps | (uintptr_t)x_out | (uintptr_t)noise) % 16 == 0,
                  "ipdm_sampler_step: buffers must be 16-byte aligned");
@@ -497,7 +498,7 @@ extern "C" int ipdm_sampler_step(const float* x_t, const float* x0c, const float
     cudaStream_t st = (cudaStream_t)stream;
     ProfScope prof(PROF_SAMPLER, st, (lam_map ? 44.0 : 32.0) * batch * (double)h * w);        // algorithmic bytes
     Ws ws = carve(workspace, batch);
-    StepCoef k{coef7[0], coef7[1], coef7[2], coef7[3], coef7[4], coef7[5], coef7[6]};
+    StepCoef k{coef7[0], coef7[1], coef7[2], coef7[3], coef7[4], coef7[5], coef7[6], coef_e};
     const int nblk = (int)std::min<size_t>(MOM_BLOCKS, (n / 4 + MOM_THREADS - 1) / MOM_THREADS > 0 ? (n / 4 + MOM_THREADS - 1) / MOM_THREADS : 1);
     moments1_kernel<<<dim3(nblk, batch), MOM_THREADS, 0, st>>>(x_t, x0c, eps, ws.partials, n, k.sa);
     finalize1_kernel<<<batch, 32, 0, st>>>(ws.partials, ws.stats, nblk, (double)n, lam_scalar, lam_map != nullptr);
@@ -516,6 +517,22 @@ extern "C" int ipdm_sampler_step(const float* x_t, const float* x0c, const float
     }
     IPDM_CHECK_LAUNCH();
     return IPDM_OK;
+}
+
+extern "C" int ipdm_sampler_step(const float* x_t, const float* x0c, const float* eps, const float* noise, float* x_out,
+                                 int batch, int h, int w, const float coef7[7], float lam_scalar, const float* lam_map,
+                                 int ks, int clip, int t_nonzero, uint64_t seed, uint64_t call_id, void* workspace,
+                                 void* stream) {
+    return sampler_step_impl(x_t, x0c, eps, noise, x_out, batch, h, w, coef7, 0.0f, lam_scalar, lam_map, ks, clip, t_nonzero, seed, call_id,
+                             workspace, stream);
+}
+
+extern "C" int ipdm_sampler_step_ddim(const float* x_t, const float* x0c, const float* eps, const float* noise, float* x_out,
+                                      int batch, int h, int w, const float coef8[8], float lam_scalar, int clip, int with_noise,
+                                      uint64_t seed, uint64_t call_id, void* workspace, void* stream) {
+    IPDM_REQUIRE(coef8, "ipdm_sampler_step_ddim: bad arguments");
+    return sampler_step_impl(x_t, x0c, eps, noise, x_out, batch, h, w, coef8, coef8[7], lam_scalar, nullptr, 1, clip, with_noise, seed, call_id,
+                             workspace, stream);
 }
 
 extern "C" int ipdm_q_sample(const float* x, const float* noise, float* out, float a, float b, size_t n_per_slice,

@@ -201,6 +201,32 @@ def sampler_step(x_t, x0c, eps, coef7, lam, noise=None, clip=False, t_nonzero=Tr
     return out
 
 
+def ddim_coefficients(timesteps, schedule_power, t, t_prev, ddim_eta=0.0):
+    """coef8 of ipdm_sampler_step_ddim for the pair (t, t_prev), from the fp64 schedule tables cast to fp32 like the reference's
+    `_extract(...).float()` (Model/model.py ddim_sample :688-712)."""
+    f = schedule_at(timesteps, schedule_power, int(t))
+    fp = schedule_at(timesteps, schedule_power, int(t_prev))
+    a_t, a_p = np.float32(f["alphas_cumprod"]), np.float32(fp["alphas_cumprod"])
+    one = np.float32(1.0)
+    sig_dir = np.float32(ddim_eta) * np.sqrt((one - a_p) / (one - a_t) * (one - a_t / a_p))
+    coef_e = np.sqrt(one - a_p - sig_dir * sig_dir)
+    sigma = np.float32(ddim_eta) * np.float32(f["posterior_variance"])
+    return [float(f["sqrt_alphas_cumprod"]), float(f["sqrt_one_minus_alphas_cumprod"]), float(one / np.sqrt(a_t)),
+            float(np.sqrt(one - a_t) / np.sqrt(a_t)), float(np.sqrt(a_p)), 0.0, float(sigma), float(coef_e)]
+
+
+def sampler_step_ddim(x_t, x0c, eps, coef8, lam, noise=None, clip=True, with_noise=False, seed=0, call_id=0, out=None):
+    """One guided DDIM step (see ipdm_sampler_step_ddim); `lam` is the scalar condition_lambda."""
+    b, h, w = x_t.shape[0], x_t.shape[-2], x_t.shape[-1]
+    out = torch.empty_like(x_t) if out is None else out
+    ws = _workspace(_lib.lib().ipdm_sampler_workspace_bytes(b, h, w), x_t.device)
+    coef = (ctypes.c_float * 8)(*[float(c) for c in coef8])
+    check(_lib.lib().ipdm_sampler_step_ddim(_dev(x_t), _dev(x0c), _dev(eps), _opt(noise), _dev(out), b, h, w, coef, float(lam),
+                                            int(bool(clip)), int(bool(with_noise)), int(seed), int(call_id), _dev(ws), _stream()),
+          "ipdm_sampler_step_ddim")
+    return out
+
+
 def delta_lambda_map(x, img, ks=4, amplitude=7.0, kind="proj", return_median=False):
     b, h, w = x.shape[0], x.shape[-2], x.shape[-1]
     out = torch.empty(b, h // ks, w // ks, device=x.device, dtype=torch.float32)

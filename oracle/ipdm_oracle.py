@@ -338,6 +338,43 @@ def guided_reverse_process(unet, tab, img, t_start, clip, lambda_ratio, eta, mod
     return iters_out
 
 
+def ddim_sample(unet, tab, x, condition, t_start, condition_lambda, ddim_timesteps, clip, noise, ddim_eta=0.0):
+    """GaussianDiffusion.ddim_sample (Model/model.py:654-720), 'uniform' discretisation, ONE slice."""
+    seq = np.linspace(t_start - 1, 0, ddim_timesteps + 1).astype(int)[0:-1]                         # :670
+    prev = np.append(seq[1:], np.array([0]))                                                        # :680
+    for i in range(ddim_timesteps):
+        t, tp = int(seq[i]), int(prev[i])
+        a_t, a_p = tab.at("alphas_cumprod", t), tab.at("alphas_cumprod", tp)                       # :690-691
+        eps = unet(x, torch.full((1,), t, dtype=torch.long))
+        cond = (x - tab.at("sqrt_alphas_cumprod", t) * condition) / tab.at("sqrt_one_minus_alphas_cumprod", t)   # :695
+        mix = _std((1 - condition_lambda) * _std(eps) + condition_lambda * _std(cond))             # :696-697
+        x0 = (x - torch.sqrt(1.0 - a_t) * mix) / torch.sqrt(a_t)                                   # :699
+        if clip:
+            x0 = torch.clamp(x0, -1.0, 1.0)
+        sig = ddim_eta * torch.sqrt((1 - a_p) / (1 - a_t) * (1 - a_t / a_p))                       # :705-706
+        direction = torch.sqrt(1 - a_p - sig ** 2) * mix                                            # :710
+        sig2 = ddim_eta * tab.at("posterior_variance", t)                                          # :711
+        x = torch.sqrt(a_p) * x0 + direction + sig2 * next(noise)                                   # :713-714
+    return x
+
+
+def sparse_guided_reverse_process(unet, tab, condition, t_start, lam_max, lam_min, ddim_timesteps, eta, clip, noise):
+    """GaussianDiffusion.sparse_guided_reverse_process (Model/model.py:726-759), ONE slice; `noise` iterates the tape."""
+    noise = iter(noise)
+    ts0 = t_start[0]
+    x = tab.at("sqrt_alphas_cumprod", ts0) * condition + tab.at("sqrt_one_minus_alphas_cumprod", ts0) * next(noise)   # :740, q_sample :438-445
+    cond0 = condition.clone()
+    step = (lam_max - lam_min) / len(t_start)
+    lams = np.arange(lam_max, lam_min - step, -step)                                                # :743-744
+    out = []
+    with torch.no_grad():
+        for i, t in enumerate(t_start):
+            x = ddim_sample(unet, tab, x, condition, t, lams[i], ddim_timesteps[i], clip, noise)
+            condition = eta * x.clone() + (1 - eta) * cond0                                          # :757
+            out.append(x.clone())
+    return out
+
+
 def tensor_sharpen(img, N):
     """Utils/train_test_utils.py:868-878 for one slice [1,1,H,W]."""
     if N == -1:

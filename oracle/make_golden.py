@@ -3,6 +3,7 @@
 Run in the build container (needs /root/reference):
 
     python oracle/make_golden.py small      # schedule, small UNet / guided-process cases, one FBP slice (~2 min)
+    python oracle/make_golden.py sparse     # sparse (DDIM) guided sampler on the small fields
     python oracle/make_golden.py full       # one full 2000x912 -> 512x512 progressive slice (~12 min on 8 cores)
 
 Every case fixes (weights seed, input seed, noise-tape seed); tests re-create the
@@ -132,6 +133,34 @@ def case_grp_small(MM, TT):
     return out
 
 
+def case_sparse_small(MM):
+    """sparse_guided_reverse_process (DDIM, model.py:654-759) on the small fields with the arguments proj_denoiser / img_denoiser
+    pass (train_test_utils.py:445-453, :505-514) and the notebook's cell-3 schedules."""
+    import torch
+    out = {}
+    torch.manual_seed(0)
+    pnet = MM.UNetModel(**PROJ_CFG).eval()
+    pgd = MM.GaussianDiffusion(1000, "cosine", schedule_power=5)
+    for sid in (0, 1):
+        x = small_proj_input(200 + sid)
+        with NoiseTape(tape(x.shape, 7, 700 + sid)) as nt:
+            res = pgd.sparse_guided_reverse_process(model=pnet, condition=x, t_start=[15, 15, 5], condition_lambda_max=0.49,
+                                                    condition_lambda_min=0.35, clip_denoised=False, ddim_timesteps=[1, 2, 3], eta=0.5)
+        assert nt.used == 7 and len(res) == 3
+        out[f"proj{sid}"] = np.stack([r.numpy()[0, 0] for r in res])
+    torch.manual_seed(1)
+    inet = MM.UNetModel(**IMG_CFG).eval()
+    igd = MM.GaussianDiffusion(1000, "cosine", schedule_power=1)
+    for sid in (0, 1):
+        x = small_img_input(400 + sid)
+        with NoiseTape(tape(x.shape, 7, 800 + sid)) as nt:
+            res = igd.sparse_guided_reverse_process(model=inet, condition=x, t_start=[18, 18, 5], condition_lambda_max=0.5,
+                                                    condition_lambda_min=0.3, clip_denoised=True, ddim_timesteps=[1, 2, 3], eta=0.7)
+        assert nt.used == 7
+        out[f"img{sid}"] = np.stack([r.numpy()[0, 0] for r in res])
+    return out
+
+
 def case_fbp(RF):
     import numba
     numba.set_num_threads(1)
@@ -233,6 +262,9 @@ def main():
         save("unet_small", case_unet_small(MM))
         save("grp_small", case_grp_small(MM, TT))
         save("fbp_slice0", case_fbp(RF))
+    elif what == "sparse":
+        MM, RF, TT, CFG = load_reference()
+        save("sparse_small", case_sparse_small(MM))
     elif what == "fbp":
         MM, RF, TT, CFG = load_reference()
         save("fbp_slice0", case_fbp(RF))

@@ -81,3 +81,50 @@ def test_philox_path_is_deterministic_and_unsupported_modes_fail_loudly(cuda):
         gd.guided_reverse_process(net, x, t_start=[2], mode="img", constant_guidance=None, ldct=x, only_convertor=False)
     out, _, _ = gd.guided_reverse_process(net, x, t_start=[2], mode="img", constant_guidance=0.45, ldct=x, only_convertor=True)
     assert out[0] is x
+
+
+# ---- sparse (DDIM) guided sampler, notebook cell 3 -----------------------------------------------------------
+@pytest.mark.parametrize("prec,tol", [("tf32", GRP_TOL), ("fp32", GRP_TOL_FP32)])
+def test_sparse_sampler_matches_reference_golden(cuda, prec, tol):
+    """sparse_guided_reverse_process with the arguments proj_denoiser / img_denoiser pass for sample_method='sparse'
+    (reference train_test_utils.py:445-453, :505-514); goldens from the unmodified reference (make_golden.py sparse)."""
+    from Model.model import GaussianDiffusion, UNetModel
+    g = golden("sparse_small")
+    torch.manual_seed(0)
+    pnet = UNetModel(**PROJ_CFG).to(cuda).eval()
+    pnet.set_precision(prec)
+    pgd = GaussianDiffusion(1000, "cosine", schedule_power=5)
+    xs = [small_proj_input(200 + s) for s in (0, 1)]
+    noise = torch.cat([_tape(xs[0].shape, 7, 700 + s, cuda) for s in (0, 1)], dim=1).contiguous()      # two slices in one batch
+    res = pgd.sparse_guided_reverse_process(model=pnet, condition=torch.cat(xs).to(cuda), t_start=[15, 15, 5], condition_lambda_max=0.49,
+                                            condition_lambda_min=0.35, clip_denoised=False, ddim_timesteps=[1, 2, 3], eta=0.5, noise=noise)
+    assert len(res) == 3
+    for s in (0, 1):
+        err = [rel_l2(res[k][s, 0].cpu().numpy(), g[f"proj{s}"][k]) for k in range(3)]
+        print(f"sparse proj slice {s} ({prec}): rel-L2 per iterate {['%.2e' % e for e in err]}")
+        assert max(err) < tol
+    torch.manual_seed(1)
+    inet = UNetModel(**IMG_CFG).to(cuda).eval()
+    inet.set_precision(prec)
+    igd = GaussianDiffusion(1000, "cosine", schedule_power=1)
+    for s in (0, 1):
+        x = small_img_input(400 + s).to(cuda)
+        res = igd.sparse_guided_reverse_process(model=inet, condition=x, t_start=[18, 18, 5], condition_lambda_max=0.5, condition_lambda_min=0.3,
+                                                clip_denoised=True, ddim_timesteps=[1, 2, 3], eta=0.7, noise=_tape(x.shape, 7, 800 + s, cuda))
+        err = [rel_l2(res[k][0, 0].cpu().numpy(), g[f"img{s}"][k]) for k in range(3)]
+        print(f"sparse img slice {s} ({prec}): rel-L2 per iterate {['%.2e' % e for e in err]}")
+        assert max(err) < tol
+
+
+def test_notebook_cell3_sparse_progressive_runs(cuda, tmp_path):
+    """test_sample.ipynb cell 3: update_opt(sample_method_proj='sparse', sample_method_img='sparse', ddim_timesteps=[1,2,3]) then
+    progressive_denoiser(); Philox noise, two slices, result layout as in the dense mode."""
+    import ipdm_pytorch_b200.synthetic as S
+    from test_progressive_gpu import _model
+    model = _model(tmp_path, dict(t_start_proj=[15, 15, 5], sample_method_proj="sparse", ddim_timesteps_proj=[1, 2, 3], t_start_img=[18, 18, 5],
+                                  ddim_timesteps_img=[1, 2, 3], sample_method_img="sparse", noise_seed=3))
+    ld = torch.from_numpy(np.stack([S.make_slice(s)[0] for s in (0, 1)]))[:, None]
+    model.data_sample_load(ldct=None, ldproj=ld, fdproj=None, fdct=None)
+    out = model.progressive_denoiser(sharpen_num=70, save_proj_state=True)
+    assert out.shape == (2, 1, 512, 512) and torch.isfinite(out).all()
+    assert len(model.proj_denoise_result) == 3                            # one entry per sparse proj iteration

@@ -135,3 +135,20 @@ def test_metrics_oracle_matches_the_definition_and_its_properties():
     from Dataset.npz_data_loader import miu2pixel
     mu = (0.25 * rng.random((8, 9))).astype(np.float32)
     np.testing.assert_array_equal(M.miu2pixel(mu), miu2pixel(mu.copy()))
+
+
+# ---- N3: sparse (DDIM) guided sampler ------------------------------------------------------------------------------------
+def test_sparse_sampler_oracle_matches_reference():
+    g = golden("sparse_small")
+    torch.manual_seed(0)
+    pnet = O.UNetOracle(**PROJ_CFG).eval()
+    x = small_proj_input(200)
+    res = O.sparse_guided_reverse_process(pnet, O.Tables(1000, 5), x, [15, 15, 5], 0.49, 0.35, [1, 2, 3], eta=0.5, clip=False,
+                                          noise=noise_tape(x.shape, 7, 700))
+    assert rel_l2(np.stack([r.numpy()[0, 0] for r in res]), g["proj0"]) < 2e-5
+    torch.manual_seed(1)
+    inet = O.UNetOracle(**IMG_CFG).eval()
+    x = small_img_input(400)
+    res = O.sparse_guided_reverse_process(inet, O.Tables(1000, 1), x, [18, 18, 5], 0.5, 0.3, [1, 2, 3], eta=0.7, clip=True,
+                                          noise=noise_tape(x.shape, 7, 800))
+    assert rel_l2(np.stack([r.numpy()[0, 0] for r in res]), g["img0"]) < 2e-5
