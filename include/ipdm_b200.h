@@ -146,6 +146,11 @@ int ipdm_q_sample(const float* x_dev, const float* noise_dev, float* out_dev, fl
 int ipdm_delta_lambda_map(const float* x_dev, const float* img_dev, float* lam_exp_out_dev, float* median_out_dev,
                           int batch, int h, int w, int ks, float amplitude, int curve_kind, void* workspace_dev,
                           void* stream);
+/* Image-domain variant (Model/model.py:591-595): avgpool_ks(|miu2pixel(x) - miu2pixel(img)|) - median(pooled map) -> relu ->
+ * exp(amp*.) -> curve.  pooled_tmp_dev: scratch [B][H/ks][W/ks]. */
+int ipdm_delta_lambda_map_img(const float* x_dev, const float* img_dev, float* lam_exp_out_dev, float* median_out_dev,
+                              float* pooled_tmp_dev, int batch, int h, int w, int ks, float amplitude, int curve_kind,
+                              void* workspace_dev, void* stream);
 /* per-step guidance map clip(1 - (abar(i+1)/abar(i))^Lambda, .05, .99), fp64 math, n cells */
 int ipdm_lambda_step_map(const float* lam_exp_dev, float* lam_out_dev, size_t n, int i, int ts, void* stream);
 /* host evaluation of the piecewise lambda curve (fp64 polyfit coefficients), for tests */

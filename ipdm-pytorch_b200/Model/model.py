@@ -10,8 +10,8 @@ libipdm_b200.so:
     `ipdm_guided_process` (one stream, no host round trips); the extra keyword `noise=` carries a
     caller-supplied tape [count,B,1,H,W] in the reference's randn_like order, `seed=` keys the
     in-kernel Philox generator otherwise.
-Out of scope here (reference lines): ddim_sample / sparse_guided_reverse_process
-:654-759, train_losses :645-652, Yeo-Johnson :762-807, adaptive t_start=None :582-613.
+  * `ddim_sample` / `sparse_guided_reverse_process` (:654-759): host loop over UNet forward + fused DDIM step.
+Out of scope here (reference lines): train_losses :645-652, Yeo-Johnson :762-807, adaptive t_start=None :582-613.
 """
 import math
 from copy import copy

@@ -47,7 +47,6 @@ extern "C" int ipdm_guided_process(ipdm_unet* net, const ipdm_guided_params* p, 
     IPDM_REQUIRE(net && p && img && iters_out && workspace && batch > 0, "ipdm_guided_process: bad arguments");
     IPDM_REQUIRE(p->n_iters >= 1 && p->n_iters <= 8, "ipdm_guided_process: n_iters must be in [1, 8] (adaptive t_start=None is not on this path)");
     IPDM_REQUIRE(p->mode == 0 || p->mode == 1, "ipdm_guided_process: mode must be 0 (proj) or 1 (img)");
-    IPDM_REQUIRE(p->constant_guidance_set || p->mode == 0, "ipdm_guided_process: adaptive lambda in the image domain is not implemented");
     IPDM_REQUIRE(p->mode == 0 || ldct != nullptr, "ipdm_guided_process: img mode needs ldct");
     const bool adaptive = !p->constant_guidance_set;
     if (adaptive) IPDM_REQUIRE(p->kernel_size > 0 && h % p->kernel_size == 0 && w % p->kernel_size == 0,
@@ -89,11 +88,16 @@ extern "C" int ipdm_guided_process(ipdm_unet* net, const ipdm_guided_params* p, 
         IPDM_CHECK_CUDA(cudaMemcpyAsync(out_it, ws.x, n * sizeof(float), cudaMemcpyDeviceToDevice, st));                  // :619
         if (adaptive) {
             if (it == 0) {
-                IPDM_CHECK(ipdm_delta_lambda_map(ws.x, img, ws.lam_exp, nullptr, batch, h, w, p->kernel_size, (float)p->amplitude,
-                                                 p->curve_kind, ws.sampler, st));                                       // :596-600, :614
+                if (p->mode == 0)
+                    IPDM_CHECK(ipdm_delta_lambda_map(ws.x, img, ws.lam_exp, nullptr, batch, h, w, p->kernel_size, (float)p->amplitude,
+                                                     p->curve_kind, ws.sampler, st));                                   // :596-600, :614
+                else                                                                                                     // :591-595 (lam_map is free scratch here)
+                    IPDM_CHECK(ipdm_delta_lambda_map_img(ws.x, img, ws.lam_exp, nullptr, ws.lam_map, batch, h, w, p->kernel_size,
+                                                         (float)p->amplitude, p->curve_kind, ws.sampler, st));
                 IPDM_CHECK_CUDA(cudaMemcpyAsync(ws.x, img, n * sizeof(float), cudaMemcpyDeviceToDevice, st));             // :630
             } else {
-                IPDM_CHECK(ipdm_lincomb(ws.guide, (float)p->eta, out_it, (float)(1 - p->eta), img, 0.f, nullptr, n, st)); // :626
+                if (p->mode == 0) IPDM_CHECK(ipdm_lincomb(ws.guide, (float)p->eta, out_it, (float)(1 - p->eta), img, 0.f, nullptr, n, st));   // :626
+                else IPDM_CHECK(ipdm_lincomb(ws.guide, (float)p->eta, out_it, (float)(0.95 - p->eta), img, 0.05f, ldct, n, st));                // :628
                 guide = ws.guide;
             }
         } else {

@@ -299,9 +299,9 @@ select_hist_kernel(const float* __restrict__ x, const float* __restrict__ img, u
     const unsigned pmask = pass == 0 ? 0u : (pass == 1 ? 0xFFE00000u : 0xFFFFFC00u);
     const int shift = pass == 0 ? 21 : (pass == 1 ? 10 : 0);
     const unsigned bmask = pass == 2 ? 0x3FFu : 0x7FFu;
-    const float* X = x + (size_t)b * n; const float* G = img + (size_t)b * n;
+    const float* X = x + (size_t)b * n; const float* G = img ? img + (size_t)b * n : nullptr;
     for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
-        const unsigned u = __float_as_uint(fabsf(X[i] - G[i]));
+        const unsigned u = __float_as_uint(fabsf(G ? X[i] - G[i] : X[i]));
         if ((u & pmask) == prefix) atomicAdd(&sh[(u >> shift) & bmask], 1u);
     }
     __syncthreads();
@@ -359,6 +359,43 @@ __global__ void delta_map_kernel(const float* __restrict__ x, const float* __res
         d = d <= 0.f ? 0.f : d;
         const float e = expf(__fmul_rn(amplitude, d));
         lam_exp[(size_t)b * lh * lw + cidx] = (float)curve_eval(cc, e);
+    }
+}
+
+// Image-domain variant (model.py:591-595): delt = avg_pool(|miu2pixel(x) - miu2pixel(img)|); delt -= median(delt); relu; curve(exp(amp * delt)).
+// Note the order: pool first, median of the POOLED map.  miu2pixel as Dataset/npz_data_loader.py:20-36 in fp32.
+__device__ __forceinline__ float miu2pixel_dev(float mu) {
+    const float w = 0.183f;
+    const float hu = __fsub_rn(__fdiv_rn(__fmul_rn(__fsub_rn(mu, w), 1e3f), w), 24.f);
+    const float p = __fdiv_rn(__fsub_rn(hu, -1024.f), 4096.f);
+    return hu < -1024.f ? 0.f : (hu > 3072.f ? 1.f : p);
+}
+
+__global__ void pool_absdiff_pixel_kernel(const float* __restrict__ x, const float* __restrict__ img, float* __restrict__ pooled,
+                                          int h, int w, int ks, int lh, int lw) {
+    const int b = blockIdx.y;
+    const size_t n = (size_t)h * w;
+    for (int cidx = blockIdx.x * blockDim.x + threadIdx.x; cidx < lh * lw; cidx += gridDim.x * blockDim.x) {
+        const int cy = cidx / lw, cx = cidx - cy * lw;
+        float s = 0.f;
+        for (int dy = 0; dy < ks; ++dy)
+            for (int dxx = 0; dxx < ks; ++dxx) {
+                const size_t i = (size_t)b * n + (size_t)(cy * ks + dy) * w + cx * ks + dxx;
+                s = __fadd_rn(s, fabsf(__fsub_rn(miu2pixel_dev(x[i]), miu2pixel_dev(img[i]))));
+            }
+        pooled[(size_t)b * lh * lw + cidx] = s / (float)(ks * ks);
+    }
+}
+
+__global__ void delta_map_pooled_kernel(const float* __restrict__ pooled, const unsigned* __restrict__ sel, float* __restrict__ lam_exp,
+                                        float* __restrict__ med_out, int cells, float amplitude, CurveCoef cc) {
+    const int b = blockIdx.y;
+    const float med = __uint_as_float(sel[b * 4 + 0]);
+    if (med_out && blockIdx.x == 0 && threadIdx.x == 0) med_out[b] = med;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < cells; c += gridDim.x * blockDim.x) {
+        float d = __fsub_rn(pooled[(size_t)b * cells + c], med);
+        d = d <= 0.f ? 0.f : d;
+        lam_exp[(size_t)b * cells + c] = (float)curve_eval(cc, expf(__fmul_rn(amplitude, d)));
     }
 }
 
@@ -560,6 +597,27 @@ extern "C" int ipdm_delta_lambda_map(const float* x, const float* img, float* la
     const int lh = h / ks, lw = w / ks;                       // avg_pool2d floors (model.py:598)
     delta_map_kernel<<<dim3(ceil_div((long long)lh * lw, 256), batch), 256, 0, st>>>(x, img, ws.sel, lam_exp_out, median_out, h, w, ks, lh, lw, amplitude, make_curve(curve_kind));
     count_launch(7);
+    IPDM_CHECK_LAUNCH();
+    return IPDM_OK;
+}
+
+extern "C" int ipdm_delta_lambda_map_img(const float* x, const float* img, float* lam_exp_out, float* median_out, float* pooled_tmp,
+                                         int batch, int h, int w, int ks, float amplitude, int curve_kind, void* workspace, void* stream) {
+    IPDM_REQUIRE(x && img && lam_exp_out && pooled_tmp && workspace && batch > 0 && ks > 0, "ipdm_delta_lambda_map_img: bad arguments");
+    IPDM_REQUIRE(h % ks == 0 && w % ks == 0, "ipdm_delta_lambda_map_img: H and W must be multiples of ks");
+    cudaStream_t st = (cudaStream_t)stream;
+    Ws ws = carve(workspace, batch);
+    const int lh = h / ks, lw = w / ks, cells = lh * lw;
+    const int gc = ceil_div((long long)cells, 256);
+    pool_absdiff_pixel_kernel<<<dim3(gc, batch), 256, 0, st>>>(x, img, pooled_tmp, h, w, ks, lh, lw);
+    IPDM_CHECK_CUDA(cudaMemsetAsync(ws.hist, 0, ws_hist(batch), st));
+    const int g = (int)std::min<size_t>((size_t)kNumSMs * 2, (size_t)gc);
+    for (int pass = 0; pass < 3; ++pass) {                               // exact lower median of the pooled map (values >= 0)
+        select_hist_kernel<<<dim3(g, batch), 256, 0, st>>>(pooled_tmp, nullptr, ws.hist, ws.sel, (size_t)cells, pass);
+        select_scan_kernel<<<batch, 256, 0, st>>>(ws.hist, ws.sel, (size_t)cells, pass);
+    }
+    delta_map_pooled_kernel<<<dim3(gc, batch), 256, 0, st>>>(pooled_tmp, ws.sel, lam_exp_out, median_out, cells, amplitude, make_curve(curve_kind));
+    count_launch(8);
     IPDM_CHECK_LAUNCH();
     return IPDM_OK;
 }

@@ -316,16 +316,22 @@ def guided_reverse_process(unet, tab, img, t_start, clip, lambda_ratio, eta, mod
         if clip:
             x = x.clamp(0, 1) if mode == "img" else x.clamp(min=0)        # :569-573
         if it == 0 and constant_guidance is None:
-            assert mode == "proj", "img-domain adaptive lambda (N4) is not on the progressive path"
-            d = torch.abs(x - img)                                        # :596-600
-            d = d - torch.median(d)
-            d = F.avg_pool2d(d, kernel_size)
-            d = torch.where(d <= 0, torch.zeros_like(d), d)
-            Lam = lambda_curve(torch.exp(amplitude * d).cpu().numpy(), "proj")  # :600, :614
+            if mode == "img":                                             # :591-595: pool first, median of the pooled map
+                d = torch.abs(miu2pixel(x) - miu2pixel(img.clone()))
+                d = F.avg_pool2d(d, kernel_size)
+                d = d - torch.median(d)
+                d = torch.where(d <= 0, torch.zeros_like(d), d)
+                Lam = lambda_curve(torch.exp(amplitude * d).cpu().numpy(), "img")
+            else:
+                d = torch.abs(x - img)                                    # :596-600
+                d = d - torch.median(d)
+                d = F.avg_pool2d(d, kernel_size)
+                d = torch.where(d <= 0, torch.zeros_like(d), d)
+                Lam = lambda_curve(torch.exp(amplitude * d).cpu().numpy(), "proj")  # :600, :614
         iters_out.append(x.contiguous())
         if constant_guidance is None:
             if it >= 1:
-                guide = eta * x + (1 - eta) * img                         # :626 (proj)
+                guide = eta * x + (1 - eta) * img if mode == "proj" else eta * x + (0.95 - eta) * img + 0.05 * ldct   # :626 / :628
             if it == 0:
                 x = img.clone()                                           # :630
         else:

@@ -4,6 +4,7 @@ Run in the build container (needs /root/reference):
 
     python oracle/make_golden.py small      # schedule, small UNet / guided-process cases, one FBP slice (~2 min)
     python oracle/make_golden.py sparse     # sparse (DDIM) guided sampler on the small fields
+    python oracle/make_golden.py imgadaptive  # image-domain adaptive lambda
     python oracle/make_golden.py full       # one full 2000x912 -> 512x512 progressive slice (~12 min on 8 cores)
 
 Every case fixes (weights seed, input seed, noise-tape seed); tests re-create the
@@ -161,6 +162,25 @@ def case_sparse_small(MM):
     return out
 
 
+def case_img_adaptive_small(MM, TT):
+    """Image-domain guided process with constant_guidance=None (the argparse default): scalar cosine lambda in iteration 0, the
+    per-pixel lambda map built from |miu2pixel(x) - miu2pixel(img)| afterwards (model.py:575-595)."""
+    import torch
+    out = {}
+    torch.manual_seed(1)
+    inet = MM.UNetModel(**IMG_CFG).eval()
+    igd = MM.GaussianDiffusion(1000, "cosine", schedule_power=1)
+    for sid in (0, 1):
+        x = small_img_input(400 + sid)
+        with NoiseTape(tape(x.shape, 30, 900 + sid)) as nt:
+            res, _, _ = igd.guided_reverse_process(model=inet, img=x, t_start=[10, 9, 8], clip=True, lambda_ratio=10, eta=0.7, save_states=False,
+                                                   mode="img", constant_guidance=None, lambda_curve=TT.curve_init(), noise_strength=None, ldct=x,
+                                                   kernel_size_img=4, amplitude_img=20, only_convertor=False, normal=False, transformer=None)
+        assert nt.used == 30 and len(res) == 4
+        out[f"img{sid}"] = np.stack([r.numpy()[0, 0] for r in res])
+    return out
+
+
 def case_fbp(RF):
     import numba
     numba.set_num_threads(1)
@@ -265,6 +285,9 @@ def main():
     elif what == "sparse":
         MM, RF, TT, CFG = load_reference()
         save("sparse_small", case_sparse_small(MM))
+    elif what == "imgadaptive":
+        MM, RF, TT, CFG = load_reference()
+        save("img_adaptive_small", case_img_adaptive_small(MM, TT))
     elif what == "fbp":
         MM, RF, TT, CFG = load_reference()
         save("fbp_slice0", case_fbp(RF))

@@ -77,8 +77,8 @@ def test_philox_path_is_deterministic_and_unsupported_modes_fail_loudly(cuda):
     assert torch.allclose(a[2], (a[0] + a[1]) / 2)
     with pytest.raises(NotImplementedError):
         gd.guided_reverse_process(net, x, t_start=None, mode="img", constant_guidance=0.45, ldct=x, only_convertor=False)
-    with pytest.raises(RuntimeError):
-        gd.guided_reverse_process(net, x, t_start=[2], mode="img", constant_guidance=None, ldct=x, only_convertor=False)
+    with pytest.raises(RuntimeError):                                   # img mode blends with ldct: it must be given
+        gd.guided_reverse_process(net, x, t_start=[2], mode="img", constant_guidance=0.45, ldct=None, only_convertor=False)
     out, _, _ = gd.guided_reverse_process(net, x, t_start=[2], mode="img", constant_guidance=0.45, ldct=x, only_convertor=True)
     assert out[0] is x
 
@@ -128,3 +128,22 @@ def test_notebook_cell3_sparse_progressive_runs(cuda, tmp_path):
     out = model.progressive_denoiser(sharpen_num=70, save_proj_state=True)
     assert out.shape == (2, 1, 512, 512) and torch.isfinite(out).all()
     assert len(model.proj_denoise_result) == 3                            # one entry per sparse proj iteration
+
+
+# ---- image-domain adaptive lambda (constant_guidance_img=None, the argparse default) ---------------------------
+@pytest.mark.parametrize("prec,tol", [("tf32", GRP_TOL), ("fp32", GRP_TOL_FP32)])
+def test_img_domain_adaptive_lambda_matches_reference_golden(cuda, prec, tol):
+    from Model.model import GaussianDiffusion, UNetModel
+    g = golden("img_adaptive_small")
+    torch.manual_seed(1)
+    net = UNetModel(**IMG_CFG).to(cuda).eval()
+    net.set_precision(prec)
+    gd = GaussianDiffusion(1000, "cosine", schedule_power=1)
+    for s in (0, 1):
+        x = small_img_input(400 + s).to(cuda)
+        res, _, _ = gd.guided_reverse_process(model=net, img=x, t_start=[10, 9, 8], clip=True, lambda_ratio=10, eta=0.7, mode="img",
+                                              constant_guidance=None, ldct=x, kernel_size_img=4, amplitude_img=20, only_convertor=False,
+                                              normal=False, noise=_tape(x.shape, 30, 900 + s, cuda))
+        err = [rel_l2(res[k][0, 0].cpu().numpy(), g[f"img{s}"][k]) for k in range(4)]
+        print(f"img adaptive slice {s} ({prec}): rel-L2 per iterate {['%.2e' % e for e in err]}")
+        assert max(err) < tol

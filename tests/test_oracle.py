@@ -152,3 +152,14 @@ def test_sparse_sampler_oracle_matches_reference():
     res = O.sparse_guided_reverse_process(inet, O.Tables(1000, 1), x, [18, 18, 5], 0.5, 0.3, [1, 2, 3], eta=0.7, clip=True,
                                           noise=noise_tape(x.shape, 7, 800))
     assert rel_l2(np.stack([r.numpy()[0, 0] for r in res]), g["img0"]) < 2e-5
+
+
+# ---- N4: image-domain adaptive lambda (constant_guidance_img=None) -----------------------------------------------------------
+def test_img_adaptive_lambda_oracle_matches_reference():
+    g = golden("img_adaptive_small")
+    torch.manual_seed(1)
+    net = O.UNetOracle(**IMG_CFG).eval()
+    x = small_img_input(400)
+    res = O.guided_reverse_process(net, O.Tables(1000, 1), x, [10, 9, 8], clip=True, lambda_ratio=10, eta=0.7, mode="img",
+                                   constant_guidance=None, noise=iter(noise_tape(x.shape, 30, 900)), kernel_size=4, amplitude=20.0, ldct=x)
+    assert rel_l2(np.stack([r.numpy()[0, 0] for r in res]), g["img0"]) < 2e-5
