@@ -453,8 +453,49 @@ class progressive_domain_denoiser:
             f.write(json.dumps(self.metric_total, sort_keys=False, indent=4, separators=(',', ': ')))
 
     # ---- evaluation loop (reference test() :274-315, fit() :326-348) ---------------------------
+    # `test_batch_size` slices go through the path together (the reference loops one slice at a time; batching is exact
+    # here because every statistic is per slice), and the files of the NEXT batch are read and pinned on a worker thread while the
+    # GPU works on the current one.  Results, metrics and save paths stay per slice, as the reference writes them.
+    def _fetch_batch(self, ids):
+        cols = self.test_dataset.collate([self.test_dataset[int(i)] for i in ids])
+        pin = torch.cuda.is_available()
+        return tuple(None if c is None else (c.contiguous().pin_memory() if pin else c.contiguous()) for c in cols)
+
+    def _run_batch(self, epoch, ids, cols):
+        ld_img, fd_proj, fd_img, ld_proj = cols
+        self.temp_clear()
+        self.data_sample_load(ldct=ld_img, ldproj=ld_proj, fdproj=fd_proj, fdct=fd_img)
+        if self.opt.mode == "test_proj":
+            self.proj_denoiser(self.ldproj)
+            fig_mode = "dproj2img"
+        elif self.opt.mode == "test_img":
+            self.img_denoiser(self.ldct, mode="img_only")
+            fig_mode = "dimg"
+        else:
+            self.progressive_denoiser()
+            fig_mode = "progressive"
+        names = ("progressive_denoise_result", "proj_denoise_result", "img_denoise_result", "proj_denoise_convert2img_result")
+        full = {n: getattr(self, n) for n in names}
+        per_slice = {n: getattr(self, n) for n in ("fdct", "ldct_np", "fdproj", "ldproj_np")}
+        nb = len(ids)
+        for j, idx in enumerate(ids):
+            for n, d in full.items():                           # views of slice j, shaped like the reference's B = 1 results
+                setattr(self, n, ResultTempDict({k: v[j:j + 1] for k, v in d.items()}))
+            for n, v in per_slice.items():
+                setattr(self, n, v[j] if (v is not None and nb > 1 and getattr(v, "ndim", 0) >= 3) else v)
+            self.metric_clear()
+            self.save_path_load(epoch, self.test_dataset.patient_name[idx], self.test_dataset.slice_name[idx])
+            self.result_figure_save(mode=fig_mode, display=False)
+            self.result_data_save(data_save=self.opt.test_result_data_save)
+            self.metric_update()
+        for n, d in full.items():
+            setattr(self, n, d)
+        for n, v in per_slice.items():
+            setattr(self, n, v)
+
     @torch.no_grad()
     def test(self, epoch):
+        from concurrent.futures import ThreadPoolExecutor
         n = len(self.test_dataset)
         if self.opt.test_numbers <= 0:
             self.opt.test_numbers = n
@@ -463,23 +504,15 @@ class progressive_domain_denoiser:
             return
         np.random.seed(9527)
         ids = np.sort(np.random.choice(n, self.opt.test_numbers, replace=False))
-        for idx in ids:
-            ld_img, fd_proj, fd_img, ld_proj = self.test_dataset[idx]
-            self.temp_clear()
-            self.save_path_load(epoch, self.test_dataset.patient_name[idx], self.test_dataset.slice_name[idx])
-            self.data_sample_load(ldct=None if ld_img is None else ld_img[None], ldproj=None if ld_proj is None else ld_proj[None],
-                                  fdproj=fd_proj, fdct=None if fd_img is None else fd_img[None])
-            if self.opt.mode == "test_proj":
-                self.proj_denoiser(self.ldproj)
-                self.result_figure_save(mode="dproj2img", display=False)
-            elif self.opt.mode == "test_img":
-                self.img_denoiser(self.ldct, mode="img_only")
-                self.result_figure_save(mode="dimg", display=False)
-            else:
-                self.progressive_denoiser()
-                self.result_figure_save(mode="progressive", display=False)
-            self.result_data_save(data_save=self.opt.test_result_data_save)
-            self.metric_update()
+        bs = max(1, int(getattr(self.opt, "test_batch_size", 1)))
+        batches = [ids[k:k + bs] for k in range(0, len(ids), bs)]
+        with ThreadPoolExecutor(max_workers=1) as pool:
+            fut = pool.submit(self._fetch_batch, batches[0])
+            for k, b in enumerate(batches):
+                cols = fut.result()
+                if k + 1 < len(batches):
+                    fut = pool.submit(self._fetch_batch, batches[k + 1])      # disk -> pinned host overlaps the GPU work below
+                self._run_batch(epoch, b, cols)
         self.metric_total_save(epoch)
 
     def fit(self):

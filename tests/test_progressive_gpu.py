@@ -165,3 +165,41 @@ def test_cuda_graph_replay_equals_eager_and_draws_fresh_noise(cuda, tmp_path):
     assert torch.equal(g1, eager1) and torch.equal(g2, eager2) and not torch.equal(g1, g2)
     assert model.progressive_denoise_result[-1].shape == (2, 1, 512, 512)
     engine.set_noise_epoch(0)
+
+
+def test_batched_prefetching_evaluation_loop(cuda, tmp_path):
+    """model.test() over a file dataset (<root>/<patient>/<slice>.npy) with test_batch_size = 2: three slices in two
+    batches, the next batch's files read on a worker thread; per-slice save paths / metric.json / totals as the reference writes them."""
+    import json
+    import ipdm_pytorch_b200.synthetic as S
+    from Config.default_config import default_cfg
+    from Utils.train_test_utils import progressive_domain_denoiser
+    roots = {k: tmp_path / k for k in ("ldproj", "fdimg", "ldimg")}
+    for sid in range(3):
+        noisy, _, ndct = S.make_slice(sid)
+        for k, arr in (("ldproj", noisy), ("fdimg", ndct), ("ldimg", (ndct * np.float32(1.01)).astype(np.float32))):
+            d = roots[k] / "P001"
+            d.mkdir(parents=True, exist_ok=True)
+            np.save(d / f"S{sid:03d}.npy", arr)
+    opt = default_cfg(["--load_option_path", os.path.join(PKG, "Config/Mayo-Config/test_progressive_option.json"), "--device", "cuda:0"])
+    opt.load_img_model_path = opt.load_proj_model_path = None
+    opt.test_dataset_path_LD_proj, opt.test_dataset_path_FD_img, opt.test_dataset_path_LD_img = (str(roots[k]) for k in ("ldproj", "fdimg", "ldimg"))
+    opt.test_dataset_path_FD_proj = None
+    opt.data_type = "siemens"
+    torch.manual_seed(0)
+    model = progressive_domain_denoiser(opt, result_save_path=str(tmp_path / "out"))
+    model.update_opt(dict(convertor="FBP", save_it_state_img=False, save_it_state_proj=False, ultra_img_denoise=False, t_start_proj=[2, 1],
+                          t_start_img=[2, 1], test_batch_size=2, test_numbers=-1, test_result_data_save=True, noise_seed=11))
+    assert len(model.test_dataset) == 3
+    model.fit()
+    assert len(model.metric_each_sample) == 3
+    for sid in range(3):
+        d = os.path.join(model.save_root_path, "Save_Iter_0", "P001", f"S{sid:03d}")
+        with open(os.path.join(d, "metric.json")) as f:
+            m = json.load(f)
+        assert np.isfinite(m["LDCT"]["psnr_iter_0"]) and np.isfinite(m["deProg"]["ssim_iter_1"])
+        z = np.load(os.path.join(d, "prog_denoise_result.npz"))
+        assert z["iter_1"].shape == (1, 1, 512, 512)                     # per-slice files, B = 1 layout as in the reference
+    with open(os.path.join(model.save_root_path, "Save_Iter_0", "metric.json")) as f:
+        total = json.load(f)
+    assert "psnr_iter_1" in total["deProg"] and "psnr_iter_1_std" in total["deProg"]
