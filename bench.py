@@ -208,14 +208,19 @@ def run_b200(args, rank, world, local_rank):
             ms = float(t)
         return ms, out
 
-    for _ in range(args.warmup):
+    engine.launch_count_reset()
+    for w_i in range(args.warmup):
         step_resident()
+        if w_i == 0:
+            launches_first_step = engine.launch_count()          # graph mode: the kernels recorded by the capture pass = kernels per replay
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     engine.launch_count_reset()
     ms, out = timed(step_resident, args.steps)
     launches = engine.launch_count()
+    if args.cuda_graph and launches == 0 and args.warmup > 0:
+        launches = launches_first_step * args.steps                  # replays do not pass through the host-side launch counter
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:                                   # the only collective: final gather of the results
         from ipdm_pytorch_b200.sharding import gather_slices
