@@ -22,7 +22,8 @@
 namespace ipdm {
 
 constexpr int TH_RP = 32, TH_TWV = 30, TH_ROWS = 4;     // row pitch (pixels), valid columns, output rows per tile
-constexpr int TH_NACC = 4;
+constexpr int TH_NACC = 8;                              // accumulators in flight (16 TMEM columns each)
+constexpr int TH_ACC_COLS = 16, TH_TMEM_COLS = TH_NACC * TH_ACC_COLS;
 constexpr int TH_THREADS = 256;                         // warp 0 producer, 1 MMA, 2 TMEM alloc, 4-7 epilogue
 // The epilogue (TMEM -> registers -> +bias +residual -> global) is a latency chain of ~1.7 k cycles per tile on one warpgroup, four
 // times the MMA issue time of a C = 8 tile; two or three co-resident CTAs per SM (short operand rings, 128 TMEM columns each) keep
@@ -31,7 +32,7 @@ constexpr int TH_STG_PITCH = 20;                         // floats per pixel row
 constexpr int TH_STG_BYTES = 4 * 32 * TH_STG_PITCH * 4;  // one 32-pixel staging tile per epilogue warp
 
 template <int RB> struct ThinCfg {                      // RB = bytes per pixel row of the operand tensor
-    static constexpr int CTAS = RB == 128 ? 2 : 3;      // co-resident CTAs per SM
+    static constexpr int CTAS = RB == 128 ? 2 : 3;      // co-resident CTAs per SM (4 was tried for RB = 32: 64 registers spill, 733 vs 583 us)
     static constexpr int W_BYTES = (9 * 16 * RB + 1023) / 1024 * 1024;
     static constexpr int BOX_BYTES = (TH_ROWS + 2) * TH_RP * RB;
     static constexpr int SLOT = (BOX_BYTES + 2 * RB + 1023) / 1024 * 1024;   // + the 2 pixels the last tap over-reads
@@ -79,7 +80,7 @@ conv_thin_kernel(const __grid_constant__ ConvThinParams P) {
         tc::mbar_init(w_full, 1);
         tc::fence_barrier_init();
     }
-    if (warp == 2) tc::tmem_alloc(tmem_slot, 32 * TH_NACC);
+    if (warp == 2) tc::tmem_alloc(tmem_slot, TH_TMEM_COLS);
     if (threadIdx.x < 16) {
         const float* bias = P.bias ? P.bias + (P.t_dev ? (size_t)(*P.t_dev) * P.bias_t_stride : 0) : nullptr;
         sbias[threadIdx.x] = (bias && (int)threadIdx.x < P.cout) ? __ldg(bias + threadIdx.x) : 0.f;
@@ -89,6 +90,22 @@ conv_thin_kernel(const __grid_constant__ ConvThinParams P) {
     tc::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // tile = blockIdx.x, blockIdx.x + gridDim.x, ...: (slice, tile row, tile column) kept with adds and compares instead of two
+    // integer divisions per tile and warp
+    struct TileWalk {
+        int b, tyi, txi, sb, sy, sx, tx, ty;
+        __device__ void init(int tile, int g, int tiles_x, int tiles_y) {
+            tx = tiles_x; ty = tiles_y;
+            const int per = tx * ty;
+            b = tile / per; const int tr = tile - b * per; tyi = tr / tx; txi = tr - tyi * tx;
+            sb = g / per; const int gr = g - sb * per; sy = gr / tx; sx = gr - sy * tx;
+        }
+        __device__ void next() {
+            txi += sx; if (txi >= tx) { txi -= tx; ++tyi; }
+            tyi += sy; if (tyi >= ty) { tyi -= ty; ++b; }
+            b += sb;
+        }
+    };
     auto decode = [&](int tile, int& b, int& x0, int& y0) {
         b = tile / tiles_per_img;
         const int tr = tile - b * tiles_per_img;
@@ -102,8 +119,9 @@ conv_thin_kernel(const __grid_constant__ ConvThinParams P) {
             tc::tma_load_2d(smem, &P.mapW, w_full, 0, 0);
             const int off = P.ntaps == 9 ? 1 : 0;                 // 1x1: the tile is its own halo
             int it = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-                int b, x0, y0; decode(tile, b, x0, y0);
+            TileWalk tw; tw.init(blockIdx.x, gridDim.x, P.tiles_x, P.tiles_y);
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it, tw.next()) {
+                const int b = tw.b, x0 = tw.txi * TH_TWV, y0 = tw.tyi * TH_ROWS;
                 const int s = it % C::NSA;
                 tc::mbar_wait(&a_empty[s], ((uint32_t)(it / C::NSA) & 1u) ^ 1u);
                 if (P.dbg & 8) { tc::mbar_arrive(&a_full[s]); continue; }          // experiment: no operand loads at all
@@ -124,7 +142,7 @@ conv_thin_kernel(const __grid_constant__ ConvThinParams P) {
                 tc::mbar_wait(P.norm_scale ? &a_ready[s] : &a_full[s], (uint32_t)(it / C::NSA) & 1u);
                 tc::tc_fence_after();
                 const uint32_t a_base = tc::smem_u32(smem + C::OFF_A + s * C::SLOT);
-                const uint32_t d_tmem = tmem_base + acc * 32;
+                const uint32_t d_tmem = tmem_base + acc * TH_ACC_COLS;
                 for (int tap = 0; tap < ((P.dbg & 4) ? 1 : P.ntaps); ++tap) {
                     const int dy = P.ntaps == 9 ? tap / 3 : 0, dx = P.ntaps == 9 ? tap - (tap / 3) * 3 : 0;
                     const uint64_t ad = thin_desc(a_base + (uint32_t)((dy * TH_RP + dx) * RB), C::LAYOUT, C::SBO);
@@ -201,10 +219,12 @@ conv_thin_kernel(const __grid_constant__ ConvThinParams P) {
         const int cg_log2 = P.cout == 8 ? 1 : 2, cg = 1 << cg_log2;          // 128-bit vectors per pixel
         float* stg = reinterpret_cast<float*>(smem + C::STG_OFF) + q * (32 * TH_STG_PITCH);
         bool nvalid = false; size_t npix = 0; int nrun = 0; float4 nrr[4];
-        auto request = [&](int tile) {
+        TileWalk tw; tw.init(blockIdx.x, gridDim.x, P.tiles_x, P.tiles_y);
+        auto request = [&](int tile) {                                         // called with blockIdx.x, +gridDim.x, ... in order
             nvalid = false; nrun = 0;
             if (tile >= total_tiles) return;
-            int b, x0, y0; decode(tile, b, x0, y0);
+            if (tile != (int)blockIdx.x) tw.next();
+            const int b = tw.b, x0 = tw.txi * TH_TWV, y0 = tw.tyi * TH_ROWS;
             const int py = y0 + q, px = x0 + lane;
             nvalid = lane < TH_TWV && py < P.H && px < P.W;
             if (packed) {
@@ -237,7 +257,7 @@ conv_thin_kernel(const __grid_constant__ ConvThinParams P) {
             tc::mbar_wait(&t_full[acc], (uint32_t)(it / TH_NACC) & 1u);
             tc::tc_fence_after();
             uint32_t r[16];
-            tc::tmem_ld16(tmem_base + acc * 32 + ((uint32_t)(q * 32) << 16), r);
+            tc::tmem_ld16(tmem_base + acc * TH_ACC_COLS + ((uint32_t)(q * 32) << 16), r);
             tc::tmem_ld_wait();
             tc::tc_fence_before();
             tc::mbar_arrive(&t_empty[acc]);                        // values are in registers: release the accumulator early
@@ -281,7 +301,7 @@ conv_thin_kernel(const __grid_constant__ ConvThinParams P) {
     }
     tc::tc_fence_before();
     __syncthreads();
-    if (warp == 2) tc::tmem_dealloc(tmem_base, 32 * TH_NACC);
+    if (warp == 2) tc::tmem_dealloc(tmem_base, TH_TMEM_COLS);
 }
 
 int conv_thin_prepare(ConvThinParams& P, const ConvThinDesc& d) {
