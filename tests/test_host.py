@@ -139,3 +139,20 @@ def test_no_gpu_means_loud_failure_not_fallback():
     from Recon.FBP_kernel import FBP
     with pytest.raises(RuntimeError):
         FBP(device="cpu")
+
+
+def test_ddim_coefficients_follow_the_reference_formulas():
+    """engine.ddim_coefficients (host, fp64 tables -> fp32 like `_extract(...).float()`) against the oracle tables and the DDIM
+    algebra of Model/model.py:688-712."""
+    import torch
+    from ipdm_pytorch_b200 import engine
+    from oracle.ipdm_oracle import Tables
+    for power, (t, tp), eta in ((5, (14, 0), 0.0), (1, (17, 8), 0.0), (1, (8, 0), 0.3)):
+        tab = Tables(1000, power)
+        c = engine.ddim_coefficients(1000, power, t, tp, ddim_eta=eta)
+        a_t, a_p = tab.at("alphas_cumprod", t), tab.at("alphas_cumprod", tp)
+        sig = eta * torch.sqrt((1 - a_p) / (1 - a_t) * (1 - a_t / a_p))
+        want = [tab.at("sqrt_alphas_cumprod", t), tab.at("sqrt_one_minus_alphas_cumprod", t), 1.0 / torch.sqrt(a_t),
+                torch.sqrt(1.0 - a_t) / torch.sqrt(a_t), torch.sqrt(a_p), torch.tensor(0.0), eta * tab.at("posterior_variance", t),
+                torch.sqrt(1 - a_p - sig ** 2)]
+        np.testing.assert_allclose(np.array(c, dtype=np.float64), np.array([float(w) for w in want]), rtol=3e-7, atol=1e-12)
