@@ -547,17 +547,16 @@ int attention_prepare(AttentionParams& P, const AttentionDesc& d) {
 }
 
 int attention_launch(const AttentionParams& P, cudaStream_t st) {
-    static bool configured = false;
+    static DeviceOnce once;
     static_assert(AtL<AT_SPLIT>::SMEM <= 227 * 1024, "fp32-mode attention tiles do not fit in shared memory");
     static_assert(3 * (AtL<AT_BF16>::SMEM + 1024) <= 227 * 1024, "bf16 attention is sized for three CTAs per SM");
-    if (!configured) {
+    if (once.need()) {
         IPDM_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<AT_TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, AtL<AT_TF32>::SMEM));
         IPDM_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<AT_SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, AtL<AT_SPLIT>::SMEM));
         IPDM_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<AT_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, AtL<AT_BF16>::SMEM));
         static_assert(AtP<AT_TF32>::SMEM <= 227 * 1024 && 2 * (AtP<AT_BF16>::SMEM + 1024) <= 227 * 1024, "pipelined attention tiles do not fit");
         IPDM_CHECK_CUDA(cudaFuncSetAttribute(attention_pipe_kernel<AT_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, AtP<AT_BF16>::SMEM));
         IPDM_CHECK_CUDA(cudaFuncSetAttribute(attention_pipe_kernel<AT_TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, AtP<AT_TF32>::SMEM));
-        configured = true;
     }
     dim3 grid((P.T + AT_BQ - 1) / AT_BQ, P.heads, P.batch);
     ProfScope prof(PROF_ATTENTION, st, (P.split ? 3.0 : 1.0) * 4.0 * P.batch * P.heads * (double)P.T * P.T * AT_D);

@@ -48,6 +48,19 @@ extern unsigned long long g_launch_count;
 inline void count_launch(int n = 1) { g_launch_count += (unsigned long long)n; }
 
 // per-kernel-family profiler (off by default): CUDA events around every launch, summed by family.
+// cudaFuncSetAttribute applies to the CURRENT device: a launcher remembers per device whether it has configured its kernels
+// (one process per GPU is the normal deployment, but a host that drives several devices must not inherit the first one's state).
+struct DeviceOnce {
+    bool done[64] = {};
+    bool need() {
+        int d = 0;
+        if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return true;
+        if (done[d]) return false;
+        done[d] = true;
+        return true;
+    }
+};
+
 enum ProfKind { PROF_CONV_TC = 0, PROF_ATTENTION, PROF_CONV_DIRECT, PROF_GROUPNORM, PROF_UPSAMPLE, PROF_FBP_FILTER,
                 PROF_FBP_BACKPROJECT, PROF_SAMPLER, PROF_CONV_HALO_PERS, PROF_KINDS };
 extern bool g_prof_on;

@@ -855,12 +855,11 @@ conv_halo_persistent_kernel(const __grid_constant__ ConvTcParams P) {
 
 template <int BN, int NB>
 static int launch_halo_pers(const ConvTcParams& P, cudaStream_t st) {
-    static bool configured = false;
+    static DeviceOnce once;
     constexpr int smem = HaloPersSmem<BN, NB>::TOTAL;
     static_assert(smem <= 227 * 1024, "persistent halo rings do not fit in shared memory");
-    if (!configured) {
+    if (once.need()) {
         IPDM_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_persistent_kernel<BN, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = true;
     }
     const int total = P.tiles_x * P.tiles_y * P.batch * (P.cout / BN);
     conv_halo_persistent_kernel<BN, NB><<<std::min(total, kNumSMs), HP_THREADS, smem, st>>>(P);
@@ -871,12 +870,11 @@ static int launch_halo_pers(const ConvTcParams& P, cudaStream_t st) {
 
 template <int BN, int ST>
 static int launch_pers(const ConvTcParams& P, cudaStream_t st) {
-    static bool configured = false;
+    static DeviceOnce once;
     constexpr int smem = PersSmem<BN, ST>::TOTAL;
     static_assert(smem <= 227 * 1024, "persistent ring does not fit in shared memory");
-    if (!configured) {
+    if (once.need()) {
         IPDM_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_persistent_kernel<BN, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = true;
     }
     const int total = P.tiles_x * P.tiles_y * P.batch * (P.cout / BN);
     conv_tc_persistent_kernel<BN, ST><<<std::min(total, kNumSMs), PERS_THREADS, smem, st>>>(P);
@@ -991,12 +989,11 @@ int conv_tc_prepare(ConvTcParams& P, const ConvTcDesc& d) {
 
 template <int BN, int ST, bool SPLIT>
 static int launch_tc(const ConvTcParams& P, cudaStream_t st) {
-    static bool configured = false;
+    static DeviceOnce once;
     constexpr int smem = TcSmem<BN, ST, SPLIT>::TOTAL;
     static_assert(smem <= 227 * 1024, "stage ring does not fit in shared memory");
-    if (!configured) {
+    if (once.need()) {
         IPDM_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, ST, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = true;
     }
     dim3 grid(P.tiles_x * P.tiles_y * P.batch, P.cout / BN);
     conv_tc_kernel<BN, ST, SPLIT><<<grid, TC_THREADS, smem, st>>>(P);
@@ -1007,12 +1004,11 @@ static int launch_tc(const ConvTcParams& P, cudaStream_t st) {
 
 template <int BN, int NB>
 static int launch_halo(const ConvTcParams& P, cudaStream_t st) {
-    static bool configured = false;
+    static DeviceOnce once;
     constexpr int smem = HaloSmem<BN, NB>::TOTAL;
     static_assert(smem <= 227 * 1024, "halo ring does not fit in shared memory");
-    if (!configured) {
+    if (once.need()) {
         IPDM_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<BN, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = true;
     }
     dim3 grid(P.tiles_x * P.tiles_y * P.batch, P.cout / BN);
     conv_halo_kernel<BN, NB><<<grid, HALO_THREADS, smem, st>>>(P);

@@ -337,13 +337,12 @@ int conv_thin_prepare(ConvThinParams& P, const ConvThinDesc& d) {
 
 template <int RB>
 static int launch_thin(const ConvThinParams& P, cudaStream_t st) {
-    static bool configured = false;
+    static DeviceOnce once;
     constexpr int smem = ThinCfg<RB>::TOTAL;
     static_assert(ThinCfg<RB>::CTAS * (smem + 1024) <= 227 * 1024, "thin conv: operand rings of the co-resident CTAs do not fit in shared memory");
     static_assert((3 * ThinCfg<RB>::NSA + 2 * TH_NACC + 1) * 8 + 16 <= 384, "barrier block");
-    if (!configured) {
+    if (once.need()) {
         IPDM_CHECK_CUDA(cudaFuncSetAttribute(conv_thin_kernel<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = true;
     }
     const int total = P.tiles_x * P.tiles_y * P.batch;
     conv_thin_kernel<RB><<<std::min(total, kNumSMs * ThinCfg<RB>::CTAS), TH_THREADS, smem, st>>>(P);

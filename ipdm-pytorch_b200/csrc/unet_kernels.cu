@@ -399,10 +399,12 @@ template <int COUT_T, int KS, int STRIDE>
 static int launch_direct(const ConvDirectParams& P, int batch, cudaStream_t st) {
     constexpr int TIN_W = (CD_TW - 1) * STRIDE + KS, TIN_H = (CD_TH - 1) * STRIDE + KS, TIN_WP = (TIN_W + 3) & ~3;
     const size_t smem = ((((size_t)P.cin_chunk * (TIN_WP * TIN_H + 4) + 3) & ~(size_t)3) + (size_t)KS * KS * P.cin_chunk * COUT_T) * sizeof(float);
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
+    static size_t configured[64] = {};                         // largest opt-in so far, per device
+    int dev = 0;
+    IPDM_CHECK_CUDA(cudaGetDevice(&dev));
+    if (smem > 48 * 1024 && (dev < 0 || dev >= 64 || smem > configured[dev])) {
         IPDM_CHECK_CUDA(cudaFuncSetAttribute(conv_direct_kernel<COUT_T, KS, STRIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
+        if (dev >= 0 && dev < 64) configured[dev] = smem;
     }
     dim3 grid(ceil_div(P.wout, CD_TW), ceil_div(P.hout, CD_TH), batch * P.co_tiles), block(CD_BX, CD_BY);
     conv_direct_kernel<COUT_T, KS, STRIDE><<<grid, block, smem, st>>>(P);
