@@ -9,9 +9,11 @@
 //   * ONE halo tile [(4+2) rows x 32 pixels] per output tile, read in place by all nine taps through descriptors that
 //     start at row dy*32 + dx (30 of the 32 columns are outputs),
 //   * all tap weights (<= 18 KB) resident in shared memory for the lifetime of the persistent CTA,
-//   * four TMEM accumulators (16 columns each) so that epilogues overlap the next tiles' MMAs.
-// Per tile the tensor pipe issues 9 * C_in/8 instructions of ~45 cycles; the layer becomes HBM / issue bound
-// (2000x912, 8 -> 8: 117 MB, ~25 us) instead of FP32-FMA bound (~160 us).
+//   * eight TMEM accumulators (16 columns each) so that epilogues overlap the next tiles' MMAs.
+// Per tile the tensor pipe issues 9 * C_in/8 instructions of ~45 cycles (14 % busy); measured at 16 slices, 2000x912, 8 -> 8:
+// 583 us for 2.3 GB (3.9 TB/s) against ~1.0 ms for the CUDA-core kernel.  The kernel is bound by the per-tile latency chain of its
+// epilogue warps (barrier wait -> tcgen05.ld -> staging -> stores, ~1350 warp instructions per tile; ablations with no loads,
+// MMAs or stores still take 430 us), not by TMA, the tensor pipe or HBM: see profiles/r01_thin_gnapply_attention_ncu_full.md.
 #include "common.cuh"
 #include "tc.cuh"
 #include "unet_ops.cuh"
