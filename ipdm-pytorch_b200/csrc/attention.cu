@@ -6,13 +6,15 @@
 // [B][T][3C] (head h: q at channel 3dh, k at 3dh+d, the reference's reshape(B*heads, 3d, T).chunk(3)),
 // v is stored transposed [B][heads][d][t_pad] so that P.V^T is a K-major UMMA like everything else.
 //
-// CTA = 128 queries of one (slice, head); 64-key blocks stream through a 2-stage TMA ring.
+// CTA = 128 queries of one (slice, head); 64-key blocks stream through a TMA ring.
 //   warp 4 lane*: TMA producer            warp 5 lane*: MMA issuer (+ TMEM alloc)
 //   warps 0-3  : one query row per thread (row == TMEM lane): online softmax in registers,
 //                P written to shared memory in the 128B-swizzled K-major layout UMMA expects,
 //                O accumulated in registers (O_blk = P.V is a fresh TMEM tile per key block).
-// S = QK^T: kind::tf32 M=128 N=64 K=8 x8;  O_blk = P V: M=128 N=64 K=8 x8.  Out-of-range keys are
+// S = QK^T and O_blk = P V: M=128 N=64, 32 bytes of K per instruction (8 tf32 / 16 bf16).  Out-of-range keys are
 // zero-filled by TMA and masked to -inf; out-of-range query rows are computed and dropped.
+// Two kernels: attention_kernel (serial schedule; kept for the 3xTF32 split of the fp32 mode) and
+// attention_pipe_kernel (tf32 / bf16 modes: S, P and O double-buffered, see its comment).
 #include <cuda_bf16.h>
 #include <cstdlib>
 #include "common.cuh"

@@ -12,11 +12,20 @@
 // Stride-2 convolutions read four parity sub-lattices of the input through four tensor maps.
 // Two virtual-concat sources (torch.cat([h, skip]) :306) are two tensor maps walked back to back.
 //
-// Roles (128 threads): warp 0 lane* = TMA producer, warp 1 lane* = MMA issuer (tcgen05.mma
-// kind::tf32, M=128, N=BLOCK_N, K=8 x4 per 128-byte stage), warp 2 = TMEM allocator; then all four
-// warps run the epilogue: tcgen05.ld 32 lanes x 32 columns, + bias[t] (+ residual), 128-bit NHWC stores.
-// 3 stages x 32 KB of shared memory -> two CTAs per SM, so one CTA's epilogue overlaps the other's
-// main loop without a persistent scheduler.
+// Operands are fp32 words rounded to TF32 (kind::tf32; tf32 and fp32 modes, K chunk = 32 channels) or bf16 (kind::f16;
+// bf16 mode, K chunk = 64 channels); accumulation is fp32 in TMEM in every mode.
+//
+// Four kernels share this file (conv_tc_prepare picks one per layer, see there):
+//   conv_halo_persistent_kernel  stride-1 3x3, the dominant kernel: one halo tile per K chunk feeds all nine taps, persistent
+//                                CTAs, double-buffered accumulator pairs, two epilogue warpgroups          (~0.8 of the bf16 peak)
+//   conv_tc_persistent_kernel    per-tap variant for 1x1 / stride-2 / small images (L2 -> SM bound on 3x3 layers)
+//   conv_halo_kernel             one halo tile per CTA, for the N = 16 layer
+//   conv_tc_kernel               one tile per CTA: the 3xTF32 split of the fp32 mode and the qkv epilogue
+// Roles in the one-tile kernel (128 threads): warp 0 lane* = TMA producer, warp 1 lane* = MMA issuer (tcgen05.mma,
+// M=128, N=BLOCK_N, 32 bytes of K x4 per 128-byte stage), warp 2 = TMEM allocator; then all four warps run the
+// epilogue: tcgen05.ld 32 lanes x 32 columns, + bias[t] (+ residual), 128-bit NHWC stores.  The persistent kernels
+// add dedicated epilogue warps that transpose through shared memory for full-line stores and emit the GroupNorm
+// statistics of their output (ConvTcDesc::stats_out).
 #include <cuda_bf16.h>
 #include "common.cuh"
 #include "tc.cuh"
