@@ -23,7 +23,7 @@
 
 namespace ipdm {
 
-constexpr int TH_RP = 32, TH_TWV = 30, TH_ROWS = 4;     // row pitch (pixels), valid columns, output rows per tile
+constexpr int TH_RP = 32, TH_TWV = 30;                  // row pitch (pixels), valid columns; output rows per tile: template ROWS (4 or 8)
 constexpr int TH_NACC = 8;                              // accumulators in flight (16 TMEM columns each)
 constexpr int TH_ACC_COLS = 16, TH_TMEM_COLS = TH_NACC * TH_ACC_COLS;
 constexpr int TH_THREADS = 256;                         // warp 0 producer, 1 MMA, 2 TMEM alloc, 4-7 epilogue
@@ -33,12 +33,14 @@ constexpr int TH_THREADS = 256;                         // warp 0 producer, 1 MM
 constexpr int TH_STG_PITCH = 20;                         // floats per pixel row of the epilogue staging tile (80 B: conflict-free)
 constexpr int TH_STG_BYTES = 4 * 32 * TH_STG_PITCH * 4;  // one 32-pixel staging tile per epilogue warp
 
-template <int RB> struct ThinCfg {                      // RB = bytes per pixel row of the operand tensor
+template <int RB, int ROWS> struct ThinCfg {            // RB = bytes per pixel row of the operand tensor; ROWS = output rows per tile
+    static constexpr int SUB = ROWS / 4;                // 128-row MMA groups (accumulators) per tile
+    static constexpr int NT = TH_NACC / SUB;            // tiles whose accumulators are in flight
     static constexpr int CTAS = RB == 128 ? 2 : 3;      // co-resident CTAs per SM (4 was tried for RB = 32: 64 registers spill, 733 vs 583 us)
     static constexpr int W_BYTES = (9 * 16 * RB + 1023) / 1024 * 1024;
-    static constexpr int BOX_BYTES = (TH_ROWS + 2) * TH_RP * RB;
+    static constexpr int BOX_BYTES = (ROWS + 2) * TH_RP * RB;
     static constexpr int SLOT = (BOX_BYTES + 2 * RB + 1023) / 1024 * 1024;   // + the 2 pixels the last tap over-reads
-    static constexpr int NSA = RB == 32 ? 8 : (RB == 64 ? 4 : 3);
+    static constexpr int NSA = ROWS == 4 ? (RB == 32 ? 8 : (RB == 64 ? 4 : 3)) : (RB == 32 ? 5 : 2);
     static constexpr int LAYOUT = RB == 32 ? 6 : (RB == 64 ? 4 : 2);         // UMMA layout_type: SWIZZLE_32B / 64B / 128B
     static constexpr int SBO = 8 * RB;
     static constexpr int OFF_A = W_BYTES;
@@ -57,10 +59,11 @@ __device__ __forceinline__ uint64_t thin_desc(uint32_t saddr, int layout, int sb
     return d;
 }
 
-template <int RB>
-__global__ void __launch_bounds__(TH_THREADS, ThinCfg<RB>::CTAS)
+template <int RB, int ROWS>
+__global__ void __launch_bounds__(TH_THREADS, ThinCfg<RB, ROWS>::CTAS)
 conv_thin_kernel(const __grid_constant__ ConvThinParams P) {
-    using C = ThinCfg<RB>;
+    using C = ThinCfg<RB, ROWS>;
+    constexpr int SUB = C::SUB, NT = C::NT;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t* a_full = (uint64_t*)(smem + C::BAR_OFF);
@@ -112,7 +115,7 @@ conv_thin_kernel(const __grid_constant__ ConvThinParams P) {
         b = tile / tiles_per_img;
         const int tr = tile - b * tiles_per_img;
         const int tyi = tr / P.tiles_x, txi = tr - tyi * P.tiles_x;
-        x0 = txi * TH_TWV; y0 = tyi * TH_ROWS;
+        x0 = txi * TH_TWV; y0 = tyi * ROWS;
     };
 
     if (warp == 0) {
@@ -123,7 +126,7 @@ conv_thin_kernel(const __grid_constant__ ConvThinParams P) {
             int it = 0;
             TileWalk tw; tw.init(blockIdx.x, gridDim.x, P.tiles_x, P.tiles_y);
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it, tw.next()) {
-                const int b = tw.b, x0 = tw.txi * TH_TWV, y0 = tw.tyi * TH_ROWS;
+                const int b = tw.b, x0 = tw.txi * TH_TWV, y0 = tw.tyi * ROWS;
                 const int s = it % C::NSA;
                 tc::mbar_wait(&a_empty[s], ((uint32_t)(it / C::NSA) & 1u) ^ 1u);
                 if (P.dbg & 8) { tc::mbar_arrive(&a_full[s]); continue; }          // experiment: no operand loads at all
@@ -139,22 +142,25 @@ conv_thin_kernel(const __grid_constant__ ConvThinParams P) {
             tc::mbar_wait(w_full, 0);
             int it = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-                const int s = it % C::NSA, acc = it % TH_NACC;
-                tc::mbar_wait(&t_empty[acc], ((uint32_t)(it / TH_NACC) & 1u) ^ 1u);
+                const int s = it % C::NSA, slot = it % NT;
+                tc::mbar_wait(&t_empty[slot], ((uint32_t)(it / NT) & 1u) ^ 1u);
                 tc::mbar_wait(P.norm_scale ? &a_ready[s] : &a_full[s], (uint32_t)(it / C::NSA) & 1u);
                 tc::tc_fence_after();
                 const uint32_t a_base = tc::smem_u32(smem + C::OFF_A + s * C::SLOT);
-                const uint32_t d_tmem = tmem_base + acc * TH_ACC_COLS;
                 for (int tap = 0; tap < ((P.dbg & 4) ? 1 : P.ntaps); ++tap) {
                     const int dy = P.ntaps == 9 ? tap / 3 : 0, dx = P.ntaps == 9 ? tap - (tap / 3) * 3 : 0;
-                    const uint64_t ad = thin_desc(a_base + (uint32_t)((dy * TH_RP + dx) * RB), C::LAYOUT, C::SBO);
                     const uint64_t bd = thin_desc(w_base + (uint32_t)(tap * 16 * RB), C::LAYOUT, C::SBO);
 #pragma unroll
-                    for (int k = 0; k < RB / 32; ++k)
-                        tc::umma_tf32(d_tmem, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (uint32_t)((tap | k) != 0));
+                    for (int sub = 0; sub < SUB; ++sub) {          // tile rows 4*sub .. 4*sub+3: their own 128-row accumulator
+                        const uint64_t ad = thin_desc(a_base + (uint32_t)(((4 * sub + dy) * TH_RP + dx) * RB), C::LAYOUT, C::SBO);
+#pragma unroll
+                        for (int k = 0; k < RB / 32; ++k)
+                            tc::umma_tf32(tmem_base + (slot * SUB + sub) * TH_ACC_COLS, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc,
+                                          (uint32_t)((tap | k) != 0));
+                    }
                 }
                 tc::umma_commit(&a_empty[s]);
-                tc::umma_commit(&t_full[acc]);
+                tc::umma_commit(&t_full[slot]);
             }
         }
         __syncwarp();
@@ -163,7 +169,7 @@ conv_thin_kernel(const __grid_constant__ ConvThinParams P) {
         // only matters for finding the channel of a 16-byte unit: physical unit = logical ^ f(row) with f = (row>>2)&1 / (row>>1)&3 /
         // row&7 for 32 / 64 / 128-byte rows.  Pixels outside the image stay 0 (the conv pads the NORMALISED tensor with zeros).
         if (P.norm_scale) {
-            constexpr int UPR = RB / 16, NU = (TH_ROWS + 2) * TH_RP * UPR;
+            constexpr int UPR = RB / 16, NU = (ROWS + 2) * TH_RP * UPR;
             const int t2 = (warp - 2) * 32 + lane;
             const int off = P.ntaps == 9 ? 1 : 0;
             int it = 0;
@@ -187,8 +193,8 @@ conv_thin_kernel(const __grid_constant__ ConvThinParams P) {
                     for (int k = 0; k < BATCH; ++k) {
                         const int u = u0 + 64 * k, row = u / UPR;
                         const int gy = y0 - off + (row >> 5), gx = x0 - off + (row & 31);
-                        in[k] = gy >= 0 && gy < P.H && gx >= 0 && gx < P.W;
-                        v[k] = *reinterpret_cast<const float4*>(base + u * 16);
+                        in[k] = u < NU && gy >= 0 && gy < P.H && gx >= 0 && gx < P.W;
+                        v[k] = in[k] ? *reinterpret_cast<const float4*>(base + u * 16) : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
 #pragma unroll
                     for (int k = 0; k < BATCH; ++k) {
@@ -222,11 +228,11 @@ conv_thin_kernel(const __grid_constant__ ConvThinParams P) {
         float* stg = reinterpret_cast<float*>(smem + C::STG_OFF) + q * (32 * TH_STG_PITCH);
         bool nvalid = false; size_t npix = 0; int nrun = 0; float4 nrr[4];
         TileWalk tw; tw.init(blockIdx.x, gridDim.x, P.tiles_x, P.tiles_y);
-        auto request = [&](int tile) {                                         // called with blockIdx.x, +gridDim.x, ... in order
+        int rt = blockIdx.x, rs = 0;                                           // tile and 4-row group of the NEXT request
+        auto request = [&]() {                                                 // (tile, group) in processing order
             nvalid = false; nrun = 0;
-            if (tile >= total_tiles) return;
-            if (tile != (int)blockIdx.x) tw.next();
-            const int b = tw.b, x0 = tw.txi * TH_TWV, y0 = tw.tyi * TH_ROWS;
+            if (rt >= total_tiles) return;
+            const int b = tw.b, x0 = tw.txi * TH_TWV, y0 = tw.tyi * ROWS + 4 * rs;
             const int py = y0 + q, px = x0 + lane;
             nvalid = lane < TH_TWV && py < P.H && px < P.W;
             if (packed) {
@@ -246,23 +252,30 @@ conv_thin_kernel(const __grid_constant__ ConvThinParams P) {
                         if (4 * i < P.cout) nrr[i] = __ldg(reinterpret_cast<const float4*>(P.res + npix * P.res_cs) + i);
                 }
             }
+            if (++rs == SUB) { rs = 0; rt += gridDim.x; tw.next(); }
         };
-        request(blockIdx.x);
+        request();
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-            const int acc = it % TH_NACC;
+          const int slot = it % NT;
+#pragma unroll
+          for (int sub = 0; sub < SUB; ++sub) {
             const bool valid = nvalid; const size_t pix = npix; const int run = nrun;
             float4 rr[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) rr[i] = nrr[i];
-            request(tile + gridDim.x);
-            tc::mbar_wait(&t_full[acc], (uint32_t)(it / TH_NACC) & 1u);
-            tc::tc_fence_after();
+            request();
+            if (sub == 0) {                                        // one barrier round trip per tile (SUB accumulators)
+                tc::mbar_wait(&t_full[slot], (uint32_t)(it / NT) & 1u);
+                tc::tc_fence_after();
+            }
             uint32_t r[16];
-            tc::tmem_ld16(tmem_base + acc * TH_ACC_COLS + ((uint32_t)(q * 32) << 16), r);
+            tc::tmem_ld16(tmem_base + (slot * SUB + sub) * TH_ACC_COLS + ((uint32_t)(q * 32) << 16), r);
             tc::tmem_ld_wait();
-            tc::tc_fence_before();
-            tc::mbar_arrive(&t_empty[acc]);                        // values are in registers: release the accumulator early
+            if (sub == SUB - 1) {
+                tc::tc_fence_before();
+                tc::mbar_arrive(&t_empty[slot]);                   // values are in registers: release the accumulators early
+            }
             if (packed) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
@@ -299,6 +312,7 @@ conv_thin_kernel(const __grid_constant__ ConvThinParams P) {
                 }
                 for (int c = 16; c < P.out_cs; c += 4) op[c / 4] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
+          }
         }
     }
     tc::tc_fence_before();
@@ -315,11 +329,14 @@ int conv_thin_prepare(ConvThinParams& P, const ConvThinDesc& d) {
     IPDM_REQUIRE(!t.bf16 && ((uintptr_t)t.p % 16) == 0 && d.out.cs % 4 == 0 && d.out.cs >= d.cout, "conv_thin: bad tensor layout");
     IPDM_REQUIRE(d.out.h == t.h && d.out.w == t.w && d.out.n == t.n, "conv_thin: output shape mismatch");
     P.H = t.h; P.W = t.w; P.batch = t.n; P.ntaps = d.ntaps; P.cs = t.cs; P.cout = d.cout;
-    P.tiles_x = ceil_div(P.W, TH_TWV); P.tiles_y = ceil_div(P.H, TH_ROWS);
+    // output rows per tile: 4 (one accumulator) or 8 (two accumulators per barrier round trip; IPDM_THIN_ROWS=8)
+    static const int env_rows = getenv("IPDM_THIN_ROWS") ? atoi(getenv("IPDM_THIN_ROWS")) : 4;
+    P.rows = env_rows == 8 ? 8 : 4;
+    P.tiles_x = ceil_div(P.W, TH_TWV); P.tiles_y = ceil_div(P.H, P.rows);
     const CUtensorMapSwizzle sw = t.cs == 8 ? CU_TENSOR_MAP_SWIZZLE_32B : (t.cs == 16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
     const uint64_t dims[4] = {(uint64_t)t.cs, (uint64_t)t.w, (uint64_t)t.h, (uint64_t)t.n};
     const uint64_t str[3] = {(uint64_t)t.cs * 4, (uint64_t)t.w * t.cs * 4, (uint64_t)t.h * t.w * t.cs * 4};
-    const uint32_t box[4] = {(uint32_t)t.cs, TH_RP, TH_ROWS + 2, 1};
+    const uint32_t box[4] = {(uint32_t)t.cs, TH_RP, (uint32_t)P.rows + 2, 1};
     IPDM_CHECK(tmap_encode(&P.mapA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, t.p, dims, str, box, sw));
     const uint64_t wd[2] = {(uint64_t)t.cs, (uint64_t)d.ntaps * 16};
     const uint64_t ws[1] = {(uint64_t)t.cs * 4};
@@ -337,17 +354,18 @@ int conv_thin_prepare(ConvThinParams& P, const ConvThinDesc& d) {
     return IPDM_OK;
 }
 
-template <int RB>
+template <int RB, int ROWS>
 static int launch_thin(const ConvThinParams& P, cudaStream_t st) {
     static DeviceOnce once;
-    constexpr int smem = ThinCfg<RB>::TOTAL;
-    static_assert(ThinCfg<RB>::CTAS * (smem + 1024) <= 227 * 1024, "thin conv: operand rings of the co-resident CTAs do not fit in shared memory");
-    static_assert((3 * ThinCfg<RB>::NSA + 2 * TH_NACC + 1) * 8 + 16 <= 384, "barrier block");
+    using C = ThinCfg<RB, ROWS>;
+    constexpr int smem = C::TOTAL;
+    static_assert(C::CTAS * (smem + 1024) <= 227 * 1024, "thin conv: operand rings of the co-resident CTAs do not fit in shared memory");
+    static_assert((3 * C::NSA + 2 * TH_NACC + 1) * 8 + 16 <= 384, "barrier block");
     if (once.need()) {
-        IPDM_CHECK_CUDA(cudaFuncSetAttribute(conv_thin_kernel<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        IPDM_CHECK_CUDA(cudaFuncSetAttribute(conv_thin_kernel<RB, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     }
     const int total = P.tiles_x * P.tiles_y * P.batch;
-    conv_thin_kernel<RB><<<std::min(total, kNumSMs * ThinCfg<RB>::CTAS), TH_THREADS, smem, st>>>(P);
+    conv_thin_kernel<RB, ROWS><<<std::min(total, kNumSMs * C::CTAS), TH_THREADS, smem, st>>>(P);
     count_launch();
     IPDM_CHECK_LAUNCH();
     return IPDM_OK;
@@ -355,12 +373,15 @@ static int launch_thin(const ConvThinParams& P, cudaStream_t st) {
 
 int conv_thin_launch(const ConvThinParams& P, cudaStream_t st) {
     ProfScope prof(PROF_CONV_DIRECT, st, 4.0 * P.batch * (double)P.H * P.W * (P.cs + P.cout));    // bytes (same family as the direct convs)
-    switch (P.cs) {
-        case 8: return launch_thin<32>(P, st);
-        case 16: return launch_thin<64>(P, st);
-        case 32: return launch_thin<128>(P, st);
+    switch (P.cs * 16 + P.rows) {
+        case 8 * 16 + 4: return launch_thin<32, 4>(P, st);
+        case 16 * 16 + 4: return launch_thin<64, 4>(P, st);
+        case 32 * 16 + 4: return launch_thin<128, 4>(P, st);
+        case 8 * 16 + 8: return launch_thin<32, 8>(P, st);
+        case 16 * 16 + 8: return launch_thin<64, 8>(P, st);
+        case 32 * 16 + 8: return launch_thin<128, 8>(P, st);
     }
-    set_error("conv_thin_launch: unsupported channel stride %d", P.cs);
+    set_error("conv_thin_launch: unsupported channel stride %d / rows %d", P.cs, P.rows);
     return IPDM_ERR_UNSUPPORTED;
 }
 

@@ -72,7 +72,7 @@ struct ConvThinDesc {
 };
 struct ConvThinParams {
     CUtensorMap mapA, mapW;
-    int H, W, tiles_x, tiles_y, batch, ntaps, cs, cout;
+    int H, W, tiles_x, tiles_y, batch, ntaps, cs, cout, rows;
     float* out; int out_cs;
     const float* bias; int bias_t_stride; const int* t_dev;
     const float* res; int res_cs;
