@@ -81,7 +81,7 @@ conv_thin_kernel(const __grid_constant__ ConvThinParams P) {
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < C::NSA; ++i) { tc::mbar_init(&a_full[i], 1); tc::mbar_init(&a_empty[i], 1); tc::mbar_init(&a_ready[i], 64); }
-        for (int i = 0; i < TH_NACC; ++i) { tc::mbar_init(&t_full[i], 1); tc::mbar_init(&t_empty[i], 128); }
+        for (int i = 0; i < TH_NACC; ++i) { tc::mbar_init(&t_full[i], 1); tc::mbar_init(&t_empty[i], 4); }      // one arrival per epilogue warp
         tc::mbar_init(w_full, 1);
         tc::fence_barrier_init();
     }
@@ -272,9 +272,10 @@ conv_thin_kernel(const __grid_constant__ ConvThinParams P) {
             uint32_t r[16];
             tc::tmem_ld16(tmem_base + (slot * SUB + sub) * TH_ACC_COLS + ((uint32_t)(q * 32) << 16), r);
             tc::tmem_ld_wait();
-            if (sub == SUB - 1) {
+            if (sub == SUB - 1) {                                  // values are in registers: release the accumulators early
                 tc::tc_fence_before();
-                tc::mbar_arrive(&t_empty[slot]);                   // values are in registers: release the accumulators early
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&t_empty[slot]);    // one arrival per warp, not 32 serialized ones on the same barrier
             }
             if (packed) {
 #pragma unroll
