@@ -19,6 +19,13 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert not missing, missing
     assert set(_lib._SIGNATURES) == set(names)
     assert _lib.lib().ipdm_abi_version() == 1
+    # ... and nothing is exported behind the header's back: every `ipdm_*` text symbol of the library is declared
+    import shutil
+    import subprocess
+    if shutil.which("nm"):
+        out = subprocess.run(["nm", "-D", "--defined-only", _lib.SO_PATH], capture_output=True, text=True).stdout
+        exported = {ln.split()[-1] for ln in out.splitlines() if len(ln.split()) == 3 and ln.split()[1] == "T" and ln.split()[-1].startswith("ipdm_")}
+        assert exported == set(names), exported ^ set(names)
 
 
 def test_missing_library_fails_loudly(monkeypatch):
