@@ -110,6 +110,7 @@ class UNetModel(nn.Module):
         self.num_res_blocks, self.attention_resolutions, self.dropout = num_res_blocks, attention_resolutions, dropout
         self.channel_mult, self.conv_resample, self.num_heads = channel_mult, conv_resample, num_heads
         self.precision = "tf32"
+        self.max_t = 64                      # rows of the per-ResBlock bias + time-embedding table (t in [0, max_t))
         self._handle = None
         self._handle_key = None
 
@@ -152,15 +153,24 @@ class UNetModel(nn.Module):
             self.precision, self._handle = precision, None
 
     def _weights_key(self):
-        return (self.precision,) + tuple((p.data_ptr(), p._version) for p in self.parameters())
+        return (self.precision, self.max_t) + tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def ensure_max_t(self, t_count):
+        """Grows the precomputed time-embedding table when a schedule reaches past it (t_start >= 64)."""
+        if t_count > self.max_t:
+            self.max_t, self._handle = int(t_count), None
 
     def cuda_handle(self):
-        """Packs the current parameters for the CUDA plan (re-packed if any parameter changed)."""
+        """Packs the current parameters for the CUDA plan on the device that holds them (re-packed if any parameter changed or moved)."""
         key = self._weights_key()
         if self._handle is None or key != self._handle_key:
+            dev = next(self.parameters()).device
+            if dev.type != "cuda":
+                raise RuntimeError("UNetModel: parameters must live on a CUDA device (the B200 build has no CPU path); call .to('cuda:N')")
             cfg = _eng.unet_config(self.in_channels, self.model_channels, self.out_channels, self.num_res_blocks,
-                                   list(self.attention_resolutions), list(self.channel_mult), self.num_heads, self.precision)
-            self._handle = _eng.UNetHandle(cfg, self.state_dict())
+                                   list(self.attention_resolutions), list(self.channel_mult), self.num_heads, self.precision, self.max_t)
+            with torch.cuda.device(dev):
+                self._handle = _eng.UNetHandle(cfg, self.state_dict(), device=dev)
             self._handle_key = key
         return self._handle
 
@@ -170,6 +180,7 @@ class UNetModel(nn.Module):
         t0 = int(t[0])
         if t.numel() > 1 and not bool((t == t0).all()):
             raise NotImplementedError("per-sample timesteps are a training feature; the inference path shares t across the batch")
+        self.ensure_max_t(t0 + 1)
         return self.cuda_handle().forward(x.contiguous().float(), t0)
 
 
@@ -223,6 +234,7 @@ class GaussianDiffusion:
                                self.timesteps, seed)
         img = img.contiguous().float()
         ldct = kwargs.get("ldct", None)
+        model.ensure_max_t(max(t_start) + 1)
         out = _eng.guided_process(model.cuda_handle(), p, img, None if ldct is None else ldct.contiguous().float(), noise)
         return [out[k] for k in range(out.shape[0])], [], None
 

@@ -132,6 +132,7 @@ class progressive_domain_denoiser:
     # ---- options ---------------------------------------------------------------------------
     def update_opt(self, ultra_cfg=None):
         if ultra_cfg is not None:
+            self._drop_graph()                                   # a captured pass freezes every option as kernel arguments
             cfg_load(ultra_cfg, self.opt.__dict__)
             self.logger.save_option(self.opt)
             if "convertor" in ultra_cfg.keys():
@@ -140,9 +141,31 @@ class progressive_domain_denoiser:
                 for m in (self.proj_model, self.img_model):
                     if m is not None:
                         m.set_precision(self.opt.precision)
+            if "noise_seed" in ultra_cfg.keys():
+                self._noise_calls = 0                            # same seed => same noise sequence from here on
 
     def reset_opt(self):
+        self._drop_graph()
         self.opt = copy.deepcopy(self.opt_temp)
+
+    def _drop_graph(self):
+        """Forget the captured CUDA graph: it holds raw pointers into the FBP plan, both UNet handles and their arenas."""
+        self.__dict__["_graph"] = None
+
+    # ---- in-kernel noise keys ----------------------------------------------------------------
+    def _stage_seed(self, stage):
+        """Philox key of one stage (0 proj, 1 img, 2 ultra): a hash of (noise_seed, stage), so that neighbouring seeds (e.g. the
+        per-rank seeds of bench.py) never share a stream with another stage."""
+        z = (int(getattr(self.opt, "noise_seed", 0)) * 0x9E3779B97F4A7C15 + (stage + 1) * 0xBF58476D1CE4E5B9) & (2 ** 64 - 1)
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & (2 ** 64 - 1)
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & (2 ** 64 - 1)
+        return z ^ (z >> 31)
+
+    def _next_noise_epoch(self):
+        """Every call of a denoiser entry point draws fresh noise, as the reference's randn_like does: the device-resident half of
+        the Philox key is a per-model call counter (reset by update_opt(dict(noise_seed=...)))."""
+        self._noise_calls = getattr(self, "_noise_calls", 0) + 1
+        _eng.set_noise_epoch(self._noise_calls)
 
     # ---- models / convertor ----------------------------------------------------------------
     def _make_unet(self, suffix):
@@ -169,7 +192,8 @@ class progressive_domain_denoiser:
                                                          schedule_power=self.opt.schedule_power_proj)
 
     def init_convertor(self, convertor):
-        self._fbp = None
+        self._drop_graph()
+        self._fbp, self._fbp_cap = None, 0
         if convertor == "FBP":
             self._fbp = FBP(device=self.opt.device)
             self.convertor = self._fbp.convert
@@ -181,6 +205,7 @@ class progressive_domain_denoiser:
         self.projection = functools.partial(proj_torch, lut_area=None, betas=None)
 
     def load_model(self):
+        self._drop_graph()
         o = self.opt
         if o.resume_epochs_img > 0 and o.load_img_model_path is not None and self.img_model is not None:
             self.logger.load_checkpoints(o.resume_epochs_img, o.load_img_model_path)
@@ -220,13 +245,13 @@ class progressive_domain_denoiser:
             return self.proj_gaussian_diffusion.sparse_guided_reverse_process(
                 model=self.proj_model, condition=x.type(self.proj_dtype), t_start=o.t_start_proj, condition_lambda_max=0.49,
                 condition_lambda_min=0.35, clip_denoised=o.clip_proj, ddim_timesteps=o.ddim_timesteps_proj, eta=o.eta_proj,
-                noise=noise, seed=getattr(o, "noise_seed", 0))
+                noise=noise, seed=self._stage_seed(0))
         res, _, ns = self.proj_gaussian_diffusion.guided_reverse_process(
             model=self.proj_model, img=x.type(self.proj_dtype), t_start=o.t_start_proj, clip=o.clip_proj,
             lambda_ratio=o.lambda_ratio_proj, eta=o.eta_proj, lambda_curve=self.proj_lambda_curve, mode="proj",
             constant_guidance=o.constant_guidance_proj, kernel_size_proj=o.kernel_size_proj, amplitude_proj=o.amplitude_proj,
             only_convertor=o.benchmark_test, normal=o.normal, transformer=self.trans_ldproj, noise=noise,
-            seed=getattr(o, "noise_seed", 0))
+            seed=self._stage_seed(0))
         self.noise_strength = ns
         return res
 
@@ -235,6 +260,10 @@ class progressive_domain_denoiser:
         if self._fbp is None:
             self.convertor(None)
         G = 10 if self.opt.clip_proj else 1
+        if sino.shape[0] > getattr(self, "_fbp_cap", 0):            # the plan re-allocates its filtered-sinogram workspace for a larger batch
+            if not torch.cuda.is_current_stream_capturing():
+                self._drop_graph()
+            self._fbp_cap = int(sino.shape[0])
         s = sino[:, 0].float()
         return self._fbp.convert_device(s * G if G != 1 else s)[:, None]
 
@@ -250,22 +279,24 @@ class progressive_domain_denoiser:
             result = self.img_gaussian_diffusion.sparse_guided_reverse_process(
                 model=self.img_model, condition=x, t_start=o.t_start_img, condition_lambda_max=0.5, condition_lambda_min=0.3,
                 clip_denoised=True, ddim_timesteps=o.ddim_timesteps_img, eta=o.eta_img,
-                noise=None if noise is None else noise[:n_count], seed=getattr(o, "noise_seed", 0) + 1)
+                noise=None if noise is None else noise[:n_count], seed=self._stage_seed(1))
         else:
             n_count = sum(o.t_start_img) + len(o.t_start_img)
             result, _, _ = self.img_gaussian_diffusion.guided_reverse_process(
                 img=x, t_start=o.t_start_img, eta=o.eta_img, constant_guidance=o.constant_guidance_img,
-                noise=None if noise is None else noise[:n_count], seed=getattr(o, "noise_seed", 0) + 1, **common)
+                noise=None if noise is None else noise[:n_count], seed=self._stage_seed(1), **common)
         if o.ultra_img_denoise:
             n_ultra = None if noise is None else noise[n_count:]
             extra, _, _ = self.img_gaussian_diffusion.guided_reverse_process(
                 img=result[-1], t_start=[5, 5, 5], eta=0.6, constant_guidance=0.6, noise=n_ultra,
-                seed=getattr(o, "noise_seed", 0) + 2, **common)
+                seed=self._stage_seed(2), **common)
             result = result + extra
         return result
 
     # ---- reference entry points --------------------------------------------------------------
     def proj_denoiser(self, x: Tensor, convert=True, save_state=True, save_proj_state=False, return_idx=-1, noise=None):
+        if noise is None:
+            self._next_noise_epoch()
         result = self._proj_stage(x, noise)
         self.proj_temp_clear()
         if save_proj_state:
@@ -286,6 +317,8 @@ class progressive_domain_denoiser:
         return result[return_idx], self.noise_strength
 
     def img_denoiser(self, x, return_idx=-1, noise_strength=None, mode="progressive", sharpen_num=45, save_state=True, noise=None):
+        if noise is None:
+            self._next_noise_epoch()
         result = self._img_stage(x, noise, noise_strength)
         self.img_temp_clear()
         store = self.progressive_denoise_result if mode == "progressive" else self.img_denoise_result
@@ -296,27 +329,34 @@ class progressive_domain_denoiser:
             store["iter_1"] = result[return_idx].cpu().numpy()
         return result[return_idx]
 
+    def _graph_key(self, sharpen_num):
+        """Everything a captured pass freezes: the whole option table, the input shape, and the identity + weights of the FBP plan and of
+        both UNet handles (their device pointers are baked into the graph)."""
+        opts = json.dumps({k: v for k, v in sorted(vars(self.opt).items())}, sort_keys=True, default=str)
+        nets = tuple((id(m.cuda_handle()), m._weights_key()) for m in (self.proj_model, self.img_model))
+        return (tuple(self.ldproj.shape), str(self.ldproj.device), int(sharpen_num), opts, id(self._fbp), nets)
+
     def _progressive_graphed(self, sharpen_num):
-        """Whole progressive pass as ONE CUDA graph (north_star item 4): captured once per (batch, options) after an eager
-        warm-up that builds every plan, replayed with fresh Philox noise (device-resident epoch) and a refreshed input."""
-        o = self.opt
-        key = (tuple(self.ldproj.shape), tuple(o.t_start_proj), tuple(o.t_start_img), bool(o.ultra_img_denoise), int(sharpen_num),
-               o.precision, bool(o.clip_proj), bool(o.clip_img), o.constant_guidance_proj, o.constant_guidance_img, o.eta_proj, o.eta_img)
-        cache = self.__dict__.setdefault("_graphs", {})
-        if key not in cache:
+        """Whole progressive pass as ONE CUDA graph (north_star item 4): captured after an eager warm-up that builds every plan and
+        workspace, replayed with fresh Philox noise (device-resident epoch) and a refreshed input.  Exactly one graph is kept: any
+        change of an option, the batch shape, the convertor, the precision or the weights drops it and re-captures, so a replay never
+        touches freed plans, arenas or workspaces; the cache entry keeps the captured objects alive."""
+        key = self._graph_key(sharpen_num)
+        ent = self.__dict__.get("_graph")
+        if ent is None or ent["key"] != key:
+            self._drop_graph()
             static_in = self.ldproj.clone()
             self._progressive_eager(static_in, sharpen_num, None, None)            # warm-up: plans, workspaces, attributes
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 outs = self._progressive_eager(static_in, sharpen_num, None, None)
-            cache[key] = (g, static_in, outs)
-        g, static_in, outs = cache[key]
-        self._graph_runs = getattr(self, "_graph_runs", 0) + 1
-        _eng.set_noise_epoch(self._graph_runs)
-        static_in.copy_(self.ldproj, non_blocking=True)
-        g.replay()
-        return outs
+            ent = dict(key=key, graph=g, static_in=static_in, outs=outs,
+                       keep=(self._fbp, self.proj_model.cuda_handle(), self.img_model.cuda_handle()))
+            self._graph = ent
+        ent["static_in"].copy_(self.ldproj, non_blocking=True)
+        ent["graph"].replay()
+        return ent["outs"]                           # graph-static memory: the caller copies what it hands out
 
     def _progressive_eager(self, ldproj, sharpen_num, pn, inn):
         o = self.opt
@@ -330,6 +370,8 @@ class progressive_domain_denoiser:
     def progressive_denoiser(self, save_proj_state=False, convert=True, sharpen_num=42, noise=None):
         """proj stage -> FBP -> sharpen -> img stage, all on the GPU; returns [B,1,512,512] on the device."""
         o = self.opt
+        if noise is None:
+            self._next_noise_epoch()                                   # eager and graph replays alike: call k of a model uses epoch k
         if getattr(o, "cuda_graph", False) and noise is None and convert:
             result, recs, out = self._progressive_graphed(sharpen_num)
             self.proj_temp_clear()
@@ -341,7 +383,7 @@ class progressive_domain_denoiser:
                 self.proj_denoise_convert2img_result[f"iter_{k + 1}"] = r.cpu().numpy()
             for k, r in enumerate(out if o.save_it_state_img else out[-1:]):
                 self.progressive_denoise_result[f"iter_{k + 1}"] = r.cpu().numpy()
-            return out[-1]
+            return out[-1].clone()                                     # the next replay overwrites the graph's own output buffer
         pn, inn = (None, None) if noise is None else noise
         result = self._proj_stage(self.ldproj, pn)
         self.proj_temp_clear()

@@ -531,7 +531,8 @@ static int sampler_step_impl(const float* x_t, const float* x0c, const float* ep
                  "ipdm_sampler_step: buffers must be 16-byte aligned");
     const size_t n = (size_t)h * w;
     IPDM_REQUIRE(batch == 1 || n % 4 == 0, "ipdm_sampler_step: H*W must be a multiple of 4 for batch > 1");
-    IPDM_REQUIRE(lam_map == nullptr || ks > 0, "ipdm_sampler_step: ks must be positive with a lambda map");
+    IPDM_REQUIRE(lam_map == nullptr || (ks > 0 && h % ks == 0 && w % ks == 0),
+                 "ipdm_sampler_step: a lambda map is [B][H/ks][W/ks] (as ipdm_delta_lambda_map writes it): H and W must be multiples of ks");
     cudaStream_t st = (cudaStream_t)stream;
     ProfScope prof(PROF_SAMPLER, st, (lam_map ? 44.0 : 32.0) * batch * (double)h * w);        // algorithmic bytes
     Ws ws = carve(workspace, batch);

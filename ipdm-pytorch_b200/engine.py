@@ -303,16 +303,23 @@ def unet_config(in_channels, model_channels, out_channels, num_res_blocks, atten
 class UNetHandle:
     """Packed weights + execution plans of one UNet on the current device."""
 
-    def __init__(self, cfg, state_dict):
+    def __init__(self, cfg, state_dict, device=None):
         _require_cuda()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         flat = torch.cat([v.detach().reshape(-1).to(torch.float32).cpu() for v in state_dict.values()]).contiguous()
         expect = int(_lib.lib().ipdm_unet_param_count(ctypes.byref(cfg)))
         if flat.numel() != expect:
             raise ValueError(f"state_dict holds {flat.numel()} values, the architecture needs {expect}")
         self.cfg = cfg
         self._h = ctypes.c_void_p()
-        check(_lib.lib().ipdm_unet_create(ctypes.byref(self._h), ctypes.byref(cfg), ctypes.c_void_p(flat.data_ptr()), flat.numel()),
-              "ipdm_unet_create")
+        with torch.cuda.device(self.device):
+            check(_lib.lib().ipdm_unet_create(ctypes.byref(self._h), ctypes.byref(cfg), ctypes.c_void_p(flat.data_ptr()), flat.numel()),
+                  "ipdm_unet_create")
+
+    def _on_device(self, x, name):
+        if x.device != self.device:
+            raise ValueError(f"{name} lives on {x.device}, the UNet handle on {self.device}")
+        return torch.cuda.device(self.device)
 
     def __del__(self):
         if getattr(self, "_h", None) and _lib is not None and getattr(_lib, "_lib", None) is not None:
@@ -323,11 +330,13 @@ class UNetHandle:
         """eps[B,1,H,W] = UNet(x[B,1,H,W], t) with one integer timestep for the whole batch."""
         b, h, w = x.shape[0], x.shape[-2], x.shape[-1]
         out = torch.empty_like(x) if out is None else out
-        check(_lib.lib().ipdm_unet_forward(self._h, _dev(x, "x"), int(t), _dev(out, "out"), b, h, w, _stream()), "ipdm_unet_forward")
+        with self._on_device(x, "x"):
+            check(_lib.lib().ipdm_unet_forward(self._h, _dev(x, "x"), int(t), _dev(out, "out"), b, h, w, _stream()), "ipdm_unet_forward")
         return out
 
     def flops(self, b, h, w):
-        return float(_lib.lib().ipdm_unet_flops(self._h, int(b), int(h), int(w)))
+        with torch.cuda.device(self.device):                     # builds (and keeps) the plan of this shape
+            return float(_lib.lib().ipdm_unet_flops(self._h, int(b), int(h), int(w)))
 
 
 # ---------------------------------------------------------------------------------------------
@@ -367,7 +376,8 @@ def guided_process(unet, p, img, ldct=None, noise=None, out=None):
     if noise is not None and noise.shape[0] < guided_noise_count(p):
         raise ValueError(f"noise tape holds {noise.shape[0]} draws, the process consumes {guided_noise_count(p)}")
     out = torch.empty((n_out, b, 1, h, w), device=img.device, dtype=torch.float32) if out is None else out
-    ws = _workspace(_lib.lib().ipdm_guided_workspace_bytes(ctypes.byref(p), b, h, w), img.device)
-    check(_lib.lib().ipdm_guided_process(unet._h, ctypes.byref(p), _dev(img, "img"), _opt(ldct, "ldct"), _opt(noise, "noise"),
-                                         _dev(out), b, h, w, _dev(ws), _stream()), "ipdm_guided_process")
+    with unet._on_device(img, "img"):
+        ws = _workspace(_lib.lib().ipdm_guided_workspace_bytes(ctypes.byref(p), b, h, w), img.device)
+        check(_lib.lib().ipdm_guided_process(unet._h, ctypes.byref(p), _dev(img, "img"), _opt(ldct, "ldct"), _opt(noise, "noise"),
+                                             _dev(out), b, h, w, _dev(ws), _stream()), "ipdm_guided_process")
     return out

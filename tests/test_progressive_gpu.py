@@ -86,8 +86,16 @@ def test_batch_of_two_slices_equals_single_slices_philox(cuda, tmp_path):
     ld = np.stack([S.make_slice(s)[0] for s in (0, 1)])
     model.data_sample_load(ldct=None, ldproj=torch.from_numpy(ld)[:, None], fdproj=None, fdct=None)
     a = model.progressive_denoiser().clone()
-    b = model.progressive_denoiser()
-    assert tuple(a.shape) == (2, 1, 512, 512) and torch.equal(a, b)
+    b = model.progressive_denoiser().clone()
+    assert tuple(a.shape) == (2, 1, 512, 512)
+    assert not torch.equal(a, b)                       # every call draws fresh noise, as the reference's randn_like does
+    model.update_opt(dict(noise_seed=11))              # re-seeding restarts the sequence: call 1 is reproduced bit for bit
+    c = model.progressive_denoiser()
+    assert torch.equal(a, c)
+    single = _model(tmp_path, dict(t_start_proj=[2, 1], t_start_img=[2, 1], noise_seed=11))
+    single.data_sample_load(ldct=None, ldproj=torch.from_numpy(ld)[:1, None], fdproj=None, fdct=None)
+    s0 = single.progressive_denoiser()                 # slice 0 alone: same Philox key (seed, epoch, slice 0) => same noise field
+    assert float((s0[0] - a[0]).abs().max()) < 5e-2 * float(a[0].abs().max())
     assert torch.isfinite(a).all() and float(a.min()) >= 0 and float(a.max()) <= 1
     assert model.progressive_denoise_result[-1].shape == (2, 1, 512, 512)
     assert model.proj_denoise_convert2img_result["iter_1"].shape == (2, 1, 512, 512)
@@ -155,15 +163,28 @@ def test_cuda_graph_replay_equals_eager_and_draws_fresh_noise(cuda, tmp_path):
     model = _model(tmp_path, dict(t_start_proj=[2, 1], t_start_img=[2, 1], noise_seed=5))
     ld = torch.from_numpy(np.stack([S.make_slice(s)[0] for s in (0, 1)]))[:, None]
     model.data_sample_load(ldct=None, ldproj=ld, fdproj=None, fdct=None)
-    engine.set_noise_epoch(1)
-    eager1 = model.progressive_denoiser().clone()
-    engine.set_noise_epoch(2)
-    eager2 = model.progressive_denoiser().clone()
-    model.update_opt(dict(cuda_graph=True))
-    g1 = model.progressive_denoiser().clone()          # capture + replay #1 (epoch 1)
-    g2 = model.progressive_denoiser().clone()          # replay #2 (epoch 2)
+    eager1 = model.progressive_denoiser()              # call 1 of this model: noise epoch 1
+    eager2 = model.progressive_denoiser()              # call 2: epoch 2
+    model.update_opt(dict(cuda_graph=True, noise_seed=5))   # same seed => the call counter restarts
+    g1 = model.progressive_denoiser()                  # capture + replay #1 (epoch 1); the returned tensor is a copy
+    g2 = model.progressive_denoiser()                  # replay #2 (epoch 2)
     assert torch.equal(g1, eager1) and torch.equal(g2, eager2) and not torch.equal(g1, g2)
     assert model.progressive_denoise_result[-1].shape == (2, 1, 512, 512)
+    first_graph = model._graph["graph"]
+    # any option change drops the captured graph (it freezes options, plans and weights as kernel arguments / pointers)
+    model.update_opt(dict(t_start_img=[1, 1], noise_seed=5))
+    assert model._graph is None
+    g3 = model.progressive_denoiser()                  # re-captured with the new schedule
+    assert model._graph["graph"] is not first_graph
+    model.update_opt(dict(cuda_graph=False, noise_seed=5))
+    e3 = model.progressive_denoiser()
+    assert torch.equal(g3, e3) and not torch.equal(g3, g1)
+    # a precision switch rebuilds both UNet handles: the old graph must not be replayed
+    model.update_opt(dict(cuda_graph=True, precision="bf16", noise_seed=5))
+    g4 = model.progressive_denoiser()
+    model.update_opt(dict(precision="tf32", noise_seed=5))
+    g5 = model.progressive_denoiser()
+    assert torch.equal(g5, g3) and not torch.equal(g4, g3)
     engine.set_noise_epoch(0)
 
 
