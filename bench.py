@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--t_start_proj", type=int, nargs="+", default=[15, 15, 15])
     ap.add_argument("--t_start_img", type=int, nargs="+", default=[15, 15, 15])
     ap.add_argument("--skip_cpu_baseline", action="store_true")
+    ap.add_argument("--skip_cpu_whole_slice", action="store_true", help="do not run the one unsampled whole slice on the host (~150 s)")
+    ap.add_argument("--skip_extras", action="store_true", help="only the headline line: no modes / c1 / cuda_graph / C4 / C5 sub-reports")
     ap.add_argument("--cuda_graph", type=int, default=0, help="1: capture the whole progressive pass in one CUDA graph")
     return ap.parse_args()
 
@@ -94,55 +96,126 @@ class ClockSampler:
 # -------------------------------------------------------------------------------------------------
 # CPU legs (oracle port): the reference algorithm on the host cores, bounded sample
 # -------------------------------------------------------------------------------------------------
+_CPU = {}
+
+
+def _cpu_setup():
+    """Oracle networks, inputs and tables of the CPU legs (built once per process; weights are the same seed-0 random init)."""
+    if not _CPU:
+        import torch
+        from oracle import ipdm_oracle as O
+        torch.set_num_threads(len(os.sched_getaffinity(0)))
+        torch.manual_seed(0)
+        g = torch.Generator().manual_seed(0)
+        _CPU.update(O=O, pnet=O.UNetOracle(**O.PROJ_UNET).eval(), inet=O.UNetOracle(**O.IMG_UNET).eval(), g=g,
+                    xp=3 * torch.rand(1, 1, 2000, 912, generator=g), xi=0.2 * torch.rand(1, 1, 512, 512, generator=g),
+                    ptab=O.Tables(1000, 5), itab=O.Tables(1000, 1), cores=torch.get_num_threads())
+    return _CPU
+
+
+CPU_SAMPLE_PROJ, CPU_SAMPLE_IMG = 3, 4           # forwards + reverse steps per bounded sample
+
+
+def cpu_sample_fraction(t_start_proj, t_start_img):
+    """Fraction of ONE slice a bounded sample covers: 3 of the sum(t_start_proj) projection steps and 4 of the sum(t_start_img)+15
+    image steps.  For the shipped lists (45 + 60 steps) both are exactly 1/15 of the slice; otherwise the time-weighted mean is used."""
+    return CPU_SAMPLE_PROJ / sum(t_start_proj), CPU_SAMPLE_IMG / (sum(t_start_img) + 15)
+
+
 def cpu_reference_sample(t_start_proj, t_start_img):
-    """Times one proj-UNet forward, one img-UNet forward, one FBP and one sampler step of the oracle on the host and
-    extrapolates one slice: n_proj*t_proj + n_img*t_img + t_fbp + steps*t_step (the reference is serial per slice)."""
-    import numpy as np
+    """One bounded sample of the reference algorithm (oracle port) on the host cores: 3 projection-domain reverse steps (UNet forward at
+    2000x912 + p_sample_condition) and 4 image-domain ones at 512x512, i.e. 1/15 of one slice of the shipped configuration.  The
+    FBP (1 per slice, ~1 % of a slice) and the once-per-process delta-map / curve are NOT in the sample (they are in the whole-slice
+    run), so the sample slightly favours the reference.  Returns the measured seconds and the slices/s it implies."""
     import torch
-    from oracle import ipdm_oracle as O
-    torch.set_num_threads(len(os.sched_getaffinity(0)))
-    torch.manual_seed(0)
-    pnet, inet = O.UNetOracle(**O.PROJ_UNET).eval(), O.UNetOracle(**O.IMG_UNET).eval()
-    g = torch.Generator().manual_seed(0)
-    xp, xi = 3 * torch.rand(1, 1, 2000, 912, generator=g), 0.2 * torch.rand(1, 1, 512, 512, generator=g)
-    t0 = time.perf_counter(); ep = pnet(xp, torch.full((1,), 7, dtype=torch.long)); t_proj = time.perf_counter() - t0
-    t0 = time.perf_counter(); ei = inet(xi, torch.full((1,), 7, dtype=torch.long)); t_img = time.perf_counter() - t0
-    tab = O.Tables(1000, 5)
-    t0 = time.perf_counter(); O.p_sample_condition(tab, ep, xp, xp, 7, 0.4, False, torch.randn(xp.shape, generator=g)); t_sp = time.perf_counter() - t0
-    t0 = time.perf_counter(); O.p_sample_condition(tab, ei, xi, xi, 7, 0.45, True, torch.randn(xi.shape, generator=g)); t_si = time.perf_counter() - t0
-    t0 = time.perf_counter(); O.fbp_convert(xp[:, 0].numpy()); t_fbp = time.perf_counter() - t0
-    n_proj, n_img = sum(t_start_proj), sum(t_start_img) + 15
-    per_slice = n_proj * (t_proj + t_sp) + n_img * (t_img + t_si) + t_fbp
-    return dict(per_slice_s=per_slice, t_proj=t_proj, t_img=t_img, t_fbp=t_fbp, cores=torch.get_num_threads(),
-                sample=f"1 proj UNet fwd 2000x912 ({t_proj:.2f}s) + 1 img UNet fwd 512x512 ({t_img:.2f}s) + 1 sampler step each "
-                       f"+ 1 FBP ({t_fbp:.2f}s, C oracle, OpenMP); extrapolated to {n_proj}+{n_img} forwards per slice")
+    c = _cpu_setup()
+    O = c["O"]
+    t0 = time.perf_counter()
+    x = c["xp"]
+    for k in range(CPU_SAMPLE_PROJ):
+        t = 7 + k
+        eps = c["pnet"](x, torch.full((1,), t, dtype=torch.long))
+        x = O.p_sample_condition(c["ptab"], eps, x, c["xp"], t, 0.4, False, torch.randn(x.shape, generator=c["g"]))
+    t_proj = time.perf_counter() - t0
+    t1 = time.perf_counter()
+    x = c["xi"]
+    for k in range(CPU_SAMPLE_IMG):
+        t = 7 + k
+        eps = c["inet"](x, torch.full((1,), t, dtype=torch.long))
+        x = O.p_sample_condition(c["itab"], eps, x, c["xi"], t, 0.45, True, torch.randn(x.shape, generator=c["g"]))
+    t_img = time.perf_counter() - t1
+    fp, fi = cpu_sample_fraction(t_start_proj, t_start_img)
+    per_slice = t_proj / fp + t_img / fi
+    sample_s = t_proj + t_img
+    return dict(sample_s=sample_s, per_slice_s=per_slice, slice_fraction=sample_s / per_slice, t_proj_step=t_proj / CPU_SAMPLE_PROJ,
+                t_img_step=t_img / CPU_SAMPLE_IMG, cores=c["cores"],
+                sample=f"{CPU_SAMPLE_PROJ} proj reverse steps at 2000x912 ({t_proj / CPU_SAMPLE_PROJ:.2f} s each: UNet forward + guided step) + "
+                       f"{CPU_SAMPLE_IMG} img reverse steps at 512x512 ({t_img / CPU_SAMPLE_IMG:.2f} s each) of the oracle port (torch CPU fp32), "
+                       f"= {sample_s / per_slice:.4f} of one slice ({sum(t_start_proj)} + {sum(t_start_img) + 15} steps per slice; FBP and delta-map "
+                       f"not sampled)")
+
+
+def cpu_reference_whole_slice(t_start_proj, t_start_img):
+    """ONE whole slice of the reference algorithm on the host, nothing extrapolated: projection stage (incl. the delta-map / lambda
+    curve / per-step lambda maps on the host), FBP (C oracle, OpenMP), sharpen, image stage + ultra pass."""
+    import torch
+    from ipdm_pytorch_b200 import synthetic
+    c = _cpu_setup()
+    O = c["O"]
+    x = torch.from_numpy(synthetic.cheap_sinogram(1, seed=100))[:, None].contiguous()
+    g = torch.Generator().manual_seed(1)
+    n_p, n_i = sum(t_start_proj) + len(t_start_proj), sum(t_start_img) + len(t_start_img) + 18
+    pn = [torch.randn(1, 1, 2000, 912, generator=g) for _ in range(n_p)]
+    inn = [torch.randn(1, 1, 512, 512, generator=g) for _ in range(n_i)]
+    t0 = time.perf_counter()
+    st = {}
+    out = O.progressive_denoise(c["pnet"], c["inet"], x, pn, inn, t_start_proj=tuple(t_start_proj), t_start_img=tuple(t_start_img),
+                                ultra=True, stages=st)
+    dt = time.perf_counter() - t0
+    assert tuple(out.shape) == (1, 1, 512, 512)
+    return dt
 
 
 def run_reference(args, rank, world):
+    """Reference arm: the reference algorithm's CPU implementation (oracle port; the Python reference itself cannot travel to the GPU
+    box) on all host cores.  One step = one bounded sample (1/15 of a slice, ~10 s) and `ms_per_step` is its MEASURED duration, so
+    steps x ms_per_step is the real timed region; `value` = slices per second that sample implies.  During warm-up one WHOLE slice
+    is run once, unsampled, and reported beside the sampled figure."""
     if rank != 0:
         return
-    vals, last = [], None
+    whole = None
+    if args.warmup > 0 and not args.skip_cpu_whole_slice:
+        whole = cpu_reference_whole_slice(args.t_start_proj, args.t_start_img)
+    vals, secs, last = [], [], None
     for i in range(args.warmup + args.steps):
         last = cpu_reference_sample(args.t_start_proj, args.t_start_img)
         if i >= args.warmup:
-            vals.append(last["per_slice_s"])
-        if i == 0 and last["per_slice_s"] > 0 and (args.warmup + args.steps) * 25 > 600:
-            pass
+            vals.append(last["per_slice_s"]); secs.append(last["sample_s"])
     per_slice = sum(vals) / len(vals)
     v = 1.0 / per_slice
+    cfg = base_config(args, args.batch, world)
+    cfg.update(note="reference algorithm on the host CPU (oracle port: torch CPU UNet + C FBP), one slice at a time (the reference cannot batch): "
+                    "the batch of the workload is B x one slice; each step is a bounded sample of one slice")
+    cpu = dict(value=v, unit="slices/s", cores=last["cores"], kind="port", sample=last["sample"], sampled_s_per_slice=per_slice)
+    if whole is not None:
+        cpu.update(whole_slice_s=whole, whole_slice_value=1.0 / whole, sampled_over_whole=per_slice / whole,
+                   whole_note="one complete slice (45 + 60 forwards, delta-map, lambda maps, FBP, sharpen), run once during warm-up")
     line = dict(metric="ipdm_progressive_slices_per_sec", value=v, unit="slices/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
-                ms_per_step=per_slice * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
-                impl="reference",
-                config=dict(workload=workload_name(args, 1), note="reference algorithm (oracle port: torch CPU UNet + C FBP) on the host; "
-                            "the Python reference itself cannot travel to the GPU box; one slice at a time (the reference cannot batch)"),
-                cpu_baseline=dict(value=v, unit="slices/s", cores=last["cores"], kind="port", sample=last["sample"]),
-                e2e=dict(value=v, unit="slices/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+                ms_per_step=1e3 * sum(secs) / len(secs), higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                impl="reference", config=cfg, cpu_baseline=cpu,
+                e2e=dict(value=v, unit="slices/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0,
+                slices_per_step=last["slice_fraction"])
     print(json.dumps(line))
 
 
 def workload_name(args, batch):
     return (f"IPDM progressive inference, convertor=FBP, t_start_proj={args.t_start_proj}, t_start_img={args.t_start_img} + ultra [5,5,5], "
             f"{batch} slice(s)/GPU/step, sinogram 2000x912 -> image 512x512, random-init UNets (28.4M + 29.1M params)")
+
+
+def base_config(args, batch, world):
+    """`config` keys shared by both arms (the driver compares them)."""
+    return dict(workload=workload_name(args, batch), global_batch=world * batch, parallelism=f"slice-sharded x{world}, no data-path collective")
 
 
 # -------------------------------------------------------------------------------------------------
@@ -182,11 +255,24 @@ def run_b200(args, rank, world, local_rank):
         model.ldproj = resident
         return model.progressive_denoiser()
 
+    gathered_shape = []
+
     def step_e2e():
-        model.ldproj = host.to(dev, non_blocking=True)
+        """The call a user makes: pinned host tensors -> data_sample_load (H2D inside) -> progressive_denoiser -> host result; with
+        N > 1 ranks the final gather of the [B,1,512,512] results (the only collective of the path) is part of the step."""
+        model.data_sample_load(ldct=None, ldproj=host, fdproj=None, fdct=None)
         out = model.progressive_denoiser()
-        host_out.copy_(out, non_blocking=True)
+        if world > 1:
+            from ipdm_pytorch_b200.sharding import gather_slices
+            full = gather_slices(out.contiguous(), world * B)
+            gathered_shape[:] = list(full.shape)
+            if rank == 0:
+                host_full.copy_(full, non_blocking=True)
+        else:
+            host_out.copy_(out, non_blocking=True)
         return out
+
+    host_full = torch.empty(world * B, 1, 512, 512).pin_memory() if (world > 1 and rank == 0) else None
 
     def barrier():
         if world > 1:
@@ -222,12 +308,69 @@ def run_b200(args, rank, world, local_rank):
     if args.cuda_graph and launches == 0 and args.warmup > 0:
         launches = launches_first_step * args.steps                  # replays do not pass through the host-side launch counter
     clocks = sampler.stop() if rank == 0 else None
-    if world > 1:                                   # the only collective: final gather of the results
-        from ipdm_pytorch_b200.sharding import gather_slices
-        gathered = gather_slices(out.contiguous(), world * B)
-        assert gathered.shape[0] == world * B
     step_e2e()
     ms_e2e, _ = timed(step_e2e, args.steps)
+    if world > 1:
+        assert gathered_shape and gathered_shape[0] == world * B
+
+    # ---- sub-reports: the other BASELINE configs and precision modes (short: 1 warm-up + 1-2 steps each) ----
+    extras = {}
+    if not args.skip_extras:
+        def sub(batch, steps, host_src=None, **opts):
+            """slices/s of `steps` resident steps at `batch` slices per GPU after one warm-up step, with `opts` applied to the model."""
+            with contextlib.redirect_stdout(io.StringIO()):
+                model.update_opt(dict(opts))
+            src = resident if host_src is None else host_src
+            model.ldproj = src[:batch].contiguous()
+            fn = lambda: model.progressive_denoiser()
+            fn()
+            m, _ = timed(fn, steps)
+            return dict(slices_per_s=world * batch * steps / (m / 1e3), ms_per_step=m / steps, slices_per_gpu_per_step=batch, steps=steps, warmup=1)
+
+        base = dict(precision=args.precision, cuda_graph=bool(args.cuda_graph), t_start_proj=args.t_start_proj, t_start_img=args.t_start_img)
+        if world == 1:
+            extras["modes"] = {
+                "tf32": dict(sub(B, 2, precision="tf32"), note="tf32 mode: kind::tf32 tensor-core layers, exact CUDA-core thin layers (what the reference does on its own GPU)"),
+                "fp32": dict(sub(B, 1, precision="fp32"), note="fp32 mode: 3xTF32 split, the mode that meets the 1 HU parity bar"),
+            }
+            extras["c1_single_slice_fp32"] = dict(sub(1, 2, precision="fp32"), note="BASELINE configs[0]: one slice, fp32 mode, default lists, ultra on")
+            extras["c1_single_slice_bf16"] = sub(1, 2, precision="bf16")
+            extras["cuda_graph"] = dict(sub(B, 2, precision=args.precision, cuda_graph=True), note="whole progressive pass replayed as ONE CUDA graph (capture in the warm-up step)")
+            with contextlib.redirect_stdout(io.StringIO()):
+                model.update_opt(base)
+        else:
+            # BASELINE configs[3]: t_start_proj=[15,12,10,10] + image stage, a FIXED global batch of 64 slices split over the ranks (strong scaling)
+            per_rank = 64 // world
+            micro = min(per_rank, 16)
+            c4_host = torch.from_numpy(synthetic.cheap_sinogram(micro, seed=300 + rank))[:, None].contiguous().to(dev)
+            with contextlib.redirect_stdout(io.StringIO()):
+                model.update_opt(dict(t_start_proj=[15, 12, 10, 10]))
+
+            def c4_step():
+                for _ in range(per_rank // micro):
+                    model.ldproj = c4_host
+                    o = model.progressive_denoiser()
+                return o
+            c4_step()
+            m, _ = timed(c4_step, 1)
+            extras["c4_strong_global64"] = dict(slices_per_s=64 / (m / 1e3), ms_per_step=m, global_batch=64, slices_per_gpu=per_rank, micro_batch=micro, scaling="strong",
+                                                t_start_proj=[15, 12, 10, 10], steps=1, warmup=1,
+                                                note="BASELINE configs[3]: 64 slices in total, 64/N per GPU in micro-batches of <= 16; time = max over ranks")
+            with contextlib.redirect_stdout(io.StringIO()):
+                model.update_opt(base)
+            if world == 8:
+                # BASELINE configs[4]: a 512-slice volume over 8 GPUs = 64 slices per GPU in 4 micro-batches of 16, then ONE gather of the volume
+                from ipdm_pytorch_b200.sharding import gather_slices
+                vol_out = torch.empty(64, 1, 512, 512, device=dev)
+
+                def c5_step():
+                    for k in range(4):
+                        model.ldproj = resident
+                        vol_out[k * 16:(k + 1) * 16] = model.progressive_denoiser()
+                    return gather_slices(vol_out, 512)
+                m, full = timed(c5_step, 1)
+                extras["c5_volume512_8gpu"] = dict(slices_per_s=512 / (m / 1e3), ms=m, slices=512, gathered_shape=list(full.shape), steps=1,
+                                                   note="BASELINE configs[4]: 512 slices, 64 per GPU in micro-batches of 16, final all-gather of the 512 MiB volume inside the timed region")
 
     if rank != 0:
         return
@@ -273,17 +416,26 @@ def run_b200(args, rank, world, local_rank):
                 ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
                 dtype={"tf32": "tf32 (fp32 state, tcgen05 kind::tf32, fp32 accumulate)", "fp32": "f32 (3xTF32)", "bf16": "bf16"}[args.precision],
                 data="synthetic",
-                config=dict(workload=workload_name(args, B), global_batch=world * B, parallelism=f"slice-sharded x{world}, no data-path collective",
+                config=dict(base_config(args, B, world),
                             l2="working set (activation arena of several GB per step) >> 126 MB L2; no explicit flush needed",
                             noise="in-kernel Philox4x32-10", cuda_graph=bool(args.cuda_graph), unet_tflop_per_step=step_flops / 1e12),
-                e2e=dict(value=e2e, unit="slices/s", h2d_bytes_per_step=int(host.numel() * 4), d2h_bytes_per_step=int(host_out.numel() * 4),
+                e2e=dict(value=e2e, unit="slices/s", h2d_bytes_per_step=int(world * host.numel() * 4), d2h_bytes_per_step=int(world * host_out.numel() * 4),
                          ms_per_step=ms_e2e / args.steps),
                 gpu_launches=int(launches), clocks=clocks, roofline=roof, kernel_families=families,
                 unet_effective_tflops=step_flops * args.steps / (ms * 1e-3) / 1e12)
+    line["e2e"]["note"] = ("data_sample_load(pinned host sinograms) + progressive_denoiser + D2H of the result" +
+                           ("; the final all-gather of the results over NCCL is inside the timed region" if world > 1 else ""))
+    line.update(extras)
     line["fbp_batch64"] = fbp_batch64(dev, pk)
     if not args.skip_cpu_baseline and world == 1:             # rank 0 at N=1 only
+        cpu_reference_sample(args.t_start_proj, args.t_start_img)                       # warm-up (thread pools, oneDNN primitives)
         c = cpu_reference_sample(args.t_start_proj, args.t_start_img)
-        line["cpu_baseline"] = dict(value=1.0 / c["per_slice_s"], unit="slices/s", cores=c["cores"], kind="port", sample=c["sample"])
+        line["cpu_baseline"] = dict(value=1.0 / c["per_slice_s"], unit="slices/s", cores=c["cores"], kind="port", sample=c["sample"],
+                                    sampled_s_per_slice=c["per_slice_s"])
+        if not args.skip_cpu_whole_slice:
+            whole = cpu_reference_whole_slice(args.t_start_proj, args.t_start_img)
+            line["cpu_baseline"].update(whole_slice_s=whole, whole_slice_value=1.0 / whole, sampled_over_whole=c["per_slice_s"] / whole,
+                                        whole_note="one complete slice on the host (45 + 60 forwards, delta-map, lambda maps, FBP, sharpen), nothing extrapolated")
     print(json.dumps(line))
 
 

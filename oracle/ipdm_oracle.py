@@ -386,7 +386,7 @@ def tensor_sharpen(img, N):
     if N == -1:
         return img
     k = torch.tensor([[-2, -2, -2], [-2, N, -2], [-2, -2, -2]])[None, None].float() / (N - 16)
-    return F.conv2d(img, k, stride=1, padding=1)
+    return F.conv2d(img, k.to(img.device), stride=1, padding=1)
 
 
 def fbp_convert(pj):
@@ -401,7 +401,7 @@ def progressive_denoise(proj_unet, img_unet, ldproj, proj_noise, img_noise, t_st
     ptab, itab = Tables(1000, 5), Tables(1000, 1)
     res = guided_reverse_process(proj_unet, ptab, ldproj, list(t_start_proj), clip=False, lambda_ratio=1, eta=0.5,
                                  mode="proj", constant_guidance=None, noise=iter(proj_noise), kernel_size=4, amplitude=7.0)
-    rec = torch.from_numpy(fbp_convert(res[-1][:, 0].numpy()))[:, None]           # :475-477
+    rec = torch.from_numpy(fbp_convert(res[-1][:, 0].cpu().numpy()))[:, None].to(ldproj.device)   # :475-477 (FBP on the host, as the reference)
     x = tensor_sharpen(rec, sharpen_num)                                           # :556-564
     out = guided_reverse_process(img_unet, itab, x, list(t_start_img), clip=True, lambda_ratio=10, eta=0.7,
                                  mode="img", constant_guidance=0.45, noise=iter(img_noise[:48]), ldct=x)

@@ -42,8 +42,14 @@ def test_art_convertor_fails_loudly_until_switched(cuda, tmp_path):
     assert m.opt.convertor == "ART"
 
 
+BF16_IMG_STAGE_HU = 86.0          # 1.5 x the 57 HU measured in round 1 (bf16 operands on every tensor-core layer)
+
+# how far above the reference's own GPU-vs-CPU distance a mode of the CUDA path may land (same arithmetic class: fp32 vs fp32, TF32 vs TF32)
+FLOOR_FACTOR_ITERATE, FLOOR_FACTOR_FINAL = 2.0, 1.25
+
+
 @pytest.mark.parametrize("prec", ["tf32", "fp32"])
-def test_full_slice_matches_reference_golden(cuda, tmp_path, prec):
+def test_full_slice_matches_reference_golden(cuda, tmp_path, prec, ref_floor):
     import ipdm_pytorch_b200.synthetic as S
     from inputs import noise_tape
     g = golden("full_slice0")
@@ -71,12 +77,16 @@ def test_full_slice_matches_reference_golden(cuda, tmp_path, prec):
     rmse_hu = float(np.sqrt(np.mean((fin.astype(np.float64) - g["final"]) ** 2))) * HU_PER_MU
     print(f"full slice ({prec}): proj iterates rel-L2 {['%.2e' % e for e in perr]}; FBP image rel-L2 {ferr:.2e}; final RMSE {rmse_hu:.2f} HU "
           f"(final image spans [{g['final'].min():.2f}, {g['final'].max():.2f}] mu with random-init weights)")
-    # tf32 mode with RANDOM-INIT weights: the per-forward tf32 error (4e-3 at 2000x912, tests/test_unet_gpu.py) is re-fed
-    # 45 times through an untrained, expansive network; DESIGN.md "Parity" reports these numbers and the fp32-mode ones.
-    # Even the fp32 mode cannot beat the reference's OWN reproducibility here: torch-fp32-on-GPU vs torch-fp32-on-CPU differ by
-    # 1.6e-3 / 7.8e-3 / 1.8e-2 / 1.2e-2 on these four iterates (test_reference_own_noise_floor_full_size_proj_stage).
-    assert max(perr) < 5e-2
-    assert ferr < 0.2
+    # With RANDOM-INIT weights every per-forward difference is re-fed 45 + 60 times through an untrained, expansive network, so the
+    # whole-slice distance to the CPU golden is set by the amplification, not by the kernels (tests/test_teacher_forced_gpu.py bounds
+    # every step in isolation).  The yardstick is the reference's OWN reproducibility in the same arithmetic class: the oracle in
+    # torch on this GPU (fp32, or with TF32 allowed as the reference ran on its authors' GPU) against the same CPU golden.
+    f = ref_floor[prec]
+    print(f"    reference floor ({prec}): proj iterates {['%.2e' % e for e in f['perr']]}; FBP {f['ferr']:.2e}; final {f['final_hu']:.2f} HU")
+    for k in range(4):
+        assert perr[k] <= FLOOR_FACTOR_ITERATE * f["perr"][k], (k, perr[k], f["perr"][k])
+    assert ferr <= FLOOR_FACTOR_ITERATE * f["ferr"], (ferr, f["ferr"])
+    assert rmse_hu <= FLOOR_FACTOR_FINAL * f["final_hu"], (rmse_hu, f["final_hu"])
 
 
 def test_batch_of_two_slices_equals_single_slices_philox(cuda, tmp_path):
@@ -101,33 +111,68 @@ def test_batch_of_two_slices_equals_single_slices_philox(cuda, tmp_path):
     assert model.proj_denoise_convert2img_result["iter_1"].shape == (2, 1, 512, 512)
 
 
-def test_reference_own_noise_floor_full_size_proj_stage(cuda):
-    """How reproducible is the reference itself?  The oracle restatement (pinned to the reference on CPU) is run in
-    fp32 on the GPU (torch/cuDNN, TF32 disabled) for the projection stage of the SAME slice / weights / noise tape and
-    compared with the CPU golden.  Two fp32 implementations that differ only in summation order land this far apart
-    after 45 re-fed forwards of a random-init network; the CUDA path's fp32 mode must be (and is) inside this band."""
+class _TF32:
+    """torch.backends TF32 switches for the GPU-hosted oracle: off = true fp32; on = what the reference did on its authors' GPU
+    (torch 1.7.1 defaults: cuDNN conv and matmul TF32 both allowed)."""
+
+    def __init__(self, on):
+        self.on = on
+
+    def __enter__(self):
+        self.old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+        torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = self.on
+
+    def __exit__(self, *exc):
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = self.old
+
+
+@pytest.fixture(scope="module")
+def ref_floor(cuda):
+    """How reproducible is the reference itself?  The oracle restatement (pinned to the reference on CPU) is run in torch on the GPU
+    for the SAME slice / weights / noise tapes as the CPU goldens, once in true fp32 and once with TF32 allowed (the reference's own
+    published GPU behaviour), through the whole progressive slice (proj stage -> FBP -> sharpen -> img stage + ultra) and through the
+    image stage alone.  Two implementations of the same fp32 arithmetic that differ only in summation order land this far apart after
+    45 + 60 re-fed forwards of a random-init network: these distances are the yardstick for the CUDA path's modes."""
     import ipdm_pytorch_b200.synthetic as S
-    from inputs import PROJ_CFG, noise_tape
+    from inputs import IMG_CFG, PROJ_CFG, noise_tape
     from oracle import ipdm_oracle as O
-    g = golden("full_slice0")
-    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
-    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = False
-    try:
-        torch.manual_seed(0)
-        net = O.UNetOracle(**PROJ_CFG).eval().to(cuda)
-        x = torch.from_numpy(S.make_slice(0)[0])[None, None].to(cuda)
-        tape = [t.to(cuda) for t in noise_tape((1, 1, 2000, 912), 48, 9527)]
-        res = O.guided_reverse_process(net, O.Tables(1000, 5), x, [15, 15, 15], clip=False, lambda_ratio=1, eta=0.5, mode="proj",
-                                       constant_guidance=None, noise=iter(tape), kernel_size=4, amplitude=7.0)
-    finally:
-        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
-    err = [rel_l2(res[k][0, 0].cpu().numpy()[1::4, 2::4], g[f"proj_iter{k + 1}_sub"]) for k in range(4)]
-    print(f"reference noise floor (torch fp32 on GPU vs torch fp32 on CPU, same seeds): proj iterates rel-L2 {['%.2e' % e for e in err]}")
-    assert max(err) < 5e-2
+    g, gi = golden("full_slice0"), golden("img_stage512")
+    torch.manual_seed(0)
+    pnet = O.UNetOracle(**PROJ_CFG).eval().to(cuda)
+    inet = O.UNetOracle(**IMG_CFG).eval().to(cuda)
+    x = torch.from_numpy(S.make_slice(0)[0])[None, None].to(cuda)
+    pn = [t.to(cuda) for t in noise_tape((1, 1, 2000, 912), 48, 9527)]
+    inn = [t.to(cuda) for t in noise_tape((1, 1, 512, 512), 66, 19527)]
+    xi = torch.from_numpy(gi["x"])[None, None].to(cuda)
+    itab = O.Tables(1000, 1)
+    out = {}
+    for name, on in (("fp32", False), ("tf32", True)):
+        with _TF32(on):
+            st = {}
+            fin = O.progressive_denoise(pnet, inet, x, pn, inn, stages=st)
+            res = O.guided_reverse_process(inet, itab, xi, [15, 15, 15], clip=True, lambda_ratio=10, eta=0.7, mode="img",
+                                           constant_guidance=0.45, noise=iter(inn[:48]), ldct=xi)
+            res += O.guided_reverse_process(inet, itab, res[-1], [5, 5, 5], clip=True, lambda_ratio=10, eta=0.6, mode="img",
+                                            constant_guidance=0.6, noise=iter(inn[48:]), ldct=xi)
+        out[name] = dict(
+            perr=[rel_l2(st["proj"][k][0, 0].cpu().numpy()[1::4, 2::4], g[f"proj_iter{k + 1}_sub"]) for k in range(4)],
+            ferr=rel_l2(st["fbp"][0, 0].cpu().numpy()[1::4, 2::4], g["fbp_img_sub"]),
+            final_hu=float(np.sqrt(np.mean((fin[0, 0].cpu().numpy().astype(np.float64) - g["final"]) ** 2))) * HU_PER_MU,
+            img_stage_hu=float(np.sqrt(np.mean((res[-1][0, 0].cpu().numpy().astype(np.float64) - gi["final"]) ** 2))) * HU_PER_MU)
+        print(f"reference floor, torch {name} on the GPU vs the CPU golden: proj iterates rel-L2 {['%.2e' % e for e in out[name]['perr']]}; "
+              f"FBP image rel-L2 {out[name]['ferr']:.2e}; full-slice final RMSE {out[name]['final_hu']:.2f} HU; "
+              f"image stage alone final RMSE {out[name]['img_stage_hu']:.3f} HU")
+    return out
+
+
+def test_reference_own_noise_floor(ref_floor):
+    """The yardstick itself: the fp32 reference-vs-reference distance stays in the band DESIGN.md reports."""
+    f = ref_floor["fp32"]
+    assert max(f["perr"]) < 5e-2 and f["img_stage_hu"] < 1.0
 
 
 @pytest.mark.parametrize("prec", ["fp32", "tf32", "bf16"])
-def test_image_stage_512_matches_reference_golden(cuda, tmp_path, prec):
+def test_image_stage_512_matches_reference_golden(cuda, tmp_path, prec, ref_floor):
     """Image-domain stage alone at the real size (60 forwards at 512x512, clip, constant guidance, ultra pass) from the
     reference's own sharpened FBP image; golden from the unmodified reference (oracle/make_golden.py img512)."""
     from inputs import noise_tape
@@ -150,9 +195,16 @@ def test_image_stage_512_matches_reference_golden(cuda, tmp_path, prec):
     d_ssim = float(ours[1]) - M.ssim(ndct, ref_pix, win_size=11)
     print(f"image stage 512^2 ({prec}): rel-L2 per iterate {['%.2e' % e for e in err]}; final RMSE {rmse_hu:.3f} HU; "
           f"vs NDCT: dPSNR {d_psnr:+.4f} dB, dSSIM {d_ssim:+.5f}")
+    assert abs(d_psnr) < 0.05 and abs(d_ssim) < 1e-3          # north_star: PSNR / SSIM against NDCT within 0.05 dB / 0.001 (every mode)
     if prec == "fp32":
         assert rmse_hu < 1.0            # north_star: final images within 1 HU RMSE in the fp32 mode
-        assert abs(d_psnr) < 0.05 and abs(d_ssim) < 1e-3      # north_star: PSNR / SSIM against NDCT within 0.05 dB / 0.001
+    elif prec == "tf32":
+        # the reference's own TF32 path (cuDNN / cuBLAS TF32 allowed) on the same inputs is this far from its fp32 CPU result; the
+        # tf32 mode of the CUDA path (TF32 tensor-core layers, exact CUDA-core thin layers) must not be further away
+        print(f"    reference's own TF32 path vs its fp32 golden: {ref_floor['tf32']['img_stage_hu']:.2f} HU")
+        assert rmse_hu <= FLOOR_FACTOR_FINAL * ref_floor["tf32"]["img_stage_hu"], (rmse_hu, ref_floor["tf32"]["img_stage_hu"])
+    else:
+        assert rmse_hu <= BF16_IMG_STAGE_HU, rmse_hu              # bf16 mode: reported separately with its own stated error
 
 
 def test_cuda_graph_replay_equals_eager_and_draws_fresh_noise(cuda, tmp_path):
