@@ -151,6 +151,11 @@ int ipdm_delta_lambda_map(const float* x_dev, const float* img_dev, float* lam_e
 int ipdm_delta_lambda_map_img(const float* x_dev, const float* img_dev, float* lam_exp_out_dev, float* median_out_dev,
                               float* pooled_tmp_dev, int batch, int h, int w, int ks, float amplitude, int curve_kind,
                               void* workspace_dev, void* stream);
+/* Adaptive schedule selection of the projection domain (Model/model.py:596-613, t_start=None): per slice
+ * max_out[b] = max over the slice of exp(amp * relu(avgpool_ks(|x - img| - median(|x - img|)))), the quantity the reference compares
+ * with 30 / 4.5 to pick [30,25,20] / [20,18,15] / [15,15,15].  One D2H read of B floats is the only host round trip of that branch. */
+int ipdm_delta_exp_max(const float* x_dev, const float* img_dev, float* max_out_dev, int batch, int h, int w, int ks,
+                       float amplitude, void* workspace_dev, void* stream);
 /* per-step guidance map clip(1 - (abar(i+1)/abar(i))^Lambda, .05, .99), fp64 math, n cells */
 int ipdm_lambda_step_map(const float* lam_exp_dev, float* lam_out_dev, size_t n, int i, int ts, void* stream);
 /* host evaluation of the piecewise lambda curve (fp64 polyfit coefficients), for tests */
@@ -225,6 +230,17 @@ size_t ipdm_guided_workspace_bytes(const ipdm_guided_params* p, int batch, int h
 int ipdm_guided_process(ipdm_unet* net, const ipdm_guided_params* p, const float* img_dev, const float* ldct_dev,
                         const float* noise_dev, float* iters_out_dev, int batch, int h, int w, void* workspace_dev,
                         void* stream);
+/*
+ * Continuation of the adaptive-schedule branch (Model/model.py:582-613, 629-630): the probing iteration (t_start = 20) has been run
+ * with ipdm_guided_process (n_iters = 1) and its lambda-exponent map built with ipdm_delta_lambda_map[_img]; this call runs the
+ * iterations of the schedule the host picked (p->t_start, p->eta; n_iters >= 2) as iterations 1, 2, ... of the SAME process: x restarts
+ * from img, every step uses the per-pixel lambda map of lam_exp_dev [B][H/ks][W/ks], the guidance blend follows every iteration.
+ * noise_dev (optional) points at the first draw of the continuation; call_base = number of draws already consumed (keeps the
+ * Philox call ids of the two halves apart).  iters_out_dev [n_iters + 1][B][H][W] as for ipdm_guided_process.
+ */
+int ipdm_guided_process_resume(ipdm_unet* net, const ipdm_guided_params* p, const float* img_dev, const float* ldct_dev,
+                               const float* noise_dev, const float* lam_exp_dev, uint64_t call_base, float* iters_out_dev,
+                               int batch, int h, int w, void* workspace_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Single-kernel entry points used by the per-kernel parity tests (tests/test_unet_kernels_gpu.py).

@@ -11,7 +11,7 @@ libipdm_b200.so:
     caller-supplied tape [count,B,1,H,W] in the reference's randn_like order, `seed=` keys the
     in-kernel Philox generator otherwise.
   * `ddim_sample` / `sparse_guided_reverse_process` (:654-759): host loop over UNet forward + fused DDIM step.
-Out of scope here (reference lines): train_losses :645-652, Yeo-Johnson :762-807, adaptive t_start=None :582-613.
+Out of scope here (reference lines): train_losses :645-652, Yeo-Johnson :762-807.
 """
 import math
 from copy import copy
@@ -230,13 +230,73 @@ class GaussianDiffusion:
             raise NotImplementedError("save_states=True copies every reverse step to the host; not on the B200 path")
         ks = kwargs.get("kernel_size_proj" if mode == "proj" else "kernel_size_img", 4)
         amp = kwargs.get("amplitude_proj" if mode == "proj" else "amplitude_img", 7.0)
-        p = _eng.guided_params(mode, copy(t_start), clip, lambda_ratio, eta, constant_guidance, ks, amp, self.schedule_power,
-                               self.timesteps, seed)
         img = img.contiguous().float()
         ldct = kwargs.get("ldct", None)
+        ldct = None if ldct is None else ldct.contiguous().float()
+        if t_start is None:
+            return self._adaptive_schedule_process(model, img, clip, lambda_ratio, mode, constant_guidance, ks, amp, ldct,
+                                                   kwargs.get("noise_strength", None), noise, seed)
+        p = _eng.guided_params(mode, copy(t_start), clip, lambda_ratio, eta, constant_guidance, ks, amp, self.schedule_power,
+                               self.timesteps, seed)
         model.ensure_max_t(max(t_start) + 1)
-        out = _eng.guided_process(model.cuda_handle(), p, img, None if ldct is None else ldct.contiguous().float(), noise)
+        out = _eng.guided_process(model.cuda_handle(), p, img, ldct, noise)
         return [out[k] for k in range(out.shape[0])], [], None
+
+    # schedules of the adaptive branch (reference Model/model.py:582-613): (t_start list, eta) per noise-strength class
+    _ADAPTIVE_PROJ = {"high": ([30, 25, 20], 0.6), "mid": ([20, 18, 15], 0.5), "low": ([15, 15, 15], 0.5)}
+    _ADAPTIVE_IMG = {"high": ([15, 15, 15], 0.6), "mid": ([15, 12, 10], 0.55), "low": ([10, 10, 10], 0.5)}
+
+    def _adaptive_schedule_process(self, model, img, clip, lambda_ratio, mode, constant_guidance, ks, amp, ldct, noise_strength, noise, seed):
+        """t_start=None (reference :531-535, 582-613, 639-640): a probing iteration with t_start = 20 and the cosine lambda schedule,
+        then the schedule and eta are picked PER SLICE -- projection domain: from max(exp(amplitude * delta-map)) (>= 30 high, >= 4.5 mid,
+        else low); image domain: from the `noise_strength` the projection stage reported -- and the process continues from the input
+        with the per-pixel lambda map.  The only host round trip is one read of B floats (projection domain); slices that picked the
+        same schedule continue as one batch.  Returns (iterates without the probe + mean of the last two, [], noise_strength) where
+        noise_strength is the reference's string for one slice (or when all slices agree) and a per-slice list otherwise."""
+        if constant_guidance is not None:
+            raise ValueError("t_start=None with a constant guidance returns an empty list in the reference (the schedule is only "
+                             "selected in the adaptive-lambda branch, Model/model.py:575); pass constant_guidance=None or explicit lists")
+        B = img.shape[0]
+        model.ensure_max_t(31)
+        handle = model.cuda_handle()
+        probe_p = _eng.guided_params(mode, [20], clip, lambda_ratio, 0.5, None, ks, amp, self.schedule_power, self.timesteps, seed)
+        probe = _eng.guided_process(handle, probe_p, img, ldct, None if noise is None else noise[:21])[0]
+        if mode == "proj":
+            lam_exp = _eng.delta_lambda_map(probe, img, ks, amp, "proj")
+            dmax = _eng.delta_exp_max(probe, img, ks, amp).cpu().numpy()            # the one device -> host read of this branch
+            classes = ["high" if v >= 30 else ("mid" if v >= 4.5 else "low") for v in dmax]
+            table = self._ADAPTIVE_PROJ
+        else:
+            lam_exp = _eng.delta_lambda_map_img(probe, img, ks, amp)
+            ns = noise_strength if isinstance(noise_strength, (list, tuple)) else [noise_strength] * B
+            if len(ns) != B:
+                raise ValueError(f"noise_strength holds {len(ns)} entries for a batch of {B} slices")
+            classes = ["low" if v is None else v for v in ns]
+            table = self._ADAPTIVE_IMG
+        if any(c not in table for c in classes):
+            raise ValueError(f"noise_strength must be 'high', 'mid', 'low' or None, got {sorted(set(classes))}")
+        out = None
+        for cls in sorted(set(classes)):
+            idx = [j for j, c in enumerate(classes) if c == cls]
+            whole = len(idx) == B
+            sel = torch.tensor(idx, device=img.device)
+            take = (lambda t: t) if whole else (lambda t: t.index_select(0, sel).contiguous())
+            ts_list, eta = table[cls]
+            p = _eng.guided_params(mode, list(ts_list), clip, lambda_ratio, eta, None, ks, amp, self.schedule_power, self.timesteps, seed)
+            tape = None
+            if noise is not None:
+                tape = noise[21:] if whole else noise[21:].index_select(1, sel).contiguous()
+            res = _eng.guided_process_resume(handle, p, take(img), take(lam_exp), 21, None if ldct is None else take(ldct), tape)
+            if whole:
+                out = res
+            else:
+                out = torch.empty((res.shape[0], B) + tuple(res.shape[2:]), device=img.device) if out is None else out
+                out.index_copy_(1, sel, res)
+        if mode == "img":
+            strength = noise_strength
+        else:
+            strength = classes[0] if len(set(classes)) == 1 else classes
+        return [out[k] for k in range(out.shape[0])], [], strength
 
     @torch.no_grad()
     def ddim_sample(self, sample_img, model, condition, t_start, condition_lambda=0.5, batch_size=1, ddim_timesteps=2,

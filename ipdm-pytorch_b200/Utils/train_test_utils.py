@@ -281,7 +281,13 @@ class progressive_domain_denoiser:
                 clip_denoised=True, ddim_timesteps=o.ddim_timesteps_img, eta=o.eta_img,
                 noise=None if noise is None else noise[:n_count], seed=self._stage_seed(1))
         else:
-            n_count = sum(o.t_start_img) + len(o.t_start_img)
+            if o.t_start_img is not None:
+                n_count = sum(o.t_start_img) + len(o.t_start_img)
+            elif noise is not None:                                            # adaptive schedule (t_start_img=None) with a noise tape
+                cls = set(noise_strength) if isinstance(noise_strength, (list, tuple)) else {noise_strength}
+                if len(cls) != 1:
+                    raise ValueError("a noise tape with t_start_img=None needs one noise_strength class for the whole batch (the tape order is per slice)")
+                n_count = 21 + sum(GaussianDiffusion._ADAPTIVE_IMG[cls.pop() or "low"][0]) + 3
             result, _, _ = self.img_gaussian_diffusion.guided_reverse_process(
                 img=x, t_start=o.t_start_img, eta=o.eta_img, constant_guidance=o.constant_guidance_img,
                 noise=None if noise is None else noise[:n_count], seed=self._stage_seed(1), **common)

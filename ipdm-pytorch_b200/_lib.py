@@ -62,6 +62,7 @@ _SIGNATURES = {
                                              ctypes.c_int, vp, vp]),
     "ipdm_delta_lambda_map_img": (ctypes.c_int, [vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float,
                                                  ctypes.c_int, vp, vp]),
+    "ipdm_delta_exp_max": (ctypes.c_int, [vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float, vp, vp]),
     "ipdm_lambda_step_map": (ctypes.c_int, [vp, vp, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, vp]),
     "ipdm_lambda_curve_host": (ctypes.c_int, [vp, vp, ctypes.c_size_t, ctypes.c_int]),
     "ipdm_sharpen3x3": (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp]),
@@ -74,6 +75,8 @@ _SIGNATURES = {
     "ipdm_guided_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(GuidedParams), ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "ipdm_guided_process": (ctypes.c_int, [vp, ctypes.POINTER(GuidedParams), vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                            vp, vp]),
+    "ipdm_guided_process_resume": (ctypes.c_int, [vp, ctypes.POINTER(GuidedParams), vp, vp, vp, vp, ctypes.c_uint64, vp, ctypes.c_int,
+                                                  ctypes.c_int, ctypes.c_int, vp, vp]),
     "ipdm_debug_conv": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                        vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, vp, ctypes.c_int,
                                        vp, ctypes.c_int, ctypes.c_int, vp]),

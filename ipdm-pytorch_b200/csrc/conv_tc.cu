@@ -862,6 +862,250 @@ conv_halo_persistent_kernel(const __grid_constant__ ConvTcParams P) {
     if (warp == 2) tc::tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
+// ================================================================================================
+// GroupNorm-fused persistent halo kernel: the conv reads the RAW fp32 residual-stream tensor(s) and applies the GroupNorm
+// affine + SiLU of the reference's `norm -> SiLU -> conv` (Model/model.py:98-101, 110-113) on the operand path, so the
+// separate apply pass (4 B read + 2-4 B written per element, 18 % of the step in round 1) and the operand tensor disappear.
+//
+//   warp 0          TMA producer: ring of 2 RAW halo tiles [10 rows][32 px][32 ch fp32 = 128 B] (one 4-D box per 32-channel
+//                   K chunk of the virtual concat, OOB zero fill), ring of NB weight tiles
+//   warps 2,3,12,13 transform: raw tile -> y = silu(x * scale[slice][c] + shift[slice][c]), zero outside the image (the conv's
+//                   zero padding applies to the normalised activation), rounded exactly like the unfused apply pass:
+//                     BF16: bf16, written as a K-major SWIZZLE_64B operand tile (64-byte pixel rows) into a second ring of 2
+//                     TF32: tf32, written back IN PLACE (the TMA tile is already a SWIZZLE_128B operand tile)
+//                   then fence.proxy.async + arrive on `a_ready`
+//   warp 1          MMA issuer: as conv_halo_persistent_kernel, operands from the transformed tile
+//   warps 4-11      two epilogue warpgroups (unchanged)
+// The per-(slice, channel) scale / shift come from gn_finalize (statistics from the producer conv's epilogue), so the results are
+// bit-identical to apply + conv.
+// ================================================================================================
+constexpr int HF_THREADS = 448;
+constexpr int HF_RAW_BYTES = HALO_A_BYTES;                            // 40 KB: [10][32 px][128 B]
+constexpr int HF_OP_BYTES_BF16 = (HALO_TH + 2) * HALO_RP * 64;        // 20 KB: [10][32 px][64 B]
+constexpr int HF_OP_STRIDE_BF16 = HF_OP_BYTES_BF16 + 1024;            // + the 2 pixels the last tap over-reads
+template <int BLOCK_N, int NB, bool BF16>
+struct HaloFusedSmem {
+    static constexpr int B_BYTES = BLOCK_N * (BF16 ? 64 : 128);
+    static constexpr int RAW_STRIDE = BF16 ? HF_RAW_BYTES : HALO_A_STRIDE;
+    static constexpr int OFF_OP = 2 * RAW_STRIDE;                      // BF16 only
+    static constexpr int OFF_B = OFF_OP + (BF16 ? 2 * HF_OP_STRIDE_BF16 : 0);
+    static constexpr int BAR_OFF = OFF_B + NB * B_BYTES;
+    static constexpr int BIAS_OFF = BAR_OFF + 512;
+    static constexpr int MAX_COUT = 512;
+    static constexpr int EPI_OFF = BIAS_OFF + MAX_COUT * 4;
+    static constexpr int TOTAL = EPI_OFF + 8 * EPI_WARP_FLOATS * 4 + 1024;
+    static_assert((2 * NB + 14) * 8 + 16 <= 512, "barrier block");
+};
+
+template <int BLOCK_N, int NB, bool BF16>
+__global__ void __launch_bounds__(HF_THREADS, 1)
+conv_halo_fused_kernel(const __grid_constant__ ConvTcParams P) {
+    using S = HaloFusedSmem<BLOCK_N, NB, BF16>;
+    constexpr int ACC_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
+    constexpr int TMEM_COLS = 4 * ACC_COLS;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* raw_full = (uint64_t*)(smem + S::BAR_OFF);   // [2] TMA landed a raw tile
+    uint64_t* raw_empty = raw_full + 2;                    // [2] BF16: the transform warps have read it (4 arrivals)
+    uint64_t* a_ready = raw_empty + 2;                     // [2] operand tile written (4 arrivals)
+    uint64_t* a_empty = a_ready + 2;                       // [2] MMAs have read the operand tile
+    uint64_t* b_full = a_empty + 2;
+    uint64_t* b_empty = b_full + NB;
+    uint64_t* tfull = b_empty + NB;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
+    float* sbias = (float*)(smem + S::BIAS_OFF);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_per_img = P.tiles_x * P.tiles_y;
+    const int n_ntiles = P.cout / BLOCK_N;
+    const int total_tiles = tiles_per_img * P.batch * n_ntiles;
+    const int nk = P.nk0 + P.nk1;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; ++i) { tc::mbar_init(&raw_full[i], 1); tc::mbar_init(&raw_empty[i], 4); tc::mbar_init(&a_ready[i], 4); tc::mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < NB; ++i) { tc::mbar_init(&b_full[i], 1); tc::mbar_init(&b_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { tc::mbar_init(&tfull[i], 1); tc::mbar_init(&tempty[i], 256); }
+        tc::fence_barrier_init();
+    }
+    if (warp == 2) tc::tmem_alloc(tmem_slot, TMEM_COLS);
+    if (warp == 0 && lane == 0) { tc::prefetch_tmap(&P.mapA[0]); tc::prefetch_tmap(&P.mapB); }
+    {
+        const float* bias = P.bias ? P.bias + (P.t_dev ? (size_t)(*P.t_dev) * P.bias_t_stride : 0) : nullptr;
+        for (int i = threadIdx.x; i < P.cout; i += HF_THREADS) sbias[i] = bias ? __ldg(bias + i) : 0.f;
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    auto decode = [&](int tile, int& b, int& x0, int& y0, int& n0) {
+        const int nt = tile % n_ntiles, mt = tile / n_ntiles;
+        b = mt / tiles_per_img;
+        const int tr = mt - b * tiles_per_img;
+        const int tyi = tr / P.tiles_x, txi = tr - tyi * P.tiles_x;
+        x0 = txi * HALO_TWV; y0 = tyi * HALO_TH; n0 = nt * BLOCK_N;
+    };
+    const bool is_transform = warp == 2 || warp == 3 || warp == 12 || warp == 13;
+
+    if (warp == 0) {
+        if (tc::elect_one()) {
+            int ia = 0, ib = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                int b, x0, y0, n0; decode(tile, b, x0, y0, n0);
+                for (int kc = 0; kc < nk; ++kc, ++ia) {
+                    const int sa = ia & 1;
+                    // the raw buffer is free once the transform warps have read it (BF16) / once the MMAs have read the in-place tile (TF32)
+                    tc::mbar_wait(BF16 ? &raw_empty[sa] : &a_empty[sa], (((uint32_t)ia >> 1) & 1u) ^ 1u);
+                    tc::mbar_expect_tx(&raw_full[sa], HF_RAW_BYTES);
+                    const bool first = kc < P.nk0;
+                    tc::tma_load_4d(smem + sa * S::RAW_STRIDE, first ? &P.mapA[0] : &P.mapA[1], &raw_full[sa], (first ? kc : kc - P.nk0) * 32,
+                                    x0 - 1, y0 - 1, b);
+                    for (int tap = 0; tap < 9; ++tap, ++ib) {
+                        const int sb = ib % NB;
+                        tc::mbar_wait(&b_empty[sb], ((uint32_t)(ib / NB) & 1u) ^ 1u);
+                        tc::mbar_expect_tx(&b_full[sb], S::B_BYTES);
+                        tc::tma_load_2d(smem + S::OFF_B + sb * S::B_BYTES, &P.mapB, &b_full[sb], kc * 32, tap * P.cout_rows + n0);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (tc::elect_one()) {
+            const uint32_t idesc = tc::make_idesc(BF16 ? tc::FMT_BF16 : tc::FMT_TF32, 128, BLOCK_N);
+            constexpr int ROWB = BF16 ? 64 : 128;              // bytes per pixel row of the operand tile
+            constexpr int KSTEPS = ROWB / 32;                  // 32 bytes of K per MMA
+            int ia = 0, ib = 0, tl = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
+                const int buf = tl & 1;
+                tc::mbar_wait(&tempty[buf], (((uint32_t)tl >> 1) & 1u) ^ 1u);
+                tc::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + buf * 2 * ACC_COLS;
+                for (int kc = 0; kc < nk; ++kc, ++ia) {
+                    const int sa = ia & 1;
+                    tc::mbar_wait(&a_ready[sa], ((uint32_t)ia >> 1) & 1u);
+                    const uint32_t a_base = tc::smem_u32(smem + (BF16 ? S::OFF_OP + sa * HF_OP_STRIDE_BF16 : sa * S::RAW_STRIDE));
+                    for (int tap = 0; tap < 9; ++tap, ++ib) {
+                        const int sb = ib % NB;
+                        tc::mbar_wait(&b_full[sb], (uint32_t)(ib / NB) & 1u);
+                        tc::tc_fence_after();
+                        const int dy = tap / 3, dx = tap - dy * 3;
+                        const uint32_t b_addr = tc::smem_u32(smem + S::OFF_B + sb * S::B_BYTES);
+                        const uint64_t bdesc = BF16 ? tc::smem_desc_k(b_addr, 4, 512) : tc::smem_desc_k_sw128(b_addr);
+#pragma unroll
+                        for (int mt = 0; mt < 2; ++mt) {
+                            const uint32_t a_addr = a_base + (uint32_t)(((4 * mt + dy) * HALO_RP + dx) * ROWB);
+                            const uint64_t adesc = BF16 ? tc::smem_desc_k(a_addr, 4, 512) : tc::smem_desc_k_sw128(a_addr);
+#pragma unroll
+                            for (int k = 0; k < KSTEPS; ++k) {
+                                const uint32_t acc = (uint32_t)((kc | tap | k) != 0);
+                                if (BF16) tc::umma_f16(d_tmem + mt * ACC_COLS, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, acc);
+                                else tc::umma_tf32(d_tmem + mt * ACC_COLS, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, acc);
+                            }
+                        }
+                        tc::umma_commit(&b_empty[sb]);
+                    }
+                    tc::umma_commit(&a_empty[sa]);
+                }
+                tc::umma_commit(&tfull[buf]);
+            }
+        }
+        __syncwarp();
+    } else if (is_transform) {
+        const int w4 = warp < 4 ? warp - 2 : warp - 10;              // 0..3: 80 of the 320 tile pixels each
+        const int c8 = lane & 7, psub = lane >> 3;                   // 16-byte chunk (4 channels) of the pixel row; pixel within a group of 4
+        const int Ctot = P.gn_c0 + P.gn_c1;
+        int ia = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            int b, x0, y0, n0; decode(tile, b, x0, y0, n0);
+            for (int kc = 0; kc < nk; ++kc, ++ia) {
+                const int sa = ia & 1;
+                // per-lane affine of its 4 channels (pad channels of the source tensors: scale = shift = 0 -> silu(0) = 0)
+                float4 sc = make_float4(0.f, 0.f, 0.f, 0.f), sh = sc;
+                {
+                    const bool first = kc < P.nk0;
+                    const int cl = (first ? kc : kc - P.nk0) * 32 + 4 * c8;          // channel inside its source
+                    const int cg = first ? cl : P.gn_c0 + cl;                        // channel of the GroupNorm (virtual concat)
+                    if (cl < (first ? P.gn_c0 : P.gn_c1)) {
+                        sc = __ldg(reinterpret_cast<const float4*>(P.gn_scale + (size_t)b * Ctot + cg));
+                        sh = __ldg(reinterpret_cast<const float4*>(P.gn_shift + (size_t)b * Ctot + cg));
+                    }
+                }
+                tc::mbar_wait(&raw_full[sa], ((uint32_t)ia >> 1) & 1u);
+                if (BF16) tc::mbar_wait(&a_empty[sa], (((uint32_t)ia >> 1) & 1u) ^ 1u);     // the operand buffer of this stage is free
+                const uint8_t* raw = smem + sa * S::RAW_STRIDE;
+                uint8_t* op = smem + S::OFF_OP + sa * HF_OP_STRIDE_BF16;
+#pragma unroll 4
+                for (int j = 0; j < 20; ++j) {
+                    const int r = w4 * 80 + j * 4 + psub;                             // pixel of the halo tile: row r >> 5, column r & 31
+                    const int yy = y0 - 1 + (r >> 5), xx = x0 - 1 + (r & 31);
+                    const bool inside = (unsigned)yy < (unsigned)P.H && (unsigned)xx < (unsigned)P.W;
+                    const uint32_t roff = (uint32_t)r * 128u + (uint32_t)((c8 ^ (r & 7)) << 4);        // TMA SWIZZLE_128B: 16-byte chunk ^ (row & 7)
+                    const float4 v = *reinterpret_cast<const float4*>(raw + roff);
+                    float4 o;
+                    o.x = fmaf(v.x, sc.x, sh.x); o.y = fmaf(v.y, sc.y, sh.y); o.z = fmaf(v.z, sc.z, sh.z); o.w = fmaf(v.w, sc.w, sh.w);
+                    if (P.gn_act) { o.x = silu(o.x); o.y = silu(o.y); o.z = silu(o.z); o.w = silu(o.w); }
+                    if (!inside) o = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (BF16) {
+                        const __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+                        uint2 pk; pk.x = *reinterpret_cast<const uint32_t*>(&lo); pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+                        // SWIZZLE_64B operand row r (64 bytes): 16-byte chunk (c8 >> 1) ^ ((r >> 1) & 3), 8-byte half c8 & 1
+                        const uint32_t ooff = (uint32_t)r * 64u + (uint32_t)((((c8 >> 1) ^ ((r >> 1) & 3)) << 4) | ((c8 & 1) << 3));
+                        *reinterpret_cast<uint2*>(op + ooff) = pk;
+                    } else {
+                        o.x = tf32_rn(o.x); o.y = tf32_rn(o.y); o.z = tf32_rn(o.z); o.w = tf32_rn(o.w);
+                        *reinterpret_cast<float4*>(const_cast<uint8_t*>(raw) + roff) = o;
+                    }
+                }
+                tc::fence_proxy_async();                 // generic-proxy writes -> visible to the tensor core's async proxy
+                __syncwarp();
+                if (lane == 0) {
+                    tc::mbar_arrive(&a_ready[sa]);
+                    if (BF16) tc::mbar_arrive(&raw_empty[sa]);
+                }
+            }
+        }
+    } else if (warp >= 4 && warp < 12) {
+        const int mt = (warp - 4) >> 2;
+        float* stile = (float*)(smem + S::EPI_OFF) + (warp - 4) * EPI_WARP_FLOATS;
+        int tl = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
+            const int buf = tl & 1;
+            int b, x0, y0, n0; decode(tile, b, x0, y0, n0);
+            tc::mbar_wait(&tfull[buf], ((uint32_t)tl >> 1) & 1u);
+            tc::tc_fence_after();
+            float* srow = nullptr;
+            if (P.stats_out) {
+                const int tr = tile / n_ntiles - b * tiles_per_img;
+                srow = P.stats_out + ((size_t)b * P.stats_rows + (tr * 2 + mt) * 4 + (warp & 3)) * 2 * P.cout;
+            }
+            tc_epilogue_coalesced<BLOCK_N>(P, tmem_base + (buf * 2 + mt) * ACC_COLS, warp & 3, lane, b, x0, y0 + 4 * mt, n0, sbias + n0, stile,
+                                           HALO_TWV, srow);
+            tc::tc_fence_before();
+            tc::mbar_arrive(&tempty[buf]);
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tc::tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+template <int BN, int NB, bool BF16>
+static int launch_halo_fused(const ConvTcParams& P, cudaStream_t st) {
+    static DeviceOnce once;
+    constexpr int smem = HaloFusedSmem<BN, NB, BF16>::TOTAL;
+    static_assert(smem <= 227 * 1024, "fused halo rings do not fit in shared memory");
+    if (once.need()) {
+        IPDM_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_fused_kernel<BN, NB, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    }
+    const int total = P.tiles_x * P.tiles_y * P.batch * (P.cout / BN);
+    conv_halo_fused_kernel<BN, NB, BF16><<<std::min(total, kNumSMs), HF_THREADS, smem, st>>>(P);
+    count_launch();
+    IPDM_CHECK_LAUNCH();
+    return IPDM_OK;
+}
+
 template <int BN, int NB>
 static int launch_halo_pers(const ConvTcParams& P, cudaStream_t st) {
     static DeviceOnce once;
@@ -910,6 +1154,21 @@ int conv_tc_stats_rows_bound(int h, int w) {
     return 4 * std::max(halo, tap);
 }
 
+// auto choice of the halo-reuse kernels (see conv_tc_prepare): stride-1 3x3, enough tiles to fill the machine, and an 8x30 tiling that wastes
+// < 20 % of the MMA rows -- or a narrow (C_out < 64) layer
+static bool halo_auto(int H, int W, int batch, int cout, int ntaps, int stride) {
+    const long long htx = ceil_div(W, HALO_TWV), hty = ceil_div(H, HALO_TH);
+    const bool halo_ok = stride == 1 && ntaps == 9 && htx * hty * batch >= kNumSMs / 2;
+    const bool halo_fits = (double)W * H >= 0.8 * (double)(htx * HALO_TWV) * (double)(hty * HALO_TH);
+    return halo_ok && (cout < 64 || halo_fits);
+}
+// true when a GroupNorm(+SiLU) -> conv pair of this shape runs as ONE conv_halo_fused_kernel launch (plan builder, unet.cu)
+bool conv_tc_can_fuse_norm(int H, int W, int batch, int cout, int ntaps, int stride) {
+    static const bool off = getenv("IPDM_GN_FUSE") && atoi(getenv("IPDM_GN_FUSE")) == 0;
+    static const int env_variant = getenv("IPDM_CONV_VARIANT") ? atoi(getenv("IPDM_CONV_VARIANT")) : 0;
+    return !off && env_variant == 0 && cout >= 64 && cout <= 512 && cout % 64 == 0 && halo_auto(H, W, batch, cout, ntaps, stride);
+}
+
 int conv_tc_prepare(ConvTcParams& P, const ConvTcDesc& d) {
     IPDM_REQUIRE(d.nsrc >= 1 && d.nsrc <= 2, "conv_tc: 1 or 2 sources");
     IPDM_REQUIRE(d.stride == 1 || (d.stride == 2 && d.nsrc == 1), "conv_tc: stride 2 takes one source");
@@ -931,8 +1190,7 @@ int conv_tc_prepare(ConvTcParams& P, const ConvTcDesc& d) {
     const bool narrow = d.cout < 64;
     const long long htx = ceil_div(P.W, HALO_TWV), hty = ceil_div(P.H, HALO_TH);
     const bool halo_ok = plain && d.stride == 1 && d.ntaps == 9 && htx * hty * P.batch >= kNumSMs / 2;
-    const bool halo_fits = (double)P.W * P.H >= 0.8 * (double)(htx * HALO_TWV) * (double)(hty * HALO_TH);
-    P.halo = halo_ok && (variant == 2 || variant == 4 || (variant == 0 && (narrow || halo_fits)));
+    P.halo = halo_ok && (variant == 2 || variant == 4 || (variant == 0 && halo_auto(P.H, P.W, P.batch, d.cout, d.ntaps, d.stride)));
     P.persistent = plain && (P.halo ? (variant == 4 || (variant == 0 && !narrow)) : (variant == 0 || variant == 3 || variant == 4));
     P.tw_log2 = P.halo ? 5 : pick_tw_log2(P.H, P.W);
     const int TW = P.halo ? HALO_RP : 1 << P.tw_log2, TH = P.halo ? HALO_TH + 2 : 128 >> P.tw_log2;     // TMA box extent
@@ -943,14 +1201,23 @@ int conv_tc_prepare(ConvTcParams& P, const ConvTcDesc& d) {
     IPDM_REQUIRE(d.cout % P.block_n == 0, "conv_tc: C_out %d not a multiple of the N tile %d", d.cout, P.block_n);
     P.cout_rows = d.cout;
     int ktot = 0;
-    P.bf16 = d.src[0].bf16;
-    P.kc = P.bf16 ? 64 : 32;
-    const int eb = P.bf16 ? 2 : 4;
-    const CUtensorMapDataType dt = P.bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    // fused GroupNorm: the sources are RAW fp32 tensors whatever the operand type (the kernel converts on the operand path)
+    P.fused = d.norm_scale != nullptr;
+    if (P.fused) {
+        IPDM_REQUIRE(P.halo && P.persistent && d.cout >= 64 && d.cout <= 512 && d.norm_shift, "conv_tc: GroupNorm fusion needs a persistent halo layer (3x3, stride 1, C_out 64..512)");
+        IPDM_REQUIRE(d.nsrc == 1 || d.src[0].c == d.src[0].cs, "conv_tc: fused concat needs an unpadded first source (%d channels, stride %d)", d.src[0].c, d.src[0].cs);
+        P.gn_scale = d.norm_scale; P.gn_shift = d.norm_shift; P.gn_act = d.act_silu;
+        P.gn_c0 = d.src[0].c; P.gn_c1 = d.nsrc > 1 ? d.src[1].c : 0;
+        IPDM_REQUIRE(P.gn_c0 % 4 == 0 && P.gn_c1 % 4 == 0, "conv_tc: fused GroupNorm needs channel counts that are multiples of 4");
+    }
+    P.bf16 = P.fused ? d.w_bf16 : d.src[0].bf16;
+    P.kc = P.fused ? 32 : (P.bf16 ? 64 : 32);
+    const int eb = (P.bf16 && !P.fused) ? 2 : 4;                      // element size of the activation tensors the TMA reads
+    const CUtensorMapDataType dt = (P.bf16 && !P.fused) ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
     IPDM_REQUIRE(!(P.bf16 && d.w_packed_lo), "conv_tc: bf16 operands and the 3xTF32 split are exclusive");
     for (int s = 0; s < d.nsrc; ++s) {
         const TensorNHWC& t = d.src[s];
-        IPDM_REQUIRE(t.bf16 == P.bf16, "conv_tc: concat sources differ in dtype");
+        IPDM_REQUIRE(t.bf16 == (P.bf16 && !P.fused), "conv_tc: concat sources differ in dtype");
         IPDM_REQUIRE(t.cs % P.kc == 0 && ((uintptr_t)t.p % 16) == 0, "conv_tc: source channel stride %d must be a multiple of %d", t.cs, P.kc);
         IPDM_REQUIRE(t.h == Hin && t.w == Win && t.n == P.batch, "conv_tc: concat sources differ in shape");
         (s == 0 ? P.nk0 : P.nk1) = t.cs / P.kc;
@@ -972,12 +1239,15 @@ int conv_tc_prepare(ConvTcParams& P, const ConvTcDesc& d) {
                 }
         }
     }
-    IPDM_REQUIRE(ktot == d.w_k, "conv_tc: packed weight K %d != sum of source channel strides %d", d.w_k, ktot);
+    // (fused bf16: the weights keep their operand-tensor K padding to 64; the trailing all-zero 32-column chunk is simply not walked)
+    IPDM_REQUIRE(ktot == d.w_k || (P.fused && ktot <= d.w_k), "conv_tc: packed weight K %d != sum of source channel strides %d", d.w_k, ktot);
     {
+        const int ebw = P.bf16 ? 2 : 4;
+        const CUtensorMapDataType dtw = P.bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
         const uint64_t dims[2] = {(uint64_t)d.w_k, (uint64_t)d.ntaps * d.cout};
-        const uint64_t str[1] = {(uint64_t)d.w_k * eb};
+        const uint64_t str[1] = {(uint64_t)d.w_k * ebw};
         const uint32_t box[2] = {(uint32_t)P.kc, (uint32_t)P.block_n};
-        IPDM_CHECK(tmap_encode(&P.mapB, dt, 2, d.w_packed, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B));
+        IPDM_CHECK(tmap_encode(&P.mapB, dtw, 2, d.w_packed, dims, str, box, (P.fused && P.bf16) ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B));
         P.split = d.w_packed_lo != nullptr;
         if (P.split) IPDM_CHECK(tmap_encode(&P.mapBlo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, d.w_packed_lo, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B));
     }
@@ -1029,6 +1299,12 @@ static int launch_halo(const ConvTcParams& P, cudaStream_t st) {
 int conv_tc_launch(const ConvTcParams& P, cudaStream_t st) {
     // padded-K FLOPs actually issued to the tensor pipe; the persistent halo kernel (the dominant kernel of the step) is its own family
     ProfScope prof(P.halo && P.persistent ? PROF_CONV_HALO_PERS : PROF_CONV_TC, st, conv_tc_flops(P));
+    if (P.fused) {
+        if (P.bf16) { if (P.block_n == 128) return launch_halo_fused<128, 8, true>(P, st); if (P.block_n == 64) return launch_halo_fused<64, 12, true>(P, st); }
+        else { if (P.block_n == 128) return launch_halo_fused<128, 6, false>(P, st); if (P.block_n == 64) return launch_halo_fused<64, 10, false>(P, st); }
+        set_error("conv_tc_launch: no fused kernel for N tile %d", P.block_n);
+        return IPDM_ERR_UNSUPPORTED;
+    }
     if (P.halo && P.persistent) {
         switch (P.block_n) {
             case 128: return launch_halo_pers<128, 6>(P, st);

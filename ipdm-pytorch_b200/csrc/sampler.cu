@@ -362,6 +362,34 @@ __global__ void delta_map_kernel(const float* __restrict__ x, const float* __res
     }
 }
 
+// Adaptive schedule selection (model.py:596-613): max over the slice of exp(amplitude * relu(avg_pool(|x - img| - median))).  exp is monotone,
+// so the maximum of the pooled relu map is reduced (as a uint bit pattern: the values are >= 0) and exponentiated once.
+__global__ void delta_pool_max_kernel(const float* __restrict__ x, const float* __restrict__ img, const unsigned* __restrict__ sel,
+                                      unsigned* __restrict__ dmax_bits, int h, int w, int ks, int lh, int lw) {
+    const int b = blockIdx.y;
+    const float med = __uint_as_float(sel[b * 4 + 0]);
+    const size_t n = (size_t)h * w;
+    float best = 0.f;
+    for (int cidx = blockIdx.x * blockDim.x + threadIdx.x; cidx < lh * lw; cidx += gridDim.x * blockDim.x) {
+        const int cy = cidx / lw, cx = cidx - cy * lw;
+        float s = 0.f;
+        for (int dy = 0; dy < ks; ++dy)
+            for (int dxx = 0; dxx < ks; ++dxx) {
+                const size_t i = (size_t)b * n + (size_t)(cy * ks + dy) * w + cx * ks + dxx;
+                s = __fadd_rn(s, __fsub_rn(fabsf(__fsub_rn(x[i], img[i])), med));
+            }
+        const float d = s / (float)(ks * ks);
+        best = fmaxf(best, d <= 0.f ? 0.f : d);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(&dmax_bits[b], __float_as_uint(best));
+}
+__global__ void delta_exp_kernel(const unsigned* __restrict__ dmax_bits, float* __restrict__ out, int batch, float amplitude) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < batch) out[b] = expf(__fmul_rn(amplitude, __uint_as_float(dmax_bits[b])));
+}
+
 // Image-domain variant (model.py:591-595): delt = avg_pool(|miu2pixel(x) - miu2pixel(img)|); delt -= median(delt); relu; curve(exp(amp * delt)).
 // Note the order: pool first, median of the POOLED map.  miu2pixel as Dataset/npz_data_loader.py:20-36 in fp32.
 __device__ __forceinline__ float miu2pixel_dev(float mu) {
@@ -599,6 +627,29 @@ extern "C" int ipdm_delta_lambda_map(const float* x, const float* img, float* la
     delta_map_kernel<<<dim3(ceil_div((long long)lh * lw, 256), batch), 256, 0, st>>>(x, img, ws.sel, lam_exp_out, median_out, h, w, ks, lh, lw, amplitude, make_curve(curve_kind));
     count_launch(7);
     IPDM_CHECK_LAUNCH();
+    return IPDM_OK;
+}
+
+extern "C" int ipdm_delta_exp_max(const float* x, const float* img, float* max_out, int batch, int h, int w, int ks, float amplitude,
+                                  void* workspace, void* stream) {
+    IPDM_REQUIRE(x && img && max_out && workspace && batch > 0 && ks > 0, "ipdm_delta_exp_max: bad arguments");
+    IPDM_REQUIRE(h % ks == 0 && w % ks == 0, "ipdm_delta_exp_max: H and W must be multiples of ks");
+    cudaStream_t st = (cudaStream_t)stream;
+    Ws ws = carve(workspace, batch);
+    const size_t n = (size_t)h * w;
+    IPDM_CHECK_CUDA(cudaMemsetAsync(ws.hist, 0, ws_hist(batch), st));
+    const int g = (int)std::min<size_t>((size_t)kNumSMs * 2, (n + 255) / 256);
+    for (int pass = 0; pass < 3; ++pass) {                                   // exact lower median of |x - img| per slice
+        select_hist_kernel<<<dim3(g, batch), 256, 0, st>>>(x, img, ws.hist, ws.sel, n, pass);
+        select_scan_kernel<<<batch, 256, 0, st>>>(ws.hist, ws.sel, n, pass);
+    }
+    const int lh = h / ks, lw = w / ks;
+    unsigned* bits = ws.hist;                                                // the histogram is idle (zeroed by the last scan pass)
+    delta_pool_max_kernel<<<dim3(std::min(ceil_div((long long)lh * lw, 256), kNumSMs * 4), batch), 256, 0, st>>>(x, img, ws.sel, bits, h, w, ks, lh, lw);
+    delta_exp_kernel<<<ceil_div(batch, 128), 128, 0, st>>>(bits, max_out, batch, amplitude);
+    count_launch(8);
+    IPDM_CHECK_LAUNCH();
+    IPDM_CHECK_CUDA(cudaMemsetAsync(ws.hist, 0, (size_t)batch * sizeof(unsigned), st));
     return IPDM_OK;
 }
 

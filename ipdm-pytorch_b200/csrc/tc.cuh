@@ -116,6 +116,16 @@ __device__ __forceinline__ uint64_t smem_desc_k_sw128(uint32_t saddr) {
     d |= (uint64_t)2 << 61;                       // SWIZZLE_128B
     return d;
 }
+// same for any swizzle width: layout 2 = SWIZZLE_128B, 4 = SWIZZLE_64B, 6 = SWIZZLE_32B; sbo = 8 rows x row bytes
+__device__ __forceinline__ uint64_t smem_desc_k(uint32_t saddr, int layout, int sbo) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(sbo >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)layout << 61;
+    return d;
+}
 // instruction descriptor: D fp32, A/B both `fmt` (1 = bf16, 2 = tf32), both K-major, M x N
 __host__ __device__ constexpr uint32_t make_idesc(int fmt, int m, int n) {
     return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);

@@ -409,6 +409,12 @@ struct PlanBuilder {
             push(ap);
             Op cv; cv.kind = Op::CONV_THIN; cv.nsrc = 1; cv.src[0] = a; cv.cw = &cw; cv.dst = dst; cv.res = res; cv.bias = bias; cv.bias_t_stride = bstride; cv.use_t = use_t;
             push(cv);
+        } else if (cw.tc && net->precision != IPDM_PREC_FP32 && cw.k == 3 && (nsrc == 1 || s0.c % 32 == 0) &&
+                   conv_tc_can_fuse_norm(s0.h, s0.w, pl->B, cw.cout, 9, 1)) {
+            // the conv applies the GroupNorm affine + SiLU itself on its operand path (conv_halo_fused_kernel): no apply pass, no operand tensor
+            Op cv; cv.kind = Op::CONV_TC; cv.nsrc = nsrc; cv.src[0] = src[0]; cv.src[1] = st.src[1]; cv.cw = &cw; cv.dst = dst; cv.res = res;
+            cv.bias = bias; cv.bias_t_stride = bstride; cv.use_t = use_t; cv.norm_slot = st.norm_slot; cv.gn = &gn; cv.act = act_silu;
+            push(cv);
         } else if (cw.tc) {
             const int a = new_tensor(pl->B, s0.h, s0.w, gn.C, cw.bf16 ? round_up(gn.C, 64) : round_up(gn.C, 32));
             pl->vt[a].bf16 = cw.bf16;
@@ -624,6 +630,7 @@ static int build_plan(ipdm_unet* net, int B, int H, int W, Plan** out) {
                     d.qkv_bf16 = v.bf16;
                 }
                 if (o.stats >= 0) d.stats_out = resolve(*pl, o.stats).p;
+                if (o.gn) { d.norm_scale = nscale; d.norm_shift = nshift; d.act_silu = o.act; d.w_bf16 = o.cw->bf16; }
                 IPDM_CHECK(conv_tc_prepare(o.tcp, d));
                 pl->vt[o.dst].stats_rows = o.tcp.stats_out ? o.tcp.stats_rows : 0;
                 o.flops = 2.0 * B * o.tcp.H * o.tcp.W * (double)o.cw->cin * o.cw->cout * d.ntaps;
@@ -809,10 +816,12 @@ extern "C" int ipdm_debug_conv(const float* src0, int c0, int cs0, const float* 
     const int ho = stride == 1 ? hin : (hin + 1) / 2, wo = stride == 1 ? win : (win + 1) / 2;
     int rc;
     if (use_tc) {
-        IPDM_REQUIRE(cs0 == cw.cs0 && (c1 == 0 || cs1 == cw.cs1), "ipdm_debug_conv: tensor-core sources need channel strides %d / %d", cw.cs0, cw.cs1);
-        IPDM_REQUIRE(upsample_h == 0 && !norm_scale, "ipdm_debug_conv: upsample / fused norm are direct-path features");
+        if (norm_scale) IPDM_REQUIRE(cs0 % 32 == 0 && cs1 % 32 == 0 && cs0 + cs1 <= cw.kpad && (c1 == 0 || c0 == cs0), "ipdm_debug_conv: fused sources need channel strides that are multiples of 32");
+        else IPDM_REQUIRE(cs0 == cw.cs0 && (c1 == 0 || cs1 == cw.cs1), "ipdm_debug_conv: tensor-core sources need channel strides %d / %d", cw.cs0, cw.cs1);
+        IPDM_REQUIRE(upsample_h == 0, "ipdm_debug_conv: upsample is a direct-path feature");
         ConvTcDesc d; d.nsrc = c1 ? 2 : 1; d.src[0] = mk(src0, n, h, w, c0, cs0); if (c1) d.src[1] = mk(src1, n, h, w, c1, cs1);
-        d.src[0].bf16 = cw.bf16;
+        d.src[0].bf16 = cw.bf16 && !norm_scale;
+        if (norm_scale) { d.norm_scale = norm_scale; d.norm_shift = norm_shift; d.w_bf16 = cw.bf16; }       // fused GroupNorm + SiLU: raw fp32 sources
         d.ntaps = k * k; d.stride = stride; d.cout = cout; d.w_packed = cw.w_dev; d.w_packed_lo = cw.w_dev_lo; d.w_k = cw.kpad; d.bias = cw.b_dev;
         if (res) d.res = mk(res, n, ho, wo, cout, res_cs);
         d.out = mk(out, n, ho, wo, cout, out_cs);

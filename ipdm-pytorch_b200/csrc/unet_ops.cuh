@@ -37,8 +37,12 @@ struct ConvTcDesc {
     // GroupNorm statistics of the OUTPUT, fused into the persistent kernels' epilogue: per (slice, 32-pixel warp row) partial sums
     // [batch][stats_rows][2][cout] (sum, sum of squares; fp32 over 32 pixels, reduced in fp64 by gn_finalize).  nullptr: off.
     float* stats_out = nullptr;
+    // fused GroupNorm(+SiLU) of the input (conv_halo_fused_kernel): src[] are the RAW fp32 tensors, y = act(x*scale[n][c] + shift[n][c]) is
+    // applied on the operand path; w_bf16 says whether w_packed (and hence the MMA) is bf16 or tf32
+    const float* norm_scale = nullptr; const float* norm_shift = nullptr; int act_silu = 1; int w_bf16 = 0;
 };
-int conv_tc_stats_rows_bound(int h, int w);            // upper bound of stats_rows for an h x w output, any kernel variant
+int conv_tc_stats_rows_bound(int h, int w);
+bool conv_tc_can_fuse_norm(int H, int W, int batch, int cout, int ntaps, int stride);            // upper bound of stats_rows for an h x w output, any kernel variant
 
 struct ConvTcParams {
     CUtensorMap mapA[4];
@@ -53,6 +57,7 @@ struct ConvTcParams {
     int qkv_mode; float* vt; int t_pad, heads, head_dim;
     float* out_lo; float* vt_lo; int qkv_bf16;
     float* stats_out; int stats_rows;                  // set by prepare only for the persistent kernels (else nullptr / 0)
+    int fused; const float* gn_scale; const float* gn_shift; int gn_c0, gn_c1, gn_act;    // conv_halo_fused_kernel
 };
 
 int conv_tc_prepare(ConvTcParams& P, const ConvTcDesc& d);

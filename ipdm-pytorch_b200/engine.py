@@ -237,6 +237,26 @@ def delta_lambda_map(x, img, ks=4, amplitude=7.0, kind="proj", return_median=Fal
     return (out, med) if return_median else out
 
 
+def delta_lambda_map_img(x, img, ks=4, amplitude=7.0):
+    """Image-domain lambda-exponent map (Model/model.py:591-595): pool |miu2pixel(x) - miu2pixel(img)| first, median of the pooled map."""
+    b, h, w = x.shape[0], x.shape[-2], x.shape[-1]
+    out = torch.empty(b, h // ks, w // ks, device=x.device, dtype=torch.float32)
+    pooled = torch.empty_like(out)
+    ws = _workspace(_lib.lib().ipdm_sampler_workspace_bytes(b, h, w), x.device)
+    check(_lib.lib().ipdm_delta_lambda_map_img(_dev(x), _dev(img), _dev(out), None, _dev(pooled), b, h, w, int(ks), float(amplitude), 1,
+                                               _dev(ws), _stream()), "ipdm_delta_lambda_map_img")
+    return out
+
+
+def delta_exp_max(x, img, ks=4, amplitude=7.0):
+    """Per-slice max of exp(amplitude * relu(avgpool(|x - img| - median))) as a CUDA tensor [B] (adaptive schedule selection, :596-613)."""
+    b, h, w = x.shape[0], x.shape[-2], x.shape[-1]
+    out = torch.empty(b, device=x.device, dtype=torch.float32)
+    ws = _workspace(_lib.lib().ipdm_sampler_workspace_bytes(b, h, w), x.device)
+    check(_lib.lib().ipdm_delta_exp_max(_dev(x), _dev(img), _dev(out), b, h, w, int(ks), float(amplitude), _dev(ws), _stream()), "ipdm_delta_exp_max")
+    return out
+
+
 def lambda_step_map(lam_exp, i, ts):
     out = torch.empty_like(lam_exp)
     check(_lib.lib().ipdm_lambda_step_map(_dev(lam_exp), _dev(out), lam_exp.numel(), int(i), int(ts), _stream()), "ipdm_lambda_step_map")
@@ -347,7 +367,7 @@ def guided_params(mode, t_start, clip, lambda_ratio, eta, constant_guidance, ker
     p = GuidedParams()
     p.mode = 0 if mode == "proj" else 1
     if t_start is None:
-        raise NotImplementedError("adaptive t_start=None (SURVEY N3) is not implemented on the B200 path; pass explicit lists")
+        raise ValueError("guided_params needs an explicit t_start list (the adaptive branch picks one on the host first, Model/model.py)")
     if not 1 <= len(t_start) <= 8:
         raise ValueError("t_start must hold 1..8 entries")
     p.n_iters = len(t_start)
@@ -380,4 +400,19 @@ def guided_process(unet, p, img, ldct=None, noise=None, out=None):
         ws = _workspace(_lib.lib().ipdm_guided_workspace_bytes(ctypes.byref(p), b, h, w), img.device)
         check(_lib.lib().ipdm_guided_process(unet._h, ctypes.byref(p), _dev(img, "img"), _opt(ldct, "ldct"), _opt(noise, "noise"),
                                              _dev(out), b, h, w, _dev(ws), _stream()), "ipdm_guided_process")
+    return out
+
+
+def guided_process_resume(unet, p, img, lam_exp, call_base, ldct=None, noise=None):
+    """Runs ipdm_guided_process_resume: iterations 1.. of an adaptive-lambda process whose probing iteration produced `lam_exp`
+    [B,H/ks,W/ks]; noise None or the tape of the continuation [count,B,1,H,W]; returns [n_iters+1, B, 1, H, W]."""
+    b, h, w = img.shape[0], img.shape[-2], img.shape[-1]
+    if noise is not None and noise.shape[0] < guided_noise_count(p):
+        raise ValueError(f"noise tape holds {noise.shape[0]} draws, the continuation consumes {guided_noise_count(p)}")
+    out = torch.empty((p.n_iters + 1, b, 1, h, w), device=img.device, dtype=torch.float32)
+    with unet._on_device(img, "img"):
+        ws = _workspace(_lib.lib().ipdm_guided_workspace_bytes(ctypes.byref(p), b, h, w), img.device)
+        check(_lib.lib().ipdm_guided_process_resume(unet._h, ctypes.byref(p), _dev(img, "img"), _opt(ldct, "ldct"), _opt(noise, "noise"),
+                                                    _dev(lam_exp, "lam_exp"), int(call_base), _dev(out), b, h, w, _dev(ws), _stream()),
+              "ipdm_guided_process_resume")
     return out
