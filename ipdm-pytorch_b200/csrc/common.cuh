@@ -95,13 +95,19 @@ __device__ __forceinline__ void st_stream(float4* p, const float4& v) {
                  :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
-__device__ __forceinline__ float silu(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
 // Round to the nearest TF32 value (10-bit mantissa).  The tensor core only reads the upper 19 bits of an
 // fp32 operand, i.e. it TRUNCATES; truncation shrinks every product coherently (measured: 4.3e-4 rel-L2 on a
 // K=1152 conv), whereas pre-rounded operands leave only zero-mean noise.  Operand producers call this.
 // 2^x in one MUFU instruction (exp2f adds a range fix-up of three more per call); arguments here are <= 0, underflow flushes to 0
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// x * sigmoid(x) with two MUFU operations (ex2, rcp) and no range fix-up: ex2 overflows to +inf for x < -88 (x * rcp(inf) = -0, the limit)
+// and flushes to 0 for x > 88 (x / 1 = x); every GroupNorm + SiLU in the library (apply pass, direct conv, fused operand path) uses this one
+__device__ __forceinline__ float silu(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + ex2_approx(-1.4426950408889634f * x)));
+    return x * r;
+}
 
 __device__ __forceinline__ float tf32_rn(float x) {
     uint32_t r;

@@ -1034,28 +1034,36 @@ conv_halo_fused_kernel(const __grid_constant__ ConvTcParams P) {
                 }
                 tc::mbar_wait(&raw_full[sa], ((uint32_t)ia >> 1) & 1u);
                 if (BF16) tc::mbar_wait(&a_empty[sa], (((uint32_t)ia >> 1) & 1u) ^ 1u);     // the operand buffer of this stage is free
-                const uint8_t* raw = smem + sa * S::RAW_STRIDE;
-                uint8_t* op = smem + S::OFF_OP + sa * HF_OP_STRIDE_BF16;
-#pragma unroll 4
-                for (int j = 0; j < 20; ++j) {
-                    const int r = w4 * 80 + j * 4 + psub;                             // pixel of the halo tile: row r >> 5, column r & 31
-                    const int yy = y0 - 1 + (r >> 5), xx = x0 - 1 + (r & 31);
-                    const bool inside = (unsigned)yy < (unsigned)P.H && (unsigned)xx < (unsigned)P.W;
-                    const uint32_t roff = (uint32_t)r * 128u + (uint32_t)((c8 ^ (r & 7)) << 4);        // TMA SWIZZLE_128B: 16-byte chunk ^ (row & 7)
-                    const float4 v = *reinterpret_cast<const float4*>(raw + roff);
-                    float4 o;
-                    o.x = fmaf(v.x, sc.x, sh.x); o.y = fmaf(v.y, sc.y, sh.y); o.z = fmaf(v.z, sc.z, sh.z); o.w = fmaf(v.w, sc.w, sh.w);
-                    if (P.gn_act) { o.x = silu(o.x); o.y = silu(o.y); o.z = silu(o.z); o.w = silu(o.w); }
-                    if (!inside) o = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (BF16) {
-                        const __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
-                        uint2 pk; pk.x = *reinterpret_cast<const uint32_t*>(&lo); pk.y = *reinterpret_cast<const uint32_t*>(&hi);
-                        // SWIZZLE_64B operand row r (64 bytes): 16-byte chunk (c8 >> 1) ^ ((r >> 1) & 3), 8-byte half c8 & 1
-                        const uint32_t ooff = (uint32_t)r * 64u + (uint32_t)((((c8 >> 1) ^ ((r >> 1) & 3)) << 4) | ((c8 & 1) << 3));
-                        *reinterpret_cast<uint2*>(op + ooff) = pk;
-                    } else {
-                        o.x = tf32_rn(o.x); o.y = tf32_rn(o.y); o.z = tf32_rn(o.z); o.w = tf32_rn(o.w);
-                        *reinterpret_cast<float4*>(const_cast<uint8_t*>(raw) + roff) = o;
+                const uint32_t raw_s = tc::smem_u32(smem + sa * S::RAW_STRIDE);
+                const uint32_t op_s = tc::smem_u32(smem + S::OFF_OP + sa * HF_OP_STRIDE_BF16);
+                // 20 pixels per lane in two batches of 10: all loads of a batch are issued before the first SiLU so that the shared-memory
+                // and MUFU latencies overlap (explicit ld/st.shared: generic accesses made the compiler serialise load -> store -> load)
+#pragma unroll
+                for (int half = 0; half < (P.gn_act == 3 ? 0 : 2); ++half) {
+                    float4 v[10];
+#pragma unroll
+                    for (int j = 0; j < 10; ++j) {
+                        const int r = w4 * 80 + (half * 10 + j) * 4 + psub;              // pixel of the halo tile: row r >> 5, column r & 31
+                        v[j] = tc::lds128(raw_s + (uint32_t)r * 128u + (uint32_t)((c8 ^ (r & 7)) << 4));   // TMA SWIZZLE_128B: 16-byte chunk ^ (row & 7)
+                    }
+#pragma unroll
+                    for (int j = 0; j < 10; ++j) {
+                        const int r = w4 * 80 + (half * 10 + j) * 4 + psub;
+                        const int yy = y0 - 1 + (r >> 5), xx = x0 - 1 + (r & 31);
+                        const bool inside = (unsigned)yy < (unsigned)P.H && (unsigned)xx < (unsigned)P.W;
+                        float4 o;
+                        o.x = fmaf(v[j].x, sc.x, sh.x); o.y = fmaf(v[j].y, sc.y, sh.y); o.z = fmaf(v[j].z, sc.z, sh.z); o.w = fmaf(v[j].w, sc.w, sh.w);
+                        if (P.gn_act == 1) { o.x = silu(o.x); o.y = silu(o.y); o.z = silu(o.z); o.w = silu(o.w); }
+                        if (!inside) o = make_float4(0.f, 0.f, 0.f, 0.f);                 // the conv pads the ACTIVATION with zeros
+                        if (BF16) {
+                            const __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+                            // SWIZZLE_64B operand row r (64 bytes): 16-byte chunk (c8 >> 1) ^ ((r >> 1) & 3), 8-byte half c8 & 1
+                            tc::sts64(op_s + (uint32_t)r * 64u + (uint32_t)((((c8 >> 1) ^ ((r >> 1) & 3)) << 4) | ((c8 & 1) << 3)),
+                                      *reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+                        } else {
+                            tc::sts128(raw_s + (uint32_t)r * 128u + (uint32_t)((c8 ^ (r & 7)) << 4),
+                                       make_float4(tf32_rn(o.x), tf32_rn(o.y), tf32_rn(o.z), tf32_rn(o.w)));
+                        }
                     }
                 }
                 tc::fence_proxy_async();                 // generic-proxy writes -> visible to the tensor core's async proxy
@@ -1206,7 +1214,11 @@ int conv_tc_prepare(ConvTcParams& P, const ConvTcDesc& d) {
     if (P.fused) {
         IPDM_REQUIRE(P.halo && P.persistent && d.cout >= 64 && d.cout <= 512 && d.norm_shift, "conv_tc: GroupNorm fusion needs a persistent halo layer (3x3, stride 1, C_out 64..512)");
         IPDM_REQUIRE(d.nsrc == 1 || d.src[0].c == d.src[0].cs, "conv_tc: fused concat needs an unpadded first source (%d channels, stride %d)", d.src[0].c, d.src[0].cs);
+        IPDM_REQUIRE(d.act_silu, "conv_tc: the fused operand path is GroupNorm + SiLU (the attention norm has no activation and feeds a 1x1 conv)");
         P.gn_scale = d.norm_scale; P.gn_shift = d.norm_shift; P.gn_act = d.act_silu;
+        // experiments (tools only): IPDM_FUSE_DBG=2 affine without SiLU, 3 the transform warps only hand the barriers on (operands are garbage)
+        static const int fuse_dbg = getenv("IPDM_FUSE_DBG") ? atoi(getenv("IPDM_FUSE_DBG")) : 0;
+        if (fuse_dbg) P.gn_act = fuse_dbg;
         P.gn_c0 = d.src[0].c; P.gn_c1 = d.nsrc > 1 ? d.src[1].c : 0;
         IPDM_REQUIRE(P.gn_c0 % 4 == 0 && P.gn_c1 % 4 == 0, "conv_tc: fused GroupNorm needs channel counts that are multiples of 4");
     }

@@ -136,23 +136,45 @@ __global__ void finalize1_kernel(const double* __restrict__ partials, SliceStats
 // ------------------------------------------------------------------------------------------------
 // pass 2 (per-pixel lambda): moments of m = (1-lam) a + lam b
 // ------------------------------------------------------------------------------------------------
+// lambda-map cell of element i (row-major [h][w] field, cells of ks x ks): 32-bit arithmetic, shifts when ks is a power of two
+__device__ __forceinline__ unsigned lam_cell(unsigned i, unsigned w, unsigned ks, int ks_shift, unsigned lw) {
+    const unsigned yy = i / w, xx = i - yy * w;
+    return ks_shift >= 0 ? (yy >> ks_shift) * lw + (xx >> ks_shift) : (yy / ks) * lw + xx / ks;
+}
+
+// VEC: w % 4 == 0 and ks % 4 == 0, so the four elements of a 128-bit vector share one lambda cell
+template <bool VEC>
 __global__ void __launch_bounds__(MOM_THREADS)
 moments2_kernel(const float* __restrict__ xt, const float* __restrict__ x0c, const float* __restrict__ eps,
                 const float* __restrict__ lam_map, const SliceStats* __restrict__ stats, double* __restrict__ partials,
-                int h, int w, int ks, int lw, int lh, float sa) {
+                int h, int w, int ks, int ks_shift, int lw, int lh, float sa) {
     const int b = blockIdx.y;
-    const size_t n = (size_t)h * w;
+    const unsigned n = (unsigned)h * (unsigned)w;
     const SliceStats st = stats[b];
     const float* X = xt + (size_t)b * n; const float* G = x0c + (size_t)b * n; const float* E = eps + (size_t)b * n;
     const float* L = lam_map + (size_t)b * lw * lh;
     double v[5] = {0, 0, 0, 0, 0};
-    for (size_t i = (size_t)blockIdx.x * MOM_THREADS + threadIdx.x; i < n; i += (size_t)gridDim.x * MOM_THREADS) {
-        const int yy = (int)(i / w), xx = (int)(i - (size_t)yy * w);
-        const float lam = __ldg(L + (size_t)(yy / ks) * lw + xx / ks);
-        const float a = (E[i] - st.mu_e) * st.inv_se;
-        const float bb = ((X[i] - sa * G[i]) - st.mu_d) * st.inv_sd;
-        const float m = (1.0f - lam) * a + lam * bb;
-        v[0] += m; v[1] += (double)m * m;
+    if (VEC) {
+        const unsigned nq = n / 4;
+        for (unsigned q = blockIdx.x * MOM_THREADS + threadIdx.x; q < nq; q += gridDim.x * MOM_THREADS) {
+            const float4 x = ld_stream(reinterpret_cast<const float4*>(X) + q), g = ld_stream(reinterpret_cast<const float4*>(G) + q),
+                         e = ld_stream(reinterpret_cast<const float4*>(E) + q);
+            const float lam = __ldg(L + lam_cell(q * 4, (unsigned)w, (unsigned)ks, ks_shift, (unsigned)lw)), oml = 1.0f - lam;
+            const float m0 = oml * ((e.x - st.mu_e) * st.inv_se) + lam * (((x.x - sa * g.x) - st.mu_d) * st.inv_sd);
+            const float m1 = oml * ((e.y - st.mu_e) * st.inv_se) + lam * (((x.y - sa * g.y) - st.mu_d) * st.inv_sd);
+            const float m2 = oml * ((e.z - st.mu_e) * st.inv_se) + lam * (((x.z - sa * g.z) - st.mu_d) * st.inv_sd);
+            const float m3 = oml * ((e.w - st.mu_e) * st.inv_se) + lam * (((x.w - sa * g.w) - st.mu_d) * st.inv_sd);
+            v[0] += (double)((m0 + m1) + (m2 + m3));
+            v[1] += (double)(fmaf(m0, m0, m1 * m1) + fmaf(m2, m2, m3 * m3));
+        }
+    } else {
+        for (unsigned i = blockIdx.x * MOM_THREADS + threadIdx.x; i < n; i += gridDim.x * MOM_THREADS) {
+            const float lam = __ldg(L + lam_cell(i, (unsigned)w, (unsigned)ks, ks_shift, (unsigned)lw));
+            const float a = (E[i] - st.mu_e) * st.inv_se;
+            const float bb = ((X[i] - sa * G[i]) - st.mu_d) * st.inv_sd;
+            const float m = (1.0f - lam) * a + lam * bb;
+            v[0] += m; v[1] += (double)m * m;
+        }
     }
     block_reduce5(v, partials + ((size_t)b * gridDim.x + blockIdx.x) * 5);
 }
@@ -184,7 +206,7 @@ template <bool MAP>
 __global__ void __launch_bounds__(256)
 apply_kernel(const float* xt, const float* __restrict__ x0c, const float* __restrict__ eps,
              const float* __restrict__ noise, float* out, const SliceStats* __restrict__ stats,
-             const float* __restrict__ lam_map, int h, int w, int ks, int lw, int lh, StepCoef k, int clip,
+             const float* __restrict__ lam_map, int h, int w, int ks, int ks_shift, int lw, int lh, StepCoef k, int clip,
              int t_nonzero, uint64_t seed, uint64_t call_id) {
     const int b = blockIdx.y;
     const size_t n = (size_t)h * w, nq = n / 4;
@@ -206,17 +228,13 @@ apply_kernel(const float* xt, const float* __restrict__ x0c, const float* __rest
         float o[4];
         float lam4[4] = {0.f, 0.f, 0.f, 0.f};
         if (MAP) {
-            const size_t i0 = q * 4;
+            const unsigned i0 = (unsigned)q * 4u;                      // a slice holds < 2^31 elements: 32-bit row / column arithmetic
             if (vec_map_ok) {
-                const int yy = (int)(i0 / w), xx = (int)(i0 - (size_t)yy * w);
-                const float l = __ldg(L + (size_t)(yy / ks) * lw + xx / ks);
+                const float l = __ldg(L + lam_cell(i0, (unsigned)w, (unsigned)ks, ks_shift, (unsigned)lw));
                 lam4[0] = lam4[1] = lam4[2] = lam4[3] = l;
             } else {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const size_t i = i0 + j; const int yy = (int)(i / w), xx = (int)(i - (size_t)yy * w);
-                    lam4[j] = __ldg(L + (size_t)(yy / ks) * lw + xx / ks);
-                }
+                for (int j = 0; j < 4; ++j) lam4[j] = __ldg(L + lam_cell(i0 + j, (unsigned)w, (unsigned)ks, ks_shift, (unsigned)lw));
             }
         }
 #pragma unroll
@@ -569,16 +587,22 @@ static int sampler_step_impl(const float* x_t, const float* x0c, const float* ep
     moments1_kernel<<<dim3(nblk, batch), MOM_THREADS, 0, st>>>(x_t, x0c, eps, ws.partials, n, k.sa);
     finalize1_kernel<<<batch, 32, 0, st>>>(ws.partials, ws.stats, nblk, (double)n, lam_scalar, lam_map != nullptr);
     count_launch(2);
-    const int lw = lam_map ? (w + ks - 1) / ks : 0, lh = lam_map ? (h + ks - 1) / ks : 0;
+    const int lw = lam_map ? w / ks : 0, lh = lam_map ? h / ks : 0;
+    int ks_shift = -1;
+    for (int sft = 0; sft < 16; ++sft) if (ks == (1 << sft)) ks_shift = sft;
+    IPDM_REQUIRE(n < (1ull << 31), "ipdm_sampler_step: a slice may hold at most 2^31 elements");
     const int ablk = (int)std::min<size_t>((size_t)kNumSMs * 4, (n / 4 + 255) / 256 > 0 ? (n / 4 + 255) / 256 : 1);
     if (lam_map) {
         const int nblk2 = (int)std::min<size_t>(MOM_BLOCKS, (n + MOM_THREADS - 1) / MOM_THREADS);
-        moments2_kernel<<<dim3(nblk2, batch), MOM_THREADS, 0, st>>>(x_t, x0c, eps, lam_map, ws.stats, ws.partials, h, w, ks, lw, lh, k.sa);
-        finalize2_kernel<<<batch, 32, 0, st>>>(ws.partials, ws.stats, nblk2, (double)n);
-        apply_kernel<true><<<dim3(ablk, batch), 256, 0, st>>>(x_t, x0c, eps, noise, x_out, ws.stats, lam_map, h, w, ks, lw, lh, k, clip, t_nonzero, seed, call_id);
+        if (w % 4 == 0 && ks % 4 == 0 && n % 4 == 0)
+            moments2_kernel<true><<<dim3(nblk, batch), MOM_THREADS, 0, st>>>(x_t, x0c, eps, lam_map, ws.stats, ws.partials, h, w, ks, ks_shift, lw, lh, k.sa);
+        else
+            moments2_kernel<false><<<dim3(nblk2, batch), MOM_THREADS, 0, st>>>(x_t, x0c, eps, lam_map, ws.stats, ws.partials, h, w, ks, ks_shift, lw, lh, k.sa);
+        finalize2_kernel<<<batch, 32, 0, st>>>(ws.partials, ws.stats, (w % 4 == 0 && ks % 4 == 0 && n % 4 == 0) ? nblk : nblk2, (double)n);
+        apply_kernel<true><<<dim3(ablk, batch), 256, 0, st>>>(x_t, x0c, eps, noise, x_out, ws.stats, lam_map, h, w, ks, ks_shift, lw, lh, k, clip, t_nonzero, seed, call_id);
         count_launch(3);
     } else {
-        apply_kernel<false><<<dim3(ablk, batch), 256, 0, st>>>(x_t, x0c, eps, noise, x_out, ws.stats, nullptr, h, w, 1, 0, 0, k, clip, t_nonzero, seed, call_id);
+        apply_kernel<false><<<dim3(ablk, batch), 256, 0, st>>>(x_t, x0c, eps, noise, x_out, ws.stats, nullptr, h, w, 1, 0, 0, 0, k, clip, t_nonzero, seed, call_id);
         count_launch();
     }
     IPDM_CHECK_LAUNCH();

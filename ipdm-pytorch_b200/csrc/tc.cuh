@@ -48,6 +48,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         if (clock64() - t0 > 4000000000LL) { asm volatile("trap;"); }   // ~2 s at 1.9 GHz
 }
 
+// explicit shared-state-space accesses (32-bit shared addresses): the compiler keeps them out of the generic path and may reorder them freely
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t saddr, const float4& v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" :: "r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts64(uint32_t saddr, uint32_t a, uint32_t b) {
+    asm volatile("st.shared.v2.b32 [%0], {%1,%2};" :: "r"(saddr), "r"(a), "r"(b) : "memory");
+}
+
 // ---- TMA -----------------------------------------------------------------------------------
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" :: "l"((uint64_t)m) : "memory");

@@ -842,29 +842,41 @@ extern "C" int ipdm_debug_conv(const float* src0, int c0, int cs0, const float* 
 }
 
 // times `iters` launches of one tensor-core conv (weights random, data whatever is in the buffers); ms_out = average per launch
+// times `iters` launches of one tensor-core conv (weights random, data whatever is in the buffers); ms_out = average per launch.
+// variant 5 = GroupNorm-fused persistent halo kernel (raw fp32 sources, scale = 1 / shift = 0 per channel)
 extern "C" int ipdm_debug_conv_time(int c0, int c1, int n, int h, int w, int cout, int k, int stride, int mode, int variant,
                                     int with_res, int iters, float* ms_out, double* flops_out) {
     ipdm_unet holder;
     holder.precision = mode == 2 ? IPDM_PREC_FP32 : (mode == 3 ? IPDM_PREC_BF16 : IPDM_PREC_TF32);
+    const bool fused = variant == 5;
     ConvW cw; cw.cin = c0 + c1; cw.cout = cout; cw.k = k;
     cw.w_host.assign((size_t)cout * cw.cin * k * k, 0.01f);
     cw.b_host.assign(cout, 0.1f);
     IPDM_CHECK(pack_conv(&holder, cw, c0, c1, true, 1, mode == 3));
-    const int eb = cw.bf16 ? 2 : 4;
+    const int scs0 = fused ? round_up(c0, 32) : cw.cs0, scs1 = fused ? (c1 ? round_up(c1, 32) : 0) : cw.cs1;
+    const int sc0 = fused ? c0 : cw.c0, sc1 = fused ? c1 : cw.c1;
+    const int eb = (cw.bf16 && !fused) ? 2 : 4;
     const int ho = stride == 1 ? h : (h + 1) / 2, wo = stride == 1 ? w : (w + 1) / 2;
-    float *s0 = nullptr, *s1 = nullptr, *out = nullptr, *res = nullptr;
-    IPDM_CHECK_CUDA(cudaMalloc(&s0, (size_t)n * h * w * cw.cs0 * eb));
-    IPDM_CHECK_CUDA(cudaMemset(s0, 0, (size_t)n * h * w * cw.cs0 * eb));
-    if (cw.cs1) { IPDM_CHECK_CUDA(cudaMalloc(&s1, (size_t)n * h * w * cw.cs1 * 4)); IPDM_CHECK_CUDA(cudaMemset(s1, 0, (size_t)n * h * w * cw.cs1 * 4)); }
+    float *s0 = nullptr, *s1 = nullptr, *out = nullptr, *res = nullptr, *nsc = nullptr, *nsh = nullptr;
+    IPDM_CHECK_CUDA(cudaMalloc(&s0, (size_t)n * h * w * scs0 * eb));
+    IPDM_CHECK_CUDA(cudaMemset(s0, 0, (size_t)n * h * w * scs0 * eb));
+    if (scs1) { IPDM_CHECK_CUDA(cudaMalloc(&s1, (size_t)n * h * w * scs1 * 4)); IPDM_CHECK_CUDA(cudaMemset(s1, 0, (size_t)n * h * w * scs1 * 4)); }
     const int ocs = alloc_cs(cout);
     IPDM_CHECK_CUDA(cudaMalloc(&out, (size_t)n * ho * wo * ocs * 4));
     if (with_res) { IPDM_CHECK_CUDA(cudaMalloc(&res, (size_t)n * ho * wo * ocs * 4)); IPDM_CHECK_CUDA(cudaMemset(res, 0, (size_t)n * ho * wo * ocs * 4)); }
-    ConvTcDesc d; d.nsrc = cw.cs1 ? 2 : 1; d.src[0] = mk(s0, n, h, w, cw.c0, cw.cs0); d.src[0].bf16 = cw.bf16;
-    if (cw.cs1) d.src[1] = mk(s1, n, h, w, cw.c1, cw.cs1);
+    ConvTcDesc d; d.nsrc = scs1 ? 2 : 1; d.src[0] = mk(s0, n, h, w, sc0, scs0); d.src[0].bf16 = cw.bf16 && !fused;
+    if (scs1) d.src[1] = mk(s1, n, h, w, sc1, scs1);
+    if (fused) {
+        std::vector<float> one((size_t)n * cw.cin, 1.f);
+        IPDM_CHECK_CUDA(cudaMalloc(&nsc, one.size() * 4)); IPDM_CHECK_CUDA(cudaMalloc(&nsh, one.size() * 4));
+        IPDM_CHECK_CUDA(cudaMemcpy(nsc, one.data(), one.size() * 4, cudaMemcpyHostToDevice));
+        IPDM_CHECK_CUDA(cudaMemset(nsh, 0, one.size() * 4));
+        d.norm_scale = nsc; d.norm_shift = nsh; d.w_bf16 = cw.bf16;
+    }
     d.ntaps = k * k; d.stride = stride; d.cout = cout; d.w_packed = cw.w_dev; d.w_packed_lo = cw.w_dev_lo; d.w_k = cw.kpad; d.bias = cw.b_dev;
     if (res) d.res = mk(res, n, ho, wo, cout, ocs);
     d.out = mk(out, n, ho, wo, cout, ocs);
-    d.variant = variant;
+    d.variant = fused ? 0 : variant;
     ConvTcParams P;
     IPDM_CHECK(conv_tc_prepare(P, d));
     cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
@@ -876,7 +888,7 @@ extern "C" int ipdm_debug_conv_time(int c0, int c1, int n, int h, int w, int cou
     float ms = 0; cudaEventElapsedTime(&ms, a, b);
     *ms_out = ms / iters;
     if (flops_out) *flops_out = 2.0 * n * ho * wo * (double)cw.cin * cout * k * k;
-    cudaFree(s0); cudaFree(s1); cudaFree(out); cudaFree(res); cudaEventDestroy(a); cudaEventDestroy(b);
+    cudaFree(s0); cudaFree(s1); cudaFree(out); cudaFree(res); cudaFree(nsc); cudaFree(nsh); cudaEventDestroy(a); cudaEventDestroy(b);
     return IPDM_OK;
 }
 

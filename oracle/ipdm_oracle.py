@@ -289,17 +289,29 @@ def p_sample_condition(tab, eps, x_t, x0c, t, lam, clip, noise):
     return mean + mask * (0.5 * tab.at("posterior_log_variance_clipped", t)).exp() * noise           # :514
 
 
+ADAPTIVE_PROJ = {"high": ([30, 25, 20], 0.6), "mid": ([20, 18, 15], 0.5), "low": ([15, 15, 15], 0.5)}      # :601-613
+ADAPTIVE_IMG = {"high": ([15, 15, 15], 0.6), "mid": ([15, 12, 10], 0.55), "low": ([10, 10, 10], 0.5)}    # :582-594
+
+
 def guided_reverse_process(unet, tab, img, t_start, clip, lambda_ratio, eta, mode, constant_guidance,
-                           noise, kernel_size=4, amplitude=7.0, ldct=None):
+                           noise, kernel_size=4, amplitude=7.0, ldct=None, noise_strength=None, info=None):
     """Dense guided process (:517-642) for ONE slice `img` [1,1,H,W]; `noise` is an iterator of
-    [1,1,H,W] tensors consumed in the reference's randn_like order.  Only the branches the
-    progressive path takes (explicit t_start; proj adaptive-lambda or constant guidance)."""
-    assert img.shape[0] == 1 and t_start is not None
+    [1,1,H,W] tensors consumed in the reference's randn_like order.  t_start=None is the adaptive
+    schedule (:531-535): a probing iteration with t_start = 20, after which the list and eta are picked
+    from max(exp(amplitude * delta-map)) (proj, :601-613) or from `noise_strength` (img, :582-594), and
+    the probing iterate is dropped from the result (:639-640).  `info` (dict) receives the class."""
+    assert img.shape[0] == 1
+    adaptive_schedule = t_start is None
+    assert not (adaptive_schedule and constant_guidance is not None)
+    t_list = [20] if adaptive_schedule else list(t_start)
     x = img.clone()
     guide = img.clone()
     iters_out = []
     Lam = None
-    for it, ts in enumerate(t_start):
+    it = -1
+    while t_list:
+        ts = t_list.pop(0)
+        it += 1
         x = tab.at("sqrt_alphas_cumprod", ts) * x + tab.at("sqrt_one_minus_alphas_cumprod", ts) * next(noise)  # :545
         lam_cos = cosine_beta_schedule(ts, schedule_power=lambda_ratio)
         for i in reversed(range(ts)):
@@ -322,12 +334,21 @@ def guided_reverse_process(unet, tab, img, t_start, clip, lambda_ratio, eta, mod
                 d = d - torch.median(d)
                 d = torch.where(d <= 0, torch.zeros_like(d), d)
                 Lam = lambda_curve(torch.exp(amplitude * d).cpu().numpy(), "img")
+                if adaptive_schedule:                                     # :582-594
+                    cls = "low" if noise_strength is None else noise_strength
+                    t_list, eta = list(ADAPTIVE_IMG[cls][0]), ADAPTIVE_IMG[cls][1]
             else:
                 d = torch.abs(x - img)                                    # :596-600
                 d = d - torch.median(d)
                 d = F.avg_pool2d(d, kernel_size)
                 d = torch.where(d <= 0, torch.zeros_like(d), d)
-                Lam = lambda_curve(torch.exp(amplitude * d).cpu().numpy(), "proj")  # :600, :614
+                e = torch.exp(amplitude * d).cpu().numpy()
+                if adaptive_schedule:                                     # :601-613
+                    cls = "high" if e.max() >= 30 else ("mid" if e.max() >= 4.5 else "low")
+                    t_list, eta = list(ADAPTIVE_PROJ[cls][0]), ADAPTIVE_PROJ[cls][1]
+                Lam = lambda_curve(e, "proj")                             # :600, :614
+            if adaptive_schedule and info is not None:
+                info["class"] = cls
         iters_out.append(x.contiguous())
         if constant_guidance is None:
             if it >= 1:
@@ -341,7 +362,7 @@ def guided_reverse_process(unet, tab, img, t_start, clip, lambda_ratio, eta, mod
                 guide = eta * x + (0.95 - eta) * img + 0.05 * ldct        # :635
     if len(iters_out) > 1:
         iters_out.append((iters_out[-1] + iters_out[-2]) / 2)             # :637-638
-    return iters_out
+    return iters_out[1:] if adaptive_schedule else iters_out              # :639-642
 
 
 def ddim_sample(unet, tab, x, condition, t_start, condition_lambda, ddim_timesteps, clip, noise, ddim_eta=0.0):

@@ -5,6 +5,7 @@ Run in the build container (needs /root/reference):
     python oracle/make_golden.py small      # schedule, small UNet / guided-process cases, one FBP slice (~2 min)
     python oracle/make_golden.py sparse     # sparse (DDIM) guided sampler on the small fields
     python oracle/make_golden.py imgadaptive  # image-domain adaptive lambda
+    python oracle/make_golden.py adaptive   # adaptive t_start=None schedule selection, both domains
     python oracle/make_golden.py full       # one full 2000x912 -> 512x512 progressive slice (~12 min on 8 cores)
 
 Every case fixes (weights seed, input seed, noise-tape seed); tests re-create the
@@ -181,6 +182,43 @@ def case_img_adaptive_small(MM, TT):
     return out
 
 
+def case_adaptive_schedule_small(MM, TT):
+    """t_start=None (the argparse default; Model/model.py:531-535, 582-613, 639-640): probing iteration with t_start = 20, then the
+    schedule is picked from max(exp(amplitude * delta-map)) in the projection domain (three slices with amplitude_proj = 7 (shipped), 3, 15 so that
+    the reference itself lands in three different classes) and from `noise_strength` in the image domain (second half)."""
+    import torch
+    out = {}
+    torch.manual_seed(0)
+    pnet = MM.UNetModel(**PROJ_CFG).eval()
+    pgd = MM.GaussianDiffusion(1000, "cosine", schedule_power=5)
+    for sid, amp in ((0, 7), (1, 3), (2, 15)):
+        x = small_proj_input(200 + sid)
+        with NoiseTape(tape(x.shape, 21 + 75 + 3, 1100 + sid)) as nt:
+            res, _, ns = pgd.guided_reverse_process(
+                model=pnet, img=x, t_start=None, clip=False, lambda_ratio=1, eta=0.5, lambda_curve=TT.proj_curv_init(), mode="proj",
+                constant_guidance=None, kernel_size_proj=4, amplitude_proj=amp, only_convertor=False, normal=False, transformer=None)
+        want = {"high": 75, "mid": 53, "low": 45}[ns]
+        assert nt.used == 21 + want + 3 and len(res) == 4, (nt.used, ns, len(res))
+        out[f"proj{sid}"] = np.stack([r.numpy()[0, 0] for r in res])
+        out[f"proj{sid}_class"] = np.array(ns)
+        out[f"proj{sid}_amplitude"] = np.float32(amp)
+        print(f"adaptive proj slice {sid} (amplitude {amp}): class {ns}, {nt.used} noise draws", flush=True)
+    torch.manual_seed(1)
+    inet = MM.UNetModel(**IMG_CFG).eval()
+    igd = MM.GaussianDiffusion(1000, "cosine", schedule_power=1)
+    for sid, ns in ((0, "mid"), (1, None), (2, "high")):
+        x = small_img_input(400 + sid)
+        with NoiseTape(tape(x.shape, 21 + 45 + 3, 1200 + sid)) as nt:
+            res, _, _ = igd.guided_reverse_process(model=inet, img=x, t_start=None, clip=True, lambda_ratio=10, eta=0.7, save_states=False,
+                                                   mode="img", constant_guidance=None, lambda_curve=TT.curve_init(), noise_strength=ns, ldct=x,
+                                                   kernel_size_img=4, amplitude_img=20, only_convertor=False, normal=False, transformer=None)
+        assert len(res) == 4
+        out[f"img{sid}"] = np.stack([r.numpy()[0, 0] for r in res])
+        out[f"img{sid}_class"] = np.array("none" if ns is None else ns)
+        print(f"adaptive img slice {sid}: noise_strength {ns}, {nt.used} noise draws", flush=True)
+    return out
+
+
 def case_fbp(RF):
     import numba
     numba.set_num_threads(1)
@@ -288,6 +326,9 @@ def main():
     elif what == "imgadaptive":
         MM, RF, TT, CFG = load_reference()
         save("img_adaptive_small", case_img_adaptive_small(MM, TT))
+    elif what == "adaptive":
+        MM, RF, TT, CFG = load_reference()
+        save("adaptive_schedule_small", case_adaptive_schedule_small(MM, TT))
     elif what == "fbp":
         MM, RF, TT, CFG = load_reference()
         save("fbp_slice0", case_fbp(RF))

@@ -75,7 +75,7 @@ def test_philox_path_is_deterministic_and_unsupported_modes_fail_loudly(cuda):
     c, _, _ = gd.guided_reverse_process(seed=8, **kw)
     assert len(a) == 3 and torch.equal(a[-1], b[-1]) and not torch.equal(a[-1], c[-1])
     assert torch.allclose(a[2], (a[0] + a[1]) / 2)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(ValueError, match="empty list"):                 # t_start=None + constant guidance: the reference returns []
         gd.guided_reverse_process(net, x, t_start=None, mode="img", constant_guidance=0.45, ldct=x, only_convertor=False)
     with pytest.raises(RuntimeError):                                   # img mode blends with ldct: it must be given
         gd.guided_reverse_process(net, x, t_start=[2], mode="img", constant_guidance=0.45, ldct=None, only_convertor=False)
@@ -147,3 +147,84 @@ def test_img_domain_adaptive_lambda_matches_reference_golden(cuda, prec, tol):
         err = [rel_l2(res[k][0, 0].cpu().numpy(), g[f"img{s}"][k]) for k in range(4)]
         print(f"img adaptive slice {s} ({prec}): rel-L2 per iterate {['%.2e' % e for e in err]}")
         assert max(err) < tol
+
+
+# ---- SURVEY N3 (second half): adaptive t_start=None schedule selection -----------------------------------------------------
+@pytest.mark.parametrize("prec,tol", [("tf32", 1.2e-2), ("fp32", 5e-4)])
+def test_adaptive_schedule_proj_matches_reference_golden(cuda, prec, tol):
+    """t_start=None in the projection domain (reference Model/model.py:531-535, 596-613, 639-640): probing iteration with t_start = 20,
+    max(exp(amplitude * delta-map)) reduced on the device (ipdm_delta_exp_max), ONE host read, then the [30,25,20] / [20,18,15] /
+    [15,15,15] continuation.  Goldens from the unmodified reference (make_golden.py adaptive): amplitude 7 / 3 / 15 land in mid / low / high."""
+    from Model.model import GaussianDiffusion, UNetModel
+    g = golden("adaptive_schedule_small")
+    torch.manual_seed(0)
+    net = UNetModel(**PROJ_CFG).to(cuda).eval()
+    net.set_precision(prec)
+    gd = GaussianDiffusion(1000, "cosine", schedule_power=5)
+    seen = set()
+    for sid, amp in ((0, 7), (1, 3), (2, 15)):
+        x = small_proj_input(200 + sid).to(cuda)
+        tape = _tape(x.shape, 99, 1100 + sid, cuda)
+        res, _, ns = gd.guided_reverse_process(net, x, t_start=None, clip=False, lambda_ratio=1, eta=0.5, mode="proj", constant_guidance=None,
+                                               kernel_size_proj=4, amplitude_proj=amp, only_convertor=False, normal=False, noise=tape)
+        assert ns == str(g[f"proj{sid}_class"]) and len(res) == 4
+        seen.add(ns)
+        err = [rel_l2(res[k][0, 0].cpu().numpy(), g[f"proj{sid}"][k]) for k in range(4)]
+        print(f"adaptive proj slice {sid} ({prec}, amplitude {amp}): class {ns}, rel-L2 per iterate {['%.2e' % e for e in err]}")
+        assert max(err) < tol
+    assert seen == {"low", "mid", "high"}
+    # a batch of three slices: per-slice decision, one continuation per class, results scattered back in slice order
+    xs = torch.cat([small_proj_input(200 + s) for s in range(3)]).to(cuda)
+    tapes = torch.cat([_tape(xs[:1].shape, 99, 1100 + s, cuda) for s in range(3)], dim=1).contiguous()
+    res, _, ns = gd.guided_reverse_process(net, xs, t_start=None, clip=False, lambda_ratio=1, eta=0.5, mode="proj", constant_guidance=None,
+                                           kernel_size_proj=4, amplitude_proj=7, only_convertor=False, normal=False, noise=tapes)
+    assert ns == "mid" and tuple(res[-1].shape) == tuple(xs.shape)
+    assert rel_l2(res[-1][0, 0].cpu().numpy(), g["proj0"][3]) < tol
+
+
+@pytest.mark.parametrize("prec,tol", [("tf32", 1.2e-2), ("fp32", 5e-4)])
+def test_adaptive_schedule_img_per_slice_classes(cuda, prec, tol):
+    """t_start=None in the image domain (reference :582-594): the schedule follows the noise_strength reported by the projection stage.
+    Three slices with three different classes run as ONE call (per-slice list): three continuations, scattered back."""
+    from Model.model import GaussianDiffusion, UNetModel
+    g = golden("adaptive_schedule_small")
+    torch.manual_seed(1)
+    net = UNetModel(**IMG_CFG).to(cuda).eval()
+    net.set_precision(prec)
+    gd = GaussianDiffusion(1000, "cosine", schedule_power=1)
+    kw = dict(t_start=None, clip=True, lambda_ratio=10, eta=0.7, mode="img", constant_guidance=None, kernel_size_img=4, amplitude_img=20,
+              only_convertor=False, normal=False)
+    classes = ["mid", None, "high"]
+    xs = torch.cat([small_img_input(400 + s) for s in range(3)]).to(cuda)
+    tapes = torch.cat([_tape(xs[:1].shape, 69, 1200 + s, cuda) for s in range(3)], dim=1).contiguous()
+    res, _, _ = gd.guided_reverse_process(net, xs, ldct=xs, noise_strength=classes, noise=tapes, **kw)
+    assert len(res) == 4
+    for s in range(3):
+        err = [rel_l2(res[k][s, 0].cpu().numpy(), g[f"img{s}"][k]) for k in range(4)]
+        print(f"adaptive img slice {s} ({prec}, noise_strength {classes[s]}): rel-L2 per iterate {['%.2e' % e for e in err]}")
+        assert max(err) < tol
+    one, _, _ = gd.guided_reverse_process(net, xs[2:3].contiguous(), ldct=xs[2:3].contiguous(), noise_strength="high", noise=tapes[:, 2:3].contiguous(), **kw)
+    assert rel_l2(one[-1].cpu().numpy(), res[-1][2:3].cpu().numpy()) < 1e-5
+
+
+def test_adaptive_schedule_through_the_drop_in_api(cuda, tmp_path):
+    """update_opt(dict(t_start_proj=None, t_start_img=None)) (the argparse defaults, train_img_option.json): the projection stage picks the
+    schedule, reports noise_strength, the image stage follows it (constant_guidance_img=None), Philox noise."""
+    import os
+    import ipdm_pytorch_b200.synthetic as S
+    from conftest import PKG
+    from Config.default_config import default_cfg
+    from Utils.train_test_utils import progressive_domain_denoiser
+    opt = default_cfg(["--load_option_path", os.path.join(PKG, "Config/Mayo-Config/test_progressive_option.json"), "--device", "cuda:0"])
+    opt.load_img_model_path = opt.load_proj_model_path = None
+    opt.test_dataset_path_FD_img = opt.test_dataset_path_LD_img = opt.test_dataset_path_FD_proj = opt.test_dataset_path_LD_proj = None
+    torch.manual_seed(0)
+    model = progressive_domain_denoiser(opt, result_save_path=str(tmp_path))
+    model.update_opt(dict(convertor="FBP", ultra_img_denoise=False, constant_guidance_img=None, noise_seed=3, precision="bf16",
+                          t_start_proj=None, t_start_img=None))
+    ld = np.stack([S.make_slice(s)[0] for s in (0, 1)])
+    model.data_sample_load(ldct=None, ldproj=torch.from_numpy(ld)[:, None], fdproj=None, fdct=None)
+    out = model.progressive_denoiser()
+    assert tuple(out.shape) == (2, 1, 512, 512) and torch.isfinite(out).all()
+    ns = model.noise_strength
+    assert (ns in ("low", "mid", "high")) or (isinstance(ns, list) and all(c in ("low", "mid", "high") for c in ns))

@@ -163,3 +163,43 @@ def test_img_adaptive_lambda_oracle_matches_reference():
     res = O.guided_reverse_process(net, O.Tables(1000, 1), x, [10, 9, 8], clip=True, lambda_ratio=10, eta=0.7, mode="img",
                                    constant_guidance=None, noise=iter(noise_tape(x.shape, 30, 900)), kernel_size=4, amplitude=20.0, ldct=x)
     assert rel_l2(np.stack([r.numpy()[0, 0] for r in res]), g["img0"]) < 2e-5
+
+
+# ---- N3 (second half): adaptive t_start=None schedule selection ------------------------------------------------------------------
+def test_adaptive_schedule_oracle_matches_reference():
+    """t_start=None in both domains (reference Model/model.py:531-535, 582-613, 639-640): golden from the unmodified reference
+    (oracle/make_golden.py adaptive), three projection slices that land in three classes, three image slices with three noise_strength values."""
+    g = golden("adaptive_schedule_small")
+    torch.manual_seed(0)
+    pnet = O.UNetOracle(**PROJ_CFG).eval()
+    for sid, amp in ((0, 7.0), (1, 3.0), (2, 15.0)):
+        x = small_proj_input(200 + sid)
+        info = {}
+        res = O.guided_reverse_process(pnet, O.Tables(1000, 5), x, None, clip=False, lambda_ratio=1, eta=0.5, mode="proj", constant_guidance=None,
+                                       noise=iter(noise_tape(x.shape, 99, 1100 + sid)), kernel_size=4, amplitude=amp, info=info)
+        assert info["class"] == str(g[f"proj{sid}_class"]) and len(res) == 4
+        assert rel_l2(np.stack([r.numpy()[0, 0] for r in res]), g[f"proj{sid}"]) < 2e-5, sid
+    assert {str(g[f"proj{s}_class"]) for s in range(3)} == {"low", "mid", "high"}
+    torch.manual_seed(1)
+    inet = O.UNetOracle(**IMG_CFG).eval()
+    for sid, ns in ((0, "mid"), (1, None), (2, "high")):
+        x = small_img_input(400 + sid)
+        res = O.guided_reverse_process(inet, O.Tables(1000, 1), x, None, clip=True, lambda_ratio=10, eta=0.7, mode="img", constant_guidance=None,
+                                       noise=iter(noise_tape(x.shape, 69, 1200 + sid)), kernel_size=4, amplitude=20.0, ldct=x, noise_strength=ns)
+        assert len(res) == 4 and rel_l2(np.stack([r.numpy()[0, 0] for r in res]), g[f"img{sid}"]) < 2e-5, sid
+
+
+def test_ssim_oracle_matches_the_skimage_code_path_on_scipy():
+    """skimage is absent, scipy is not.  `ssim_skimage_path` replays skimage 0.19's structural_similarity on the
+    scipy.ndimage.uniform_filter it calls; the cumulative-sum oracle (what the device metric is tested against) must agree with it,
+    for the reference's arguments (win_size=11, data_range=1) on a CT-like image pair and on noise, and for an even/odd size mix."""
+    from oracle import metrics_oracle as M
+    import ipdm_pytorch_b200.synthetic as S
+    nd = M.miu2pixel(S.rasterize(S.phantom_ellipses(0)))
+    rng = np.random.default_rng(3)
+    pairs = [(nd, np.clip(nd + 0.02 * rng.standard_normal(nd.shape).astype(np.float32), 0, 1)),
+             (rng.random((97, 130)).astype(np.float32), rng.random((97, 130)).astype(np.float32))]
+    for ref, test in pairs:
+        for win in (11, 7):
+            a, b = M.ssim(ref, test, win_size=win), M.ssim_skimage_path(ref, test, win_size=win)
+            assert a == pytest.approx(b, abs=1e-12), (win, a, b)
