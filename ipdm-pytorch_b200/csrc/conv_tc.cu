@@ -205,11 +205,11 @@ __device__ __forceinline__ void tc_epilogue(const ConvTcParams& P, uint32_t tmem
 // so that 8 lanes cover one pixel's 128 contiguous bytes: every global load (residual) and store is a full line.
 constexpr int EPI_PITCH = 36;
 constexpr int EPI_WARP_FLOATS = 32 * EPI_PITCH;
-template <int BLOCK_N>
+template <int BLOCK_N, int CHUNK_W = 32>
 __device__ __forceinline__ void tc_epilogue_coalesced(const ConvTcParams& P, uint32_t tmem_acc, int quarter, int lane, int b, int x0, int y0,
                                                       int n0, const float* sbias, float* stile, int tw_valid, float* stats_row) {
     const int TW = 1 << P.tw_log2;                    // tile row pitch; only the first tw_valid columns are outputs
-    constexpr int CHUNK = BLOCK_N < 32 ? 16 : 32;
+    constexpr int CHUNK = BLOCK_N < 32 ? 16 : CHUNK_W; // columns per TMEM load: 16 halves the registers (r[], residual lines) of the 32-wide form
     constexpr int LPP = CHUNK / 4;                    // lanes per pixel row segment (8 for 32 channels, 4 for 16)
     constexpr int PPI = 32 / LPP;                     // pixels per warp instruction
     const int c4 = (lane % LPP) * 4, psub = lane / LPP;
@@ -867,9 +867,10 @@ conv_halo_persistent_kernel(const __grid_constant__ ConvTcParams P) {
 // affine + SiLU of the reference's `norm -> SiLU -> conv` (Model/model.py:98-101, 110-113) on the operand path, so the
 // separate apply pass (4 B read + 2-4 B written per element, 18 % of the step in round 1) and the operand tensor disappear.
 //
-//   warp 0          TMA producer: ring of 2 RAW halo tiles [10 rows][32 px][32 ch fp32 = 128 B] (one 4-D box per 32-channel
-//                   K chunk of the virtual concat, OOB zero fill), ring of NB weight tiles
-//   warps 2,3,12,13 transform: raw tile -> y = silu(x * scale[slice][c] + shift[slice][c]), zero outside the image (the conv's
+//   warp 2          TMA producer of the RAW halo tiles: ring of 2 [10 rows][32 px][32 ch fp32 = 128 B] (one 4-D box per 32-channel
+//                   K chunk of the virtual concat, OOB zero fill)
+//   warp 0          TMA producer of the weight tiles (ring of NB)
+//   warps 12-19     transform: raw tile -> y = silu(x * scale[slice][c] + shift[slice][c]), zero outside the image (the conv's
 //                   zero padding applies to the normalised activation), rounded exactly like the unfused apply pass:
 //                     BF16: bf16, written as a K-major SWIZZLE_64B operand tile (64-byte pixel rows) into a second ring of 2
 //                     TF32: tf32, written back IN PLACE (the TMA tile is already a SWIZZLE_128B operand tile)
@@ -879,7 +880,8 @@ conv_halo_persistent_kernel(const __grid_constant__ ConvTcParams P) {
 // The per-(slice, channel) scale / shift come from gn_finalize (statistics from the producer conv's epilogue), so the results are
 // bit-identical to apply + conv.
 // ================================================================================================
-constexpr int HF_THREADS = 448;
+constexpr int HF_THREADS = 640;       // warps 0 weights TMA, 1 MMA, 2 TMEM alloc + raw-tile TMA, 4-11 epilogue, 12-19 transform
+constexpr int HF_TWARPS = 8;
 constexpr int HF_RAW_BYTES = HALO_A_BYTES;                            // 40 KB: [10][32 px][128 B]
 constexpr int HF_OP_BYTES_BF16 = (HALO_TH + 2) * HALO_RP * 64;        // 20 KB: [10][32 px][64 B]
 constexpr int HF_OP_STRIDE_BF16 = HF_OP_BYTES_BF16 + 1024;            // + the 2 pixels the last tap over-reads
@@ -923,7 +925,7 @@ conv_halo_fused_kernel(const __grid_constant__ ConvTcParams P) {
     const int nk = P.nk0 + P.nk1;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 2; ++i) { tc::mbar_init(&raw_full[i], 1); tc::mbar_init(&raw_empty[i], 4); tc::mbar_init(&a_ready[i], 4); tc::mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { tc::mbar_init(&raw_full[i], 1); tc::mbar_init(&raw_empty[i], HF_TWARPS); tc::mbar_init(&a_ready[i], HF_TWARPS); tc::mbar_init(&a_empty[i], 1); }
         for (int i = 0; i < NB; ++i) { tc::mbar_init(&b_full[i], 1); tc::mbar_init(&b_empty[i], 1); }
         for (int i = 0; i < 2; ++i) { tc::mbar_init(&tfull[i], 1); tc::mbar_init(&tempty[i], 256); }
         tc::fence_barrier_init();
@@ -946,11 +948,30 @@ conv_halo_fused_kernel(const __grid_constant__ ConvTcParams P) {
         const int tyi = tr / P.tiles_x, txi = tr - tyi * P.tiles_x;
         x0 = txi * HALO_TWV; y0 = tyi * HALO_TH; n0 = nt * BLOCK_N;
     };
-    const bool is_transform = warp == 2 || warp == 3 || warp == 12 || warp == 13;
+    const bool is_transform = warp >= 12;
 
     if (warp == 0) {
+        // weight tiles only.  The raw activation tiles have their own producer (warp 14): issued from this loop they would queue behind
+        // the nine weight loads of the previous chunk, i.e. until the MMAs of that chunk start, and land one TMA latency + one
+        // transform too late (measured: 0.82 ms instead of 0.53 for 128 -> 128 at 16 x 500 x 228)
         if (tc::elect_one()) {
-            int ia = 0, ib = 0;
+            int ib = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                int b, x0, y0, n0; decode(tile, b, x0, y0, n0);
+                for (int kc = 0; kc < nk; ++kc) {
+                    for (int tap = 0; tap < 9; ++tap, ++ib) {
+                        const int sb = ib % NB;
+                        tc::mbar_wait(&b_empty[sb], ((uint32_t)(ib / NB) & 1u) ^ 1u);
+                        tc::mbar_expect_tx(&b_full[sb], S::B_BYTES);
+                        tc::tma_load_2d(smem + S::OFF_B + sb * S::B_BYTES, &P.mapB, &b_full[sb], kc * 32, tap * P.cout_rows + n0);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 2) {
+        if (tc::elect_one()) {
+            int ia = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 int b, x0, y0, n0; decode(tile, b, x0, y0, n0);
                 for (int kc = 0; kc < nk; ++kc, ++ia) {
@@ -961,12 +982,6 @@ conv_halo_fused_kernel(const __grid_constant__ ConvTcParams P) {
                     const bool first = kc < P.nk0;
                     tc::tma_load_4d(smem + sa * S::RAW_STRIDE, first ? &P.mapA[0] : &P.mapA[1], &raw_full[sa], (first ? kc : kc - P.nk0) * 32,
                                     x0 - 1, y0 - 1, b);
-                    for (int tap = 0; tap < 9; ++tap, ++ib) {
-                        const int sb = ib % NB;
-                        tc::mbar_wait(&b_empty[sb], ((uint32_t)(ib / NB) & 1u) ^ 1u);
-                        tc::mbar_expect_tx(&b_full[sb], S::B_BYTES);
-                        tc::tma_load_2d(smem + S::OFF_B + sb * S::B_BYTES, &P.mapB, &b_full[sb], kc * 32, tap * P.cout_rows + n0);
-                    }
                 }
             }
         }
@@ -1013,7 +1028,7 @@ conv_halo_fused_kernel(const __grid_constant__ ConvTcParams P) {
         }
         __syncwarp();
     } else if (is_transform) {
-        const int w4 = warp < 4 ? warp - 2 : warp - 10;              // 0..3: 80 of the 320 tile pixels each
+        const int w4 = warp - 12;                                    // 0..7: 40 of the 320 tile pixels each
         const int c8 = lane & 7, psub = lane >> 3;                   // 16-byte chunk (4 channels) of the pixel row; pixel within a group of 4
         const int Ctot = P.gn_c0 + P.gn_c1;
         int ia = 0;
@@ -1033,22 +1048,31 @@ conv_halo_fused_kernel(const __grid_constant__ ConvTcParams P) {
                     }
                 }
                 tc::mbar_wait(&raw_full[sa], ((uint32_t)ia >> 1) & 1u);
-                if (BF16) tc::mbar_wait(&a_empty[sa], (((uint32_t)ia >> 1) & 1u) ^ 1u);     // the operand buffer of this stage is free
                 const uint32_t raw_s = tc::smem_u32(smem + sa * S::RAW_STRIDE);
                 const uint32_t op_s = tc::smem_u32(smem + S::OFF_OP + sa * HF_OP_STRIDE_BF16);
-                // 20 pixels per lane in two batches of 10: all loads of a batch are issued before the first SiLU so that the shared-memory
-                // and MUFU latencies overlap (explicit ld/st.shared: generic accesses made the compiler serialise load -> store -> load)
+                const bool work = P.gn_act != 3;
+                // A lane owns 10 pixels x 4 channels of the chunk: all ten loads are issued before the first SiLU so that the shared-memory and
+                // MUFU latencies overlap (explicit ld/st.shared: generic accesses made the compiler serialise load -> store -> load).  BF16: the
+                // raw slot goes back to the TMA producer as soon as the values sit in registers -- the 64-channel layers are bound by bytes in
+                // flight (two 40 KB slots per SM) -- and only then the warp waits for its operand buffer.
+                constexpr int PER = 320 / HF_TWARPS / 4;
+                float4 v[PER];
+                if (work) {
 #pragma unroll
-                for (int half = 0; half < (P.gn_act == 3 ? 0 : 2); ++half) {
-                    float4 v[10];
-#pragma unroll
-                    for (int j = 0; j < 10; ++j) {
-                        const int r = w4 * 80 + (half * 10 + j) * 4 + psub;              // pixel of the halo tile: row r >> 5, column r & 31
+                    for (int j = 0; j < PER; ++j) {
+                        const int r = w4 * (4 * PER) + j * 4 + psub;                      // pixel of the halo tile: row r >> 5, column r & 31
                         v[j] = tc::lds128(raw_s + (uint32_t)r * 128u + (uint32_t)((c8 ^ (r & 7)) << 4));   // TMA SWIZZLE_128B: 16-byte chunk ^ (row & 7)
                     }
+                }
+                if (BF16) {
+                    __syncwarp();
+                    if (lane == 0) tc::mbar_arrive(&raw_empty[sa]);                      // raw tile consumed (its values live in registers)
+                    tc::mbar_wait(&a_empty[sa], (((uint32_t)ia >> 1) & 1u) ^ 1u);       // the operand buffer of this stage is free
+                }
+                if (work) {
 #pragma unroll
-                    for (int j = 0; j < 10; ++j) {
-                        const int r = w4 * 80 + (half * 10 + j) * 4 + psub;
+                    for (int j = 0; j < PER; ++j) {
+                        const int r = w4 * (4 * PER) + j * 4 + psub;
                         const int yy = y0 - 1 + (r >> 5), xx = x0 - 1 + (r & 31);
                         const bool inside = (unsigned)yy < (unsigned)P.H && (unsigned)xx < (unsigned)P.W;
                         float4 o;
@@ -1068,10 +1092,7 @@ conv_halo_fused_kernel(const __grid_constant__ ConvTcParams P) {
                 }
                 tc::fence_proxy_async();                 // generic-proxy writes -> visible to the tensor core's async proxy
                 __syncwarp();
-                if (lane == 0) {
-                    tc::mbar_arrive(&a_ready[sa]);
-                    if (BF16) tc::mbar_arrive(&raw_empty[sa]);
-                }
+                if (lane == 0) tc::mbar_arrive(&a_ready[sa]);
             }
         }
     } else if (warp >= 4 && warp < 12) {
@@ -1088,8 +1109,8 @@ conv_halo_fused_kernel(const __grid_constant__ ConvTcParams P) {
                 const int tr = tile / n_ntiles - b * tiles_per_img;
                 srow = P.stats_out + ((size_t)b * P.stats_rows + (tr * 2 + mt) * 4 + (warp & 3)) * 2 * P.cout;
             }
-            tc_epilogue_coalesced<BLOCK_N>(P, tmem_base + (buf * 2 + mt) * ACC_COLS, warp & 3, lane, b, x0, y0 + 4 * mt, n0, sbias + n0, stile,
-                                           HALO_TWV, srow);
+            tc_epilogue_coalesced<BLOCK_N, 16>(P, tmem_base + (buf * 2 + mt) * ACC_COLS, warp & 3, lane, b, x0, y0 + 4 * mt, n0, sbias + n0, stile,
+                                               HALO_TWV, srow);
             tc::tc_fence_before();
             tc::mbar_arrive(&tempty[buf]);
         }
