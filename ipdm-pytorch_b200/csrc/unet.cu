@@ -48,7 +48,6 @@ struct ConvW {
     bool bf16 = false;                       // operands (activation tile and packed weights) are bf16
     float* w_dev_direct = nullptr;           // thin layers: the [tap][cin][cout] copy for the direct-kernel fallback
     bool thin = false; int thin_cs = 0;      // thin tensor-core path (conv_thin.cu): operand channel stride 8 / 16 / 32
-    bool warp = false;                       // warp-MMA thin path (conv_warp.cu): w_dev / w_dev_lo hold its TF32 hi / lo weights
 };
 struct ResW { GNW gn1, gn2; ConvW conv1, conv2, shortcut; bool has_shortcut = false; std::vector<float> temb_w, temb_b; float* bias1_t = nullptr; int cin = 0, cout = 0; };
 struct AttnW { GNW norm; ConvW qkv, proj; int C = 0; };
@@ -59,14 +58,14 @@ struct VTensor { int n = 0, h = 0, w = 0, c = 0, cs = 0; int def = -1, last = -1
                  int stats_t = -1, stats_rows = 0; };   // companion tensor with the producer's GroupNorm partials (conv_tc epilogue), rows per slice
 
 struct Op {
-    enum Kind { GN_STATS, GN_APPLY, CONV_TC, CONV_DIRECT, CONV_THIN, UPSAMPLE, ATTN, CONV_WARP } kind;
+    enum Kind { GN_STATS, GN_APPLY, CONV_TC, CONV_DIRECT, CONV_THIN, UPSAMPLE, ATTN } kind;
     int src[2] = {-1, -1}; int nsrc = 0; int dst = -1, res = -1, aux = -1, aux2 = -1, aux3 = -1;
     const GNW* gn = nullptr; int norm_slot = -1; int act = 1;
     const ConvW* cw = nullptr; const float* bias = nullptr; int bias_t_stride = 0; bool use_t = false;
     int stride = 1, upsample = 0, qkv = 0;
     int stats = -1;                            // CONV_TC: tensor that receives the GroupNorm partials of the output
     // materialised
-    ConvTcParams tcp; ConvThinParams thp; ConvWarpParams wp; ConvDirectDesc cd; GroupNormDesc gd; TensorNHWC out_t, src_t; AttentionParams ap; AttentionDesc ad;
+    ConvTcParams tcp; ConvThinParams thp; ConvDirectDesc cd; GroupNormDesc gd; TensorNHWC out_t, src_t; AttentionParams ap; AttentionDesc ad;
     double flops = 0;
 };
 
@@ -156,23 +155,9 @@ static int pack_conv(ipdm_unet* net, ConvW& c, int c0, int c1, bool raw_sources,
     // signal with ~2 % of fine detail, so a 10-bit operand mantissa there costs 6x on the whole-net error (measured: 4.3e-3 -> 2.8e-2
     // rel-L2 at 2000x912); the tf32 and fp32 modes keep these layers on the exact CUDA-core kernel.  Needs a single operand tensor
     // whose channel stride is 8 / 16 / 32 floats: a GroupNorm-apply or upsample output, or a raw tensor that already has one.
-    c.thin = false; c.warp = false;
-    // warp-MMA thin path (3xTF32, fused GroupNorm, statistics in the epilogue): every thin stride-1 layer in every precision mode
-    if (!c.tc && force < 0 && !net->force_thin && conv_warp_supported(c.cin, c.cout, c.k, 1)) {
-        std::vector<float> hi, lo;
-        IPDM_CHECK(conv_warp_pack_weights(c.w_host.data(), c.cout, c.cin, c.k, hi, lo, nullptr, nullptr));
-        IPDM_CHECK(upload(net, hi, &c.w_dev));
-        IPDM_CHECK(upload(net, lo, &c.w_dev_lo));
-        std::vector<float> pd((size_t)kk * c.cin * c.cout);                // direct-kernel copy: stride-2 / upsampling uses of the same weights
-        for (int co = 0; co < c.cout; ++co)
-            for (int ci = 0; ci < c.cin; ++ci)
-                for (int t = 0; t < kk; ++t) pd[((size_t)t * c.cin + ci) * c.cout + co] = c.w_host[((size_t)co * c.cin + ci) * kk + t];
-        IPDM_CHECK(upload(net, pd, &c.w_dev_direct));
-        if (!c.b_host.empty()) IPDM_CHECK(upload(net, c.b_host, &c.b_dev));
-        c.warp = true;
-        return IPDM_OK;
-    }
-    if (!c.tc && force < 0 && (net->precision == IPDM_PREC_BF16 || net->force_thin) && (c.cout == 8 || c.cout == 16) && c.cin <= 32 && c1 == 0) {
+    c.thin = false;
+    static const bool thin_off = getenv("IPDM_THIN") && atoi(getenv("IPDM_THIN")) == 0;   // experiment: exact CUDA-core thin layers in the bf16 mode too
+    if (!c.tc && force < 0 && ((net->precision == IPDM_PREC_BF16 && !thin_off) || net->force_thin) && (c.cout == 8 || c.cout == 16) && c.cin <= 32 && c1 == 0) {
         if (operand_tensor || !raw_sources) { c.thin = true; c.thin_cs = thin_cs_of(c.cin); }
         else if (c.k == 1 && c0 >= 8 && (alloc_cs(c0) == 8 || alloc_cs(c0) == 16 || alloc_cs(c0) == 32)) { c.thin = true; c.thin_cs = alloc_cs(c0); }
     }
@@ -414,12 +399,7 @@ struct PlanBuilder {
         // the two spare warps per CTA doing the transform it is SLOWER than the separate apply pass (measured at 16 slices: 8 -> 8 at
         // 2000x912 1025 us fused vs 600 + 311 us; 16 -> 16 at 1000x456 526 vs 283 + 155 us).
         static const bool thin_fuse = getenv("IPDM_THIN_FUSE") && atoi(getenv("IPDM_THIN_FUSE")) == 1;
-        if (cw.warp) {
-            // the conv stages the raw source(s) itself: GroupNorm affine + SiLU on the way into shared memory, no apply pass, no operand tensor
-            Op cv; cv.kind = Op::CONV_WARP; cv.nsrc = nsrc; cv.src[0] = src[0]; cv.src[1] = st.src[1]; cv.cw = &cw; cv.dst = dst; cv.res = res;
-            cv.bias = bias; cv.bias_t_stride = bstride; cv.use_t = use_t; cv.norm_slot = st.norm_slot; cv.gn = &gn; cv.act = act_silu;
-            push(cv);
-        } else if (cw.thin && thin_fuse && nsrc == 1 && s0.c == cw.thin_cs && s0.cs == cw.thin_cs && !s0.bf16) {
+if (cw.thin && thin_fuse && nsrc == 1 && s0.c == cw.thin_cs && s0.cs == cw.thin_cs && !s0.bf16) {
             // single dense source: the thin kernel normalises the TMA-landed tile itself, no operand tensor and no apply pass
             Op cv; cv.kind = Op::CONV_THIN; cv.nsrc = 1; cv.src[0] = src[0]; cv.cw = &cw; cv.dst = dst; cv.res = res; cv.bias = bias; cv.bias_t_stride = bstride; cv.use_t = use_t;
             cv.norm_slot = st.norm_slot; cv.gn = &gn; cv.act = act_silu;
@@ -450,12 +430,6 @@ struct PlanBuilder {
         }
     }
     void plain_conv(const int* src, int nsrc, const ConvW& cw, int dst, int res, int stride, int upsample) {
-        if (cw.warp && stride == 1 && !upsample) {
-            Op cv; cv.kind = Op::CONV_WARP; cv.nsrc = nsrc; cv.src[0] = src[0]; cv.src[1] = nsrc > 1 ? src[1] : -1;
-            cv.cw = &cw; cv.dst = dst; cv.res = res; cv.bias = cw.b_dev;
-            push(cv);
-            return;
-        }
         Op cv; cv.kind = cw.tc ? Op::CONV_TC : ((cw.thin && stride == 1 && !upsample && nsrc == 1 && pl->vt[src[0]].cs == cw.thin_cs) ? Op::CONV_THIN : Op::CONV_DIRECT); cv.nsrc = nsrc; cv.src[0] = src[0]; cv.src[1] = nsrc > 1 ? src[1] : -1;
         cv.cw = &cw; cv.dst = dst; cv.res = res; cv.bias = cw.b_dev; cv.stride = stride; cv.upsample = upsample;
         push(cv);
@@ -504,8 +478,8 @@ struct PlanBuilder {
                 case LayerRef::UP: {
                     const ConvW& cw = net->convs[l.idx];
                     out = act(up_h, up_w, s0.c);
-                    if (cw.tc || cw.thin || cw.warp) {
-                        const int u = cw.warp ? act(up_h, up_w, s0.c) : cw.thin ? new_tensor(pl->B, up_h, up_w, s0.c, cw.thin_cs)
+                    if (cw.tc || cw.thin) {
+                        const int u = cw.thin ? new_tensor(pl->B, up_h, up_w, s0.c, cw.thin_cs)
                                               : (cw.bf16 ? new_tensor(pl->B, up_h, up_w, s0.c, round_up(s0.c, 64)) : act(up_h, up_w, s0.c));
                         pl->vt[u].bf16 = cw.bf16;
                         Op up; up.kind = Op::UPSAMPLE; up.nsrc = 1; up.src[0] = cur[0]; up.dst = u; push(up);
@@ -570,10 +544,9 @@ static int build_plan(ipdm_unet* net, int B, int H, int W, Plan** out) {
                 const int t = pl->ops[gi].src[sidx];
                 const int pi = t < (int)producer.size() ? producer[t] : -1;
                 // (the thin kernel's epilogue is its bottleneck: statistics there cost more than the separate read, measured)
-                if (pi < 0 || (pl->ops[pi].kind != Op::CONV_TC && pl->ops[pi].kind != Op::CONV_WARP) || pl->ops[pi].qkv || pl->vt[t].c % 4 != 0) continue;
+                if (pi < 0 || pl->ops[pi].kind != Op::CONV_TC || pl->ops[pi].qkv || pl->vt[t].c % 4 != 0) continue;
                 if (pl->vt[t].stats_t < 0) {
-                    const int rows = pl->ops[pi].kind == Op::CONV_WARP ? conv_warp_stats_rows(B, pl->vt[t].h, pl->vt[t].w, pl->ops[pi].cw->cin, pl->ops[pi].cw->k)
-                                                                       : conv_tc_stats_rows_bound(pl->vt[t].h, pl->vt[t].w);
+                    const int rows = conv_tc_stats_rows_bound(pl->vt[t].h, pl->vt[t].w);
                     const int len = rows * 2 * pl->vt[t].c;
                     const int id = pb.new_tensor(B, 1, 1, len, len);
                     pl->vt[id].def = pi; pl->vt[id].last = gi;
@@ -663,19 +636,6 @@ static int build_plan(ipdm_unet* net, int B, int H, int W, Plan** out) {
                 pl->vt[o.dst].stats_rows = o.tcp.stats_out ? o.tcp.stats_rows : 0;
                 o.flops = 2.0 * B * o.tcp.H * o.tcp.W * (double)o.cw->cin * o.cw->cout * d.ntaps;
             } break;
-            case Op::CONV_WARP: {
-                ConvWarpDesc d;
-                d.nsrc = o.nsrc; d.src[0] = resolve(*pl, o.src[0]); if (o.nsrc > 1) d.src[1] = resolve(*pl, o.src[1]);
-                if (o.gn) { d.norm_scale = nscale; d.norm_shift = nshift; d.act_silu = o.act; }
-                d.ksize = o.cw->k; d.cout = o.cw->cout; d.w_hi = o.cw->w_dev; d.w_lo = o.cw->w_dev_lo;
-                d.bias = o.bias; d.bias_t_stride = o.bias_t_stride; d.t_dev = o.use_t ? net->t_dev : nullptr;
-                if (o.res >= 0) d.res = resolve(*pl, o.res);
-                d.out = resolve(*pl, o.dst);
-                if (o.stats >= 0) d.stats_out = resolve(*pl, o.stats).p;
-                IPDM_CHECK(conv_warp_prepare(o.wp, d));
-                pl->vt[o.dst].stats_rows = o.wp.stats_out ? o.wp.stats_rows : 0;
-                o.flops = 2.0 * B * d.out.h * d.out.w * (double)o.cw->cin * o.cw->cout * o.cw->k * o.cw->k;
-            } break;
             case Op::CONV_THIN: {
                 ConvThinDesc d;
                 d.src = resolve(*pl, o.src[0]); d.ntaps = o.cw->k * o.cw->k; d.cout = o.cw->cout; d.w_packed = o.cw->w_dev;
@@ -691,7 +651,7 @@ static int build_plan(ipdm_unet* net, int B, int H, int W, Plan** out) {
                 d.nsrc = o.nsrc; d.src[0] = resolve(*pl, o.src[0]); if (o.nsrc > 1) d.src[1] = resolve(*pl, o.src[1]);
                 d.norm_scale = o.gn ? nscale : nullptr; d.norm_shift = o.gn ? nshift : nullptr;
                 d.ksize = o.cw->k; d.stride = o.stride; d.upsample = o.upsample; d.cin = o.cw->cin; d.cout = o.cw->cout;
-                d.w = (o.cw->thin || o.cw->warp) ? o.cw->w_dev_direct : o.cw->w_dev;
+                d.w = o.cw->thin ? o.cw->w_dev_direct : o.cw->w_dev;
                 d.bias = o.bias; d.bias_t_stride = o.bias_t_stride; d.t_dev = o.use_t ? net->t_dev : nullptr;
                 if (o.res >= 0) d.res = resolve(*pl, o.res);
                 d.out = resolve(*pl, o.dst);
@@ -736,7 +696,6 @@ static int run_plan(ipdm_unet* net, Plan* pl, const float* x, int t, float* eps,
             case Op::GN_APPLY: IPDM_CHECK(groupnorm_apply_launch(o.gd, o.out_t, o.act, net->precision != IPDM_PREC_FP32, st)); break;
             case Op::CONV_TC: IPDM_CHECK(conv_tc_launch(o.tcp, st)); break;
             case Op::CONV_THIN: IPDM_CHECK(conv_thin_launch(o.thp, st)); break;
-            case Op::CONV_WARP: IPDM_CHECK(conv_warp_launch(o.wp, st)); break;
             case Op::CONV_DIRECT: {
                 ConvDirectDesc d = o.cd;
                 if ((int)i == pl->first_op) d.src[0].p = const_cast<float*>(x);
@@ -750,7 +709,7 @@ static int run_plan(ipdm_unet* net, Plan* pl, const float* x, int t, float* eps,
     if (trace_path) {
         cudaStreamSynchronize(st);
         if (FILE* f = fopen(trace_path, "a")) {
-            static const char* names[] = {"gn_stats", "gn_apply", "conv_tc", "conv_direct", "conv_thin", "upsample", "attention", "conv_warp"};
+            static const char* names[] = {"gn_stats", "gn_apply", "conv_tc", "conv_direct", "conv_thin", "upsample", "attention"};
             fprintf(f, "# forward B=%d\n", pl->B);
             for (size_t i = 0; i < pl->ops.size(); ++i) {
                 const Op& o = pl->ops[i];
@@ -838,25 +797,6 @@ extern "C" int ipdm_debug_conv(const float* src0, int c0, int cs0, const float* 
     ConvW cw; cw.cin = c0 + c1; cw.cout = cout; cw.k = k;
     cw.w_host.assign(w_host, w_host + (size_t)cout * cw.cin * k * k);
     if (bias_host) cw.b_host.assign(bias_host, bias_host + cout);
-    if (use_tc == 5) {                                   // warp-MMA thin path (conv_warp.cu): raw sources, optional fused GroupNorm + SiLU
-        IPDM_REQUIRE(stride == 1 && upsample_h == 0, "ipdm_debug_conv: the warp path is stride 1, no upsampling");
-        IPDM_CHECK(pack_conv(&holder, cw, c0, c1, true));
-        IPDM_REQUIRE(cw.warp, "ipdm_debug_conv: shape is not eligible for the warp path");
-        ConvWarpDesc d; d.nsrc = c1 ? 2 : 1; d.src[0] = mk(src0, n, h, w, c0, cs0); if (c1) d.src[1] = mk(src1, n, h, w, c1, cs1);
-        d.norm_scale = norm_scale; d.norm_shift = norm_shift; d.act_silu = 1;
-        d.ksize = k; d.cout = cout; d.w_hi = cw.w_dev; d.w_lo = cw.w_dev_lo; d.bias = cw.b_dev;
-        if (res) d.res = mk(res, n, h, w, cout, res_cs);
-        d.out = mk(out, n, h, w, cout, out_cs);
-        ConvWarpParams WP;
-        IPDM_CHECK(conv_warp_prepare(WP, d));
-        float* stats = nullptr;                          // exercise the statistics epilogue too: rows land behind a scratch pointer
-        IPDM_CHECK_CUDA(cudaMalloc(&stats, (size_t)n * WP.stats_rows * 2 * cout * sizeof(float)));
-        WP.stats_out = stats;
-        int rc2 = conv_warp_launch(WP, (cudaStream_t)stream);
-        cudaStreamSynchronize((cudaStream_t)stream);
-        cudaFree(stats);
-        return rc2;
-    }
     if (use_tc == 4) {                                   // thin tensor-core path: src0 is the operand tensor (channel stride cs0 in {8,16,32})
         IPDM_REQUIRE(c1 == 0 && stride == 1 && upsample_h == 0 && !norm_scale, "ipdm_debug_conv: thin path takes one plain source");
         holder.force_thin = true;

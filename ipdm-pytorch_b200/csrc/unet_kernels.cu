@@ -533,7 +533,16 @@ gn_tile_reduce_kernel(const float* __restrict__ tile, int rows, int C, double* _
     if (t < R * V) {
         const int cv = t % V;
         const float* base = tile + (size_t)n * rows * 2 * C + 4 * cv;
-        for (int r = blockIdx.x * R + t / V; r < rows; r += gridDim.x * R) {
+        const int stride = gridDim.x * R;
+        int r = blockIdx.x * R + t / V;
+        for (; r + 3 * stride < rows; r += 4 * stride) {            // four independent loads in flight (the loop is latency-bound otherwise)
+            float4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = __ldg(reinterpret_cast<const float4*>(base + (size_t)(r + u * stride) * 2 * C));
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { a0 += v[u].x; a1 += v[u].y; a2 += v[u].z; a3 += v[u].w; }
+        }
+        for (; r < rows; r += stride) {
             const float4 v = __ldg(reinterpret_cast<const float4*>(base + (size_t)r * 2 * C));
             a0 += v.x; a1 += v.y; a2 += v.z; a3 += v.w;
         }

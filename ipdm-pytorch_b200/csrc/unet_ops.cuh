@@ -3,7 +3,6 @@
 #include "common.cuh"
 #include <cuda.h>
 #include <cstring>
-#include <vector>
 
 namespace ipdm {
 
@@ -87,35 +86,6 @@ struct ConvThinParams {
 };
 int conv_thin_prepare(ConvThinParams& P, const ConvThinDesc& d);
 int conv_thin_launch(const ConvThinParams& P, cudaStream_t st);
-
-// ---- warp-level TF32 MMA convolution for thin layers with fused GroupNorm + SiLU, 3xTF32 accuracy (conv_warp.cu) -----------------
-struct ConvWarpDesc {
-    int nsrc = 1;
-    TensorNHWC src[2];                 // raw fp32 sources (virtual concat), channel counts multiples of 4, total <= 32
-    const float* norm_scale = nullptr; // optional fused GroupNorm: y = act(x*scale[n][c] + shift[n][c]); both [batch][cin_total]
-    const float* norm_shift = nullptr; int act_silu = 1;
-    int ksize = 3, cout = 0;
-    const float* w_hi = nullptr; const float* w_lo = nullptr;      // conv_warp_pack_weights layout
-    const float* bias = nullptr; int bias_t_stride = 0; const int* t_dev = nullptr;
-    TensorNHWC res, out;
-    float* stats_out = nullptr;        // GroupNorm partials of the output, [batch][stats_rows][2][cout] (ConvTcDesc::stats_out format)
-    int dry = 0;                       // prepare only computes the launch geometry
-};
-struct ConvWarpParams {
-    const float* src0; const float* src1; int c0, cs0, c1, cs1;
-    const float* nscale; const float* nshift; int act_silu;
-    const float* w_hi; const float* w_lo;
-    const float* bias; int bias_t_stride; const int* t_dev;
-    const float* res; int res_cs;
-    float* out; int out_cs, cout;
-    float* stats_out; int stats_rows;
-    int K, NT, taps, TH, H, W, batch, tiles_x, tiles_y, grid_x, dbg;
-};
-int conv_warp_pack_weights(const float* w_host, int cout, int cin, int k, std::vector<float>& hi, std::vector<float>& lo, int* kpad_out, int* nt_out);
-bool conv_warp_supported(int cin, int cout, int k, int stride);
-int conv_warp_stats_rows(int batch, int h, int w, int cin, int k);
-int conv_warp_prepare(ConvWarpParams& P, const ConvWarpDesc& d);
-int conv_warp_launch(const ConvWarpParams& P, cudaStream_t st);
 
 // ---- direct (CUDA-core) convolution for thin layers (unet_kernels.cu) -------------------------------
 struct ConvDirectDesc {

@@ -250,29 +250,6 @@ def test_tc_conv_fused_groupnorm(cuda, c0, c1, cout, hw):
     assert e_bf16 < 8e-3 and e_exact < 3e-4          # (the device SiLU uses ex2.approx: a few operands round to the neighbouring bf16)
 
 
-@pytest.mark.parametrize("c0,c1,cout,k,hw", [(8, 0, 8, 3, (40, 70)), (4, 0, 8, 3, (33, 65)), (8, 4, 8, 3, (21, 47)), (16, 8, 8, 3, (37, 95)), (16, 0, 16, 3, (50, 38)),
-                                            (16, 16, 16, 3, (19, 33)), (8, 0, 16, 3, (64, 31)), (16, 8, 8, 1, (37, 95)), (8, 8, 8, 1, (21, 47)), (16, 16, 16, 1, (21, 47)),
-                                            (8, 0, 16, 1, (17, 64)), (4, 0, 8, 1, (16, 32))])
-def test_warp_mma_thin_conv(cuda, c0, c1, cout, k, hw):
-    """conv_warp_kernel: warp-level TF32 MMAs with the 3xTF32 split (fp32-class accuracy), fused GroupNorm + SiLU on the staged tile,
-    virtual concat, zero padding of the ACTIVATION, residual, ragged edges, padded (16 -> 32) and dense source strides."""
-    n, C = 2, c0 + c1
-    x0 = rnd(n, c0, *hw, seed=1) * 3 + 1.0                       # large signal + detail, like the sinogram levels
-    x1 = rnd(n, c1, *hw, seed=2) if c1 else None
-    w = rnd(cout, C, k, k, seed=3, scale=0.2)
-    b = rnd(cout, seed=4)
-    res = rnd(n, cout, *hw, seed=5)
-    scale, shift = 0.5 + torch.rand(n, C, generator=torch.Generator().manual_seed(6)), rnd(n, C, seed=7, scale=0.5)
-    for norm in (None, (scale, shift)):
-        for dense in (False, True):
-            want = ref_conv(x0, x1, w, b, k, 1, res=res, norm=norm)
-            got = run_conv(cuda, x0, x1, w, b, k, 1, 5, res=res, norm=norm, dense_out=True, dense_src=dense)
-            err = rel_l2(got.numpy(), want.numpy())
-            assert err < SPLIT_TOL, (norm is not None, dense, err)
-    got = run_conv(cuda, x0, x1, w, b, k, 1, 5, norm=(scale, shift))             # no residual, padded output stride (16 -> 32)
-    assert rel_l2(got.numpy(), ref_conv(x0, x1, w, b, k, 1, norm=(scale, shift)).numpy()) < SPLIT_TOL
-
-
 @pytest.mark.parametrize("cin,cs,cout,k,hw,batch", [(8, 8, 8, 3, (40, 70), 2), (4, 8, 8, 3, (33, 65), 1), (8, 8, 16, 1, (21, 47), 2), (16, 16, 16, 3, (50, 38), 2),
                                                     (12, 16, 8, 3, (25, 61), 1), (24, 32, 8, 3, (37, 95), 2), (32, 32, 16, 3, (64, 64), 1),
                                                     (8, 8, 8, 3, (300, 400), 2)])
