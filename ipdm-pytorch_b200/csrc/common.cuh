@@ -114,6 +114,9 @@ __device__ __forceinline__ float tf32_rn(float x) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return __uint_as_float(r);
 }
+// Same rounding for a value that only the tensor core will read (kind::tf32 ignores the low 13 bits): the add alone, no mask.
+// Finite inputs only (activations); +-inf would turn into NaN.
+__device__ __forceinline__ float tf32_rn_hw(float x) { return __uint_as_float(__float_as_uint(x) + 0x1000u); }
 inline float tf32_rn_host(float x) {
     uint32_t b; memcpy(&b, &x, 4);
     if ((b & 0x7F800000u) == 0x7F800000u) return x;

@@ -283,6 +283,82 @@ __device__ __forceinline__ void tc_epilogue_coalesced(const ConvTcParams& P, uin
     }
 }
 
+// ---------------- coalesced epilogue of the halo kernels ----------------
+// Same data flow as tc_epilogue_coalesced, specialised for the halo tiling (tile row pitch 32): the 32 accumulator rows of a warp are
+// the 32 consecutive pixels x0 .. x0+31 of ONE image row, so every address is row base + pixel * channel stride -- one 64-bit base per
+// tile and 32-bit offsets, where the generic form spent ~6 integer instructions per 128-bit access on (slice, y, x) arithmetic
+// (ncu, width-folded layers: the epilogue warps issued 6.4 k instructions per 240-pixel x 32-channel tile and the SM was issue-bound).
+template <int BLOCK_N, int CHUNK_W = 32>
+__device__ __forceinline__ void tc_epilogue_row(const ConvTcParams& P, uint32_t tmem_acc, int quarter, int lane, int b, int x0, int py,
+                                                int n0, const float* sbias, float* stile, int tw_valid, float* stats_row) {
+    constexpr int CHUNK = BLOCK_N < 32 ? 16 : CHUNK_W;
+    constexpr int LPP = CHUNK / 4, PPI = 32 / LPP, NJ = 32 / PPI;
+    const int c4 = (lane % LPP) * 4, psub = lane / LPP;
+    const int nvalid = py < P.H ? min(tw_valid, P.W - x0) : 0;           // valid pixels of this warp's row
+    uint32_t vmask = 0;                                                  // bit j: pixel j * PPI + psub is an output
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) vmask |= (j * PPI + psub < nvalid ? 1u : 0u) << j;
+    const size_t pix0 = ((size_t)b * P.H + py) * P.W + x0;
+    float* const obase = P.out + pix0 * P.out_cs;
+    const bool has_res = P.res != nullptr;
+    const float* const rbase = has_res ? P.res + pix0 * P.res_cs : P.out;          // (never read without has_res)
+    const int ostep = PPI * P.out_cs, rstep = PPI * P.res_cs;
+    const int oo = psub * P.out_cs + c4 + n0, ro = psub * P.res_cs + c4 + n0;
+#pragma unroll 1
+    for (int cc = 0; cc < BLOCK_N; cc += CHUNK) {
+        const int n = n0 + cc + c4;
+        const bool nok = n < P.cout;
+        const uint32_t vm = nok ? vmask : 0u;
+        uint32_t r[32];
+        const uint32_t taddr = tmem_acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)cc;
+        if constexpr (CHUNK == 32) tc::tmem_ld32(taddr, r);
+        else { uint32_t r16[16]; tc::tmem_ld16(taddr, r16);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) r[i] = r16[i]; }
+        float4 rres[NJ];                               // all residual lines of the chunk are requested before anything waits
+#pragma unroll
+        for (int j = 0; j < NJ; ++j)
+            rres[j] = (has_res && ((vm >> j) & 1u)) ? ld_stream(reinterpret_cast<const float4*>(rbase + (ro + cc + j * rstep))) : make_float4(0.f, 0.f, 0.f, 0.f);
+        tc::tmem_ld_wait();
+        __syncwarp();                                  // previous chunk's readers are done with the tile
+        float4* row = reinterpret_cast<float4*>(stile + lane * EPI_PITCH);
+#pragma unroll
+        for (int i = 0; i < CHUNK / 4; ++i)
+            row[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+        __syncwarp();
+        const float4 bq = *reinterpret_cast<const float4*>(sbias + cc + c4);
+        float4 ss = make_float4(0.f, 0.f, 0.f, 0.f), sq = ss;          // GroupNorm partials of this lane's 4 channels
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            if ((vm >> j) & 1u) {
+                float4 v = *reinterpret_cast<const float4*>(stile + (j * PPI + psub) * EPI_PITCH + c4);
+                v.x += bq.x + rres[j].x; v.y += bq.y + rres[j].y; v.z += bq.z + rres[j].z; v.w += bq.w + rres[j].w;
+                st_stream(reinterpret_cast<float4*>(obase + (oo + cc + j * ostep)), v);
+                ss.x += v.x; ss.y += v.y; ss.z += v.z; ss.w += v.w;
+                sq.x = fmaf(v.x, v.x, sq.x); sq.y = fmaf(v.y, v.y, sq.y); sq.z = fmaf(v.z, v.z, sq.z); sq.w = fmaf(v.w, v.w, sq.w);
+            }
+        }
+        if (stats_row) {
+#pragma unroll
+            for (int o = LPP; o < 32; o <<= 1) {
+                ss.x += __shfl_xor_sync(0xffffffffu, ss.x, o); ss.y += __shfl_xor_sync(0xffffffffu, ss.y, o);
+                ss.z += __shfl_xor_sync(0xffffffffu, ss.z, o); ss.w += __shfl_xor_sync(0xffffffffu, ss.w, o);
+                sq.x += __shfl_xor_sync(0xffffffffu, sq.x, o); sq.y += __shfl_xor_sync(0xffffffffu, sq.y, o);
+                sq.z += __shfl_xor_sync(0xffffffffu, sq.z, o); sq.w += __shfl_xor_sync(0xffffffffu, sq.w, o);
+            }
+            if (lane < LPP && nok) {
+                *reinterpret_cast<float4*>(stats_row + n) = ss;
+                *reinterpret_cast<float4*>(stats_row + P.cout + n) = sq;
+            }
+        }
+    }
+    // keep the channel padding of the output at zero (layers with C_out < channel stride: 16 -> 32)
+    if (P.out_cs > P.cout && n0 + BLOCK_N >= P.cout && lane < nvalid) {
+        float* o = P.out + (pix0 + lane) * P.out_cs;
+        for (int c = P.cout; c < P.out_cs; ++c) o[c] = 0.f;
+    }
+}
+
 // SPLIT = fp32-accurate "3xTF32" mode: every fp32 operand x is used as x_hi + x_lo (x_hi = rn_tf32(x), x_lo =
 // rn_tf32(x - x_hi)) and D += A_hi B_hi + A_hi B_lo + A_lo B_hi.  Weights are split on the host (two packed arrays, two
 // TMA loads); the activation tile is split in shared memory by warps 2-3 right after the TMA lands (the split is
@@ -614,7 +690,8 @@ conv_tc_persistent_kernel(const __grid_constant__ ConvTcParams P) {
     if (warp == 0 && lane == 0) { tc::prefetch_tmap(&P.mapA[0]); tc::prefetch_tmap(&P.mapB); }
     {   // all bias (+ time-embedding) values of the layer -> smem, once per CTA
         const float* bias = P.bias ? P.bias + (P.t_dev ? (size_t)(*P.t_dev) * P.bias_t_stride : 0) : nullptr;
-        for (int i = threadIdx.x; i < P.cout; i += PERS_THREADS) sbias[i] = bias ? __ldg(bias + i) : 0.f;
+        const int bm = P.bias_mod ? P.bias_mod : P.cout;          // width-folded layers: output channel i is real channel i % bm
+        for (int i = threadIdx.x; i < P.cout; i += PERS_THREADS) sbias[i] = bias ? __ldg(bias + i % bm) : 0.f;
     }
     tc::tc_fence_before();
     __syncthreads();
@@ -762,7 +839,8 @@ conv_halo_persistent_kernel(const __grid_constant__ ConvTcParams P) {
     if (warp == 0 && lane == 0) { tc::prefetch_tmap(&P.mapA[0]); tc::prefetch_tmap(&P.mapB); }
     {
         const float* bias = P.bias ? P.bias + (P.t_dev ? (size_t)(*P.t_dev) * P.bias_t_stride : 0) : nullptr;
-        for (int i = threadIdx.x; i < P.cout; i += HP_THREADS) sbias[i] = bias ? __ldg(bias + i) : 0.f;
+        const int bm = P.bias_mod ? P.bias_mod : P.cout;
+        for (int i = threadIdx.x; i < P.cout; i += HP_THREADS) sbias[i] = bias ? __ldg(bias + i % bm) : 0.f;
     }
     tc::tc_fence_before();
     __syncthreads();
@@ -789,11 +867,13 @@ conv_halo_persistent_kernel(const __grid_constant__ ConvTcParams P) {
                     const bool first = kc < P.nk0;
                     tc::tma_load_4d(smem + sa * HALO_A_STRIDE, first ? &P.mapA[0] : &P.mapA[1], &a_full[sa], (first ? kc : kc - P.nk0) * P.kc,
                                     x0 - 1, y0 - 1, b);
-                    for (int tap = 0; tap < 9; ++tap, ++ib) {
+                    for (int tap = 0; tap < 9; ++tap) {
+                        if (P.masked && !((P.kmask[tap] >> (4 * kc)) & 0xFull)) continue;     // structurally zero (tap, chunk): no tile, no MMAs
                         const int sb = ib % NB;
                         tc::mbar_wait(&b_empty[sb], ((uint32_t)(ib / NB) & 1u) ^ 1u);
                         tc::mbar_expect_tx(&b_full[sb], S::B_BYTES);
                         tc::tma_load_2d(smem + S::OFF_B + sb * S::B_BYTES, &P.mapB, &b_full[sb], kc * P.kc, tap * P.cout_rows + n0);
+                        ++ib;
                     }
                 }
             }
@@ -809,11 +889,14 @@ conv_halo_persistent_kernel(const __grid_constant__ ConvTcParams P) {
                 tc::mbar_wait(&tempty[buf], (((uint32_t)tl >> 1) & 1u) ^ 1u);     // both epilogue warpgroups have drained this pair
                 tc::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + buf * 2 * ACC_COLS;
+                uint32_t started = 0;                                                // the first MMA of a tile overwrites the accumulators
                 for (int kc = 0; kc < nk; ++kc, ++ia) {
                     const int sa = ia & 1;
                     tc::mbar_wait(&a_full[sa], ((uint32_t)ia >> 1) & 1u);
                     const uint32_t a_base = tc::smem_u32(smem + sa * HALO_A_STRIDE);
-                    for (int tap = 0; tap < 9; ++tap, ++ib) {
+                    for (int tap = 0; tap < 9; ++tap) {
+                        const uint32_t km = P.masked ? (uint32_t)((P.kmask[tap] >> (4 * kc)) & 0xFull) : 0xFu;
+                        if (!km) continue;
                         const int sb = ib % NB;
                         tc::mbar_wait(&b_full[sb], (uint32_t)(ib / NB) & 1u);
                         tc::tc_fence_after();
@@ -824,12 +907,15 @@ conv_halo_persistent_kernel(const __grid_constant__ ConvTcParams P) {
                             const uint64_t adesc = tc::smem_desc_k_sw128(a_base + (uint32_t)(((4 * mt + dy) * HALO_RP + dx) * 128));
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
-                                const uint32_t acc = (uint32_t)((kc | tap | k) != 0);
+                                if (!((km >> k) & 1u)) continue;
+                                const uint32_t acc = (started >> mt) & 1u;
                                 if (bf16) tc::umma_f16(d_tmem + mt * ACC_COLS, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, acc);
                                 else tc::umma_tf32(d_tmem + mt * ACC_COLS, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, acc);
+                                started |= 1u << mt;
                             }
                         }
                         tc::umma_commit(&b_empty[sb]);
+                        ++ib;
                     }
                     tc::umma_commit(&a_empty[sa]);
                 }
@@ -851,8 +937,8 @@ conv_halo_persistent_kernel(const __grid_constant__ ConvTcParams P) {
                 const int tr = tile / n_ntiles - b * tiles_per_img;
                 srow = P.stats_out + ((size_t)b * P.stats_rows + (tr * 2 + mt) * 4 + (warp & 3)) * 2 * P.cout;
             }
-            tc_epilogue_coalesced<BLOCK_N>(P, tmem_base + (buf * 2 + mt) * ACC_COLS, warp & 3, lane, b, x0, y0 + 4 * mt, n0, sbias + n0, stile,
-                                           HALO_TWV, srow);
+            tc_epilogue_row<BLOCK_N>(P, tmem_base + (buf * 2 + mt) * ACC_COLS, warp & 3, lane, b, x0, y0 + 4 * mt + (warp & 3), n0, sbias + n0, stile,
+                                     HALO_TWV, srow);
             tc::tc_fence_before();
             tc::mbar_arrive(&tempty[buf]);
         }
@@ -885,33 +971,36 @@ constexpr int HF_TWARPS = 8;
 constexpr int HF_RAW_BYTES = HALO_A_BYTES;                            // 40 KB: [10][32 px][128 B]
 constexpr int HF_OP_BYTES_BF16 = (HALO_TH + 2) * HALO_RP * 64;        // 20 KB: [10][32 px][64 B]
 constexpr int HF_OP_STRIDE_BF16 = HF_OP_BYTES_BF16 + 1024;            // + the 2 pixels the last tap over-reads
-template <int BLOCK_N, int NB, bool BF16>
+template <int BLOCK_N, int NB, bool BF16, int NA>
 struct HaloFusedSmem {
     static constexpr int B_BYTES = BLOCK_N * (BF16 ? 64 : 128);
     static constexpr int RAW_STRIDE = BF16 ? HF_RAW_BYTES : HALO_A_STRIDE;
-    static constexpr int OFF_OP = 2 * RAW_STRIDE;                      // BF16 only
+    static constexpr int OFF_OP = NA * RAW_STRIDE;                     // BF16 only
     static constexpr int OFF_B = OFF_OP + (BF16 ? 2 * HF_OP_STRIDE_BF16 : 0);
     static constexpr int BAR_OFF = OFF_B + NB * B_BYTES;
     static constexpr int BIAS_OFF = BAR_OFF + 512;
     static constexpr int MAX_COUT = 512;
     static constexpr int EPI_OFF = BIAS_OFF + MAX_COUT * 4;
     static constexpr int TOTAL = EPI_OFF + 8 * EPI_WARP_FLOATS * 4 + 1024;
-    static_assert((2 * NB + 14) * 8 + 16 <= 512, "barrier block");
+    static_assert((2 * NB + 4 * NA + 6) * 8 + 16 <= 512, "barrier block");
+    static_assert(!BF16 || NA == 2, "the bf16 variant has two operand buffers");
 };
 
-template <int BLOCK_N, int NB, bool BF16>
+// NA = depth of the raw-tile ring (TF32: the tiles are transformed in place, so it is also the operand ring).  Layers with few K
+// chunks per tile (the width-folded thin layers: one or three) are bound by HBM latency x bytes in flight and take NA = 4.
+template <int BLOCK_N, int NB, bool BF16, int NA>
 __global__ void __launch_bounds__(HF_THREADS, 1)
 conv_halo_fused_kernel(const __grid_constant__ ConvTcParams P) {
-    using S = HaloFusedSmem<BLOCK_N, NB, BF16>;
+    using S = HaloFusedSmem<BLOCK_N, NB, BF16, NA>;
     constexpr int ACC_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
     constexpr int TMEM_COLS = 4 * ACC_COLS;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint64_t* raw_full = (uint64_t*)(smem + S::BAR_OFF);   // [2] TMA landed a raw tile
-    uint64_t* raw_empty = raw_full + 2;                    // [2] BF16: the transform warps have read it (4 arrivals)
-    uint64_t* a_ready = raw_empty + 2;                     // [2] operand tile written (4 arrivals)
-    uint64_t* a_empty = a_ready + 2;                       // [2] MMAs have read the operand tile
-    uint64_t* b_full = a_empty + 2;
+    uint64_t* raw_full = (uint64_t*)(smem + S::BAR_OFF);   // [NA] TMA landed a raw tile
+    uint64_t* raw_empty = raw_full + NA;                   // [NA] BF16: the transform warps have read it (one arrival per warp)
+    uint64_t* a_ready = raw_empty + NA;                    // [NA] operand tile written (one arrival per warp)
+    uint64_t* a_empty = a_ready + NA;                      // [NA] MMAs have read the operand tile
+    uint64_t* b_full = a_empty + NA;
     uint64_t* b_empty = b_full + NB;
     uint64_t* tfull = b_empty + NB;
     uint64_t* tempty = tfull + 2;
@@ -925,45 +1014,131 @@ conv_halo_fused_kernel(const __grid_constant__ ConvTcParams P) {
     const int nk = P.nk0 + P.nk1;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 2; ++i) { tc::mbar_init(&raw_full[i], 1); tc::mbar_init(&raw_empty[i], HF_TWARPS); tc::mbar_init(&a_ready[i], HF_TWARPS); tc::mbar_init(&a_empty[i], 1); }
-        for (int i = 0; i < NB; ++i) { tc::mbar_init(&b_full[i], 1); tc::mbar_init(&b_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { tc::mbar_init(&tfull[i], 1); tc::mbar_init(&tempty[i], 256); }
+        const uint32_t issuers = (!BF16 && P.masked) ? 2u : 1u;        // masked (width-folded) layers: one MMA issuer per accumulator
+        for (int i = 0; i < NA; ++i) { tc::mbar_init(&raw_full[i], 1); tc::mbar_init(&raw_empty[i], HF_TWARPS); tc::mbar_init(&a_ready[i], HF_TWARPS); tc::mbar_init(&a_empty[i], issuers); }
+        for (int i = 0; i < NB; ++i) { tc::mbar_init(&b_full[i], 1); tc::mbar_init(&b_empty[i], issuers); }
+        for (int i = 0; i < 2; ++i) { tc::mbar_init(&tfull[i], issuers); tc::mbar_init(&tempty[i], 256); }
         tc::fence_barrier_init();
     }
     if (warp == 2) tc::tmem_alloc(tmem_slot, TMEM_COLS);
     if (warp == 0 && lane == 0) { tc::prefetch_tmap(&P.mapA[0]); tc::prefetch_tmap(&P.mapB); }
     {
         const float* bias = P.bias ? P.bias + (P.t_dev ? (size_t)(*P.t_dev) * P.bias_t_stride : 0) : nullptr;
-        for (int i = threadIdx.x; i < P.cout; i += HF_THREADS) sbias[i] = bias ? __ldg(bias + i) : 0.f;
+        const int bm = P.bias_mod ? P.bias_mod : P.cout;
+        for (int i = threadIdx.x; i < P.cout; i += HF_THREADS) sbias[i] = bias ? __ldg(bias + i % bm) : 0.f;
     }
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // 640 threads leave 96 registers per thread; the producer / issuer warpgroup needs far fewer and hands 32 per thread to each of the
+    // two epilogue warpgroups, which then hold a whole 32-column accumulator chunk plus its residual lines (setmaxnreg, warpgroup-wide)
 
-    auto decode = [&](int tile, int& b, int& x0, int& y0, int& n0) {
-        const int nt = tile % n_ntiles, mt = tile / n_ntiles;
-        b = mt / tiles_per_img;
-        const int tr = mt - b * tiles_per_img;
-        const int tyi = tr / P.tiles_x, txi = tr - tyi * P.tiles_x;
-        x0 = txi * HALO_TWV; y0 = tyi * HALO_TH; n0 = nt * BLOCK_N;
+    // tile = blockIdx.x, blockIdx.x + gridDim.x, ...: (N tile, tile column, tile row, slice) advanced with adds and compares -- the four
+    // integer divisions of a fresh decode cost ~90 instructions per tile in each of the 20 warps (ncu, width-folded layers)
+    struct TileWalk {
+        int nt, txi, tyi, b, s_nt, s_tx, s_ty, s_b, n_nt, n_tx, n_ty;
+        __device__ __forceinline__ void split(int v, int& nt_, int& tx_, int& ty_, int& b_) const {
+            nt_ = v % n_nt; v /= n_nt; tx_ = v % n_tx; v /= n_tx; ty_ = v % n_ty; b_ = v / n_ty;
+        }
+        __device__ __forceinline__ void init(int first, int step, int n_ntiles_, int tiles_x_, int tiles_y_) {
+            n_nt = n_ntiles_; n_tx = tiles_x_; n_ty = tiles_y_;
+            split(first, nt, txi, tyi, b); split(step, s_nt, s_tx, s_ty, s_b);
+        }
+        __device__ __forceinline__ void next() {
+            nt += s_nt; if (nt >= n_nt) { nt -= n_nt; ++txi; }
+            txi += s_tx; if (txi >= n_tx) { txi -= n_tx; ++tyi; }
+            tyi += s_ty; if (tyi >= n_ty) { tyi -= n_ty; ++b; }
+            b += s_b;
+        }
+    } walk;
+    walk.init(blockIdx.x, gridDim.x, n_ntiles, P.tiles_x, P.tiles_y);
+    auto decode = [&](int, int& b, int& x0, int& y0, int& n0) {       // coordinates of the walker's current tile; callers advance it
+        b = walk.b; x0 = walk.txi * HALO_TWV; y0 = walk.tyi * HALO_TH; n0 = walk.nt * BLOCK_N;
     };
     const bool is_transform = warp >= 12;
 
-    if (warp == 0) {
+    if (warp < 4) {
+    if (!BF16 && P.masked && (warp == 0 || warp == 1 || warp == 3)) {
+        // Width-folded layers: 36 ... 100 small MMAs (N = 32 / 64, some k-steps structurally zero) per tile, so the kernel is bound by
+        // how fast ONE thread can walk the issue loop (ncu: ~900 cycles per tap with the generic loop below).  Lean variant: taps
+        // unrolled, masks in registers, ring positions kept incrementally, 32-bit descriptor arithmetic, predicated MMAs, and one
+        // issuer warp per accumulator (warp 1: tile rows 0-3, warp 3: rows 4-7; every consumer barrier counts two arrivals).
+        if (tc::elect_one()) {
+            uint64_t kmr[9];
+#pragma unroll
+            for (int t = 0; t < 9; ++t) kmr[t] = P.kmask[t];
+            int sb = 0; uint32_t phb = 0;
+            if (warp == 0) {
+                for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, walk.next()) {
+                    const int n0 = walk.nt * BLOCK_N;
+                    for (int kc = 0; kc < nk; ++kc) {
+#pragma unroll
+                        for (int tap = 0; tap < 9; ++tap) {
+                            if (!((uint32_t)(kmr[tap] >> (4 * kc)) & 0xFu)) continue;
+                            tc::mbar_wait(&b_empty[sb], phb ^ 1u);
+                            tc::mbar_expect_tx(&b_full[sb], S::B_BYTES);
+                            tc::tma_load_2d(smem + S::OFF_B + sb * S::B_BYTES, &P.mapB, &b_full[sb], kc * 32, tap * P.cout_rows + n0);
+                            if (++sb == NB) { sb = 0; phb ^= 1u; }
+                        }
+                    }
+                }
+            } else {
+                const uint32_t mt = warp == 1 ? 0u : 1u;
+                const uint32_t idesc = tc::make_idesc(tc::FMT_TF32, 128, BLOCK_N);
+                const uint32_t a_lo0 = tc::desc_lo(tc::smem_u32(smem)) + mt * (4u * HALO_RP * 128u / 16u);
+                const uint32_t b_lo0 = tc::desc_lo(tc::smem_u32(smem + S::OFF_B));
+                int sa = 0; uint32_t pha = 0, tl = 0;
+                for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl, walk.next()) {
+                    const uint32_t buf = tl & 1u;
+                    tc::mbar_wait(&tempty[buf], ((tl >> 1) & 1u) ^ 1u);
+                    tc::tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + (buf * 2u + mt) * ACC_COLS;
+                    uint32_t acc = 0;
+                    for (int kc = 0; kc < nk; ++kc) {
+                        tc::mbar_wait(&a_ready[sa], pha);
+                        const uint32_t a_lo = a_lo0 + (uint32_t)sa * (S::RAW_STRIDE / 16);
+#pragma unroll
+                        for (int tap = 0; tap < 9; ++tap) {
+                            const uint32_t km = (uint32_t)(kmr[tap] >> (4 * kc)) & 0xFu;
+                            if (!km) continue;
+                            tc::mbar_wait(&b_full[sb], phb);
+                            tc::tc_fence_after();
+                            const uint32_t a_tap = a_lo + (uint32_t)(((tap / 3) * HALO_RP + tap % 3) * 128 / 16);
+                            const uint32_t b_tap = b_lo0 + (uint32_t)sb * (S::B_BYTES / 16);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const uint32_t en = (km >> k) & 1u;
+                                tc::umma_tf32_lo(d_tmem, a_tap + 2u * k, b_tap + 2u * k, idesc, acc, en);
+                                acc |= en;
+                            }
+                            tc::umma_commit(&b_empty[sb]);
+                            if (++sb == NB) { sb = 0; phb ^= 1u; }
+                        }
+                        tc::umma_commit(&a_empty[sa]);
+                        if (++sa == NA) { sa = 0; pha ^= 1u; }
+                    }
+                    tc::umma_commit(&tfull[buf]);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 0) {
         // weight tiles only.  The raw activation tiles have their own producer (warp 14): issued from this loop they would queue behind
         // the nine weight loads of the previous chunk, i.e. until the MMAs of that chunk start, and land one TMA latency + one
         // transform too late (measured: 0.82 ms instead of 0.53 for 128 -> 128 at 16 x 500 x 228)
         if (tc::elect_one()) {
             int ib = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, walk.next()) {
                 int b, x0, y0, n0; decode(tile, b, x0, y0, n0);
                 for (int kc = 0; kc < nk; ++kc) {
-                    for (int tap = 0; tap < 9; ++tap, ++ib) {
+                    for (int tap = 0; tap < 9; ++tap) {
+                        if (P.masked && !((P.kmask[tap] >> (4 * kc)) & 0xFull)) continue;     // structurally zero (tap, chunk)
                         const int sb = ib % NB;
                         tc::mbar_wait(&b_empty[sb], ((uint32_t)(ib / NB) & 1u) ^ 1u);
                         tc::mbar_expect_tx(&b_full[sb], S::B_BYTES);
                         tc::tma_load_2d(smem + S::OFF_B + sb * S::B_BYTES, &P.mapB, &b_full[sb], kc * 32, tap * P.cout_rows + n0);
+                        ++ib;
                     }
                 }
             }
@@ -972,12 +1147,12 @@ conv_halo_fused_kernel(const __grid_constant__ ConvTcParams P) {
     } else if (warp == 2) {
         if (tc::elect_one()) {
             int ia = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, walk.next()) {
                 int b, x0, y0, n0; decode(tile, b, x0, y0, n0);
                 for (int kc = 0; kc < nk; ++kc, ++ia) {
-                    const int sa = ia & 1;
+                    const int sa = ia % NA;
                     // the raw buffer is free once the transform warps have read it (BF16) / once the MMAs have read the in-place tile (TF32)
-                    tc::mbar_wait(BF16 ? &raw_empty[sa] : &a_empty[sa], (((uint32_t)ia >> 1) & 1u) ^ 1u);
+                    tc::mbar_wait(BF16 ? &raw_empty[sa] : &a_empty[sa], ((uint32_t)(ia / NA) & 1u) ^ 1u);
                     tc::mbar_expect_tx(&raw_full[sa], HF_RAW_BYTES);
                     const bool first = kc < P.nk0;
                     tc::tma_load_4d(smem + sa * S::RAW_STRIDE, first ? &P.mapA[0] : &P.mapA[1], &raw_full[sa], (first ? kc : kc - P.nk0) * 32,
@@ -992,16 +1167,19 @@ conv_halo_fused_kernel(const __grid_constant__ ConvTcParams P) {
             constexpr int ROWB = BF16 ? 64 : 128;              // bytes per pixel row of the operand tile
             constexpr int KSTEPS = ROWB / 32;                  // 32 bytes of K per MMA
             int ia = 0, ib = 0, tl = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl, walk.next()) {
                 const int buf = tl & 1;
                 tc::mbar_wait(&tempty[buf], (((uint32_t)tl >> 1) & 1u) ^ 1u);
                 tc::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + buf * 2 * ACC_COLS;
+                uint32_t started = 0;                                                // the first MMA of a tile overwrites the accumulators
                 for (int kc = 0; kc < nk; ++kc, ++ia) {
-                    const int sa = ia & 1;
-                    tc::mbar_wait(&a_ready[sa], ((uint32_t)ia >> 1) & 1u);
+                    const int sa = ia % NA;
+                    tc::mbar_wait(&a_ready[sa], (uint32_t)(ia / NA) & 1u);
                     const uint32_t a_base = tc::smem_u32(smem + (BF16 ? S::OFF_OP + sa * HF_OP_STRIDE_BF16 : sa * S::RAW_STRIDE));
-                    for (int tap = 0; tap < 9; ++tap, ++ib) {
+                    for (int tap = 0; tap < 9; ++tap) {
+                        const uint32_t km = (!BF16 && P.masked) ? (uint32_t)((P.kmask[tap] >> (4 * kc)) & 0xFull) : 0xFu;
+                        if (!km) continue;
                         const int sb = ib % NB;
                         tc::mbar_wait(&b_full[sb], (uint32_t)(ib / NB) & 1u);
                         tc::tc_fence_after();
@@ -1014,12 +1192,15 @@ conv_halo_fused_kernel(const __grid_constant__ ConvTcParams P) {
                             const uint64_t adesc = BF16 ? tc::smem_desc_k(a_addr, 4, 512) : tc::smem_desc_k_sw128(a_addr);
 #pragma unroll
                             for (int k = 0; k < KSTEPS; ++k) {
-                                const uint32_t acc = (uint32_t)((kc | tap | k) != 0);
+                                if (!((km >> k) & 1u)) continue;
+                                const uint32_t acc = (started >> mt) & 1u;
                                 if (BF16) tc::umma_f16(d_tmem + mt * ACC_COLS, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, acc);
                                 else tc::umma_tf32(d_tmem + mt * ACC_COLS, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, acc);
+                                started |= 1u << mt;
                             }
                         }
                         tc::umma_commit(&b_empty[sb]);
+                        ++ib;
                     }
                     tc::umma_commit(&a_empty[sa]);
                 }
@@ -1027,30 +1208,33 @@ conv_halo_fused_kernel(const __grid_constant__ ConvTcParams P) {
             }
         }
         __syncwarp();
+    }
     } else if (is_transform) {
         const int w4 = warp - 12;                                    // 0..7: 40 of the 320 tile pixels each
         const int c8 = lane & 7, psub = lane >> 3;                   // 16-byte chunk (4 channels) of the pixel row; pixel within a group of 4
-        const int Ctot = P.gn_c0 + P.gn_c1;
+        const int Ctot = P.gn_m0 + P.gn_m1;                          // real channels of the GroupNorm (== gn_c0 + gn_c1 unless width-folded)
         int ia = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, walk.next()) {
             int b, x0, y0, n0; decode(tile, b, x0, y0, n0);
             for (int kc = 0; kc < nk; ++kc, ++ia) {
-                const int sa = ia & 1;
+                const int sa = ia % NA;
                 // per-lane affine of its 4 channels (pad channels of the source tensors: scale = shift = 0 -> silu(0) = 0)
                 float4 sc = make_float4(0.f, 0.f, 0.f, 0.f), sh = sc;
                 {
                     const bool first = kc < P.nk0;
                     const int cl = (first ? kc : kc - P.nk0) * 32 + 4 * c8;          // channel inside its source
-                    const int cg = first ? cl : P.gn_c0 + cl;                        // channel of the GroupNorm (virtual concat)
-                    if (cl < (first ? P.gn_c0 : P.gn_c1)) {
+                    const int cg = first ? cl % P.gn_m0 : P.gn_m0 + cl % max(P.gn_m1, 1);   // channel of the GroupNorm (virtual concat; folded: pixel-major)
+                    if (P.gn_act != 4 && cl < (first ? P.gn_c0 : P.gn_c1)) {
                         sc = __ldg(reinterpret_cast<const float4*>(P.gn_scale + (size_t)b * Ctot + cg));
                         sh = __ldg(reinterpret_cast<const float4*>(P.gn_shift + (size_t)b * Ctot + cg));
                     }
                 }
-                tc::mbar_wait(&raw_full[sa], ((uint32_t)ia >> 1) & 1u);
+                // one warp watches the barrier, the other seven sleep on a named barrier: eight pollers cost a third of the SM's issue slots
+                if (w4 == 0) tc::mbar_wait_idle(&raw_full[sa], (uint32_t)(ia / NA) & 1u);
+                tc::named_bar_sync(1, HF_TWARPS * 32);
                 const uint32_t raw_s = tc::smem_u32(smem + sa * S::RAW_STRIDE);
                 const uint32_t op_s = tc::smem_u32(smem + S::OFF_OP + sa * HF_OP_STRIDE_BF16);
-                const bool work = P.gn_act != 3;
+                const bool work = P.gn_act != 3 && P.gn_act != 4;      // 4: the tile already is the operand (tf32-rounded, no GroupNorm): hand it on
                 // A lane owns 10 pixels x 4 channels of the chunk: all ten loads are issued before the first SiLU so that the shared-memory and
                 // MUFU latencies overlap (explicit ld/st.shared: generic accesses made the compiler serialise load -> store -> load).  BF16: the
                 // raw slot goes back to the TMA producer as soon as the values sit in registers -- the 64-channel layers are bound by bytes in
@@ -1067,7 +1251,8 @@ conv_halo_fused_kernel(const __grid_constant__ ConvTcParams P) {
                 if (BF16) {
                     __syncwarp();
                     if (lane == 0) tc::mbar_arrive(&raw_empty[sa]);                      // raw tile consumed (its values live in registers)
-                    tc::mbar_wait(&a_empty[sa], (((uint32_t)ia >> 1) & 1u) ^ 1u);       // the operand buffer of this stage is free
+                    if (w4 == 0) tc::mbar_wait_idle(&a_empty[sa], ((uint32_t)(ia / NA) & 1u) ^ 1u);      // the operand buffer of this stage is free
+                    tc::named_bar_sync(1, HF_TWARPS * 32);
                 }
                 if (work) {
 #pragma unroll
@@ -1078,15 +1263,16 @@ conv_halo_fused_kernel(const __grid_constant__ ConvTcParams P) {
                         float4 o;
                         o.x = fmaf(v[j].x, sc.x, sh.x); o.y = fmaf(v[j].y, sc.y, sh.y); o.z = fmaf(v[j].z, sc.z, sh.z); o.w = fmaf(v[j].w, sc.w, sh.w);
                         if (P.gn_act == 1) { o.x = silu(o.x); o.y = silu(o.y); o.z = silu(o.z); o.w = silu(o.w); }
-                        if (!inside) o = make_float4(0.f, 0.f, 0.f, 0.f);                 // the conv pads the ACTIVATION with zeros
+                        if (BF16 && !inside) o = make_float4(0.f, 0.f, 0.f, 0.f);         // the conv pads the ACTIVATION with zeros
                         if (BF16) {
                             const __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
                             // SWIZZLE_64B operand row r (64 bytes): 16-byte chunk (c8 >> 1) ^ ((r >> 1) & 3), 8-byte half c8 & 1
                             tc::sts64(op_s + (uint32_t)r * 64u + (uint32_t)((((c8 >> 1) ^ ((r >> 1) & 3)) << 4) | ((c8 & 1) << 3)),
                                       *reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
                         } else {
-                            tc::sts128(raw_s + (uint32_t)r * 128u + (uint32_t)((c8 ^ (r & 7)) << 4),
-                                       make_float4(tf32_rn(o.x), tf32_rn(o.y), tf32_rn(o.z), tf32_rn(o.w)));
+                            // (round to nearest tf32 = add half an ulp of the 10-bit mantissa; the tensor core drops the low 13 bits itself)
+                            tc::sts128_or_zero(raw_s + (uint32_t)r * 128u + (uint32_t)((c8 ^ (r & 7)) << 4),
+                                               make_float4(tf32_rn_hw(o.x), tf32_rn_hw(o.y), tf32_rn_hw(o.z), tf32_rn_hw(o.w)), inside);
                         }
                     }
                 }
@@ -1099,18 +1285,19 @@ conv_halo_fused_kernel(const __grid_constant__ ConvTcParams P) {
         const int mt = (warp - 4) >> 2;
         float* stile = (float*)(smem + S::EPI_OFF) + (warp - 4) * EPI_WARP_FLOATS;
         int tl = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl, walk.next()) {
             const int buf = tl & 1;
             int b, x0, y0, n0; decode(tile, b, x0, y0, n0);
-            tc::mbar_wait(&tfull[buf], ((uint32_t)tl >> 1) & 1u);
+            if ((warp & 3) == 0) tc::mbar_wait_idle(&tfull[buf], ((uint32_t)tl >> 1) & 1u);
+            tc::named_bar_sync(2 + mt, 128);
             tc::tc_fence_after();
             float* srow = nullptr;
             if (P.stats_out) {
                 const int tr = tile / n_ntiles - b * tiles_per_img;
                 srow = P.stats_out + ((size_t)b * P.stats_rows + (tr * 2 + mt) * 4 + (warp & 3)) * 2 * P.cout;
             }
-            tc_epilogue_coalesced<BLOCK_N, 16>(P, tmem_base + (buf * 2 + mt) * ACC_COLS, warp & 3, lane, b, x0, y0 + 4 * mt, n0, sbias + n0, stile,
-                                               HALO_TWV, srow);
+            tc_epilogue_row<BLOCK_N, 32>(P, tmem_base + (buf * 2 + mt) * ACC_COLS, warp & 3, lane, b, x0, y0 + 4 * mt + (warp & 3), n0, sbias + n0, stile,
+                                         HALO_TWV, srow);
             tc::tc_fence_before();
             tc::mbar_arrive(&tempty[buf]);
         }
@@ -1120,16 +1307,16 @@ conv_halo_fused_kernel(const __grid_constant__ ConvTcParams P) {
     if (warp == 2) tc::tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-template <int BN, int NB, bool BF16>
+template <int BN, int NB, bool BF16, int NA = 2>
 static int launch_halo_fused(const ConvTcParams& P, cudaStream_t st) {
     static DeviceOnce once;
-    constexpr int smem = HaloFusedSmem<BN, NB, BF16>::TOTAL;
+    constexpr int smem = HaloFusedSmem<BN, NB, BF16, NA>::TOTAL;
     static_assert(smem <= 227 * 1024, "fused halo rings do not fit in shared memory");
     if (once.need()) {
-        IPDM_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_fused_kernel<BN, NB, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        IPDM_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_fused_kernel<BN, NB, BF16, NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     }
     const int total = P.tiles_x * P.tiles_y * P.batch * (P.cout / BN);
-    conv_halo_fused_kernel<BN, NB, BF16><<<std::min(total, kNumSMs), HF_THREADS, smem, st>>>(P);
+    conv_halo_fused_kernel<BN, NB, BF16, NA><<<std::min(total, kNumSMs), HF_THREADS, smem, st>>>(P);
     count_launch();
     IPDM_CHECK_LAUNCH();
     return IPDM_OK;
@@ -1216,24 +1403,30 @@ int conv_tc_prepare(ConvTcParams& P, const ConvTcDesc& d) {
     // tools/bench_conv.py at 16 slices, bf16: 788 -> 1081 TFLOP/s at 500x228x128, 394 -> 558 at 512x512x64; 64x64 and 32x32 images
     // lose 25-30 % to the tiling and stay per-tap).  N = 16 layers (144 -> 16 at 1000x456) have almost no epilogue: the
     // one-tile-per-CTA halo kernel with two CTAs per SM is the fastest there (1.59 ms against 1.85 persistent, 2.88 per-tap).
-    const bool narrow = d.cout < 64;
+    const bool narrow = d.cout < 64 && d.n_tile != 32;      // (the N = 32 tile of the width-folded layers is persistent)
     const long long htx = ceil_div(P.W, HALO_TWV), hty = ceil_div(P.H, HALO_TH);
-    const bool halo_ok = plain && d.stride == 1 && d.ntaps == 9 && htx * hty * P.batch >= kNumSMs / 2;
-    P.halo = halo_ok && (variant == 2 || variant == 4 || (variant == 0 && halo_auto(P.H, P.W, P.batch, d.cout, d.ntaps, d.stride)));
-    P.persistent = plain && (P.halo ? (variant == 4 || (variant == 0 && !narrow)) : (variant == 0 || variant == 3 || variant == 4));
+    const bool halo_ok = plain && d.stride == 1 && d.ntaps == 9 && (htx * hty * P.batch >= kNumSMs / 2 || d.fold);
+    P.halo = halo_ok && (d.fold || variant == 2 || variant == 4 || (variant == 0 && halo_auto(P.H, P.W, P.batch, d.cout, d.ntaps, d.stride)));
+    P.persistent = plain && (d.fold || (P.halo ? (variant == 4 || (variant == 0 && !narrow)) : (variant == 0 || variant == 3 || variant == 4)));
     P.tw_log2 = P.halo ? 5 : pick_tw_log2(P.H, P.W);
     const int TW = P.halo ? HALO_RP : 1 << P.tw_log2, TH = P.halo ? HALO_TH + 2 : 128 >> P.tw_log2;     // TMA box extent
     P.tiles_x = P.halo ? ceil_div(P.W, HALO_TWV) : ceil_div(P.W, TW);
     P.tiles_y = P.halo ? ceil_div(P.H, HALO_TH) : ceil_div(P.H, TH);
     P.ntaps = d.ntaps; P.stride = d.stride;
-    P.cout = d.cout; P.block_n = d.cout >= 128 ? 128 : (d.cout >= 64 ? 64 : 16);
+    P.cout = d.cout; P.block_n = d.n_tile ? d.n_tile : (d.cout >= 128 ? 128 : (d.cout >= 64 ? 64 : 16));
+    IPDM_REQUIRE(P.block_n == 16 || P.block_n == 32 || P.block_n == 64 || P.block_n == 128, "conv_tc: N tile %d", P.block_n);
+    IPDM_REQUIRE(P.block_n != 32 || P.persistent, "conv_tc: the N = 32 tile exists in the persistent kernels only");
     IPDM_REQUIRE(d.cout % P.block_n == 0, "conv_tc: C_out %d not a multiple of the N tile %d", d.cout, P.block_n);
     P.cout_rows = d.cout;
     int ktot = 0;
     // fused GroupNorm: the sources are RAW fp32 tensors whatever the operand type (the kernel converts on the operand path)
-    P.fused = d.norm_scale != nullptr;
-    if (P.fused) {
-        IPDM_REQUIRE(P.halo && P.persistent && d.cout >= 64 && d.cout <= 512 && d.norm_shift, "conv_tc: GroupNorm fusion needs a persistent halo layer (3x3, stride 1, C_out 64..512)");
+    P.fused = d.norm_scale != nullptr || d.passthrough;
+    if (d.passthrough) {
+        // the conv_halo_fused_kernel pipeline (deep raw ring, lean masked MMA issue) with an identity operand path: tf32 tiles only
+        IPDM_REQUIRE(!d.norm_scale && !d.w_bf16 && !d.src[0].bf16 && P.halo && P.persistent && P.block_n >= 32, "conv_tc: passthrough takes tf32-rounded fp32 sources on a persistent halo layer");
+        P.gn_act = 4; P.gn_c0 = d.src[0].c; P.gn_c1 = d.nsrc > 1 ? d.src[1].c : 0; P.gn_m0 = P.gn_c0; P.gn_m1 = P.gn_c1;
+    } else if (P.fused) {
+        IPDM_REQUIRE(P.halo && P.persistent && P.block_n >= 32 && d.cout <= 512 && d.norm_shift, "conv_tc: GroupNorm fusion needs a persistent halo layer (3x3, stride 1, C_out 32..512)");
         IPDM_REQUIRE(d.nsrc == 1 || d.src[0].c == d.src[0].cs, "conv_tc: fused concat needs an unpadded first source (%d channels, stride %d)", d.src[0].c, d.src[0].cs);
         IPDM_REQUIRE(d.act_silu, "conv_tc: the fused operand path is GroupNorm + SiLU (the attention norm has no activation and feeds a 1x1 conv)");
         P.gn_scale = d.norm_scale; P.gn_shift = d.norm_shift; P.gn_act = d.act_silu;
@@ -1241,7 +1434,9 @@ int conv_tc_prepare(ConvTcParams& P, const ConvTcDesc& d) {
         static const int fuse_dbg = getenv("IPDM_FUSE_DBG") ? atoi(getenv("IPDM_FUSE_DBG")) : 0;
         if (fuse_dbg) P.gn_act = fuse_dbg;
         P.gn_c0 = d.src[0].c; P.gn_c1 = d.nsrc > 1 ? d.src[1].c : 0;
-        IPDM_REQUIRE(P.gn_c0 % 4 == 0 && P.gn_c1 % 4 == 0, "conv_tc: fused GroupNorm needs channel counts that are multiples of 4");
+        P.gn_m0 = d.gn_mod[0] ? d.gn_mod[0] : P.gn_c0; P.gn_m1 = d.gn_mod[1] ? d.gn_mod[1] : P.gn_c1;
+        IPDM_REQUIRE(P.gn_c0 % 4 == 0 && P.gn_c1 % 4 == 0 && P.gn_m0 % 4 == 0 && (P.gn_c1 == 0 || P.gn_m1 % 4 == 0),
+                     "conv_tc: fused GroupNorm needs channel counts that are multiples of 4");
     }
     P.bf16 = P.fused ? d.w_bf16 : d.src[0].bf16;
     P.kc = P.fused ? 32 : (P.bf16 ? 64 : 32);
@@ -1291,6 +1486,22 @@ int conv_tc_prepare(ConvTcParams& P, const ConvTcDesc& d) {
     P.res = d.res.p; P.res_cs = d.res.cs;
     P.qkv_mode = d.qkv_mode; P.vt = d.vt; P.t_pad = d.t_pad; P.heads = d.heads; P.head_dim = d.head_dim;
     P.out_lo = d.out_lo; P.vt_lo = d.vt_lo; P.qkv_bf16 = d.qkv_bf16;
+    P.bias_mod = d.bias_mod; P.fold = d.fold;
+    P.masked = 0;
+    for (int t = 0; t < 9; ++t) { P.kmask[t] = d.kmask[t]; if (d.kmask[t]) P.masked = 1; }
+    IPDM_REQUIRE(!P.masked || (P.halo && P.persistent && !P.bf16 && d.ntaps == 9 && P.nk0 + P.nk1 <= 16),
+                 "conv_tc: k-step masks are a feature of the tf32 persistent halo kernels (<= 16 K chunks)");
+    {   // MMA work actually issued (masked k-steps are skipped)
+        double ksteps = 0;
+        const int nkk = P.nk0 + P.nk1, per = P.kc * (P.bf16 ? 2 : 4) / 32;      // k-steps (32 bytes of K) per chunk
+        for (int t = 0; t < d.ntaps; ++t)
+            for (int kc = 0; kc < nkk; ++kc) {
+                const unsigned km = P.masked ? (unsigned)((P.kmask[t] >> (4 * kc)) & 0xF) : (1u << per) - 1u;
+                ksteps += __builtin_popcount(km);
+            }
+        const int kel = P.bf16 ? 16 : 8;                                          // K elements per k-step
+        P.flops = 2.0 * P.batch * P.H * P.W * (double)P.cout * ksteps * kel;
+    }
     P.stats_out = P.persistent ? d.stats_out : nullptr;              // only the persistent kernels' epilogue produces statistics
     P.stats_rows = P.stats_out ? P.tiles_x * P.tiles_y * (P.halo ? 2 : 1) * 4 : 0;
     IPDM_REQUIRE(!P.stats_out || (d.cout % 4 == 0 && P.stats_rows <= conv_tc_stats_rows_bound(P.H, P.W)), "conv_tc: statistics rows %d exceed the bound", P.stats_rows);
@@ -1331,10 +1542,16 @@ static int launch_halo(const ConvTcParams& P, cudaStream_t st) {
 
 int conv_tc_launch(const ConvTcParams& P, cudaStream_t st) {
     // padded-K FLOPs actually issued to the tensor pipe; the persistent halo kernel (the dominant kernel of the step) is its own family
-    ProfScope prof(P.halo && P.persistent ? PROF_CONV_HALO_PERS : PROF_CONV_TC, st, conv_tc_flops(P));
+    // (width-folded thin layers are HBM-bound streaming layers: they are accounted in bytes with the other thin / direct convs)
+    ProfScope prof(P.fold ? PROF_CONV_DIRECT : (P.halo && P.persistent ? PROF_CONV_HALO_PERS : PROF_CONV_TC), st,
+                   P.fold ? 4.0 * P.batch * (double)P.H * P.W * ((P.nk0 + P.nk1) * P.kc + P.cout) : conv_tc_flops(P));
     if (P.fused) {
         if (P.bf16) { if (P.block_n == 128) return launch_halo_fused<128, 8, true>(P, st); if (P.block_n == 64) return launch_halo_fused<64, 12, true>(P, st); }
-        else { if (P.block_n == 128) return launch_halo_fused<128, 6, false>(P, st); if (P.block_n == 64) return launch_halo_fused<64, 10, false>(P, st); }
+        else {
+            if (P.block_n == 128) return launch_halo_fused<128, 6, false>(P, st);
+            if (P.block_n == 64) return P.masked ? launch_halo_fused<64, 6, false, 3>(P, st) : launch_halo_fused<64, 10, false>(P, st);
+            if (P.block_n == 32) return launch_halo_fused<32, 4, false, 4>(P, st);
+        }
         set_error("conv_tc_launch: no fused kernel for N tile %d", P.block_n);
         return IPDM_ERR_UNSUPPORTED;
     }
@@ -1342,6 +1559,7 @@ int conv_tc_launch(const ConvTcParams& P, cudaStream_t st) {
         switch (P.block_n) {
             case 128: return launch_halo_pers<128, 6>(P, st);
             case 64: return launch_halo_pers<64, 10>(P, st);
+            case 32: return launch_halo_pers<32, 12>(P, st);
             case 16: return launch_halo_pers<16, 12>(P, st);
         }
     }
@@ -1356,6 +1574,7 @@ int conv_tc_launch(const ConvTcParams& P, cudaStream_t st) {
         switch (P.block_n) {
             case 128: return launch_pers<128, 5>(P, st);
             case 64: return launch_pers<64, 7>(P, st);
+            case 32: return launch_pers<32, 8>(P, st);
             case 16: return launch_pers<16, 9>(P, st);
         }
     }
@@ -1376,8 +1595,6 @@ int conv_tc_launch(const ConvTcParams& P, cudaStream_t st) {
     return IPDM_ERR_UNSUPPORTED;
 }
 
-double conv_tc_flops(const ConvTcParams& P) {
-    return (P.split ? 3.0 : 1.0) * 2.0 * P.batch * P.H * P.W * (double)P.cout * P.ntaps * (P.nk0 + P.nk1) * P.kc;
-}
+double conv_tc_flops(const ConvTcParams& P) { return (P.split ? 3.0 : 1.0) * P.flops; }
 
 }  // namespace ipdm

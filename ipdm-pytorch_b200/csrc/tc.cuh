@@ -40,13 +40,37 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         "selp.b32 %0, 1, 0, P;\n\t}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0;
 }
+// try_wait with a suspend-time hint: the thread may sleep up to `ns` and is woken by the phase completion, so a waiting warp does
+// not burn issue slots (ncu on the width-folded layers: ~45 polls x 9 instructions per wait with the plain form, a third of all
+// instructions issued by the 16 transform / epilogue warps)
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
+        "selp.b32 %0, 1, 0, P;\n\t}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(ns) : "memory");
+    return ok != 0;
+}
 // Bounded wait: a protocol bug must surface as a trap (launch error), never as a hung GPU box.
+// mbar_wait polls (producers and MMA issuers: single threads on the critical path); mbar_wait_idle sleeps between polls (whole warps
+// that wait for data: they must not take issue slots from the working warps).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity))
         if (clock64() - t0 > 4000000000LL) { asm volatile("trap;"); }   // ~2 s at 1.9 GHz
 }
+__device__ __forceinline__ void mbar_wait_idle(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    uint32_t it = 0;
+    while (!mbar_try_wait_hint(bar, parity, 96u))
+        if (++it > 40000000u) { asm volatile("trap;"); }                 // every poll may sleep ~0.1 us: seconds before a stuck pipeline traps
+}
+// named barrier among `count` threads (count a multiple of 32): warps wait without issuing anything
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t count) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(count) : "memory"); }
+// warpgroup-wide register reallocation (all four warps of an aligned group of four execute the same instruction)
+template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(N)); }
+template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(N)); }
 
 // explicit shared-state-space accesses (32-bit shared addresses): the compiler keeps them out of the generic path and may reorder them freely
 __device__ __forceinline__ float4 lds128(uint32_t saddr) {
@@ -56,6 +80,14 @@ __device__ __forceinline__ float4 lds128(uint32_t saddr) {
 }
 __device__ __forceinline__ void sts128(uint32_t saddr, const float4& v) {
     asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" :: "r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+// v if keep, else zeros: two predicated stores instead of four selects and a store
+__device__ __forceinline__ void sts128_or_zero(uint32_t saddr, const float4& v, bool keep) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %5, 0;\n\t"
+        "@p st.shared.v4.f32 [%0], {%1,%2,%3,%4};\n\t"
+        "@!p st.shared.v4.f32 [%0], {%6,%6,%6,%6};\n\t}\n"
+        :: "r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"((uint32_t)keep), "f"(0.f) : "memory");
 }
 __device__ __forceinline__ void sts64(uint32_t saddr, uint32_t a, uint32_t b) {
     asm volatile("st.shared.v2.b32 [%0], {%1,%2};" :: "r"(saddr), "r"(a), "r"(b) : "memory");
@@ -157,6 +189,20 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
         :: "r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+// Lean form for issue-bound loops: both descriptors share the upper word (SWIZZLE_128B, SBO 1024, version 1) and differ in the
+// 14-bit start-address field, so the issuer keeps 32-bit `lo` words (advance = one integer add) and the instruction is predicated
+// on `enable` instead of being branched around.
+constexpr uint32_t DESC_SW128_HI = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr >> 4) & 0x3FFFu) | (1u << 16); }
+__device__ __forceinline__ void umma_tf32_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate, uint32_t enable) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+        "mov.b64 da, {%1, %6};\n\tmov.b64 db, {%2, %6};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %3, p;\n\t}\n"
+        :: "r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(enable), "r"(DESC_SW128_HI) : "memory");
 }
 
 }  // namespace tc

@@ -48,6 +48,8 @@ struct ConvW {
     bool bf16 = false;                       // operands (activation tile and packed weights) are bf16
     float* w_dev_direct = nullptr;           // thin layers: the [tap][cin][cout] copy for the direct-kernel fallback
     bool thin = false; int thin_cs = 0;      // thin tensor-core path (conv_thin.cu): operand channel stride 8 / 16 / 32
+    // width-folded tensor-core path (pack_fold): `fold` pixels of a row are one pixel of fold*C channels
+    int fold = 0, fold_c0 = 0, fold_c1 = 0; float* w_dev_fold = nullptr; uint64_t fold_mask[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
 };
 struct ResW { GNW gn1, gn2; ConvW conv1, conv2, shortcut; bool has_shortcut = false; std::vector<float> temb_w, temb_b; float* bias1_t = nullptr; int cin = 0, cout = 0; };
 struct AttnW { GNW norm; ConvW qkv, proj; int C = 0; };
@@ -55,7 +57,7 @@ struct LayerRef { enum Kind { CONV_IN, RES, ATTN, DOWN, UP } kind; int idx; };
 typedef std::vector<LayerRef> Block;
 
 struct VTensor { int n = 0, h = 0, w = 0, c = 0, cs = 0; int def = -1, last = -1; size_t off = 0; bool external = false; int bf16 = 0;
-                 int stats_t = -1, stats_rows = 0; };   // companion tensor with the producer's GroupNorm partials (conv_tc epilogue), rows per slice
+                 int stats_t = -1, stats_rows = 0, stats_fold = 0; };   // companion tensor with the producer's GroupNorm partials (conv_tc epilogue), rows per slice
 
 struct Op {
     enum Kind { GN_STATS, GN_APPLY, CONV_TC, CONV_DIRECT, CONV_THIN, UPSAMPLE, ATTN } kind;
@@ -64,6 +66,7 @@ struct Op {
     const ConvW* cw = nullptr; const float* bias = nullptr; int bias_t_stride = 0; bool use_t = false;
     int stride = 1, upsample = 0, qkv = 0;
     int stats = -1;                            // CONV_TC: tensor that receives the GroupNorm partials of the output
+    int fold = 0;                              // CONV_TC: width-fold factor (0: plain)
     // materialised
     ConvTcParams tcp; ConvThinParams thp; ConvDirectDesc cd; GroupNormDesc gd; TensorNHWC out_t, src_t; AttentionParams ap; AttentionDesc ad;
     double flops = 0;
@@ -97,6 +100,7 @@ struct ipdm_unet {
     int heads = 4;
     int precision = IPDM_PREC_TF32;
     bool force_thin = false;                 // tests: thin tensor-core path regardless of the precision mode
+    bool force_fold = false;                 // tests: width-folded path regardless of the precision mode
     std::map<std::tuple<int, int, int>, std::unique_ptr<Plan>> plans;
     ~ipdm_unet() { for (float* p : dev_allocs) cudaFree(p); cudaFree(t_dev); }
 };
@@ -217,6 +221,60 @@ static int pack_conv(ipdm_unet* net, ConvW& c, int c0, int c1, bool raw_sources,
     return IPDM_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Width-folded thin layers.  The 2000x912 and 1000x456 levels of the projection UNet have 4 ... 16 channels (model.py channel_mult
+// 1/16, 1/8, 1/4 of 64); as GEMMs they are K = 8 ... 24, N = 8 / 16, and every kernel written for that shape was bound by per-pixel
+// instruction issue or by the extra GroupNorm passes (r01: half of the projection forward).  A dense NHWC tensor [H][W][C] IS the
+// tensor [H][W/f][f*C]: choose f so that f*C_in and f*C_out are multiples of 32 and the layer becomes an ordinary 32/64-wide
+// tensor-core layer on an image of W/f columns, with weights
+//     Wf[dy][bdx][(bo, co)][(bi, ci)] = w[co][ci][dy][dx],  dx = f*(bdx - 1) + bi - bo in {-1, 0, 1}, else 0
+// (bo / bi = pixel inside the output / input folded pixel).  It runs on the persistent halo kernels unchanged -- TMA zero fill of
+// folded column -1 / W/f is the conv padding, the GroupNorm affine + SiLU is applied on the operand path, the epilogue adds the
+// residual and emits the GroupNorm statistics -- except that the MMA issuer skips the k-steps (8 input columns) that are
+// structurally zero: of the left / right neighbour only the last / first pixel contributes, so a 3x3 layer costs
+// 3 * (f + 2) * C_in / 8 k-steps per 128 folded pixels instead of 9 * f * C_in / 8.
+// Operands are tf32 (the accuracy-critical full-resolution layers never see bf16), accumulation fp32.
+// ------------------------------------------------------------------------------------------------
+static int fold_factor(int c0, int c1, int cout) {
+    static const bool off = getenv("IPDM_FOLD") && atoi(getenv("IPDM_FOLD")) == 0;
+    if (off || cout > 16) return 0;
+    for (int f : {2, 4, 8})
+        if ((f * c0) % 32 == 0 && (c1 == 0 || (f * c1) % 32 == 0) && (f * cout == 32 || f * cout == 64) && (f * c0 + f * c1) / 32 <= 16) return f;
+    return 0;
+}
+
+static int pack_fold(ipdm_unet* net, ConvW& c, int c0, int c1) {
+    c.fold = 0;
+    if (!(net->precision == IPDM_PREC_BF16 || net->force_fold) || (c.k != 1 && c.k != 3) || c0 + c1 != c.cin) return IPDM_OK;
+    const int f = fold_factor(c0, c1, c.cout);
+    if (!f) return IPDM_OK;
+    const int kk = c.k * c.k, N = f * c.cout, K = f * c.cin, nt = c.k == 3 ? 9 : 1;
+    std::vector<float> p((size_t)nt * N * K, 0.f);
+    for (int t = 0; t < 9; ++t) c.fold_mask[t] = 0;
+    for (int tap = 0; tap < nt; ++tap) {
+        const int dy = c.k == 3 ? tap / 3 : 0, bdx = c.k == 3 ? tap % 3 : 1;
+        for (int col = 0; col < K; ++col) {
+            const bool first = col < f * c0;
+            const int cs = first ? c0 : c1, lc = first ? col : col - f * c0;
+            const int bi = lc / cs, ci = (first ? 0 : c0) + lc % cs;
+            bool any = false;
+            for (int bo = 0; bo < f; ++bo) {
+                const int dx = f * (bdx - 1) + bi - bo;
+                if (dx < -1 || dx > 1 || (c.k == 1 && dx != 0)) continue;
+                any = true;
+                const int t = c.k == 3 ? dy * 3 + dx + 1 : 0;
+                for (int co = 0; co < c.cout; ++co)
+                    p[((size_t)tap * N + bo * c.cout + co) * K + col] = tf32_rn_host(c.w_host[((size_t)co * c.cin + ci) * kk + t]);
+            }
+            if (any) c.fold_mask[tap] |= 1ull << (col / 8);                  // bit = 4 * chunk + k-step
+        }
+    }
+    IPDM_CHECK(upload(net, p, &c.w_dev_fold));
+    if (!c.b_host.empty() && !c.b_dev) IPDM_CHECK(upload(net, c.b_host, &c.b_dev));
+    c.fold = f; c.fold_c0 = c0; c.fold_c1 = c1;
+    return IPDM_OK;
+}
+
 static inline float silu_h(float x) { return x / (1.0f + std::exp(-x)); }
 
 // architecture walk shared by create() and param_count(): calls back for every parameter tensor in state_dict order
@@ -312,6 +370,8 @@ struct BuildVisitor : ArchVisitor {
         fail(pack_conv(net, w.conv1, ci, 0, false));
         fail(pack_conv(net, w.conv2, co, 0, false));
         if (w.has_shortcut) fail(pack_conv(net, w.shortcut, c0, c1, true));
+        fail(pack_fold(net, w.conv1, c0, c1)); fail(pack_fold(net, w.conv2, co, 0));
+        if (w.has_shortcut) fail(pack_fold(net, w.shortcut, c0, c1));
         cur->push_back({LayerRef::RES, (int)net->res.size() - 1});
     }
     void attn(int c, int) override {
@@ -333,6 +393,7 @@ struct BuildVisitor : ArchVisitor {
     void up(int c) override {
         net->convs.emplace_back(); read_conv(r, net->convs.back(), c, c, 3, true);
         fail(pack_conv(net, net->convs.back(), c, 0, true, -1, true));
+        fail(pack_fold(net, net->convs.back(), c, 0));
         cur->push_back({LayerRef::UP, (int)net->convs.size() - 1});
     }
     void out(int c, int co) override {
@@ -388,6 +449,18 @@ struct PlanBuilder {
         pl->ops.push_back(o); return i;
     }
     int cin_of(const int* src, int nsrc) { int c = 0; for (int i = 0; i < nsrc; ++i) c += pl->vt[src[i]].c; return c; }
+    // width-folded path (pack_fold): every tensor the conv touches is dense fp32 with the channel split the weights were folded for,
+    // and the row length is a multiple of the fold factor
+    bool can_fold(const ConvW& cw, const int* src, int nsrc, int dst, int res) {
+        if (!cw.fold) return false;
+        const VTensor& s0 = pl->vt[src[0]];
+        if (s0.w % cw.fold != 0 || s0.c != cw.fold_c0 || (nsrc > 1 ? pl->vt[src[1]].c : 0) != cw.fold_c1) return false;
+        for (int i = 0; i < nsrc; ++i) { const VTensor& t = pl->vt[src[i]]; if (t.cs != t.c || t.bf16 || t.external) return false; }
+        const VTensor& d = pl->vt[dst];
+        if (d.cs != d.c || d.external || d.c != cw.cout) return false;
+        if (res >= 0) { const VTensor& r = pl->vt[res]; if (r.cs != r.c || r.c != cw.cout || r.external) return false; }
+        return true;
+    }
 
     // GroupNorm(+SiLU) followed by a conv; returns nothing, writes `dst`
     void norm_conv(const int* src, int nsrc, const GNW& gn, const ConvW& cw, int dst, int res, const float* bias, int bstride, bool use_t, int act_silu) {
@@ -399,7 +472,12 @@ struct PlanBuilder {
         // the two spare warps per CTA doing the transform it is SLOWER than the separate apply pass (measured at 16 slices: 8 -> 8 at
         // 2000x912 1025 us fused vs 600 + 311 us; 16 -> 16 at 1000x456 526 vs 283 + 155 us).
         static const bool thin_fuse = getenv("IPDM_THIN_FUSE") && atoi(getenv("IPDM_THIN_FUSE")) == 1;
-if (cw.thin && thin_fuse && nsrc == 1 && s0.c == cw.thin_cs && s0.cs == cw.thin_cs && !s0.bf16) {
+        if (cw.k == 3 && can_fold(cw, src, nsrc, dst, res)) {
+            // width-folded: the persistent halo kernel normalises the raw tile(s) on its operand path and emits the output statistics
+            Op cv; cv.kind = Op::CONV_TC; cv.nsrc = nsrc; cv.src[0] = src[0]; cv.src[1] = st.src[1]; cv.cw = &cw; cv.dst = dst; cv.res = res;
+            cv.bias = bias; cv.bias_t_stride = bstride; cv.use_t = use_t; cv.norm_slot = st.norm_slot; cv.gn = &gn; cv.act = act_silu; cv.fold = cw.fold;
+            push(cv);
+        } else if (cw.thin && thin_fuse && nsrc == 1 && s0.c == cw.thin_cs && s0.cs == cw.thin_cs && !s0.bf16) {
             // single dense source: the thin kernel normalises the TMA-landed tile itself, no operand tensor and no apply pass
             Op cv; cv.kind = Op::CONV_THIN; cv.nsrc = 1; cv.src[0] = src[0]; cv.cw = &cw; cv.dst = dst; cv.res = res; cv.bias = bias; cv.bias_t_stride = bstride; cv.use_t = use_t;
             cv.norm_slot = st.norm_slot; cv.gn = &gn; cv.act = act_silu;
@@ -430,6 +508,12 @@ if (cw.thin && thin_fuse && nsrc == 1 && s0.c == cw.thin_cs && s0.cs == cw.thin_
         }
     }
     void plain_conv(const int* src, int nsrc, const ConvW& cw, int dst, int res, int stride, int upsample) {
+        if (stride == 1 && !upsample && can_fold(cw, src, nsrc, dst, res)) {
+            Op cv; cv.kind = Op::CONV_TC; cv.nsrc = nsrc; cv.src[0] = src[0]; cv.src[1] = nsrc > 1 ? src[1] : -1;
+            cv.cw = &cw; cv.dst = dst; cv.res = res; cv.bias = cw.b_dev; cv.fold = cw.fold;
+            push(cv);
+            return;
+        }
         Op cv; cv.kind = cw.tc ? Op::CONV_TC : ((cw.thin && stride == 1 && !upsample && nsrc == 1 && pl->vt[src[0]].cs == cw.thin_cs) ? Op::CONV_THIN : Op::CONV_DIRECT); cv.nsrc = nsrc; cv.src[0] = src[0]; cv.src[1] = nsrc > 1 ? src[1] : -1;
         cv.cw = &cw; cv.dst = dst; cv.res = res; cv.bias = cw.b_dev; cv.stride = stride; cv.upsample = upsample;
         push(cv);
@@ -478,7 +562,11 @@ if (cw.thin && thin_fuse && nsrc == 1 && s0.c == cw.thin_cs && s0.cs == cw.thin_
                 case LayerRef::UP: {
                     const ConvW& cw = net->convs[l.idx];
                     out = act(up_h, up_w, s0.c);
-                    if (cw.tc || cw.thin) {
+                    if (cw.fold && up_w % cw.fold == 0 && pl->vt[out].cs == pl->vt[out].c) {
+                        const int u = new_tensor(pl->B, up_h, up_w, s0.c, s0.c);          // dense tf32-rounded operand of the folded conv
+                        Op up; up.kind = Op::UPSAMPLE; up.nsrc = 1; up.src[0] = cur[0]; up.dst = u; push(up);
+                        plain_conv(&u, 1, cw, out, -1, 1, 0);
+                    } else if (cw.tc || cw.thin) {
                         const int u = cw.thin ? new_tensor(pl->B, up_h, up_w, s0.c, cw.thin_cs)
                                               : (cw.bf16 ? new_tensor(pl->B, up_h, up_w, s0.c, round_up(s0.c, 64)) : act(up_h, up_w, s0.c));
                         pl->vt[u].bf16 = cw.bf16;
@@ -500,6 +588,21 @@ static TensorNHWC resolve(const Plan& pl, int id) {
     t.n = v.n; t.h = v.h; t.w = v.w; t.c = v.c; t.cs = v.cs; t.bf16 = v.bf16;
     t.p = v.external ? nullptr : (float*)((char*)pl.arena + v.off);
     return t;
+}
+
+// turns the descriptor of a conv over dense thin tensors into its width-folded form (views, folded weights, k-step masks)
+static void fold_view(TensorNHWC& t, int f) { if (t.p || t.c) { t.w /= f; t.c *= f; t.cs *= f; } }
+static void fold_desc(ConvTcDesc& d, const ConvW& cw) {
+    const int f = cw.fold;
+    d.gn_mod[0] = d.src[0].c; d.gn_mod[1] = d.nsrc > 1 ? d.src[1].c : 0; d.bias_mod = cw.cout;
+    for (int s = 0; s < d.nsrc; ++s) fold_view(d.src[s], f);
+    fold_view(d.out, f);
+    if (d.res.p) fold_view(d.res, f);
+    d.cout = f * cw.cout; d.n_tile = d.cout;
+    d.w_packed = cw.w_dev_fold; d.w_packed_lo = nullptr; d.w_k = f * cw.cin; d.w_bf16 = 0;
+    for (int t = 0; t < 9; ++t) d.kmask[t] = cw.k == 3 ? cw.fold_mask[t] : 0;
+    d.fold = f;
+    if (cw.k == 3 && !d.norm_scale) d.passthrough = 1;     // plain folded 3x3 (the Upsample conv): same kernel, identity operand path
 }
 
 static int build_plan(ipdm_unet* net, int B, int H, int W, Plan** out) {
@@ -525,13 +628,18 @@ static int build_plan(ipdm_unet* net, int B, int H, int W, Plan** out) {
     // raw fp32 sources of tensor-core convs are read in 128-byte K chunks: widen the (16-channel) tensors they touch, and send
     // thin-path convs whose source no longer has the packed stride to the direct kernel
     for (const Op& o : pl->ops)
-        if (o.kind == Op::CONV_TC)
+        if (o.kind == Op::CONV_TC && !o.fold)
             for (int s = 0; s < o.nsrc; ++s) {
                 VTensor& t = pl->vt[o.src[s]];
                 if (!t.bf16 && !t.external && t.cs % 32 != 0) t.cs = round_up(t.c, 32);
             }
     for (Op& o : pl->ops)
         if (o.kind == Op::CONV_THIN && pl->vt[o.src[0]].cs != o.cw->thin_cs) o.kind = Op::CONV_DIRECT;
+    for (const Op& o : pl->ops)
+        if (o.kind == Op::CONV_TC && o.fold)
+            for (int id : {o.src[0], o.src[1], o.dst, o.res})
+                IPDM_REQUIRE(id < 0 || pl->vt[id].cs == pl->vt[id].c, "unet: a width-folded conv shares a tensor with a layer that needs it padded (%d -> %d channels)",
+                             pl->vt[id].c, pl->vt[id].cs);
     // GroupNorm statistics come from the epilogue of the conv that writes the tensor when that conv runs a persistent tensor-core
     // kernel (decided in conv_tc_prepare; the 3xTF32 and qkv kernels do not): a companion tensor holds the per-warp-row partials
     // from the producer to the last GroupNorm that reads the tensor, and that GroupNorm skips its own read of the tensor.
@@ -546,8 +654,10 @@ static int build_plan(ipdm_unet* net, int B, int H, int W, Plan** out) {
                 // (the thin kernel's epilogue is its bottleneck: statistics there cost more than the separate read, measured)
                 if (pi < 0 || pl->ops[pi].kind != Op::CONV_TC || pl->ops[pi].qkv || pl->vt[t].c % 4 != 0) continue;
                 if (pl->vt[t].stats_t < 0) {
-                    const int rows = conv_tc_stats_rows_bound(pl->vt[t].h, pl->vt[t].w);
-                    const int len = rows * 2 * pl->vt[t].c;
+                    const int fold = pl->ops[pi].fold > 1 ? pl->ops[pi].fold : 1;
+                    const int rows = conv_tc_stats_rows_bound(pl->vt[t].h, pl->vt[t].w / fold);
+                    const int len = rows * 2 * pl->vt[t].c * fold;
+                    pl->vt[t].stats_fold = fold;
                     const int id = pb.new_tensor(B, 1, 1, len, len);
                     pl->vt[id].def = pi; pl->vt[id].last = gi;
                     pl->vt[t].stats_t = id; pl->ops[pi].stats = id;
@@ -612,7 +722,7 @@ static int build_plan(ipdm_unet* net, int B, int H, int W, Plan** out) {
                 g.groups = o.gn->groups; g.gamma = o.gn->gamma; g.beta = o.gn->beta; g.scale = nscale; g.shift = nshift; g.partials = pl->gn_partials;
                 for (int sidx = 0; sidx < o.nsrc; ++sidx) {
                     const VTensor& v = pl->vt[o.src[sidx]];
-                    if (v.stats_t >= 0 && v.stats_rows > 0) { g.tile_stats[sidx] = resolve(*pl, v.stats_t).p; g.tile_rows[sidx] = v.stats_rows; }
+                    if (v.stats_t >= 0 && v.stats_rows > 0) { g.tile_stats[sidx] = resolve(*pl, v.stats_t).p; g.tile_rows[sidx] = v.stats_rows; g.tile_fold[sidx] = v.stats_fold; }
                 }
                 if (o.kind == Op::GN_APPLY) o.out_t = resolve(*pl, o.dst);
             } break;
@@ -632,9 +742,10 @@ static int build_plan(ipdm_unet* net, int B, int H, int W, Plan** out) {
                 }
                 if (o.stats >= 0) d.stats_out = resolve(*pl, o.stats).p;
                 if (o.gn) { d.norm_scale = nscale; d.norm_shift = nshift; d.act_silu = o.act; d.w_bf16 = o.cw->bf16; }
+                if (o.fold) fold_desc(d, *o.cw);
                 IPDM_CHECK(conv_tc_prepare(o.tcp, d));
                 pl->vt[o.dst].stats_rows = o.tcp.stats_out ? o.tcp.stats_rows : 0;
-                o.flops = 2.0 * B * o.tcp.H * o.tcp.W * (double)o.cw->cin * o.cw->cout * d.ntaps;
+                o.flops = 2.0 * B * o.tcp.H * o.tcp.W * (o.fold ? o.fold : 1) * (double)o.cw->cin * o.cw->cout * d.ntaps;
             } break;
             case Op::CONV_THIN: {
                 ConvThinDesc d;
@@ -797,6 +908,28 @@ extern "C" int ipdm_debug_conv(const float* src0, int c0, int cs0, const float* 
     ConvW cw; cw.cin = c0 + c1; cw.cout = cout; cw.k = k;
     cw.w_host.assign(w_host, w_host + (size_t)cout * cw.cin * k * k);
     if (bias_host) cw.b_host.assign(bias_host, bias_host + cout);
+    if (use_tc == 6) {                                   // width-folded tensor-core path: dense thin sources, optional fused GroupNorm + SiLU
+        IPDM_REQUIRE(stride == 1 && upsample_h == 0 && cs0 == c0 && (c1 == 0 || cs1 == c1) && out_cs == cout && (!res || res_cs == cout),
+                     "ipdm_debug_conv: the folded path takes dense tensors, stride 1");
+        holder.force_fold = true;
+        IPDM_CHECK(pack_fold(&holder, cw, c0, c1));
+        IPDM_REQUIRE(cw.fold && w % cw.fold == 0, "ipdm_debug_conv: shape is not eligible for the folded path");
+        ConvTcDesc d; d.nsrc = c1 ? 2 : 1; d.src[0] = mk(src0, n, h, w, c0, cs0); if (c1) d.src[1] = mk(src1, n, h, w, c1, cs1);
+        if (norm_scale) { d.norm_scale = norm_scale; d.norm_shift = norm_shift; }
+        d.ntaps = k * k; d.stride = 1; d.bias = cw.b_dev;
+        if (res) d.res = mk(res, n, h, w, cout, res_cs);
+        d.out = mk(out, n, h, w, cout, out_cs);
+        fold_desc(d, cw);
+        float* stats = nullptr;                          // exercise the statistics epilogue too
+        IPDM_CHECK_CUDA(cudaMalloc(&stats, (size_t)n * conv_tc_stats_rows_bound(h, w / cw.fold) * 2 * d.cout * sizeof(float)));
+        d.stats_out = stats;
+        ConvTcParams P;
+        int rc2 = conv_tc_prepare(P, d);
+        if (rc2 == IPDM_OK) rc2 = conv_tc_launch(P, (cudaStream_t)stream);
+        cudaStreamSynchronize((cudaStream_t)stream);
+        cudaFree(stats);
+        return rc2;
+    }
     if (use_tc == 4) {                                   // thin tensor-core path: src0 is the operand tensor (channel stride cs0 in {8,16,32})
         IPDM_REQUIRE(c1 == 0 && stride == 1 && upsample_h == 0 && !norm_scale, "ipdm_debug_conv: thin path takes one plain source");
         holder.force_thin = true;
@@ -849,6 +982,47 @@ extern "C" int ipdm_debug_conv_time(int c0, int c1, int n, int h, int w, int cou
                                     int with_res, int iters, float* ms_out, double* flops_out) {
     ipdm_unet holder;
     holder.precision = mode == 2 ? IPDM_PREC_FP32 : (mode == 3 ? IPDM_PREC_BF16 : IPDM_PREC_TF32);
+    if (variant == 6 || variant == 7) {                  // width-folded thin layer, with (6) / without (7) the fused GroupNorm + SiLU
+        holder.force_fold = true;
+        ConvW cw; cw.cin = c0 + c1; cw.cout = cout; cw.k = k;
+        cw.w_host.assign((size_t)cout * cw.cin * k * k, 0.01f);
+        cw.b_host.assign(cout, 0.1f);
+        IPDM_CHECK(pack_fold(&holder, cw, c0, c1));
+        IPDM_REQUIRE(cw.fold && w % cw.fold == 0 && stride == 1, "ipdm_debug_conv_time: shape is not eligible for the folded path");
+        float *s0 = nullptr, *s1 = nullptr, *out = nullptr, *res = nullptr, *nsc = nullptr, *nsh = nullptr, *stats = nullptr;
+        const size_t px = (size_t)n * h * w;
+        IPDM_CHECK_CUDA(cudaMalloc(&s0, px * c0 * 4)); IPDM_CHECK_CUDA(cudaMemset(s0, 0, px * c0 * 4));
+        if (c1) { IPDM_CHECK_CUDA(cudaMalloc(&s1, px * c1 * 4)); IPDM_CHECK_CUDA(cudaMemset(s1, 0, px * c1 * 4)); }
+        IPDM_CHECK_CUDA(cudaMalloc(&out, px * cout * 4));
+        if (with_res) { IPDM_CHECK_CUDA(cudaMalloc(&res, px * cout * 4)); IPDM_CHECK_CUDA(cudaMemset(res, 0, px * cout * 4)); }
+        ConvTcDesc d; d.nsrc = c1 ? 2 : 1; d.src[0] = mk(s0, n, h, w, c0, c0); if (c1) d.src[1] = mk(s1, n, h, w, c1, c1);
+        if (variant == 6) {
+            std::vector<float> one((size_t)n * cw.cin, 1.f);
+            IPDM_CHECK_CUDA(cudaMalloc(&nsc, one.size() * 4)); IPDM_CHECK_CUDA(cudaMalloc(&nsh, one.size() * 4));
+            IPDM_CHECK_CUDA(cudaMemcpy(nsc, one.data(), one.size() * 4, cudaMemcpyHostToDevice));
+            IPDM_CHECK_CUDA(cudaMemset(nsh, 0, one.size() * 4));
+            d.norm_scale = nsc; d.norm_shift = nsh;
+        }
+        d.ntaps = k * k; d.stride = 1; d.bias = cw.b_dev;
+        if (res) d.res = mk(res, n, h, w, cout, cout);
+        d.out = mk(out, n, h, w, cout, cout);
+        fold_desc(d, cw);
+        IPDM_CHECK_CUDA(cudaMalloc(&stats, (size_t)n * conv_tc_stats_rows_bound(h, w / cw.fold) * 2 * d.cout * sizeof(float)));
+        d.stats_out = stats;
+        ConvTcParams P;
+        IPDM_CHECK(conv_tc_prepare(P, d));
+        cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+        for (int i = 0; i < 3; ++i) IPDM_CHECK(conv_tc_launch(P, nullptr));
+        cudaEventRecord(a, nullptr);
+        for (int i = 0; i < iters; ++i) IPDM_CHECK(conv_tc_launch(P, nullptr));
+        cudaEventRecord(b, nullptr);
+        IPDM_CHECK_CUDA(cudaDeviceSynchronize());
+        float ms = 0; cudaEventElapsedTime(&ms, a, b);
+        *ms_out = ms / iters;
+        if (flops_out) *flops_out = 2.0 * px * (double)cw.cin * cout * k * k;
+        cudaFree(s0); cudaFree(s1); cudaFree(out); cudaFree(res); cudaFree(nsc); cudaFree(nsh); cudaFree(stats); cudaEventDestroy(a); cudaEventDestroy(b);
+        return IPDM_OK;
+    }
     const bool fused = variant == 5;
     ConvW cw; cw.cin = c0 + c1; cw.cout = cout; cw.k = k;
     cw.w_host.assign((size_t)cout * cw.cin * k * k, 0.01f);

@@ -523,8 +523,10 @@ gn_partial_kernel(const float* __restrict__ src, int C, int cs, size_t npix, dou
 // A source whose producer conv already wrote per-warp-row statistics (ConvTcDesc::stats_out: [slice][rows][2][C] fp32) is not read
 // again: this kernel folds those rows (a few % of the tensor's bytes, coalesced) into the same fp64 partials gn_partial_kernel writes.
 // grid (nblk, slices); thread t owns the 4-float vector t % V of a row (V = 2C/4), rows t / V, t / V + R, ...
+// fold > 1: the producer was a width-folded conv, its rows are [2][fold][Creal] (pixel-major folded channels); C = fold * Creal here
+// and the fold positions of a channel are summed in the final combine.
 __global__ void __launch_bounds__(256)
-gn_tile_reduce_kernel(const float* __restrict__ tile, int rows, int C, double* __restrict__ partials, int c_off, int Ctot) {
+gn_tile_reduce_kernel(const float* __restrict__ tile, int rows, int C, double* __restrict__ partials, int c_off, int Ctot, int fold) {
     __shared__ double red[256][4];
     const int n = blockIdx.y, V = 2 * C / 4;
     const int R = 256 / V > 0 ? 256 / V : 1;
@@ -549,11 +551,14 @@ gn_tile_reduce_kernel(const float* __restrict__ tile, int rows, int C, double* _
     }
     red[t][0] = a0; red[t][1] = a1; red[t][2] = a2; red[t][3] = a3;
     __syncthreads();
-    for (int i = t; i < 2 * C; i += 256) {                        // i indexes the [2][C] row: half = sum / sum of squares
-        const int cv = i / 4, comp = i % 4;
+    const int Cr = C / fold;                                      // real channels
+    for (int i = t; i < 2 * Cr; i += 256) {                       // i indexes the [2][Cr] result: half = sum / sum of squares
+        const int half = i / Cr, ch = i - half * Cr;
         double a = 0;
-        for (int r = 0; r < R; ++r) a += red[r * V + cv][comp];
-        const int half = i / C, ch = i - half * C;
+        for (int f = 0; f < fold; ++f) {
+            const int j = half * C + f * Cr + ch, cv = j / 4, comp = j % 4;
+            for (int r = 0; r < R; ++r) a += red[r * V + cv][comp];
+        }
         partials[(((size_t)n * gridDim.x + blockIdx.x) * Ctot + c_off + ch) * 2 + half] = a;
     }
 }
@@ -606,8 +611,9 @@ int groupnorm_stats_launch(const GroupNormDesc& d, cudaStream_t st) {
         const TensorNHWC& t = d.src[s];
         IPDM_REQUIRE(t.c % 4 == 0 && t.cs % 4 == 0 && t.c <= 1024, "groupnorm: channel count %d must be a multiple of 4", t.c);
         if (d.tile_stats[s]) {                                    // statistics from the producer's epilogue: fold its partial rows
-            IPDM_REQUIRE(t.c <= 512, "groupnorm: producer statistics support at most 512 channels per source");
-            gn_tile_reduce_kernel<<<dim3(nblk, s0.n), 256, 0, st>>>(d.tile_stats[s], d.tile_rows[s], t.c, d.partials, c_off, Ctot);
+            const int fold = d.tile_fold[s] > 1 ? d.tile_fold[s] : 1;
+            IPDM_REQUIRE(t.c * fold <= 512, "groupnorm: producer statistics support at most 512 channels per source");
+            gn_tile_reduce_kernel<<<dim3(nblk, s0.n), 256, 0, st>>>(d.tile_stats[s], d.tile_rows[s], t.c * fold, d.partials, c_off, Ctot, fold);
         } else {                                                  // one read of the tensor
             gn_partial_kernel<<<dim3(nblk, s0.n), 256, 0, st>>>(t.p, t.c, t.cs, npix, d.partials, c_off, Ctot);
         }

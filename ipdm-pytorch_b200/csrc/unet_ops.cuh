@@ -40,6 +40,13 @@ struct ConvTcDesc {
     // fused GroupNorm(+SiLU) of the input (conv_halo_fused_kernel): src[] are the RAW fp32 tensors, y = act(x*scale[n][c] + shift[n][c]) is
     // applied on the operand path; w_bf16 says whether w_packed (and hence the MMA) is bf16 or tf32
     const float* norm_scale = nullptr; const float* norm_shift = nullptr; int act_silu = 1; int w_bf16 = 0;
+    // width-folded thin layers (unet.cu pack_conv_folded): a dense [H][W][C] tensor with C in {4, 8, 16, ...} is read as
+    // [H][W/f][f*C]; src / res / out are those VIEWS.  kmask[tap] holds 4 bits per 32-channel K chunk: the 8-column k-steps of that
+    // (tap, chunk) whose packed weights are structurally non-zero (0 = no mask); gn_mod / bias_mod = real channel counts behind the
+    // folded ones (per-channel GroupNorm affine and bias are indexed modulo them); n_tile forces the N tile (0 auto)
+    uint64_t kmask[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    int gn_mod[2] = {0, 0}; int bias_mod = 0; int n_tile = 0; int fold = 0;
+    int passthrough = 0;               // run a plain (no GroupNorm) tf32 layer through conv_halo_fused_kernel with an identity operand path
 };
 int conv_tc_stats_rows_bound(int h, int w);
 bool conv_tc_can_fuse_norm(int H, int W, int batch, int cout, int ntaps, int stride);            // upper bound of stats_rows for an h x w output, any kernel variant
@@ -58,6 +65,8 @@ struct ConvTcParams {
     float* out_lo; float* vt_lo; int qkv_bf16;
     float* stats_out; int stats_rows;                  // set by prepare only for the persistent kernels (else nullptr / 0)
     int fused; const float* gn_scale; const float* gn_shift; int gn_c0, gn_c1, gn_act;    // conv_halo_fused_kernel
+    uint64_t kmask[9]; int gn_m0, gn_m1, bias_mod, masked, fold;                          // width-folded thin layers
+    double flops;                                                                         // MMA work issued per launch (prepare)
 };
 
 int conv_tc_prepare(ConvTcParams& P, const ConvTcDesc& d);
@@ -120,6 +129,7 @@ struct GroupNormDesc {
     // such a source is not read again
     const float* tile_stats[2] = {nullptr, nullptr};
     int tile_rows[2] = {0, 0};
+    int tile_fold[2] = {0, 0};         // > 1: the producer was width-folded, its rows hold [2][fold][c] (see gn_tile_reduce_kernel)
 };
 constexpr int GN_MAX_BLOCKS = 888;        // 6 CTAs per SM
 int groupnorm_stats_launch(const GroupNormDesc& d, cudaStream_t st);

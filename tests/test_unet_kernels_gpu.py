@@ -250,6 +250,31 @@ def test_tc_conv_fused_groupnorm(cuda, c0, c1, cout, hw):
     assert e_bf16 < 8e-3 and e_exact < 3e-4          # (the device SiLU uses ex2.approx: a few operands round to the neighbouring bf16)
 
 
+@pytest.mark.parametrize("c0,c1,cout,k,hw", [
+    (8, 0, 8, 3, (40, 72)), (16, 0, 16, 3, (33, 66)), (4, 0, 8, 3, (20, 80)), (8, 0, 16, 3, (25, 64)), (16, 8, 8, 3, (21, 68)),
+    (8, 8, 8, 3, (19, 36)), (8, 4, 8, 3, (18, 48)), (16, 16, 16, 3, (23, 34)), (16, 8, 16, 3, (17, 44)), (128, 16, 16, 3, (20, 62)),
+    (8, 0, 8, 3, (300, 912)),
+    (4, 0, 8, 1, (20, 80)), (8, 0, 16, 1, (25, 64)), (16, 8, 8, 1, (21, 68)), (8, 8, 8, 1, (19, 36)), (16, 16, 16, 1, (23, 34)), (128, 16, 16, 1, (20, 62)),
+])
+def test_width_folded_conv(cuda, c0, c1, cout, k, hw):
+    """Thin layers as width-folded tensor-core layers (pack_fold): [H][W][C] read as [H][W/f][f*C], folded weights with structurally
+    zero k-steps skipped, GroupNorm + SiLU fused on the operand path, per-channel affine / bias indexed modulo the real channel
+    count, virtual concat, residual, ragged tile edges.  tf32 operands, fp32 accumulate."""
+    n, C = 2, c0 + c1
+    x0 = rnd(n, c0, *hw, seed=1)
+    x1 = rnd(n, c1, *hw, seed=2) if c1 else None
+    w = rnd(cout, C, k, k, seed=3, scale=0.2)
+    b = rnd(cout, seed=4)
+    res = rnd(n, cout, *hw, seed=5)
+    scale, shift = 0.5 + torch.rand(n, C, generator=torch.Generator().manual_seed(6)), rnd(n, C, seed=7, scale=0.5)
+    norms = (None, (scale, shift)) if k == 3 else (None,)           # the 1x1 layers are the shortcuts: no GroupNorm
+    for norm in norms:
+        for r in (None, res):
+            want = ref_conv(x0, x1, w, b, k, 1, res=r, norm=norm)
+            got = run_conv(cuda, x0, x1, w, b, k, 1, 6, res=r, norm=norm, dense_out=True, dense_src=True)
+            assert rel_l2(got.numpy(), want.numpy()) < TF32_TOL, (norm is not None, r is not None)
+
+
 @pytest.mark.parametrize("cin,cs,cout,k,hw,batch", [(8, 8, 8, 3, (40, 70), 2), (4, 8, 8, 3, (33, 65), 1), (8, 8, 16, 1, (21, 47), 2), (16, 16, 16, 3, (50, 38), 2),
                                                     (12, 16, 8, 3, (25, 61), 1), (24, 32, 8, 3, (37, 95), 2), (32, 32, 16, 3, (64, 64), 1),
                                                     (8, 8, 8, 3, (300, 400), 2)])
