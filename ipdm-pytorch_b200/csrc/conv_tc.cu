@@ -289,75 +289,89 @@ __device__ __forceinline__ void tc_epilogue_coalesced(const ConvTcParams& P, uin
 // tile and 32-bit offsets, where the generic form spent ~6 integer instructions per 128-bit access on (slice, y, x) arithmetic
 // (ncu, width-folded layers: the epilogue warps issued 6.4 k instructions per 240-pixel x 32-channel tile and the SM was issue-bound).
 template <int BLOCK_N, int CHUNK_W = 32>
-__device__ __forceinline__ void tc_epilogue_row(const ConvTcParams& P, uint32_t tmem_acc, int quarter, int lane, int b, int x0, int py,
-                                                int n0, const float* sbias, float* stile, int tw_valid, float* stats_row) {
-    constexpr int CHUNK = BLOCK_N < 32 ? 16 : CHUNK_W;
-    constexpr int LPP = CHUNK / 4, PPI = 32 / LPP, NJ = 32 / PPI;
-    const int c4 = (lane % LPP) * 4, psub = lane / LPP;
-    const int nvalid = py < P.H ? min(tw_valid, P.W - x0) : 0;           // valid pixels of this warp's row
-    uint32_t vmask = 0;                                                  // bit j: pixel j * PPI + psub is an output
+struct EpilogueRow {
+    static constexpr int CHUNK = BLOCK_N < 32 ? 16 : CHUNK_W;
+    static constexpr int LPP = CHUNK / 4, PPI = 32 / LPP, NJ = 32 / PPI;
+    int c4, psub, nvalid, n0, ostep, rstep, oo, ro; uint32_t vmask; bool has_res;
+    size_t pix0; float* obase; const float* rbase;
+    float4 rres[NJ];                                   // residual lines of the chunk being processed
+
+    // coordinates of this warp's row (pixels x0 .. x0+31 of image row py of slice b, output channels n0 ...)
+    __device__ __forceinline__ void setup(const ConvTcParams& P, int lane, int b, int x0, int py, int n0_, int tw_valid) {
+        c4 = (lane % LPP) * 4; psub = lane / LPP; n0 = n0_;
+        nvalid = py < P.H ? min(tw_valid, P.W - x0) : 0;
+        vmask = 0;                                     // bit j: pixel j * PPI + psub is an output
 #pragma unroll
-    for (int j = 0; j < NJ; ++j) vmask |= (j * PPI + psub < nvalid ? 1u : 0u) << j;
-    const size_t pix0 = ((size_t)b * P.H + py) * P.W + x0;
-    float* const obase = P.out + pix0 * P.out_cs;
-    const bool has_res = P.res != nullptr;
-    const float* const rbase = has_res ? P.res + pix0 * P.res_cs : P.out;          // (never read without has_res)
-    const int ostep = PPI * P.out_cs, rstep = PPI * P.res_cs;
-    const int oo = psub * P.out_cs + c4 + n0, ro = psub * P.res_cs + c4 + n0;
-#pragma unroll 1
-    for (int cc = 0; cc < BLOCK_N; cc += CHUNK) {
-        const int n = n0 + cc + c4;
-        const bool nok = n < P.cout;
-        const uint32_t vm = nok ? vmask : 0u;
-        uint32_t r[32];
-        const uint32_t taddr = tmem_acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)cc;
-        if constexpr (CHUNK == 32) tc::tmem_ld32(taddr, r);
-        else { uint32_t r16[16]; tc::tmem_ld16(taddr, r16);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) r[i] = r16[i]; }
-        float4 rres[NJ];                               // all residual lines of the chunk are requested before anything waits
+        for (int j = 0; j < NJ; ++j) vmask |= (j * PPI + psub < nvalid ? 1u : 0u) << j;
+        pix0 = ((size_t)b * P.H + py) * P.W + x0;
+        obase = P.out + pix0 * P.out_cs;
+        has_res = P.res != nullptr;
+        rbase = has_res ? P.res + pix0 * P.res_cs : P.out;               // (never read without has_res)
+        ostep = PPI * P.out_cs; rstep = PPI * P.res_cs;
+        oo = psub * P.out_cs + c4 + n0; ro = psub * P.res_cs + c4 + n0;
+    }
+    // request the residual lines of chunk cc.  Chunk 0 is requested BEFORE the warp waits for its accumulator: the addresses only depend
+    // on the tile, so the HBM latency of the residual overlaps the MMAs instead of extending the epilogue (ncu, width-folded layers:
+    // 73 % of the epilogue warps' stall samples sat on the first add that consumes a residual line)
+    __device__ __forceinline__ void load_res(const ConvTcParams& P, int cc) {
+        const bool nok = n0 + cc + c4 < P.cout;
 #pragma unroll
         for (int j = 0; j < NJ; ++j)
-            rres[j] = (has_res && ((vm >> j) & 1u)) ? ld_stream(reinterpret_cast<const float4*>(rbase + (ro + cc + j * rstep))) : make_float4(0.f, 0.f, 0.f, 0.f);
-        tc::tmem_ld_wait();
-        __syncwarp();                                  // previous chunk's readers are done with the tile
-        float4* row = reinterpret_cast<float4*>(stile + lane * EPI_PITCH);
+            rres[j] = (has_res && nok && ((vmask >> j) & 1u)) ? ld_stream(reinterpret_cast<const float4*>(rbase + (ro + cc + j * rstep))) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __device__ __forceinline__ void run(const ConvTcParams& P, uint32_t tmem_acc, int quarter, int lane, const float* sbias, float* stile, float* stats_row) {
+#pragma unroll 1
+        for (int cc = 0; cc < BLOCK_N; cc += CHUNK) {
+            const int n = n0 + cc + c4;
+            const bool nok = n < P.cout;
+            const uint32_t vm = nok ? vmask : 0u;
+            uint32_t r[32];
+            const uint32_t taddr = tmem_acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)cc;
+            if constexpr (CHUNK == 32) tc::tmem_ld32(taddr, r);
+            else { uint32_t r16[16]; tc::tmem_ld16(taddr, r16);
 #pragma unroll
-        for (int i = 0; i < CHUNK / 4; ++i)
-            row[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
-        __syncwarp();
-        const float4 bq = *reinterpret_cast<const float4*>(sbias + cc + c4);
-        float4 ss = make_float4(0.f, 0.f, 0.f, 0.f), sq = ss;          // GroupNorm partials of this lane's 4 channels
+                for (int i = 0; i < 16; ++i) r[i] = r16[i]; }
+            if (cc > 0) load_res(P, cc);
+            tc::tmem_ld_wait();
+            __syncwarp();                              // previous chunk's readers are done with the tile
+            float4* row = reinterpret_cast<float4*>(stile + lane * EPI_PITCH);
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) {
-            if ((vm >> j) & 1u) {
-                float4 v = *reinterpret_cast<const float4*>(stile + (j * PPI + psub) * EPI_PITCH + c4);
-                v.x += bq.x + rres[j].x; v.y += bq.y + rres[j].y; v.z += bq.z + rres[j].z; v.w += bq.w + rres[j].w;
-                st_stream(reinterpret_cast<float4*>(obase + (oo + cc + j * ostep)), v);
-                ss.x += v.x; ss.y += v.y; ss.z += v.z; ss.w += v.w;
-                sq.x = fmaf(v.x, v.x, sq.x); sq.y = fmaf(v.y, v.y, sq.y); sq.z = fmaf(v.z, v.z, sq.z); sq.w = fmaf(v.w, v.w, sq.w);
+            for (int i = 0; i < CHUNK / 4; ++i)
+                row[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+            __syncwarp();
+            const float4 bq = *reinterpret_cast<const float4*>(sbias + cc + c4);
+            float4 ss = make_float4(0.f, 0.f, 0.f, 0.f), sq = ss;          // GroupNorm partials of this lane's 4 channels
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                if ((vm >> j) & 1u) {
+                    float4 v = *reinterpret_cast<const float4*>(stile + (j * PPI + psub) * EPI_PITCH + c4);
+                    v.x += bq.x + rres[j].x; v.y += bq.y + rres[j].y; v.z += bq.z + rres[j].z; v.w += bq.w + rres[j].w;
+                    st_stream(reinterpret_cast<float4*>(obase + (oo + cc + j * ostep)), v);
+                    ss.x += v.x; ss.y += v.y; ss.z += v.z; ss.w += v.w;
+                    sq.x = fmaf(v.x, v.x, sq.x); sq.y = fmaf(v.y, v.y, sq.y); sq.z = fmaf(v.z, v.z, sq.z); sq.w = fmaf(v.w, v.w, sq.w);
+                }
+            }
+            if (stats_row) {
+#pragma unroll
+                for (int o = LPP; o < 32; o <<= 1) {
+                    ss.x += __shfl_xor_sync(0xffffffffu, ss.x, o); ss.y += __shfl_xor_sync(0xffffffffu, ss.y, o);
+                    ss.z += __shfl_xor_sync(0xffffffffu, ss.z, o); ss.w += __shfl_xor_sync(0xffffffffu, ss.w, o);
+                    sq.x += __shfl_xor_sync(0xffffffffu, sq.x, o); sq.y += __shfl_xor_sync(0xffffffffu, sq.y, o);
+                    sq.z += __shfl_xor_sync(0xffffffffu, sq.z, o); sq.w += __shfl_xor_sync(0xffffffffu, sq.w, o);
+                }
+                if (lane < LPP && nok) {
+                    *reinterpret_cast<float4*>(stats_row + n) = ss;
+                    *reinterpret_cast<float4*>(stats_row + P.cout + n) = sq;
+                }
             }
         }
-        if (stats_row) {
-#pragma unroll
-            for (int o = LPP; o < 32; o <<= 1) {
-                ss.x += __shfl_xor_sync(0xffffffffu, ss.x, o); ss.y += __shfl_xor_sync(0xffffffffu, ss.y, o);
-                ss.z += __shfl_xor_sync(0xffffffffu, ss.z, o); ss.w += __shfl_xor_sync(0xffffffffu, ss.w, o);
-                sq.x += __shfl_xor_sync(0xffffffffu, sq.x, o); sq.y += __shfl_xor_sync(0xffffffffu, sq.y, o);
-                sq.z += __shfl_xor_sync(0xffffffffu, sq.z, o); sq.w += __shfl_xor_sync(0xffffffffu, sq.w, o);
-            }
-            if (lane < LPP && nok) {
-                *reinterpret_cast<float4*>(stats_row + n) = ss;
-                *reinterpret_cast<float4*>(stats_row + P.cout + n) = sq;
-            }
+        // keep the channel padding of the output at zero (layers with C_out < channel stride: 16 -> 32)
+        if (P.out_cs > P.cout && n0 + BLOCK_N >= P.cout && lane < nvalid) {
+            float* o = P.out + (pix0 + lane) * P.out_cs;
+            for (int c = P.cout; c < P.out_cs; ++c) o[c] = 0.f;
         }
     }
-    // keep the channel padding of the output at zero (layers with C_out < channel stride: 16 -> 32)
-    if (P.out_cs > P.cout && n0 + BLOCK_N >= P.cout && lane < nvalid) {
-        float* o = P.out + (pix0 + lane) * P.out_cs;
-        for (int c = P.cout; c < P.out_cs; ++c) o[c] = 0.f;
-    }
-}
+};
 
 // SPLIT = fp32-accurate "3xTF32" mode: every fp32 operand x is used as x_hi + x_lo (x_hi = rn_tf32(x), x_lo =
 // rn_tf32(x - x_hi)) and D += A_hi B_hi + A_hi B_lo + A_lo B_hi.  Weights are split on the host (two packed arrays, two
@@ -894,8 +908,31 @@ conv_halo_persistent_kernel(const __grid_constant__ ConvTcParams P) {
                     const int sa = ia & 1;
                     tc::mbar_wait(&a_full[sa], ((uint32_t)ia >> 1) & 1u);
                     const uint32_t a_base = tc::smem_u32(smem + sa * HALO_A_STRIDE);
+                    if (!P.masked) {
+                        // dense layers: straight-line issue, eight MMAs per tap (the masked form below costs a branch per k-step)
+                        for (int tap = 0; tap < 9; ++tap, ++ib) {
+                            const int sb = ib % NB;
+                            tc::mbar_wait(&b_full[sb], (uint32_t)(ib / NB) & 1u);
+                            tc::tc_fence_after();
+                            const int dy = tap / 3, dx = tap - dy * 3;
+                            const uint64_t bdesc = tc::smem_desc_k_sw128(tc::smem_u32(smem + S::OFF_B + sb * S::B_BYTES));
+#pragma unroll
+                            for (int mt = 0; mt < 2; ++mt) {
+                                const uint64_t adesc = tc::smem_desc_k_sw128(a_base + (uint32_t)(((4 * mt + dy) * HALO_RP + dx) * 128));
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    const uint32_t acc = (uint32_t)((kc | tap | k) != 0);
+                                    if (bf16) tc::umma_f16(d_tmem + mt * ACC_COLS, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, acc);
+                                    else tc::umma_tf32(d_tmem + mt * ACC_COLS, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, acc);
+                                }
+                            }
+                            tc::umma_commit(&b_empty[sb]);
+                        }
+                        tc::umma_commit(&a_empty[sa]);
+                        continue;
+                    }
                     for (int tap = 0; tap < 9; ++tap) {
-                        const uint32_t km = P.masked ? (uint32_t)((P.kmask[tap] >> (4 * kc)) & 0xFull) : 0xFu;
+                        const uint32_t km = (uint32_t)((P.kmask[tap] >> (4 * kc)) & 0xFull);
                         if (!km) continue;
                         const int sb = ib % NB;
                         tc::mbar_wait(&b_full[sb], (uint32_t)(ib / NB) & 1u);
@@ -930,6 +967,9 @@ conv_halo_persistent_kernel(const __grid_constant__ ConvTcParams P) {
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
             const int buf = tl & 1;
             int b, x0, y0, n0; decode(tile, b, x0, y0, n0);
+            EpilogueRow<BLOCK_N> er;
+            er.setup(P, lane, b, x0, y0 + 4 * mt + (warp & 3), n0, HALO_TWV);
+            er.load_res(P, 0);
             tc::mbar_wait(&tfull[buf], ((uint32_t)tl >> 1) & 1u);
             tc::tc_fence_after();
             float* srow = nullptr;
@@ -937,8 +977,7 @@ conv_halo_persistent_kernel(const __grid_constant__ ConvTcParams P) {
                 const int tr = tile / n_ntiles - b * tiles_per_img;
                 srow = P.stats_out + ((size_t)b * P.stats_rows + (tr * 2 + mt) * 4 + (warp & 3)) * 2 * P.cout;
             }
-            tc_epilogue_row<BLOCK_N>(P, tmem_base + (buf * 2 + mt) * ACC_COLS, warp & 3, lane, b, x0, y0 + 4 * mt + (warp & 3), n0, sbias + n0, stile,
-                                     HALO_TWV, srow);
+            er.run(P, tmem_base + (buf * 2 + mt) * ACC_COLS, warp & 3, lane, sbias + n0, stile, srow);
             tc::tc_fence_before();
             tc::mbar_arrive(&tempty[buf]);
         }
@@ -1011,7 +1050,7 @@ conv_halo_fused_kernel(const __grid_constant__ ConvTcParams P) {
     const int tiles_per_img = P.tiles_x * P.tiles_y;
     const int n_ntiles = P.cout / BLOCK_N;
     const int total_tiles = tiles_per_img * P.batch * n_ntiles;
-    const int nk = P.nk0 + P.nk1;
+    const int nk = P.nk0 + P.nk1 + P.nk2;
 
     if (threadIdx.x == 0) {
         const uint32_t issuers = (!BF16 && P.masked) ? 2u : 1u;        // masked (width-folded) layers: one MMA issuer per accumulator
@@ -1065,17 +1104,16 @@ conv_halo_fused_kernel(const __grid_constant__ ConvTcParams P) {
         // unrolled, masks in registers, ring positions kept incrementally, 32-bit descriptor arithmetic, predicated MMAs, and one
         // issuer warp per accumulator (warp 1: tile rows 0-3, warp 3: rows 4-7; every consumer barrier counts two arrivals).
         if (tc::elect_one()) {
-            uint64_t kmr[9];
-#pragma unroll
-            for (int t = 0; t < 9; ++t) kmr[t] = P.kmask[t];
+            // (rolled tap loops on purpose: the unrolled form was 12 KB of straight-line code per issuer and spent 58 % of its cycles in
+            // instruction-fetch stalls; the masks come from the constant bank, the tap's row offset is kept incrementally)
             int sb = 0; uint32_t phb = 0;
             if (warp == 0) {
                 for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, walk.next()) {
                     const int n0 = walk.nt * BLOCK_N;
                     for (int kc = 0; kc < nk; ++kc) {
-#pragma unroll
+#pragma unroll 1
                         for (int tap = 0; tap < 9; ++tap) {
-                            if (!((uint32_t)(kmr[tap] >> (4 * kc)) & 0xFu)) continue;
+                            if (!((uint32_t)(P.kmask[tap] >> (4 * kc)) & 0xFu)) continue;
                             tc::mbar_wait(&b_empty[sb], phb ^ 1u);
                             tc::mbar_expect_tx(&b_full[sb], S::B_BYTES);
                             tc::tma_load_2d(smem + S::OFF_B + sb * S::B_BYTES, &P.mapB, &b_full[sb], kc * 32, tap * P.cout_rows + n0);
@@ -1089,7 +1127,7 @@ conv_halo_fused_kernel(const __grid_constant__ ConvTcParams P) {
                 const uint32_t a_lo0 = tc::desc_lo(tc::smem_u32(smem)) + mt * (4u * HALO_RP * 128u / 16u);
                 const uint32_t b_lo0 = tc::desc_lo(tc::smem_u32(smem + S::OFF_B));
                 int sa = 0; uint32_t pha = 0, tl = 0;
-                for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl, walk.next()) {
+                for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
                     const uint32_t buf = tl & 1u;
                     tc::mbar_wait(&tempty[buf], ((tl >> 1) & 1u) ^ 1u);
                     tc::tc_fence_after();
@@ -1097,23 +1135,26 @@ conv_halo_fused_kernel(const __grid_constant__ ConvTcParams P) {
                     uint32_t acc = 0;
                     for (int kc = 0; kc < nk; ++kc) {
                         tc::mbar_wait(&a_ready[sa], pha);
-                        const uint32_t a_lo = a_lo0 + (uint32_t)sa * (S::RAW_STRIDE / 16);
-#pragma unroll
+                        uint32_t a_tap = a_lo0 + (uint32_t)sa * (S::RAW_STRIDE / 16);      // descriptor of tap (0, 0); + 8 per pixel, + 256 per tile row
+                        int dx = 0;
+#pragma unroll 1
                         for (int tap = 0; tap < 9; ++tap) {
-                            const uint32_t km = (uint32_t)(kmr[tap] >> (4 * kc)) & 0xFu;
-                            if (!km) continue;
-                            tc::mbar_wait(&b_full[sb], phb);
-                            tc::tc_fence_after();
-                            const uint32_t a_tap = a_lo + (uint32_t)(((tap / 3) * HALO_RP + tap % 3) * 128 / 16);
-                            const uint32_t b_tap = b_lo0 + (uint32_t)sb * (S::B_BYTES / 16);
+                            const uint32_t km = (uint32_t)(P.kmask[tap] >> (4 * kc)) & 0xFu;
+                            if (km) {
+                                tc::mbar_wait(&b_full[sb], phb);
+                                tc::tc_fence_after();
+                                const uint32_t b_tap = b_lo0 + (uint32_t)sb * (S::B_BYTES / 16);
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                const uint32_t en = (km >> k) & 1u;
-                                tc::umma_tf32_lo(d_tmem, a_tap + 2u * k, b_tap + 2u * k, idesc, acc, en);
-                                acc |= en;
+                                for (int k = 0; k < 4; ++k) {
+                                    const uint32_t en = (km >> k) & 1u;
+                                    tc::umma_tf32_lo(d_tmem, a_tap + 2u * k, b_tap + 2u * k, idesc, acc, en);
+                                    acc |= en;
+                                }
+                                tc::umma_commit(&b_empty[sb]);
+                                if (++sb == NB) { sb = 0; phb ^= 1u; }
                             }
-                            tc::umma_commit(&b_empty[sb]);
-                            if (++sb == NB) { sb = 0; phb ^= 1u; }
+                            a_tap += 8u;
+                            if (++dx == 3) { dx = 0; a_tap += (HALO_RP - 3) * 8u; }
                         }
                         tc::umma_commit(&a_empty[sa]);
                         if (++sa == NA) { sa = 0; pha ^= 1u; }
@@ -1133,7 +1174,7 @@ conv_halo_fused_kernel(const __grid_constant__ ConvTcParams P) {
                 int b, x0, y0, n0; decode(tile, b, x0, y0, n0);
                 for (int kc = 0; kc < nk; ++kc) {
                     for (int tap = 0; tap < 9; ++tap) {
-                        if (P.masked && !((P.kmask[tap] >> (4 * kc)) & 0xFull)) continue;     // structurally zero (tap, chunk)
+                        if (kc >= P.nk_gn && tap != 4) continue;              // shortcut chunk: centre tap only
                         const int sb = ib % NB;
                         tc::mbar_wait(&b_empty[sb], ((uint32_t)(ib / NB) & 1u) ^ 1u);
                         tc::mbar_expect_tx(&b_full[sb], S::B_BYTES);
@@ -1154,9 +1195,9 @@ conv_halo_fused_kernel(const __grid_constant__ ConvTcParams P) {
                     // the raw buffer is free once the transform warps have read it (BF16) / once the MMAs have read the in-place tile (TF32)
                     tc::mbar_wait(BF16 ? &raw_empty[sa] : &a_empty[sa], ((uint32_t)(ia / NA) & 1u) ^ 1u);
                     tc::mbar_expect_tx(&raw_full[sa], HF_RAW_BYTES);
-                    const bool first = kc < P.nk0;
-                    tc::tma_load_4d(smem + sa * S::RAW_STRIDE, first ? &P.mapA[0] : &P.mapA[1], &raw_full[sa], (first ? kc : kc - P.nk0) * 32,
-                                    x0 - 1, y0 - 1, b);
+                    const int si = kc < P.nk0 ? 0 : (kc < P.nk0 + P.nk1 ? 1 : 2);
+                    const int kl = kc - (si == 0 ? 0 : (si == 1 ? P.nk0 : P.nk0 + P.nk1));
+                    tc::tma_load_4d(smem + sa * S::RAW_STRIDE, &P.mapA[si], &raw_full[sa], kl * 32, x0 - 1, y0 - 1, b);
                 }
             }
         }
@@ -1172,14 +1213,12 @@ conv_halo_fused_kernel(const __grid_constant__ ConvTcParams P) {
                 tc::mbar_wait(&tempty[buf], (((uint32_t)tl >> 1) & 1u) ^ 1u);
                 tc::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + buf * 2 * ACC_COLS;
-                uint32_t started = 0;                                                // the first MMA of a tile overwrites the accumulators
-                for (int kc = 0; kc < nk; ++kc, ++ia) {
+                for (int kc = 0; kc < nk; ++kc, ++ia) {                              // (dense layers only: masked ones take the lean path above)
                     const int sa = ia % NA;
                     tc::mbar_wait(&a_ready[sa], (uint32_t)(ia / NA) & 1u);
                     const uint32_t a_base = tc::smem_u32(smem + (BF16 ? S::OFF_OP + sa * HF_OP_STRIDE_BF16 : sa * S::RAW_STRIDE));
                     for (int tap = 0; tap < 9; ++tap) {
-                        const uint32_t km = (!BF16 && P.masked) ? (uint32_t)((P.kmask[tap] >> (4 * kc)) & 0xFull) : 0xFu;
-                        if (!km) continue;
+                        if (kc >= P.nk_gn && tap != 4) continue;              // shortcut chunk: centre tap only
                         const int sb = ib % NB;
                         tc::mbar_wait(&b_full[sb], (uint32_t)(ib / NB) & 1u);
                         tc::tc_fence_after();
@@ -1192,11 +1231,9 @@ conv_halo_fused_kernel(const __grid_constant__ ConvTcParams P) {
                             const uint64_t adesc = BF16 ? tc::smem_desc_k(a_addr, 4, 512) : tc::smem_desc_k_sw128(a_addr);
 #pragma unroll
                             for (int k = 0; k < KSTEPS; ++k) {
-                                if (!((km >> k) & 1u)) continue;
-                                const uint32_t acc = (started >> mt) & 1u;
+                                const uint32_t acc = (uint32_t)((kc | tap | k) != 0);
                                 if (BF16) tc::umma_f16(d_tmem + mt * ACC_COLS, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, acc);
                                 else tc::umma_tf32(d_tmem + mt * ACC_COLS, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, acc);
-                                started |= 1u << mt;
                             }
                         }
                         tc::umma_commit(&b_empty[sb]);
@@ -1220,7 +1257,9 @@ conv_halo_fused_kernel(const __grid_constant__ ConvTcParams P) {
                 const int sa = ia % NA;
                 // per-lane affine of its 4 channels (pad channels of the source tensors: scale = shift = 0 -> silu(0) = 0)
                 float4 sc = make_float4(0.f, 0.f, 0.f, 0.f), sh = sc;
-                {
+                const bool ident = kc >= P.nk_gn;                                    // shortcut chunk: x itself, rounded to the operand type
+                if (ident) sc = make_float4(1.f, 1.f, 1.f, 1.f);
+                else {
                     const bool first = kc < P.nk0;
                     const int cl = (first ? kc : kc - P.nk0) * 32 + 4 * c8;          // channel inside its source
                     const int cg = first ? cl % P.gn_m0 : P.gn_m0 + cl % max(P.gn_m1, 1);   // channel of the GroupNorm (virtual concat; folded: pixel-major)
@@ -1262,7 +1301,7 @@ conv_halo_fused_kernel(const __grid_constant__ ConvTcParams P) {
                         const bool inside = (unsigned)yy < (unsigned)P.H && (unsigned)xx < (unsigned)P.W;
                         float4 o;
                         o.x = fmaf(v[j].x, sc.x, sh.x); o.y = fmaf(v[j].y, sc.y, sh.y); o.z = fmaf(v[j].z, sc.z, sh.z); o.w = fmaf(v[j].w, sc.w, sh.w);
-                        if (P.gn_act == 1) { o.x = silu(o.x); o.y = silu(o.y); o.z = silu(o.z); o.w = silu(o.w); }
+                        if (P.gn_act == 1 && !ident) { o.x = silu(o.x); o.y = silu(o.y); o.z = silu(o.z); o.w = silu(o.w); }
                         if (BF16 && !inside) o = make_float4(0.f, 0.f, 0.f, 0.f);         // the conv pads the ACTIVATION with zeros
                         if (BF16) {
                             const __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
@@ -1288,16 +1327,18 @@ conv_halo_fused_kernel(const __grid_constant__ ConvTcParams P) {
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl, walk.next()) {
             const int buf = tl & 1;
             int b, x0, y0, n0; decode(tile, b, x0, y0, n0);
+            EpilogueRow<BLOCK_N, 32> er;
+            er.setup(P, lane, b, x0, y0 + 4 * mt + (warp & 3), n0, HALO_TWV);
+            er.load_res(P, 0);
             if ((warp & 3) == 0) tc::mbar_wait_idle(&tfull[buf], ((uint32_t)tl >> 1) & 1u);
             tc::named_bar_sync(2 + mt, 128);
             tc::tc_fence_after();
             float* srow = nullptr;
             if (P.stats_out) {
-                const int tr = tile / n_ntiles - b * tiles_per_img;
+                const int tr = walk.tyi * P.tiles_x + walk.txi;
                 srow = P.stats_out + ((size_t)b * P.stats_rows + (tr * 2 + mt) * 4 + (warp & 3)) * 2 * P.cout;
             }
-            tc_epilogue_row<BLOCK_N, 32>(P, tmem_base + (buf * 2 + mt) * ACC_COLS, warp & 3, lane, b, x0, y0 + 4 * mt + (warp & 3), n0, sbias + n0, stile,
-                                         HALO_TWV, srow);
+            er.run(P, tmem_base + (buf * 2 + mt) * ACC_COLS, warp & 3, lane, sbias + n0, stile, srow);
             tc::tc_fence_before();
             tc::mbar_arrive(&tempty[buf]);
         }
@@ -1386,7 +1427,7 @@ bool conv_tc_can_fuse_norm(int H, int W, int batch, int cout, int ntaps, int str
 }
 
 int conv_tc_prepare(ConvTcParams& P, const ConvTcDesc& d) {
-    IPDM_REQUIRE(d.nsrc >= 1 && d.nsrc <= 2, "conv_tc: 1 or 2 sources");
+    IPDM_REQUIRE(d.nsrc >= 1 && d.nsrc <= (d.n_ident ? 3 : 2) && d.n_ident >= 0 && d.n_ident < d.nsrc, "conv_tc: 1 or 2 sources (+ shortcut sources)");
     IPDM_REQUIRE(d.stride == 1 || (d.stride == 2 && d.nsrc == 1), "conv_tc: stride 2 takes one source");
     IPDM_REQUIRE(d.ntaps == 1 || d.ntaps == 9, "conv_tc: 1x1 or 3x3");
     memset(&P, 0, sizeof(P));
@@ -1427,14 +1468,15 @@ int conv_tc_prepare(ConvTcParams& P, const ConvTcDesc& d) {
         P.gn_act = 4; P.gn_c0 = d.src[0].c; P.gn_c1 = d.nsrc > 1 ? d.src[1].c : 0; P.gn_m0 = P.gn_c0; P.gn_m1 = P.gn_c1;
     } else if (P.fused) {
         IPDM_REQUIRE(P.halo && P.persistent && P.block_n >= 32 && d.cout <= 512 && d.norm_shift, "conv_tc: GroupNorm fusion needs a persistent halo layer (3x3, stride 1, C_out 32..512)");
-        IPDM_REQUIRE(d.nsrc == 1 || d.src[0].c == d.src[0].cs, "conv_tc: fused concat needs an unpadded first source (%d channels, stride %d)", d.src[0].c, d.src[0].cs);
+        const int ngn = d.nsrc - d.n_ident;                               // sources under the GroupNorm; the rest is the folded shortcut's input
+        IPDM_REQUIRE(ngn == 1 || d.src[0].c == d.src[0].cs, "conv_tc: fused concat needs an unpadded first source (%d channels, stride %d)", d.src[0].c, d.src[0].cs);
         IPDM_REQUIRE(d.act_silu, "conv_tc: the fused operand path is GroupNorm + SiLU (the attention norm has no activation and feeds a 1x1 conv)");
         P.gn_scale = d.norm_scale; P.gn_shift = d.norm_shift; P.gn_act = d.act_silu;
         // experiments (tools only): IPDM_FUSE_DBG=2 affine without SiLU, 3 the transform warps only hand the barriers on (operands are garbage)
         static const int fuse_dbg = getenv("IPDM_FUSE_DBG") ? atoi(getenv("IPDM_FUSE_DBG")) : 0;
         if (fuse_dbg) P.gn_act = fuse_dbg;
-        P.gn_c0 = d.src[0].c; P.gn_c1 = d.nsrc > 1 ? d.src[1].c : 0;
-        P.gn_m0 = d.gn_mod[0] ? d.gn_mod[0] : P.gn_c0; P.gn_m1 = d.gn_mod[1] ? d.gn_mod[1] : P.gn_c1;
+        P.gn_c0 = d.src[0].c; P.gn_c1 = ngn > 1 ? d.src[1].c : 0;
+        P.gn_m0 = d.gn_mod[0] ? d.gn_mod[0] : P.gn_c0; P.gn_m1 = ngn > 1 ? (d.gn_mod[1] ? d.gn_mod[1] : P.gn_c1) : 0;
         IPDM_REQUIRE(P.gn_c0 % 4 == 0 && P.gn_c1 % 4 == 0 && P.gn_m0 % 4 == 0 && (P.gn_c1 == 0 || P.gn_m1 % 4 == 0),
                      "conv_tc: fused GroupNorm needs channel counts that are multiples of 4");
     }
@@ -1448,7 +1490,8 @@ int conv_tc_prepare(ConvTcParams& P, const ConvTcDesc& d) {
         IPDM_REQUIRE(t.bf16 == (P.bf16 && !P.fused), "conv_tc: concat sources differ in dtype");
         IPDM_REQUIRE(t.cs % P.kc == 0 && ((uintptr_t)t.p % 16) == 0, "conv_tc: source channel stride %d must be a multiple of %d", t.cs, P.kc);
         IPDM_REQUIRE(t.h == Hin && t.w == Win && t.n == P.batch, "conv_tc: concat sources differ in shape");
-        (s == 0 ? P.nk0 : P.nk1) = t.cs / P.kc;
+        (s == 0 ? P.nk0 : (s == 1 ? P.nk1 : P.nk2)) = t.cs / P.kc;
+        if (s < d.nsrc - d.n_ident) P.nk_gn += t.cs / P.kc;
         ktot += t.cs;
         if (d.stride == 1) {
             const uint64_t dims[4] = {(uint64_t)t.cs, (uint64_t)t.w, (uint64_t)t.h, (uint64_t)t.n};
@@ -1486,16 +1529,18 @@ int conv_tc_prepare(ConvTcParams& P, const ConvTcDesc& d) {
     P.res = d.res.p; P.res_cs = d.res.cs;
     P.qkv_mode = d.qkv_mode; P.vt = d.vt; P.t_pad = d.t_pad; P.heads = d.heads; P.head_dim = d.head_dim;
     P.out_lo = d.out_lo; P.vt_lo = d.vt_lo; P.qkv_bf16 = d.qkv_bf16;
+    IPDM_REQUIRE(!d.n_ident || (P.fused && !d.passthrough && d.stride == 1), "conv_tc: a folded shortcut needs the GroupNorm-fused halo kernel");
     P.bias_mod = d.bias_mod; P.fold = d.fold;
     P.masked = 0;
     for (int t = 0; t < 9; ++t) { P.kmask[t] = d.kmask[t]; if (d.kmask[t]) P.masked = 1; }
-    IPDM_REQUIRE(!P.masked || (P.halo && P.persistent && !P.bf16 && d.ntaps == 9 && P.nk0 + P.nk1 <= 16),
+    IPDM_REQUIRE(!P.masked || (P.halo && P.persistent && !P.bf16 && d.ntaps == 9 && P.nk0 + P.nk1 + P.nk2 <= 16),
                  "conv_tc: k-step masks are a feature of the tf32 persistent halo kernels (<= 16 K chunks)");
     {   // MMA work actually issued (masked k-steps are skipped)
         double ksteps = 0;
-        const int nkk = P.nk0 + P.nk1, per = P.kc * (P.bf16 ? 2 : 4) / 32;      // k-steps (32 bytes of K) per chunk
+        const int nkk = P.nk0 + P.nk1 + P.nk2, per = P.kc * (P.bf16 ? 2 : 4) / 32;      // k-steps (32 bytes of K) per chunk
         for (int t = 0; t < d.ntaps; ++t)
             for (int kc = 0; kc < nkk; ++kc) {
+                if (!P.masked && kc >= P.nk_gn && t != 4) continue;               // shortcut chunks: centre tap only
                 const unsigned km = P.masked ? (unsigned)((P.kmask[t] >> (4 * kc)) & 0xF) : (1u << per) - 1u;
                 ksteps += __builtin_popcount(km);
             }
@@ -1544,7 +1589,7 @@ int conv_tc_launch(const ConvTcParams& P, cudaStream_t st) {
     // padded-K FLOPs actually issued to the tensor pipe; the persistent halo kernel (the dominant kernel of the step) is its own family
     // (width-folded thin layers are HBM-bound streaming layers: they are accounted in bytes with the other thin / direct convs)
     ProfScope prof(P.fold ? PROF_CONV_DIRECT : (P.halo && P.persistent ? PROF_CONV_HALO_PERS : PROF_CONV_TC), st,
-                   P.fold ? 4.0 * P.batch * (double)P.H * P.W * ((P.nk0 + P.nk1) * P.kc + P.cout) : conv_tc_flops(P));
+                   P.fold ? 4.0 * P.batch * (double)P.H * P.W * ((P.nk0 + P.nk1 + P.nk2) * P.kc + P.cout) : conv_tc_flops(P));
     if (P.fused) {
         if (P.bf16) { if (P.block_n == 128) return launch_halo_fused<128, 8, true>(P, st); if (P.block_n == 64) return launch_halo_fused<64, 12, true>(P, st); }
         else {

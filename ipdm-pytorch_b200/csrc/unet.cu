@@ -49,9 +49,9 @@ struct ConvW {
     float* w_dev_direct = nullptr;           // thin layers: the [tap][cin][cout] copy for the direct-kernel fallback
     bool thin = false; int thin_cs = 0;      // thin tensor-core path (conv_thin.cu): operand channel stride 8 / 16 / 32
     // width-folded tensor-core path (pack_fold): `fold` pixels of a row are one pixel of fold*C channels
-    int fold = 0, fold_c0 = 0, fold_c1 = 0; float* w_dev_fold = nullptr; uint64_t fold_mask[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    int fold = 0, fold_c0 = 0, fold_c1 = 0, fold_c2 = 0, fold_k = 0; float* w_dev_fold = nullptr; uint64_t fold_mask[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
 };
-struct ResW { GNW gn1, gn2; ConvW conv1, conv2, shortcut; bool has_shortcut = false; std::vector<float> temb_w, temb_b; float* bias1_t = nullptr; int cin = 0, cout = 0; };
+struct ResW { GNW gn1, gn2; ConvW conv1, conv2, shortcut, conv2sc /* conv2 with the shortcut folded in (pack_conv2_shortcut) */; bool has_shortcut = false; std::vector<float> temb_w, temb_b; float* bias1_t = nullptr; int cin = 0, cout = 0; };
 struct AttnW { GNW norm; ConvW qkv, proj; int C = 0; };
 struct LayerRef { enum Kind { CONV_IN, RES, ATTN, DOWN, UP } kind; int idx; };
 typedef std::vector<LayerRef> Block;
@@ -61,7 +61,7 @@ struct VTensor { int n = 0, h = 0, w = 0, c = 0, cs = 0; int def = -1, last = -1
 
 struct Op {
     enum Kind { GN_STATS, GN_APPLY, CONV_TC, CONV_DIRECT, CONV_THIN, UPSAMPLE, ATTN } kind;
-    int src[2] = {-1, -1}; int nsrc = 0; int dst = -1, res = -1, aux = -1, aux2 = -1, aux3 = -1;
+    int src[3] = {-1, -1, -1}; int nsrc = 0; int n_ident = 0; int dst = -1, res = -1, aux = -1, aux2 = -1, aux3 = -1;
     const GNW* gn = nullptr; int norm_slot = -1; int act = 1;
     const ConvW* cw = nullptr; const float* bias = nullptr; int bias_t_stride = 0; bool use_t = false;
     int stride = 1, upsample = 0, qkv = 0;
@@ -235,43 +235,109 @@ static int pack_conv(ipdm_unet* net, ConvW& c, int c0, int c1, bool raw_sources,
 // 3 * (f + 2) * C_in / 8 k-steps per 128 folded pixels instead of 9 * f * C_in / 8.
 // Operands are tf32 (the accuracy-critical full-resolution layers never see bf16), accumulation fp32.
 // ------------------------------------------------------------------------------------------------
-static int fold_factor(int c0, int c1, int cout) {
+static int fold_factor(const int* cs, int nsrc, int cout) {
     static const bool off = getenv("IPDM_FOLD") && atoi(getenv("IPDM_FOLD")) == 0;
     if (off || cout > 16) return 0;
-    for (int f : {2, 4, 8})
-        if ((f * c0) % 32 == 0 && (c1 == 0 || (f * c1) % 32 == 0) && (f * cout == 32 || f * cout == 64) && (f * c0 + f * c1) / 32 <= 16) return f;
+    for (int f : {2, 4, 8}) {
+        bool ok = f * cout == 32 || f * cout == 64;
+        int chunks = 0;
+        for (int s = 0; s < nsrc; ++s) { ok = ok && (f * cs[s]) % 32 == 0; chunks += f * cs[s] / 32; }
+        if (ok && chunks <= 16) return f;
+    }
     return 0;
+}
+
+// General form: the folded conv reads `nsrc` dense sources of cs[s] channels; source s is contracted with wsrc[s] (a 3x3 conv, or a
+// 1x1 conv = the ResBlock shortcut folded into conv2: centre tap, same pixel only), whose input channels ci_off[s] ... belong to it.
+static int pack_fold_multi(ipdm_unet* net, ConvW& c, int nsrc, const int* cs, const ConvW* const* wsrc, const int* ci_off, const float* bias_host) {
+    c.fold = 0;
+    if (!(net->precision == IPDM_PREC_BF16 || net->force_fold)) return IPDM_OK;
+    const int f = fold_factor(cs, nsrc, c.cout);
+    if (!f) return IPDM_OK;
+    int ctot = 0; for (int s = 0; s < nsrc; ++s) ctot += cs[s];
+    const int kmain = wsrc[0]->k, N = f * c.cout, K = f * ctot, nt = kmain == 3 ? 9 : 1;
+    std::vector<float> p((size_t)nt * N * K, 0.f);
+    for (int t = 0; t < 9; ++t) c.fold_mask[t] = 0;
+    for (int tap = 0; tap < nt; ++tap) {
+        const int dy = kmain == 3 ? tap / 3 : 1, bdx = kmain == 3 ? tap % 3 : 1;
+        int col0 = 0;
+        for (int s = 0; s < nsrc; ++s) {
+            const ConvW& w = *wsrc[s];
+            const int kk = w.k * w.k;
+            for (int lc = 0; lc < f * cs[s]; ++lc) {
+                const int col = col0 + lc, bi = lc / cs[s], ci = ci_off[s] + lc % cs[s];
+                bool any = false;
+                for (int bo = 0; bo < f; ++bo) {
+                    const int dx = f * (bdx - 1) + bi - bo;
+                    if (dx < -1 || dx > 1) continue;
+                    if (w.k == 1 && (dx != 0 || dy != 1)) continue;
+                    any = true;
+                    const int t = w.k == 3 ? dy * 3 + dx + 1 : 0;
+                    for (int co = 0; co < c.cout; ++co)
+                        p[((size_t)tap * N + bo * c.cout + co) * K + col] = tf32_rn_host(w.w_host[((size_t)co * w.cin + ci) * kk + t]);
+                }
+                if (any) c.fold_mask[tap] |= 1ull << (col / 8);              // bit = 4 * chunk + k-step
+            }
+            col0 += f * cs[s];
+        }
+    }
+    IPDM_CHECK(upload(net, p, &c.w_dev_fold));
+    if (bias_host && !c.b_dev) IPDM_CHECK(upload(net, std::vector<float>(bias_host, bias_host + c.cout), &c.b_dev));
+    c.fold = f; c.fold_c0 = cs[0]; c.fold_c1 = nsrc > 1 ? cs[1] : 0; c.fold_c2 = nsrc > 2 ? cs[2] : 0; c.fold_k = K;
+    return IPDM_OK;
 }
 
 static int pack_fold(ipdm_unet* net, ConvW& c, int c0, int c1) {
     c.fold = 0;
-    if (!(net->precision == IPDM_PREC_BF16 || net->force_fold) || (c.k != 1 && c.k != 3) || c0 + c1 != c.cin) return IPDM_OK;
-    const int f = fold_factor(c0, c1, c.cout);
-    if (!f) return IPDM_OK;
-    const int kk = c.k * c.k, N = f * c.cout, K = f * c.cin, nt = c.k == 3 ? 9 : 1;
-    std::vector<float> p((size_t)nt * N * K, 0.f);
-    for (int t = 0; t < 9; ++t) c.fold_mask[t] = 0;
-    for (int tap = 0; tap < nt; ++tap) {
-        const int dy = c.k == 3 ? tap / 3 : 0, bdx = c.k == 3 ? tap % 3 : 1;
-        for (int col = 0; col < K; ++col) {
-            const bool first = col < f * c0;
-            const int cs = first ? c0 : c1, lc = first ? col : col - f * c0;
-            const int bi = lc / cs, ci = (first ? 0 : c0) + lc % cs;
-            bool any = false;
-            for (int bo = 0; bo < f; ++bo) {
-                const int dx = f * (bdx - 1) + bi - bo;
-                if (dx < -1 || dx > 1 || (c.k == 1 && dx != 0)) continue;
-                any = true;
-                const int t = c.k == 3 ? dy * 3 + dx + 1 : 0;
-                for (int co = 0; co < c.cout; ++co)
-                    p[((size_t)tap * N + bo * c.cout + co) * K + col] = tf32_rn_host(c.w_host[((size_t)co * c.cin + ci) * kk + t]);
+    if ((c.k != 1 && c.k != 3) || c0 + c1 != c.cin) return IPDM_OK;
+    const int cs[2] = {c0, c1}; const ConvW* ws[2] = {&c, &c}; const int off[2] = {0, c0};
+    return pack_fold_multi(net, c, c1 ? 2 : 1, cs, ws, off, c.b_host.empty() ? nullptr : c.b_host.data());
+}
+
+// conv2 of a channel-changing ResBlock with its 1x1 shortcut folded in (model.py:110-130: out = conv2(act(norm2(h))) + shortcut(x)):
+// K = [h | x_a | x_b]; the x columns carry the shortcut weights at the centre tap and zeros elsewhere; bias = conv2.bias + shortcut.bias.
+// Dense form for conv_halo_fused_kernel (identity chunks, see ConvTcDesc::n_ident) and width-folded form for the thin levels.
+static int pack_conv2_shortcut(ipdm_unet* net, ResW& w, int c0, int c1) {
+    static const bool off = getenv("IPDM_SC_FOLD") && atoi(getenv("IPDM_SC_FOLD")) == 0;
+    ConvW& c = w.conv2sc;
+    c.cin = w.cout + c0 + c1; c.cout = w.cout; c.k = 3; c.tc = false; c.fold = 0;
+    if (off || !w.has_shortcut || net->precision == IPDM_PREC_FP32) return IPDM_OK;
+    std::vector<float> b(w.cout);
+    for (int i = 0; i < w.cout; ++i) b[i] = w.conv2.b_host[i] + w.shortcut.b_host[i];
+    IPDM_CHECK(upload(net, b, &c.b_dev));
+    // Dense layers: built and measured (IPDM_SC_FOLD_DENSE=1), off by default -- every shortcut chunk costs a whole halo tile on the
+    // operand path (TMA + transform slot) for ONE tap of MMAs, so on the HBM-bound 64-channel image layers the folded launch is no
+    // faster than conv2 + the separate 1x1 launch (1315 vs 717 + 597 us at 16 x 512 x 512, 1722 vs 1332 us with a 192-channel input)
+    // and x would be rounded to bf16 on the skip path.  The width-folded thin layers do gain (proj forward 56.7 -> 53.7 ms).
+    static const bool dense_on = getenv("IPDM_SC_FOLD_DENSE") && atoi(getenv("IPDM_SC_FOLD_DENSE")) == 1;
+    if (dense_on && w.conv2.tc && w.cout % 64 == 0 && c0 >= 16 && (c1 == 0 || c1 >= 16)) {
+        const int csh = round_up(w.cout, 32), cs0 = round_up(c0, 32), cs1 = c1 ? round_up(c1, 32) : 0;
+        c.kpad = csh + cs0 + cs1; c.c0 = w.cout; c.cs0 = csh; c.c1 = c0; c.cs1 = cs0;
+        c.bf16 = net->precision == IPDM_PREC_BF16;
+        std::vector<float> p((size_t)9 * w.cout * c.kpad, 0.f);
+        for (int co = 0; co < w.cout; ++co) {
+            for (int ci = 0; ci < w.cout; ++ci)
+                for (int t = 0; t < 9; ++t) p[((size_t)t * w.cout + co) * c.kpad + ci] = w.conv2.w_host[((size_t)co * w.cout + ci) * 9 + t];
+            for (int ci = 0; ci < c0 + c1; ++ci) {
+                const int col = csh + (ci < c0 ? ci : cs0 + (ci - c0));
+                p[((size_t)4 * w.cout + co) * c.kpad + col] = w.shortcut.w_host[(size_t)co * (c0 + c1) + ci];
             }
-            if (any) c.fold_mask[tap] |= 1ull << (col / 8);                  // bit = 4 * chunk + k-step
         }
+        if (c.bf16) {
+            std::vector<float> packed((p.size() + 1) / 2, 0.f);
+            uint16_t* h = reinterpret_cast<uint16_t*>(packed.data());
+            for (size_t i = 0; i < p.size(); ++i) h[i] = bf16_rn_host(p[i]);
+            IPDM_CHECK(upload(net, packed, &c.w_dev));
+        } else {
+            for (float& v : p) v = tf32_rn_host(v);
+            IPDM_CHECK(upload(net, p, &c.w_dev));
+        }
+        c.tc = true;
     }
-    IPDM_CHECK(upload(net, p, &c.w_dev_fold));
-    if (!c.b_host.empty() && !c.b_dev) IPDM_CHECK(upload(net, c.b_host, &c.b_dev));
-    c.fold = f; c.fold_c0 = c0; c.fold_c1 = c1;
+    {
+        const int cs[3] = {w.cout, c0, c1}; const ConvW* ws[3] = {&w.conv2, &w.shortcut, &w.shortcut}; const int offs[3] = {0, 0, c0};
+        IPDM_CHECK(pack_fold_multi(net, c, c1 ? 3 : 2, cs, ws, offs, nullptr));
+    }
     return IPDM_OK;
 }
 
@@ -372,6 +438,7 @@ struct BuildVisitor : ArchVisitor {
         if (w.has_shortcut) fail(pack_conv(net, w.shortcut, c0, c1, true));
         fail(pack_fold(net, w.conv1, c0, c1)); fail(pack_fold(net, w.conv2, co, 0));
         if (w.has_shortcut) fail(pack_fold(net, w.shortcut, c0, c1));
+        fail(pack_conv2_shortcut(net, w, c0, c1));
         cur->push_back({LayerRef::RES, (int)net->res.size() - 1});
     }
     void attn(int c, int) override {
@@ -454,7 +521,7 @@ struct PlanBuilder {
     bool can_fold(const ConvW& cw, const int* src, int nsrc, int dst, int res) {
         if (!cw.fold) return false;
         const VTensor& s0 = pl->vt[src[0]];
-        if (s0.w % cw.fold != 0 || s0.c != cw.fold_c0 || (nsrc > 1 ? pl->vt[src[1]].c : 0) != cw.fold_c1) return false;
+        if (s0.w % cw.fold != 0 || s0.c != cw.fold_c0 || (nsrc > 1 ? pl->vt[src[1]].c : 0) != cw.fold_c1 || (nsrc > 2 ? pl->vt[src[2]].c : 0) != cw.fold_c2) return false;
         for (int i = 0; i < nsrc; ++i) { const VTensor& t = pl->vt[src[i]]; if (t.cs != t.c || t.bf16 || t.external) return false; }
         const VTensor& d = pl->vt[dst];
         if (d.cs != d.c || d.external || d.c != cw.cout) return false;
@@ -462,8 +529,21 @@ struct PlanBuilder {
         return true;
     }
 
+    bool can_fold_shortcut(const ResW& w, int h1, const int* xs, int nxs, int dst) {
+        const ConvW& cw = w.conv2sc;
+        const int all[3] = {h1, xs[0], nxs > 1 ? xs[1] : -1};
+        if (cw.fold && can_fold(cw, all, 1 + nxs, dst, -1)) return true;
+        if (!cw.tc || net->precision == IPDM_PREC_FP32) return false;
+        const VTensor& h = pl->vt[h1];
+        if (!conv_tc_can_fuse_norm(h.h, h.w, pl->B, cw.cout, 9, 1)) return false;
+        for (int i = 0; i < nxs; ++i) { const VTensor& t = pl->vt[xs[i]]; if (t.bf16 || t.external || t.c < 16) return false; }
+        return true;
+    }
+
     // GroupNorm(+SiLU) followed by a conv; returns nothing, writes `dst`
-    void norm_conv(const int* src, int nsrc, const GNW& gn, const ConvW& cw, int dst, int res, const float* bias, int bstride, bool use_t, int act_silu) {
+    // xs / nxs: the ResBlock input when its 1x1 shortcut is folded into this conv (cw then is ResW::conv2sc); the caller has checked can_fold_shortcut
+    void norm_conv(const int* src, int nsrc, const GNW& gn, const ConvW& cw, int dst, int res, const float* bias, int bstride, bool use_t, int act_silu,
+                   const int* xs = nullptr, int nxs = 0) {
         Op st; st.kind = Op::GN_STATS; st.nsrc = nsrc; st.src[0] = src[0]; st.src[1] = nsrc > 1 ? src[1] : -1; st.gn = &gn; st.norm_slot = norm_slots++;
         max_c = std::max(max_c, gn.C);
         push(st);
@@ -472,7 +552,14 @@ struct PlanBuilder {
         // the two spare warps per CTA doing the transform it is SLOWER than the separate apply pass (measured at 16 slices: 8 -> 8 at
         // 2000x912 1025 us fused vs 600 + 311 us; 16 -> 16 at 1000x456 526 vs 283 + 155 us).
         static const bool thin_fuse = getenv("IPDM_THIN_FUSE") && atoi(getenv("IPDM_THIN_FUSE")) == 1;
-        if (cw.k == 3 && can_fold(cw, src, nsrc, dst, res)) {
+        if (nxs) {
+            // conv2 + folded shortcut: sources = [h | x ...], the last nxs are read raw and meet the centre tap only
+            Op cv; cv.kind = Op::CONV_TC; cv.nsrc = 1 + nxs; cv.n_ident = nxs; cv.src[0] = src[0]; cv.src[1] = xs[0]; cv.src[2] = nxs > 1 ? xs[1] : -1;
+            cv.cw = &cw; cv.dst = dst; cv.res = -1; cv.bias = bias; cv.bias_t_stride = bstride; cv.use_t = use_t; cv.norm_slot = st.norm_slot; cv.gn = &gn; cv.act = act_silu;
+            const int all[3] = {src[0], xs[0], nxs > 1 ? xs[1] : -1};
+            cv.fold = can_fold(cw, all, 1 + nxs, dst, -1) ? cw.fold : 0;
+            push(cv);
+        } else if (cw.k == 3 && can_fold(cw, src, nsrc, dst, res)) {
             // width-folded: the persistent halo kernel normalises the raw tile(s) on its operand path and emits the output statistics
             Op cv; cv.kind = Op::CONV_TC; cv.nsrc = nsrc; cv.src[0] = src[0]; cv.src[1] = st.src[1]; cv.cw = &cw; cv.dst = dst; cv.res = res;
             cv.bias = bias; cv.bias_t_stride = bstride; cv.use_t = use_t; cv.norm_slot = st.norm_slot; cv.gn = &gn; cv.act = act_silu; cv.fold = cw.fold;
@@ -523,8 +610,14 @@ struct PlanBuilder {
         const int h1 = act(s0.h, s0.w, w.cout);
         norm_conv(src, nsrc, w.gn1, w.conv1, h1, -1, w.bias1_t, w.cout, true, 1);
         int resid = src[0];
-        if (w.has_shortcut) { resid = act(s0.h, s0.w, w.cout); plain_conv(src, nsrc, w.shortcut, resid, -1, 1, 0); }
         const int out = act(s0.h, s0.w, w.cout);
+        if (w.has_shortcut && can_fold_shortcut(w, h1, src, nsrc, out)) {
+            // out = conv2(act(norm2(h1))) + shortcut(x) as ONE launch: x rides along as extra K chunks of conv2 (no shortcut tensor, no
+            // residual read in the epilogue)
+            norm_conv(&h1, 1, w.gn2, w.conv2sc, out, -1, w.conv2sc.b_dev, 0, false, 1, src, nsrc);
+            return out;
+        }
+        if (w.has_shortcut) { resid = act(s0.h, s0.w, w.cout); plain_conv(src, nsrc, w.shortcut, resid, -1, 1, 0); }
         norm_conv(&h1, 1, w.gn2, w.conv2, out, resid, w.conv2.b_dev, 0, false, 1);
         return out;
     }
@@ -594,12 +687,12 @@ static TensorNHWC resolve(const Plan& pl, int id) {
 static void fold_view(TensorNHWC& t, int f) { if (t.p || t.c) { t.w /= f; t.c *= f; t.cs *= f; } }
 static void fold_desc(ConvTcDesc& d, const ConvW& cw) {
     const int f = cw.fold;
-    d.gn_mod[0] = d.src[0].c; d.gn_mod[1] = d.nsrc > 1 ? d.src[1].c : 0; d.bias_mod = cw.cout;
+    d.gn_mod[0] = d.src[0].c; d.gn_mod[1] = d.nsrc - d.n_ident > 1 ? d.src[1].c : 0; d.bias_mod = cw.cout;
     for (int s = 0; s < d.nsrc; ++s) fold_view(d.src[s], f);
     fold_view(d.out, f);
     if (d.res.p) fold_view(d.res, f);
     d.cout = f * cw.cout; d.n_tile = d.cout;
-    d.w_packed = cw.w_dev_fold; d.w_packed_lo = nullptr; d.w_k = f * cw.cin; d.w_bf16 = 0;
+    d.w_packed = cw.w_dev_fold; d.w_packed_lo = nullptr; d.w_k = cw.fold_k; d.w_bf16 = 0;
     for (int t = 0; t < 9; ++t) d.kmask[t] = cw.k == 3 ? cw.fold_mask[t] : 0;
     d.fold = f;
     if (cw.k == 3 && !d.norm_scale) d.passthrough = 1;     // plain folded 3x3 (the Upsample conv): same kernel, identity operand path
@@ -637,7 +730,7 @@ static int build_plan(ipdm_unet* net, int B, int H, int W, Plan** out) {
         if (o.kind == Op::CONV_THIN && pl->vt[o.src[0]].cs != o.cw->thin_cs) o.kind = Op::CONV_DIRECT;
     for (const Op& o : pl->ops)
         if (o.kind == Op::CONV_TC && o.fold)
-            for (int id : {o.src[0], o.src[1], o.dst, o.res})
+            for (int id : {o.src[0], o.src[1], o.src[2], o.dst, o.res})
                 IPDM_REQUIRE(id < 0 || pl->vt[id].cs == pl->vt[id].c, "unet: a width-folded conv shares a tensor with a layer that needs it padded (%d -> %d channels)",
                              pl->vt[id].c, pl->vt[id].cs);
     // GroupNorm statistics come from the epilogue of the conv that writes the tensor when that conv runs a persistent tensor-core
@@ -728,7 +821,8 @@ static int build_plan(ipdm_unet* net, int B, int H, int W, Plan** out) {
             } break;
             case Op::CONV_TC: {
                 ConvTcDesc d;
-                d.nsrc = o.nsrc; d.src[0] = resolve(*pl, o.src[0]); if (o.nsrc > 1) d.src[1] = resolve(*pl, o.src[1]);
+                d.nsrc = o.nsrc; d.n_ident = o.n_ident;
+                for (int sidx = 0; sidx < o.nsrc; ++sidx) d.src[sidx] = resolve(*pl, o.src[sidx]);
                 d.ntaps = o.cw->k * o.cw->k; d.stride = o.stride; d.cout = o.cw->cout; d.w_packed = o.cw->w_dev; d.w_k = o.cw->kpad;
                 d.w_packed_lo = o.cw->w_dev_lo;
                 d.bias = o.bias; d.bias_t_stride = o.bias_t_stride; d.t_dev = o.use_t ? net->t_dev : nullptr;
@@ -746,6 +840,8 @@ static int build_plan(ipdm_unet* net, int B, int H, int W, Plan** out) {
                 IPDM_CHECK(conv_tc_prepare(o.tcp, d));
                 pl->vt[o.dst].stats_rows = o.tcp.stats_out ? o.tcp.stats_rows : 0;
                 o.flops = 2.0 * B * o.tcp.H * o.tcp.W * (o.fold ? o.fold : 1) * (double)o.cw->cin * o.cw->cout * d.ntaps;
+                if (o.n_ident)                                       // conv2 (3x3 over C_out channels) + shortcut (1x1 over the block input)
+                    o.flops = 2.0 * B * o.tcp.H * o.tcp.W * (o.fold ? o.fold : 1) * (double)o.cw->cout * (9.0 * o.cw->cout + (o.cw->cin - o.cw->cout));
             } break;
             case Op::CONV_THIN: {
                 ConvThinDesc d;

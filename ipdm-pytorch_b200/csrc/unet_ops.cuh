@@ -19,7 +19,7 @@ struct TensorNHWC {
 // ---- tensor-core implicit GEMM convolution (conv_tc.cu) ---------------------------------------------
 struct ConvTcDesc {
     int nsrc = 1;
-    TensorNHWC src[2];          // virtual concat along channels; both padded to multiples of 32
+    TensorNHWC src[3];          // virtual concat along channels; all padded to multiples of 32 (three only with n_ident, see below)
     int ntaps = 9, stride = 1;
     int cout = 0;
     const float* w_packed = nullptr;   // [ntaps][cout][w_k] (tf32-rounded; the hi part in fp32 mode)
@@ -46,6 +46,10 @@ struct ConvTcDesc {
     // folded ones (per-channel GroupNorm affine and bias are indexed modulo them); n_tile forces the N tile (0 auto)
     uint64_t kmask[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     int gn_mod[2] = {0, 0}; int bias_mod = 0; int n_tile = 0; int fold = 0;
+    // 1x1 shortcut folded into the conv (model.py:130 `h + self.shortcut(x)`): the LAST n_ident sources are the ResBlock input x, read
+    // raw (no GroupNorm) on the operand path and contracted with the centre tap only -- w_packed carries the shortcut weights in the
+    // K columns of those sources at tap 4 and zeros at the other taps, bias = conv bias + shortcut bias (conv_halo_fused_kernel only)
+    int n_ident = 0;
     int passthrough = 0;               // run a plain (no GroupNorm) tf32 layer through conv_halo_fused_kernel with an identity operand path
 };
 int conv_tc_stats_rows_bound(int h, int w);
@@ -56,7 +60,7 @@ struct ConvTcParams {
     CUtensorMap mapB, mapBlo;
     int split, bf16, kc, halo, persistent;
     int H, W, tiles_x, tiles_y, tw_log2, batch;
-    int ntaps, stride, nk0, nk1;
+    int ntaps, stride, nk0, nk1, nk2, nk_gn;           // K chunks per source; chunks >= nk_gn are identity (shortcut) chunks
     int cout, cout_rows, block_n;
     float* out; int out_cs;
     const float* bias; int bias_t_stride; const int* t_dev;
