@@ -297,18 +297,21 @@ struct EpilogueRow {
     float4 rres[NJ];                                   // residual lines of the chunk being processed
 
     // coordinates of this warp's row (pixels x0 .. x0+31 of image row py of slice b, output channels n0 ...)
-    __device__ __forceinline__ void setup(const ConvTcParams& P, int lane, int b, int x0, int py, int n0_, int tw_valid) {
+    // ph: output-parity phase of an upsample conv (ph_log2 = 2): tile pixel (py, x) is output pixel (2 py + ph / 2, 2 x + ph % 2)
+    __device__ __forceinline__ void setup(const ConvTcParams& P, int lane, int b, int x0, int py, int n0_, int tw_valid, int ph = 0) {
         c4 = (lane % LPP) * 4; psub = lane / LPP; n0 = n0_;
         nvalid = py < P.H ? min(tw_valid, P.W - x0) : 0;
         vmask = 0;                                     // bit j: pixel j * PPI + psub is an output
 #pragma unroll
         for (int j = 0; j < NJ; ++j) vmask |= (j * PPI + psub < nvalid ? 1u : 0u) << j;
+        const int up = P.ph_log2 ? 2 : 1, opx = up * P.out_cs;           // elements between consecutive tile pixels in the output
         pix0 = ((size_t)b * P.H + py) * P.W + x0;
-        obase = P.out + pix0 * P.out_cs;
+        const size_t opix0 = P.ph_log2 ? ((size_t)b * (2 * P.H) + 2 * py + (ph >> 1)) * (2 * P.W) + 2 * x0 + (ph & 1) : pix0;
+        obase = P.out + opix0 * P.out_cs;
         has_res = P.res != nullptr;
         rbase = has_res ? P.res + pix0 * P.res_cs : P.out;               // (never read without has_res)
-        ostep = PPI * P.out_cs; rstep = PPI * P.res_cs;
-        oo = psub * P.out_cs + c4 + n0; ro = psub * P.res_cs + c4 + n0;
+        ostep = PPI * opx; rstep = PPI * P.res_cs;
+        oo = psub * opx + c4 + n0; ro = psub * P.res_cs + c4 + n0;
     }
     // request the residual lines of chunk cc.  Chunk 0 is requested BEFORE the warp waits for its accumulator: the addresses only depend
     // on the tile, so the HBM latency of the residual overlaps the MMAs instead of extending the epilogue (ncu, width-folded layers:
@@ -366,7 +369,7 @@ struct EpilogueRow {
             }
         }
         // keep the channel padding of the output at zero (layers with C_out < channel stride: 16 -> 32)
-        if (P.out_cs > P.cout && n0 + BLOCK_N >= P.cout && lane < nvalid) {
+        if (P.out_cs > P.cout && n0 + BLOCK_N >= P.cout && lane < nvalid && !P.ph_log2) {
             float* o = P.out + (pix0 + lane) * P.out_cs;
             for (int c = P.cout; c < P.out_cs; ++c) o[c] = 0.f;
         }
@@ -1049,7 +1052,8 @@ conv_halo_fused_kernel(const __grid_constant__ ConvTcParams P) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_per_img = P.tiles_x * P.tiles_y;
     const int n_ntiles = P.cout / BLOCK_N;
-    const int total_tiles = tiles_per_img * P.batch * n_ntiles;
+    const int ph_log2 = P.ph_log2;                                     // 2: upsample conv as four output-parity phases (see conv_tc_prepare)
+    const int total_tiles = (tiles_per_img * P.batch * n_ntiles) << ph_log2;
     const int nk = P.nk0 + P.nk1 + P.nk2;
 
     if (threadIdx.x == 0) {
@@ -1091,10 +1095,11 @@ conv_halo_fused_kernel(const __grid_constant__ ConvTcParams P) {
             b += s_b;
         }
     } walk;
-    walk.init(blockIdx.x, gridDim.x, n_ntiles, P.tiles_x, P.tiles_y);
+    walk.init(blockIdx.x, gridDim.x, n_ntiles << ph_log2, P.tiles_x, P.tiles_y);      // fastest index = N tile x phase
     auto decode = [&](int, int& b, int& x0, int& y0, int& n0) {       // coordinates of the walker's current tile; callers advance it
-        b = walk.b; x0 = walk.txi * HALO_TWV; y0 = walk.tyi * HALO_TH; n0 = walk.nt * BLOCK_N;
+        b = walk.b; x0 = walk.txi * HALO_TWV; y0 = walk.tyi * HALO_TH; n0 = (walk.nt >> ph_log2) * BLOCK_N;
     };
+    auto phase = [&]() { return walk.nt & ((1 << ph_log2) - 1); };
     const bool is_transform = warp >= 12;
 
     if (warp < 4) {
@@ -1109,7 +1114,7 @@ conv_halo_fused_kernel(const __grid_constant__ ConvTcParams P) {
             int sb = 0; uint32_t phb = 0;
             if (warp == 0) {
                 for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, walk.next()) {
-                    const int n0 = walk.nt * BLOCK_N;
+                    const int n0 = (walk.nt >> ph_log2) * BLOCK_N;
                     for (int kc = 0; kc < nk; ++kc) {
 #pragma unroll 1
                         for (int tap = 0; tap < 9; ++tap) {
@@ -1173,12 +1178,15 @@ conv_halo_fused_kernel(const __grid_constant__ ConvTcParams P) {
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, walk.next()) {
                 int b, x0, y0, n0; decode(tile, b, x0, y0, n0);
                 for (int kc = 0; kc < nk; ++kc) {
+                    const int ph = phase();
+                    const uint32_t tm = P.tapmask[ph];
                     for (int tap = 0; tap < 9; ++tap) {
                         if (kc >= P.nk_gn && tap != 4) continue;              // shortcut chunk: centre tap only
+                        if (!((tm >> tap) & 1u)) continue;                    // upsample phase: four of the nine tap positions
                         const int sb = ib % NB;
                         tc::mbar_wait(&b_empty[sb], ((uint32_t)(ib / NB) & 1u) ^ 1u);
                         tc::mbar_expect_tx(&b_full[sb], S::B_BYTES);
-                        tc::tma_load_2d(smem + S::OFF_B + sb * S::B_BYTES, &P.mapB, &b_full[sb], kc * 32, tap * P.cout_rows + n0);
+                        tc::tma_load_2d(smem + S::OFF_B + sb * S::B_BYTES, &P.mapB, &b_full[sb], kc * 32, (ph * 9 + tap) * P.cout_rows + n0);
                         ++ib;
                     }
                 }
@@ -1217,8 +1225,11 @@ conv_halo_fused_kernel(const __grid_constant__ ConvTcParams P) {
                     const int sa = ia % NA;
                     tc::mbar_wait(&a_ready[sa], (uint32_t)(ia / NA) & 1u);
                     const uint32_t a_base = tc::smem_u32(smem + (BF16 ? S::OFF_OP + sa * HF_OP_STRIDE_BF16 : sa * S::RAW_STRIDE));
+                    const uint32_t tm = P.tapmask[phase()];
+                    const int tap0 = __ffs(tm) - 1;                          // the first MMA of a tile overwrites the accumulators
                     for (int tap = 0; tap < 9; ++tap) {
                         if (kc >= P.nk_gn && tap != 4) continue;              // shortcut chunk: centre tap only
+                        if (!((tm >> tap) & 1u)) continue;                    // upsample phase: four of the nine tap positions
                         const int sb = ib % NB;
                         tc::mbar_wait(&b_full[sb], (uint32_t)(ib / NB) & 1u);
                         tc::tc_fence_after();
@@ -1231,7 +1242,7 @@ conv_halo_fused_kernel(const __grid_constant__ ConvTcParams P) {
                             const uint64_t adesc = BF16 ? tc::smem_desc_k(a_addr, 4, 512) : tc::smem_desc_k_sw128(a_addr);
 #pragma unroll
                             for (int k = 0; k < KSTEPS; ++k) {
-                                const uint32_t acc = (uint32_t)((kc | tap | k) != 0);
+                                const uint32_t acc = (uint32_t)((kc | (tap - tap0) | k) != 0);
                                 if (BF16) tc::umma_f16(d_tmem + mt * ACC_COLS, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, acc);
                                 else tc::umma_tf32(d_tmem + mt * ACC_COLS, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, acc);
                             }
@@ -1257,7 +1268,7 @@ conv_halo_fused_kernel(const __grid_constant__ ConvTcParams P) {
                 const int sa = ia % NA;
                 // per-lane affine of its 4 channels (pad channels of the source tensors: scale = shift = 0 -> silu(0) = 0)
                 float4 sc = make_float4(0.f, 0.f, 0.f, 0.f), sh = sc;
-                const bool ident = kc >= P.nk_gn;                                    // shortcut chunk: x itself, rounded to the operand type
+                const bool ident = kc >= P.nk_gn || P.gn_act == 5;                   // shortcut chunk / plain conv: x itself, rounded to the operand type
                 if (ident) sc = make_float4(1.f, 1.f, 1.f, 1.f);
                 else {
                     const bool first = kc < P.nk0;
@@ -1328,14 +1339,14 @@ conv_halo_fused_kernel(const __grid_constant__ ConvTcParams P) {
             const int buf = tl & 1;
             int b, x0, y0, n0; decode(tile, b, x0, y0, n0);
             EpilogueRow<BLOCK_N, 32> er;
-            er.setup(P, lane, b, x0, y0 + 4 * mt + (warp & 3), n0, HALO_TWV);
+            er.setup(P, lane, b, x0, y0 + 4 * mt + (warp & 3), n0, HALO_TWV, phase());
             er.load_res(P, 0);
             if ((warp & 3) == 0) tc::mbar_wait_idle(&tfull[buf], ((uint32_t)tl >> 1) & 1u);
             tc::named_bar_sync(2 + mt, 128);
             tc::tc_fence_after();
             float* srow = nullptr;
             if (P.stats_out) {
-                const int tr = walk.tyi * P.tiles_x + walk.txi;
+                const int tr = ((walk.tyi * P.tiles_x + walk.txi) << ph_log2) + phase();
                 srow = P.stats_out + ((size_t)b * P.stats_rows + (tr * 2 + mt) * 4 + (warp & 3)) * 2 * P.cout;
             }
             er.run(P, tmem_base + (buf * 2 + mt) * ACC_COLS, warp & 3, lane, sbias + n0, stile, srow);
@@ -1356,7 +1367,7 @@ static int launch_halo_fused(const ConvTcParams& P, cudaStream_t st) {
     if (once.need()) {
         IPDM_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_fused_kernel<BN, NB, BF16, NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     }
-    const int total = P.tiles_x * P.tiles_y * P.batch * (P.cout / BN);
+    const int total = (P.tiles_x * P.tiles_y * P.batch * (P.cout / BN)) << P.ph_log2;
     conv_halo_fused_kernel<BN, NB, BF16, NA><<<std::min(total, kNumSMs), HF_THREADS, smem, st>>>(P);
     count_launch();
     IPDM_CHECK_LAUNCH();
@@ -1408,7 +1419,8 @@ static int pick_tw_log2(int H, int W) {
 
 int conv_tc_stats_rows_bound(int h, int w) {
     const int halo = ceil_div(w, HALO_TWV) * ceil_div(h, HALO_TH) * 2, tap = ceil_div(w, 8) * ceil_div(h, 16);   // pick_tw_log2 never does worse than 8x16
-    return 4 * std::max(halo, tap);
+    const int phases = 4 * ceil_div((w + 1) / 2, HALO_TWV) * ceil_div((h + 1) / 2, HALO_TH) * 2;                // upsample conv: four phases of the half-size tiling
+    return 4 * std::max(std::max(halo, tap), phases);
 }
 
 // auto choice of the halo-reuse kernels (see conv_tc_prepare): stride-1 3x3, enough tiles to fill the machine, and an 8x30 tiling that wastes
@@ -1461,8 +1473,20 @@ int conv_tc_prepare(ConvTcParams& P, const ConvTcDesc& d) {
     P.cout_rows = d.cout;
     int ktot = 0;
     // fused GroupNorm: the sources are RAW fp32 tensors whatever the operand type (the kernel converts on the operand path)
-    P.fused = d.norm_scale != nullptr || d.passthrough;
-    if (d.passthrough) {
+    P.fused = d.norm_scale != nullptr || d.passthrough || d.phase_up;
+    for (int ph = 0; ph < 4; ++ph) P.tapmask[ph] = 0x1FFu;
+    if (d.phase_up) {
+        IPDM_REQUIRE(!d.norm_scale && !d.passthrough && d.nsrc == 1 && d.ntaps == 9 && d.stride == 1 && P.halo && P.persistent && P.block_n >= 64 && !d.res.p,
+                     "conv_tc: the upsample phases run on a persistent halo layer (one source, 3x3, C_out >= 64, no residual)");
+        P.gn_act = 5; P.gn_c0 = d.src[0].c; P.gn_c1 = 0; P.gn_m0 = P.gn_c0; P.gn_m1 = 0;
+        P.ph_log2 = 2;
+        for (int ph = 0; ph < 4; ++ph) {
+            const int py = ph >> 1, px = ph & 1;
+            P.tapmask[ph] = 0;
+            for (int a = 0; a < 2; ++a)
+                for (int b2 = 0; b2 < 2; ++b2) P.tapmask[ph] |= 1u << ((py + a) * 3 + px + b2);
+        }
+    } else if (d.passthrough) {
         // the conv_halo_fused_kernel pipeline (deep raw ring, lean masked MMA issue) with an identity operand path: tf32 tiles only
         IPDM_REQUIRE(!d.norm_scale && !d.w_bf16 && !d.src[0].bf16 && P.halo && P.persistent && P.block_n >= 32, "conv_tc: passthrough takes tf32-rounded fp32 sources on a persistent halo layer");
         P.gn_act = 4; P.gn_c0 = d.src[0].c; P.gn_c1 = d.nsrc > 1 ? d.src[1].c : 0; P.gn_m0 = P.gn_c0; P.gn_m1 = P.gn_c1;
@@ -1515,7 +1539,7 @@ int conv_tc_prepare(ConvTcParams& P, const ConvTcDesc& d) {
     {
         const int ebw = P.bf16 ? 2 : 4;
         const CUtensorMapDataType dtw = P.bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
-        const uint64_t dims[2] = {(uint64_t)d.w_k, (uint64_t)d.ntaps * d.cout};
+        const uint64_t dims[2] = {(uint64_t)d.w_k, (uint64_t)d.ntaps * d.cout * (d.phase_up ? 4 : 1)};
         const uint64_t str[1] = {(uint64_t)d.w_k * ebw};
         const uint32_t box[2] = {(uint32_t)P.kc, (uint32_t)P.block_n};
         IPDM_CHECK(tmap_encode(&P.mapB, dtw, 2, d.w_packed, dims, str, box, (P.fused && P.bf16) ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B));
@@ -1523,7 +1547,8 @@ int conv_tc_prepare(ConvTcParams& P, const ConvTcDesc& d) {
         if (P.split) IPDM_CHECK(tmap_encode(&P.mapBlo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, d.w_packed_lo, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B));
     }
     P.out = d.out.p; P.out_cs = d.out.cs;
-    IPDM_REQUIRE(d.qkv_mode || (d.out.h == P.H && d.out.w == P.W && d.out.n == P.batch && d.out.cs % 4 == 0 && d.out.c >= d.cout),
+    const int up = d.phase_up ? 2 : 1;
+    IPDM_REQUIRE(d.qkv_mode || (d.out.h == up * P.H && d.out.w == up * P.W && d.out.n == P.batch && d.out.cs % 4 == 0 && d.out.c >= d.cout),
                  "conv_tc: output tensor shape mismatch");
     P.bias = d.bias; P.bias_t_stride = d.bias_t_stride; P.t_dev = d.t_dev;
     P.res = d.res.p; P.res_cs = d.res.cs;
@@ -1541,15 +1566,18 @@ int conv_tc_prepare(ConvTcParams& P, const ConvTcDesc& d) {
         for (int t = 0; t < d.ntaps; ++t)
             for (int kc = 0; kc < nkk; ++kc) {
                 if (!P.masked && kc >= P.nk_gn && t != 4) continue;               // shortcut chunks: centre tap only
+                if (P.ph_log2 && !((0x1Bu >> t) & 1u)) continue;                  // upsample phases: 4 of the 9 taps each (x 4 phases below)
                 const unsigned km = P.masked ? (unsigned)((P.kmask[t] >> (4 * kc)) & 0xF) : (1u << per) - 1u;
                 ksteps += __builtin_popcount(km);
             }
         const int kel = P.bf16 ? 16 : 8;                                          // K elements per k-step
-        P.flops = 2.0 * P.batch * P.H * P.W * (double)P.cout * ksteps * kel;
+        // an upsample conv counts as the 3x3 conv on the upsampled image that it replaces (the algorithmic work of the layer):
+        // 9 taps x 4 output pixels per source pixel; the tensor pipe issues 16/36 of that
+        P.flops = 2.0 * P.batch * P.H * P.W * (double)P.cout * ksteps * kel * (P.ph_log2 ? 9.0 : 1.0);
     }
     P.stats_out = P.persistent ? d.stats_out : nullptr;              // only the persistent kernels' epilogue produces statistics
-    P.stats_rows = P.stats_out ? P.tiles_x * P.tiles_y * (P.halo ? 2 : 1) * 4 : 0;
-    IPDM_REQUIRE(!P.stats_out || (d.cout % 4 == 0 && P.stats_rows <= conv_tc_stats_rows_bound(P.H, P.W)), "conv_tc: statistics rows %d exceed the bound", P.stats_rows);
+    P.stats_rows = P.stats_out ? (P.tiles_x * P.tiles_y * (P.halo ? 2 : 1) * 4) << P.ph_log2 : 0;
+    IPDM_REQUIRE(!P.stats_out || (d.cout % 4 == 0 && P.stats_rows <= conv_tc_stats_rows_bound(up * P.H, up * P.W)), "conv_tc: statistics rows %d exceed the bound", P.stats_rows);
     IPDM_REQUIRE(!d.qkv_bf16 || (d.qkv_mode && !P.split && d.t_pad % 8 == 0 && d.out.cs % 8 == 0), "conv_tc: the bf16 qkv epilogue needs t_pad and the qk channel stride to be multiples of 8");
     IPDM_REQUIRE(!(d.qkv_mode && P.split) || (d.out_lo && d.vt_lo), "conv_tc: the fp32-mode qkv epilogue needs out_lo and vt_lo");
     return IPDM_OK;

@@ -49,6 +49,7 @@ struct ConvW {
     float* w_dev_direct = nullptr;           // thin layers: the [tap][cin][cout] copy for the direct-kernel fallback
     bool thin = false; int thin_cs = 0;      // thin tensor-core path (conv_thin.cu): operand channel stride 8 / 16 / 32
     // width-folded tensor-core path (pack_fold): `fold` pixels of a row are one pixel of fold*C channels
+    float* w_dev_phase = nullptr; int phase_k = 0;   // Upsample conv as four output-parity phases (pack_phase)
     int fold = 0, fold_c0 = 0, fold_c1 = 0, fold_c2 = 0, fold_k = 0; float* w_dev_fold = nullptr; uint64_t fold_mask[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
 };
 struct ResW { GNW gn1, gn2; ConvW conv1, conv2, shortcut, conv2sc /* conv2 with the shortcut folded in (pack_conv2_shortcut) */; bool has_shortcut = false; std::vector<float> temb_w, temb_b; float* bias1_t = nullptr; int cin = 0, cout = 0; };
@@ -67,6 +68,7 @@ struct Op {
     int stride = 1, upsample = 0, qkv = 0;
     int stats = -1;                            // CONV_TC: tensor that receives the GroupNorm partials of the output
     int fold = 0;                              // CONV_TC: width-fold factor (0: plain)
+    int phase = 0;                             // CONV_TC: Upsample conv as four output-parity phases on the low-res source
     // materialised
     ConvTcParams tcp; ConvThinParams thp; ConvDirectDesc cd; GroupNormDesc gd; TensorNHWC out_t, src_t; AttentionParams ap; AttentionDesc ad;
     double flops = 0;
@@ -341,6 +343,50 @@ static int pack_conv2_shortcut(ipdm_unet* net, ResW& w, int c0, int c1) {
     return IPDM_OK;
 }
 
+// Upsample(nearest 2x) + conv3x3 = four 2x2-tap convs on the low-resolution tensor, one per output parity (py, px)
+// (ConvTcDesc::phase_up).  Output row 2i+py reads upsampled rows 2i+py-1 .. 2i+py+1 = source rows floor((2i+py+ky-1)/2): for py = 0
+// {i-1: ky 0; i: ky 1, 2}, for py = 1 {i: ky 0, 1; i+1: ky 2}; columns alike.  In halo-tile coordinates (origin (i-1, j-1)) phase
+// (py, px) uses the tap positions (py + a, px + b), a, b in {0, 1}, with the sums of the 3x3 weights that land there.
+static int pack_phase(ipdm_unet* net, ConvW& c) {
+    static const bool off = getenv("IPDM_PHASE_UP") && atoi(getenv("IPDM_PHASE_UP")) == 0;
+    c.w_dev_phase = nullptr;
+    if (off || !c.tc || c.k != 3 || net->precision == IPDM_PREC_FP32 || c.cout % 64 != 0) return IPDM_OK;
+    const int K = round_up(c.cin, 32);
+    std::vector<float> p((size_t)4 * 9 * c.cout * K, 0.f);
+    auto taps_of = [](int parity, int a, int* k) {           // 3x3 taps that land on source offset `a` of this parity; returns the count
+        if (parity == 0) { if (a == 0) { k[0] = 0; return 1; } k[0] = 1; k[1] = 2; return 2; }
+        if (a == 0) { k[0] = 0; k[1] = 1; return 2; } k[0] = 2; return 1;
+    };
+    for (int ph = 0; ph < 4; ++ph) {
+        const int py = ph >> 1, px = ph & 1;
+        for (int a = 0; a < 2; ++a)
+            for (int b = 0; b < 2; ++b) {
+                int kys[2], kxs[2];
+                const int ny = taps_of(py, a, kys), nx = taps_of(px, b, kxs);
+                const int tap = (py + a) * 3 + px + b;
+                for (int co = 0; co < c.cout; ++co)
+                    for (int ci = 0; ci < c.cin; ++ci) {
+                        double acc = 0;
+                        for (int iy = 0; iy < ny; ++iy)
+                            for (int ix = 0; ix < nx; ++ix) acc += c.w_host[((size_t)co * c.cin + ci) * 9 + kys[iy] * 3 + kxs[ix]];
+                        p[(((size_t)ph * 9 + tap) * c.cout + co) * K + ci] = (float)acc;
+                    }
+            }
+    }
+    if (net->precision == IPDM_PREC_BF16) {
+        std::vector<float> packed((p.size() + 1) / 2, 0.f);
+        uint16_t* h = reinterpret_cast<uint16_t*>(packed.data());
+        for (size_t i = 0; i < p.size(); ++i) h[i] = bf16_rn_host(p[i]);
+        IPDM_CHECK(upload(net, packed, &c.w_dev_phase));
+    } else {
+        for (float& v : p) v = tf32_rn_host(v);
+        IPDM_CHECK(upload(net, p, &c.w_dev_phase));
+    }
+    c.phase_k = K;
+    if (!c.b_host.empty() && !c.b_dev) IPDM_CHECK(upload(net, c.b_host, &c.b_dev));
+    return IPDM_OK;
+}
+
 static inline float silu_h(float x) { return x / (1.0f + std::exp(-x)); }
 
 // architecture walk shared by create() and param_count(): calls back for every parameter tensor in state_dict order
@@ -461,6 +507,7 @@ struct BuildVisitor : ArchVisitor {
         net->convs.emplace_back(); read_conv(r, net->convs.back(), c, c, 3, true);
         fail(pack_conv(net, net->convs.back(), c, 0, true, -1, true));
         fail(pack_fold(net, net->convs.back(), c, 0));
+        fail(pack_phase(net, net->convs.back()));
         cur->push_back({LayerRef::UP, (int)net->convs.size() - 1});
     }
     void out(int c, int co) override {
@@ -655,7 +702,12 @@ struct PlanBuilder {
                 case LayerRef::UP: {
                     const ConvW& cw = net->convs[l.idx];
                     out = act(up_h, up_w, s0.c);
-                    if (cw.fold && up_w % cw.fold == 0 && pl->vt[out].cs == pl->vt[out].c) {
+                    if (cw.w_dev_phase && up_h == 2 * s0.h && up_w == 2 * s0.w && !s0.bf16 && !s0.external && s0.c >= 32 &&
+                        conv_tc_can_fuse_norm(s0.h, s0.w, pl->B, cw.cout, 9, 1)) {
+                        // exactly 2x: four 2x2-tap phases straight from the low-resolution tensor -- no upsampled operand tensor, 16/36 of the MMAs
+                        Op cv; cv.kind = Op::CONV_TC; cv.nsrc = 1; cv.src[0] = cur[0]; cv.cw = &cw; cv.dst = out; cv.bias = cw.b_dev; cv.phase = 1;
+                        push(cv);
+                    } else if (cw.fold && up_w % cw.fold == 0 && pl->vt[out].cs == pl->vt[out].c) {
                         const int u = new_tensor(pl->B, up_h, up_w, s0.c, s0.c);          // dense tf32-rounded operand of the folded conv
                         Op up; up.kind = Op::UPSAMPLE; up.nsrc = 1; up.src[0] = cur[0]; up.dst = u; push(up);
                         plain_conv(&u, 1, cw, out, -1, 1, 0);
@@ -837,9 +889,11 @@ static int build_plan(ipdm_unet* net, int B, int H, int W, Plan** out) {
                 if (o.stats >= 0) d.stats_out = resolve(*pl, o.stats).p;
                 if (o.gn) { d.norm_scale = nscale; d.norm_shift = nshift; d.act_silu = o.act; d.w_bf16 = o.cw->bf16; }
                 if (o.fold) fold_desc(d, *o.cw);
+                if (o.phase) { d.phase_up = 1; d.w_packed = o.cw->w_dev_phase; d.w_packed_lo = nullptr; d.w_k = o.cw->phase_k; d.w_bf16 = o.cw->bf16; }
                 IPDM_CHECK(conv_tc_prepare(o.tcp, d));
                 pl->vt[o.dst].stats_rows = o.tcp.stats_out ? o.tcp.stats_rows : 0;
                 o.flops = 2.0 * B * o.tcp.H * o.tcp.W * (o.fold ? o.fold : 1) * (double)o.cw->cin * o.cw->cout * d.ntaps;
+                if (o.phase) o.flops *= 4.0;                         // (reference FLOPs: a 3x3 conv on the upsampled image)
                 if (o.n_ident)                                       // conv2 (3x3 over C_out channels) + shortcut (1x1 over the block input)
                     o.flops = 2.0 * B * o.tcp.H * o.tcp.W * (o.fold ? o.fold : 1) * (double)o.cw->cout * (9.0 * o.cw->cout + (o.cw->cin - o.cw->cout));
             } break;
@@ -1004,6 +1058,27 @@ extern "C" int ipdm_debug_conv(const float* src0, int c0, int cs0, const float* 
     ConvW cw; cw.cin = c0 + c1; cw.cout = cout; cw.k = k;
     cw.w_host.assign(w_host, w_host + (size_t)cout * cw.cin * k * k);
     if (bias_host) cw.b_host.assign(bias_host, bias_host + cout);
+    if (use_tc == 7 || use_tc == 8) {                    // Upsample(2x nearest) + conv3x3 as four phases on the low-res source (7 bf16, 8 tf32)
+        IPDM_REQUIRE(stride == 1 && upsample_h == 2 * h && upsample_w == 2 * w && c1 == 0 && cs0 % 32 == 0 && k == 3 && !res && !norm_scale,
+                     "ipdm_debug_conv: the phase path is an exact 2x upsample + 3x3 conv of one padded source");
+        holder.precision = use_tc == 7 ? IPDM_PREC_BF16 : IPDM_PREC_TF32;
+        cw.tc = true; cw.bf16 = use_tc == 7;
+        IPDM_CHECK(pack_phase(&holder, cw));
+        IPDM_REQUIRE(cw.w_dev_phase, "ipdm_debug_conv: shape is not eligible for the phase path");
+        ConvTcDesc d; d.nsrc = 1; d.src[0] = mk(src0, n, h, w, c0, cs0);
+        d.ntaps = 9; d.stride = 1; d.cout = cout; d.bias = cw.b_dev;
+        d.out = mk(out, n, 2 * h, 2 * w, cout, out_cs);
+        d.phase_up = 1; d.w_packed = cw.w_dev_phase; d.w_k = cw.phase_k; d.w_bf16 = cw.bf16;
+        float* stats = nullptr;
+        IPDM_CHECK_CUDA(cudaMalloc(&stats, (size_t)n * conv_tc_stats_rows_bound(2 * h, 2 * w) * 2 * cout * sizeof(float)));
+        d.stats_out = stats;
+        ConvTcParams P;
+        int rc2 = conv_tc_prepare(P, d);
+        if (rc2 == IPDM_OK) rc2 = conv_tc_launch(P, (cudaStream_t)stream);
+        cudaStreamSynchronize((cudaStream_t)stream);
+        cudaFree(stats);
+        return rc2;
+    }
     if (use_tc == 6) {                                   // width-folded tensor-core path: dense thin sources, optional fused GroupNorm + SiLU
         IPDM_REQUIRE(stride == 1 && upsample_h == 0 && cs0 == c0 && (c1 == 0 || cs1 == c1) && out_cs == cout && (!res || res_cs == cout),
                      "ipdm_debug_conv: the folded path takes dense tensors, stride 1");
@@ -1148,6 +1223,11 @@ extern "C" int ipdm_debug_conv_time(int c0, int c1, int n, int h, int w, int cou
     if (res) d.res = mk(res, n, ho, wo, cout, ocs);
     d.out = mk(out, n, ho, wo, cout, ocs);
     d.variant = fused ? 0 : variant;
+    float* tstats = nullptr;                             // IPDM_TIME_STATS=1: with the GroupNorm statistics epilogue, as inside the network
+    if (getenv("IPDM_TIME_STATS") && atoi(getenv("IPDM_TIME_STATS")) == 1) {
+        IPDM_CHECK_CUDA(cudaMalloc(&tstats, (size_t)n * conv_tc_stats_rows_bound(ho, wo) * 2 * cout * sizeof(float)));
+        d.stats_out = tstats;
+    }
     ConvTcParams P;
     IPDM_CHECK(conv_tc_prepare(P, d));
     cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
@@ -1159,7 +1239,7 @@ extern "C" int ipdm_debug_conv_time(int c0, int c1, int n, int h, int w, int cou
     float ms = 0; cudaEventElapsedTime(&ms, a, b);
     *ms_out = ms / iters;
     if (flops_out) *flops_out = 2.0 * n * ho * wo * (double)cw.cin * cout * k * k;
-    cudaFree(s0); cudaFree(s1); cudaFree(out); cudaFree(res); cudaFree(nsc); cudaFree(nsh); cudaEventDestroy(a); cudaEventDestroy(b);
+    cudaFree(s0); cudaFree(s1); cudaFree(out); cudaFree(res); cudaFree(nsc); cudaFree(nsh); cudaFree(tstats); cudaEventDestroy(a); cudaEventDestroy(b);
     return IPDM_OK;
 }
 

@@ -50,6 +50,11 @@ struct ConvTcDesc {
     // raw (no GroupNorm) on the operand path and contracted with the centre tap only -- w_packed carries the shortcut weights in the
     // K columns of those sources at tap 4 and zeros at the other taps, bias = conv bias + shortcut bias (conv_halo_fused_kernel only)
     int n_ident = 0;
+    // Upsample (nearest, exactly 2x) + 3x3 conv as four output-parity phases on the LOW-resolution source (model.py:163-170): output
+    // pixel (2i+py, 2j+px) only sees source rows {i-1+py, i+py} and columns {j-1+px, j+px}, so each phase is a 2x2-tap conv whose
+    // weights are sums of the 3x3 taps that land on the same source pixel: 16/36 of the MMAs, no upsampled tensor.  src = the raw fp32
+    // low-res tensor (converted on the operand path), out = the high-res tensor, w_packed = [phase 4][tap 9][cout][K]
+    int phase_up = 0;
     int passthrough = 0;               // run a plain (no GroupNorm) tf32 layer through conv_halo_fused_kernel with an identity operand path
 };
 int conv_tc_stats_rows_bound(int h, int w);
@@ -70,6 +75,7 @@ struct ConvTcParams {
     float* stats_out; int stats_rows;                  // set by prepare only for the persistent kernels (else nullptr / 0)
     int fused; const float* gn_scale; const float* gn_shift; int gn_c0, gn_c1, gn_act;    // conv_halo_fused_kernel
     uint64_t kmask[9]; int gn_m0, gn_m1, bias_mod, masked, fold;                          // width-folded thin layers
+    int ph_log2; uint32_t tapmask[4];                                                     // upsample conv phases: tap positions used by each
     double flops;                                                                         // MMA work issued per launch (prepare)
 };
 

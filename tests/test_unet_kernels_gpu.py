@@ -250,6 +250,22 @@ def test_tc_conv_fused_groupnorm(cuda, c0, c1, cout, hw):
     assert e_bf16 < 8e-3 and e_exact < 3e-4          # (the device SiLU uses ex2.approx: a few operands round to the neighbouring bf16)
 
 
+@pytest.mark.parametrize("cin,cout,hw", [(128, 128, (120, 121)), (64, 64, (97, 150)), (128, 64, (128, 96)), (256, 256, (64, 150))])
+def test_upsample_conv_phases(cuda, cin, cout, hw):
+    """Upsample(nearest, exactly 2x) + conv3x3 as four output-parity 2x2-tap convs on the low-resolution tensor (pack_phase,
+    ConvTcDesc::phase_up): summed 3x3 taps per phase, zero padding of the UPSAMPLED image at all four borders, ragged tiles,
+    strided output pixels.  bf16 and tf32 operands, fp32 accumulate."""
+    n = 2
+    x = rnd(n, cin, *hw, seed=1)
+    w = rnd(cout, cin, 3, 3, seed=3, scale=0.1)
+    b = rnd(cout, seed=4)
+    up = (2 * hw[0], 2 * hw[1])
+    want = ref_conv(x, None, w, b, 3, 1, up=up)
+    for mode, tol in ((7, 8e-3), (8, TF32_TOL)):
+        got = run_conv(cuda, x, None, w, b, 3, 1, mode, up=up)
+        assert rel_l2(got.numpy(), want.numpy()) < tol, mode
+
+
 @pytest.mark.parametrize("c0,c1,cout,k,hw", [
     (8, 0, 8, 3, (40, 72)), (16, 0, 16, 3, (33, 66)), (4, 0, 8, 3, (20, 80)), (8, 0, 16, 3, (25, 64)), (16, 8, 8, 3, (21, 68)),
     (8, 8, 8, 3, (19, 36)), (8, 4, 8, 3, (18, 48)), (16, 16, 16, 3, (23, 34)), (16, 8, 16, 3, (17, 44)), (128, 16, 16, 3, (20, 62)),
