@@ -1261,9 +1261,28 @@ conv_halo_fused_kernel(const __grid_constant__ ConvTcParams P) {
         const int w4 = warp - 12;                                    // 0..7: 40 of the 320 tile pixels each
         const int c8 = lane & 7, psub = lane >> 3;                   // 16-byte chunk (4 channels) of the pixel row; pixel within a group of 4
         const int Ctot = P.gn_m0 + P.gn_m1;                          // real channels of the GroupNorm (== gn_c0 + gn_c1 unless width-folded)
+        constexpr int PER = 320 / HF_TWARPS / 4;                     // pixels per lane and chunk
+        const bool work = P.gn_act != 3 && P.gn_act != 4;            // 4: the tile already is the operand (tf32-rounded, no GroupNorm): hand it on
+        // per-lane byte offsets of its PER pixels inside a raw tile / a bf16 operand tile: fixed for the whole kernel
+        uint32_t roff[PER], ooff[PER];
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+            const int r = w4 * (4 * PER) + j * 4 + psub;             // pixel of the halo tile: row r >> 5, column r & 31
+            roff[j] = (uint32_t)r * 128u + (uint32_t)((c8 ^ (r & 7)) << 4);                                       // TMA SWIZZLE_128B: 16-byte chunk ^ (row & 7)
+            ooff[j] = (uint32_t)r * 64u + (uint32_t)((((c8 >> 1) ^ ((r >> 1) & 3)) << 4) | ((c8 & 1) << 3));      // SWIZZLE_64B row: chunk (c8 >> 1) ^ ((r >> 1) & 3), half c8 & 1
+        }
+        constexpr float NL2E = -1.4426950408889634f;
         int ia = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, walk.next()) {
             int b, x0, y0, n0; decode(tile, b, x0, y0, n0);
+            // which of this lane's pixels lie inside the image (the conv pads the ACTIVATION with zeros): once per tile, not per chunk
+            uint32_t inmask = 0;
+#pragma unroll
+            for (int j = 0; j < PER; ++j) {
+                const int r = w4 * (4 * PER) + j * 4 + psub;
+                const int yy = y0 - 1 + (r >> 5), xx = x0 - 1 + (r & 31);
+                inmask |= ((unsigned)yy < (unsigned)P.H && (unsigned)xx < (unsigned)P.W ? 1u : 0u) << j;
+            }
             for (int kc = 0; kc < nk; ++kc, ++ia) {
                 const int sa = ia % NA;
                 // per-lane affine of its 4 channels (pad channels of the source tensors: scale = shift = 0 -> silu(0) = 0)
@@ -1279,24 +1298,22 @@ conv_halo_fused_kernel(const __grid_constant__ ConvTcParams P) {
                         sh = __ldg(reinterpret_cast<const float4*>(P.gn_shift + (size_t)b * Ctot + cg));
                     }
                 }
+                const bool do_silu = P.gn_act == 1 && !ident;
+                // exponent argument of the sigmoid straight from x: -log2(e) * (x * sc + sh) as ONE fma with pre-scaled coefficients
+                const float4 sce = make_float4(sc.x * NL2E, sc.y * NL2E, sc.z * NL2E, sc.w * NL2E), she = make_float4(sh.x * NL2E, sh.y * NL2E, sh.z * NL2E, sh.w * NL2E);
                 // one warp watches the barrier, the other seven sleep on a named barrier: eight pollers cost a third of the SM's issue slots
                 if (w4 == 0) tc::mbar_wait_idle(&raw_full[sa], (uint32_t)(ia / NA) & 1u);
                 tc::named_bar_sync(1, HF_TWARPS * 32);
                 const uint32_t raw_s = tc::smem_u32(smem + sa * S::RAW_STRIDE);
                 const uint32_t op_s = tc::smem_u32(smem + S::OFF_OP + sa * HF_OP_STRIDE_BF16);
-                const bool work = P.gn_act != 3 && P.gn_act != 4;      // 4: the tile already is the operand (tf32-rounded, no GroupNorm): hand it on
                 // A lane owns 10 pixels x 4 channels of the chunk: all ten loads are issued before the first SiLU so that the shared-memory and
                 // MUFU latencies overlap (explicit ld/st.shared: generic accesses made the compiler serialise load -> store -> load).  BF16: the
                 // raw slot goes back to the TMA producer as soon as the values sit in registers -- the 64-channel layers are bound by bytes in
                 // flight (two 40 KB slots per SM) -- and only then the warp waits for its operand buffer.
-                constexpr int PER = 320 / HF_TWARPS / 4;
                 float4 v[PER];
                 if (work) {
 #pragma unroll
-                    for (int j = 0; j < PER; ++j) {
-                        const int r = w4 * (4 * PER) + j * 4 + psub;                      // pixel of the halo tile: row r >> 5, column r & 31
-                        v[j] = tc::lds128(raw_s + (uint32_t)r * 128u + (uint32_t)((c8 ^ (r & 7)) << 4));   // TMA SWIZZLE_128B: 16-byte chunk ^ (row & 7)
-                    }
+                    for (int j = 0; j < PER; ++j) v[j] = tc::lds128(raw_s + roff[j]);
                 }
                 if (BF16) {
                     __syncwarp();
@@ -1305,25 +1322,30 @@ conv_halo_fused_kernel(const __grid_constant__ ConvTcParams P) {
                     tc::named_bar_sync(1, HF_TWARPS * 32);
                 }
                 if (work) {
-#pragma unroll
-                    for (int j = 0; j < PER; ++j) {
-                        const int r = w4 * (4 * PER) + j * 4 + psub;
-                        const int yy = y0 - 1 + (r >> 5), xx = x0 - 1 + (r & 31);
-                        const bool inside = (unsigned)yy < (unsigned)P.H && (unsigned)xx < (unsigned)P.W;
-                        float4 o;
-                        o.x = fmaf(v[j].x, sc.x, sh.x); o.y = fmaf(v[j].y, sc.y, sh.y); o.z = fmaf(v[j].z, sc.z, sh.z); o.w = fmaf(v[j].w, sc.w, sh.w);
-                        if (P.gn_act == 1 && !ident) { o.x = silu(o.x); o.y = silu(o.y); o.z = silu(o.z); o.w = silu(o.w); }
-                        if (BF16 && !inside) o = make_float4(0.f, 0.f, 0.f, 0.f);         // the conv pads the ACTIVATION with zeros
+                    // (the SiLU / no-SiLU decision is uniform for the chunk: two straight-line loops instead of a branch per pixel)
+                    auto emit = [&](int j, float4 o) {
+                        const bool inside = (inmask >> j) & 1u;
                         if (BF16) {
                             const __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
-                            // SWIZZLE_64B operand row r (64 bytes): 16-byte chunk (c8 >> 1) ^ ((r >> 1) & 3), 8-byte half c8 & 1
-                            tc::sts64(op_s + (uint32_t)r * 64u + (uint32_t)((((c8 >> 1) ^ ((r >> 1) & 3)) << 4) | ((c8 & 1) << 3)),
-                                      *reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+                            tc::sts64_or_zero(op_s + ooff[j], *reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi), inside);
                         } else {
                             // (round to nearest tf32 = add half an ulp of the 10-bit mantissa; the tensor core drops the low 13 bits itself)
-                            tc::sts128_or_zero(raw_s + (uint32_t)r * 128u + (uint32_t)((c8 ^ (r & 7)) << 4),
-                                               make_float4(tf32_rn_hw(o.x), tf32_rn_hw(o.y), tf32_rn_hw(o.z), tf32_rn_hw(o.w)), inside);
+                            tc::sts128_or_zero(raw_s + roff[j], make_float4(tf32_rn_hw(o.x), tf32_rn_hw(o.y), tf32_rn_hw(o.z), tf32_rn_hw(o.w)), inside);
                         }
+                    };
+                    if (do_silu) {
+#pragma unroll
+                        for (int j = 0; j < PER; ++j) {
+                            float4 y, e;
+                            y.x = fmaf(v[j].x, sc.x, sh.x); y.y = fmaf(v[j].y, sc.y, sh.y); y.z = fmaf(v[j].z, sc.z, sh.z); y.w = fmaf(v[j].w, sc.w, sh.w);
+                            e.x = ex2_approx(fmaf(v[j].x, sce.x, she.x)); e.y = ex2_approx(fmaf(v[j].y, sce.y, she.y));
+                            e.z = ex2_approx(fmaf(v[j].z, sce.z, she.z)); e.w = ex2_approx(fmaf(v[j].w, sce.w, she.w));
+                            emit(j, make_float4(y.x * rcp_approx(1.0f + e.x), y.y * rcp_approx(1.0f + e.y), y.z * rcp_approx(1.0f + e.z), y.w * rcp_approx(1.0f + e.w)));
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < PER; ++j)
+                            emit(j, make_float4(fmaf(v[j].x, sc.x, sh.x), fmaf(v[j].y, sc.y, sh.y), fmaf(v[j].z, sc.z, sh.z), fmaf(v[j].w, sc.w, sh.w)));
                     }
                 }
                 tc::fence_proxy_async();                 // generic-proxy writes -> visible to the tensor core's async proxy

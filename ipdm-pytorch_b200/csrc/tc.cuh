@@ -89,6 +89,13 @@ __device__ __forceinline__ void sts128_or_zero(uint32_t saddr, const float4& v, 
         "@!p st.shared.v4.f32 [%0], {%6,%6,%6,%6};\n\t}\n"
         :: "r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"((uint32_t)keep), "f"(0.f) : "memory");
 }
+__device__ __forceinline__ void sts64_or_zero(uint32_t saddr, uint32_t a, uint32_t b, bool keep) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %3, 0;\n\t"
+        "@p st.shared.v2.b32 [%0], {%1,%2};\n\t"
+        "@!p st.shared.v2.b32 [%0], {%4,%4};\n\t}\n"
+        :: "r"(saddr), "r"(a), "r"(b), "r"((uint32_t)keep), "r"(0u) : "memory");
+}
 __device__ __forceinline__ void sts64(uint32_t saddr, uint32_t a, uint32_t b) {
     asm volatile("st.shared.v2.b32 [%0], {%1,%2};" :: "r"(saddr), "r"(a), "r"(b) : "memory");
 }

@@ -160,7 +160,7 @@ struct AttentionDesc {
 };
 struct AttentionParams {
     CUtensorMap mapQ, mapK, mapV, mapQlo, mapKlo, mapVlo;
-    int split, bf16;
+    int split, bf16, idle;
     float* out; int batch, T, heads, C; float scale_log2;
 };
 int attention_prepare(AttentionParams& P, const AttentionDesc& d);
