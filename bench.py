@@ -29,10 +29,10 @@ for p in (REPO, PKG):
 
 HBM_FALLBACK_GBS, TENSOR_FALLBACK_TFLOPS = 6650.0, 1590.0        # /opt/skills/guides/B200_PROFILING.md
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel from an `ncu --set full` capture
-CONV_TC_NCU_TRAFFIC = dict(bytes_per_launch=2.297e9,
-                           note="profiles/r01_conv_halo_persistent_ncu_full.md: conv_halo_persistent_kernel<128,6>, bf16, 16 x 500x228, 128->128 3x3 "
-                                "+residual: 1.401 GB read + 0.896 GB written per launch; algorithmic bytes of that layer 2.33 GB (bf16 operand 0.47 + fp32 "
-                                "residual 0.93 + fp32 output 0.93)")
+CONV_TC_NCU_TRAFFIC = dict(bytes_per_launch=2.748e9,
+                           note="profiles/r02_conv_halo_fused_ncu_full.md: conv_halo_fused_kernel<128,8,bf16>, 16 x 500x228, GroupNorm+SiLU -> 128->128 3x3 "
+                                "+residual: 1.868 GB read + 0.880 GB written per launch; algorithmic bytes of that layer 2.80 GB (raw fp32 input 0.93 + fp32 "
+                                "residual 0.93 + fp32 output 0.93).  The unfused conv_halo_persistent_kernel<128,6> moves 2.28 GB per launch.")
 
 
 def parse():
@@ -391,11 +391,12 @@ def run_b200(args, rank, world, local_rank):
         tc_ms, tc_flops, tc_n = fam_ms, fam_flops, tc_n + prof["conv_tc"][2]
         kname = f"conv_tc_kernel<N,S,SPLIT> (tcgen05 {kind} implicit-GEMM conv)"
     else:
-        kname = f"conv_halo_persistent_kernel<N,NB> (tcgen05 {kind} implicit-GEMM 3x3 conv, halo reuse, persistent)"
+        kname = (f"conv_halo_fused_kernel<N,NB,op,NA> / conv_halo_persistent_kernel<N,NB> (tcgen05 {kind} implicit-GEMM 3x3 conv, halo reuse, persistent; "
+                 "the fused form applies GroupNorm+SiLU on the operand path and runs the upsample convs as four output-parity phases)")
     roof = dict(bound="tensor", kernel=kname, achieved=tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms else None,
                 peak=pk["tensor"], unit="TFLOP/s", traffic=CONV_TC_NCU_TRAFFIC["bytes_per_launch"] if args.precision == "bf16" else None,
                 traffic_note=CONV_TC_NCU_TRAFFIC["note"], peak_source=pk["which"],
-                note="achieved = layer FLOPs (2*pixels*taps*K*C_out with K padded to the operand stride; discarded tile columns not counted) of every launch of this kernel in one profiled step / their summed "
+                note="achieved = layer FLOPs (2*pixels*taps*K*C_out with K padded to the operand stride; discarded tile columns not counted; an upsample conv counts as the 3x3 conv on the upsampled image it replaces, of which 16/36 is issued) of every launch of this kernel in one profiled step / their summed "
                      "CUDA-event time on the launching stream; peak is dense bf16 (a kind::tf32 MMA runs at half that rate, so 0.5 is the "
                      "ceiling in tf32 mode).  conv_tc_family_* = the same over ALL tensor-core conv kernels (adds 1x1 / stride-2 / N=16 / qkv "
                      "layers, most of which are HBM-bound)",
@@ -403,6 +404,13 @@ def run_b200(args, rank, world, local_rank):
                 conv_tc_family_achieved=fam_flops / (fam_ms * 1e-3) / 1e12 if fam_ms else None,
                 conv_tc_family_share_of_step=fam_ms / total_prof_ms if total_prof_ms else None)
     roof["frac"] = roof["achieved"] / roof["peak"] if roof["achieved"] else None
+    if args.precision != "fp32" and prof["conv_halo_persistent"][0]:
+        # the family straddles the ridge (128/256-channel layers tensor-bound, 64-channel image layers HBM-bound with their fp32 residual
+        # stream): time the launches would take with EACH at its own roof / their measured time
+        r_ms, m_ms, r_bytes = engine.profile_roofline("conv_halo_persistent", pk["tensor"] * (0.5 if args.precision == "tf32" else 1.0), pk["hbm"])
+        roof["mixed"] = dict(frac=r_ms / m_ms if m_ms else None, roof_ms=round(r_ms, 2), measured_ms=round(m_ms, 2), algorithmic_gb=round(r_bytes / 1e9, 1),
+                             note="sum over the launches of this kernel of max(FLOPs / tensor peak, algorithmic bytes / HBM peak), divided by their "
+                                  "measured time: the fraction of the per-launch roofline (tensor OR HBM, whichever binds that layer)")
     families = {}
     for k, (m, w, n) in prof.items():
         unit = "TFLOP/s" if k in ("conv_tc", "conv_halo_persistent", "attention") else "GB/s"

@@ -53,6 +53,9 @@ void ipdm_launch_count_reset(void);
 #define IPDM_PROF_KINDS 9
 void ipdm_profile_enable(int on);
 int ipdm_profile_collect(double ms_out[IPDM_PROF_KINDS], double work_out[IPDM_PROF_KINDS], long long launches_out[IPDM_PROF_KINDS]);
+/* Mixed roofline of one FLOP-counted family (the tensor-core conv families record their algorithmic HBM bytes too):
+ * roof_ms = sum over its launches of max(flops / peak_flops_per_s, bytes / peak_bytes_per_s), ms = their measured time. */
+int ipdm_profile_roofline(int kind, double peak_flops_per_s, double peak_bytes_per_s, double* roof_ms_out, double* ms_out, double* bytes_out);
 
 /* ------------------------------------------------------------------------------------------
  * Image-quality metrics on the device.  Replaces the skimage calls of

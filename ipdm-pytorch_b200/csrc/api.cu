@@ -1,5 +1,6 @@
 // Error plumbing and library-level entry points of libipdm_b200.so (include/ipdm_b200.h).
 #include "common.cuh"
+#include <algorithm>
 
 #include <cstring>
 #include <vector>
@@ -18,15 +19,15 @@ void set_error(const char* fmt, ...) {
 const char* last_error() { return g_err; }
 
 bool g_prof_on = false;
-struct ProfRec { int kind; cudaEvent_t a, b; double work; };
+struct ProfRec { int kind; cudaEvent_t a, b; double work, bytes; };
 static std::vector<ProfRec> g_prof;
 static cudaEvent_t g_prof_open[PROF_KINDS];
 void prof_begin(int kind, cudaStream_t st) {
     cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); g_prof_open[kind] = e;
 }
-void prof_end(int kind, cudaStream_t st, double work) {
+void prof_end(int kind, cudaStream_t st, double work, double bytes) {
     cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st);
-    g_prof.push_back({kind, g_prof_open[kind], e, work});
+    g_prof.push_back({kind, g_prof_open[kind], e, work, bytes});
 }
 
 }  // namespace ipdm
@@ -43,6 +44,25 @@ extern "C" int ipdm_profile_collect(double* ms_out, double* work_out, long long*
         float ms = 0; cudaEventElapsedTime(&ms, r.a, r.b);
         ms_out[r.kind] += ms; work_out[r.kind] += r.work; launches_out[r.kind] += 1;
     }
+    return IPDM_OK;
+}
+
+// Roofline of a FLOP-counted family whose launches are not all on the same side of the ridge (the halo conv family: 128/256-channel
+// layers are tensor-bound, the 64-channel image layers HBM-bound with an fp32 residual stream): sum over launches of
+// max(flops / peak_flops, algorithmic bytes / peak_bytes) = the time the family would take with every launch AT its own roof.
+extern "C" int ipdm_profile_roofline(int kind, double peak_flops_per_s, double peak_bytes_per_s, double* roof_ms_out, double* ms_out,
+                                     double* bytes_out) {
+    using namespace ipdm;
+    IPDM_REQUIRE(kind >= 0 && kind < PROF_KINDS && peak_flops_per_s > 0 && peak_bytes_per_s > 0 && roof_ms_out && ms_out, "ipdm_profile_roofline: bad arguments");
+    IPDM_CHECK_CUDA(cudaDeviceSynchronize());
+    double roof = 0, tot = 0, by = 0;
+    for (auto& r : g_prof) {
+        if (r.kind != kind) continue;
+        float ms = 0; cudaEventElapsedTime(&ms, r.a, r.b);
+        tot += ms; by += r.bytes;
+        roof += 1e3 * std::max(r.work / peak_flops_per_s, r.bytes / peak_bytes_per_s);
+    }
+    *roof_ms_out = roof; *ms_out = tot; if (bytes_out) *bytes_out = by;
     return IPDM_OK;
 }
 

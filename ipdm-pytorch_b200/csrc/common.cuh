@@ -65,11 +65,11 @@ enum ProfKind { PROF_CONV_TC = 0, PROF_ATTENTION, PROF_CONV_DIRECT, PROF_GROUPNO
                 PROF_FBP_BACKPROJECT, PROF_SAMPLER, PROF_CONV_HALO_PERS, PROF_KINDS };
 extern bool g_prof_on;
 void prof_begin(int kind, cudaStream_t st);
-void prof_end(int kind, cudaStream_t st, double work);
+void prof_end(int kind, cudaStream_t st, double work, double bytes);
 struct ProfScope {
-    int kind; cudaStream_t st; double work;
-    ProfScope(int k, cudaStream_t s, double w) : kind(k), st(s), work(w) { if (g_prof_on) prof_begin(kind, st); }
-    ~ProfScope() { if (g_prof_on) prof_end(kind, st, work); }
+    int kind; cudaStream_t st; double work, bytes;       // bytes: algorithmic HBM bytes of a FLOP-counted launch (ipdm_profile_roofline), else 0
+    ProfScope(int k, cudaStream_t s, double w, double b = 0) : kind(k), st(s), work(w), bytes(b) { if (g_prof_on) prof_begin(kind, st); }
+    ~ProfScope() { if (g_prof_on) prof_end(kind, st, work, bytes); }
 };
 
 // ---- device helpers ----

@@ -1638,8 +1638,11 @@ static int launch_halo(const ConvTcParams& P, cudaStream_t st) {
 int conv_tc_launch(const ConvTcParams& P, cudaStream_t st) {
     // padded-K FLOPs actually issued to the tensor pipe; the persistent halo kernel (the dominant kernel of the step) is its own family
     // (width-folded thin layers are HBM-bound streaming layers: they are accounted in bytes with the other thin / direct convs)
+    // algorithmic HBM bytes of the launch: every source once (raw fp32 when fused, else the operand type), the residual, the output
+    const double px = (double)P.batch * P.H * P.W, opx = px * (P.ph_log2 ? 4.0 : 1.0);
+    const double abytes = px * (P.nk0 + P.nk1 + P.nk2) * P.kc * ((P.bf16 && !P.fused) ? 2.0 : 4.0) + opx * P.cout * 4.0 * (P.res ? 2.0 : 1.0);
     ProfScope prof(P.fold ? PROF_CONV_DIRECT : (P.halo && P.persistent ? PROF_CONV_HALO_PERS : PROF_CONV_TC), st,
-                   P.fold ? 4.0 * P.batch * (double)P.H * P.W * ((P.nk0 + P.nk1 + P.nk2) * P.kc + P.cout) : conv_tc_flops(P));
+                   P.fold ? 4.0 * P.batch * (double)P.H * P.W * ((P.nk0 + P.nk1 + P.nk2) * P.kc + P.cout) : conv_tc_flops(P), abytes);
     if (P.fused) {
         if (P.bf16) { if (P.block_n == 128) return launch_halo_fused<128, 8, true>(P, st); if (P.block_n == 64) return launch_halo_fused<64, 12, true>(P, st); }
         else {

@@ -60,6 +60,15 @@ def profile_collect():
     return {f: (ms[i], work[i], int(n[i])) for i, f in enumerate(PROF_FAMILIES)}
 
 
+def profile_roofline(family, peak_tflops, peak_gbs):
+    """(roof_ms, ms, bytes) of one FLOP-counted family: the time its launches would take with each one at its own roof
+    (max of FLOPs / tensor peak and algorithmic bytes / HBM peak), their measured time, and their algorithmic bytes."""
+    roof, ms, by = ctypes.c_double(), ctypes.c_double(), ctypes.c_double()
+    check(_lib.lib().ipdm_profile_roofline(PROF_FAMILIES.index(family), ctypes.c_double(peak_tflops * 1e12), ctypes.c_double(peak_gbs * 1e9),
+                                           ctypes.byref(roof), ctypes.byref(ms), ctypes.byref(by)), "ipdm_profile_roofline")
+    return roof.value, ms.value, by.value
+
+
 # ---------------------------------------------------------------------------------------------
 # FBP convertor
 # ---------------------------------------------------------------------------------------------

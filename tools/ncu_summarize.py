@@ -7,7 +7,7 @@ from collections import defaultdict
 
 def family(name):
     for key, fam in (("conv_tc_persistent", "conv_tc persistent (tcgen05 implicit GEMM)"), ("conv_thin", "conv_thin (tcgen05, thin layers)"),
-                     ("conv_halo_persistent", "conv_halo_persistent (tcgen05, halo reuse, persistent)"), ("conv_halo", "conv_halo one-tile (tcgen05, N=16 layers)"),
+                     ("conv_halo_persistent", "conv_halo_persistent (tcgen05, halo reuse, persistent)"), ("conv_halo_fused", "conv_halo_fused (tcgen05, halo reuse, persistent, GroupNorm+SiLU on the operand path; width-folded thin layers, upsample phases)"), ("conv_halo", "conv_halo one-tile (tcgen05, N=16 layers)"),
                      ("conv_small", "conv_small (streaming 1x1 / stride-2 / stem)"), ("conv_tc_kernel", "conv_tc one-tile (qkv / split)"), ("attention_pipe", "attention (tcgen05 flash, pipelined S/P/O)"), ("attention_kernel", "attention (tcgen05 flash, serial / 3xTF32)"),
                      ("conv_fixed", "conv_fixed (unrolled streaming 1x1 / stride-2)"), ("gn_tile_reduce", "groupnorm fold of epilogue statistics"),
                      ("conv_direct_kernel", "conv_direct"), ("gn_partial", "groupnorm stats"), ("gn_finalize", "groupnorm finalize"),
