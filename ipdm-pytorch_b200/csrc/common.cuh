@@ -109,6 +109,7 @@ __device__ __forceinline__ float silu(float x) {
     return x * r;
 }
 
+__device__ __forceinline__ float tanh_approx(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
 __device__ __forceinline__ float tf32_rn(float x) {

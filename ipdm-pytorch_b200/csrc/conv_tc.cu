@@ -321,6 +321,15 @@ struct EpilogueRow {
 #pragma unroll
         for (int j = 0; j < NJ; ++j)
             rres[j] = (has_res && nok && ((vmask >> j) & 1u)) ? ld_stream(reinterpret_cast<const float4*>(rbase + (ro + cc + j * rstep))) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (cc == 0 && has_res && BLOCK_N > CHUNK) {
+            // the lines of the later chunks go to L2 now (no registers to hold them): their loads then cost an L2 hit, not an HBM round trip
+#pragma unroll
+            for (int c2 = CHUNK; c2 < BLOCK_N; c2 += CHUNK)
+#pragma unroll
+                for (int j = 0; j < NJ; ++j)
+                    if (((vmask >> j) & 1u) && n0 + c2 + c4 < P.cout)
+                        asm volatile("prefetch.global.L2 [%0];" :: "l"(rbase + (ro + c2 + j * rstep)));
+        }
     }
     __device__ __forceinline__ void run(const ConvTcParams& P, uint32_t tmem_acc, int quarter, int lane, const float* sbias, float* stile, float* stats_row) {
 #pragma unroll 1
@@ -1025,7 +1034,7 @@ struct HaloFusedSmem {
     static constexpr int EPI_OFF = BIAS_OFF + MAX_COUT * 4;
     static constexpr int TOTAL = EPI_OFF + 8 * EPI_WARP_FLOATS * 4 + 1024;
     static_assert((2 * NB + 4 * NA + 6) * 8 + 16 <= 512, "barrier block");
-    static_assert(!BF16 || NA == 2, "the bf16 variant has two operand buffers");
+
 };
 
 // NA = depth of the raw-tile ring (TF32: the tiles are transformed in place, so it is also the operand ring).  Layers with few K
@@ -1222,8 +1231,9 @@ conv_halo_fused_kernel(const __grid_constant__ ConvTcParams P) {
                 tc::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + buf * 2 * ACC_COLS;
                 for (int kc = 0; kc < nk; ++kc, ++ia) {                              // (dense layers only: masked ones take the lean path above)
-                    const int sa = ia % NA;
-                    tc::mbar_wait(&a_ready[sa], (uint32_t)(ia / NA) & 1u);
+                    // operand slot: the bf16 form has two operand buffers whatever the depth NA of the raw ring; tf32 tiles are transformed in place
+                    const int sa = BF16 ? (ia & 1) : ia % NA;
+                    tc::mbar_wait(&a_ready[sa], (uint32_t)(BF16 ? ia >> 1 : ia / NA) & 1u);
                     const uint32_t a_base = tc::smem_u32(smem + (BF16 ? S::OFF_OP + sa * HF_OP_STRIDE_BF16 : sa * S::RAW_STRIDE));
                     const uint32_t tm = P.tapmask[phase()];
                     const int tap0 = __ffs(tm) - 1;                          // the first MMA of a tile overwrites the accumulators
@@ -1284,7 +1294,9 @@ conv_halo_fused_kernel(const __grid_constant__ ConvTcParams P) {
                 inmask |= ((unsigned)yy < (unsigned)P.H && (unsigned)xx < (unsigned)P.W ? 1u : 0u) << j;
             }
             for (int kc = 0; kc < nk; ++kc, ++ia) {
-                const int sa = ia % NA;
+                const int sa = ia % NA;                                              // raw slot
+                const int so = BF16 ? (ia & 1) : sa;                                 // operand slot (bf16: two buffers; tf32: in place)
+                const uint32_t pho = (uint32_t)(BF16 ? ia >> 1 : ia / NA) & 1u;
                 // per-lane affine of its 4 channels (pad channels of the source tensors: scale = shift = 0 -> silu(0) = 0)
                 float4 sc = make_float4(0.f, 0.f, 0.f, 0.f), sh = sc;
                 const bool ident = kc >= P.nk_gn || P.gn_act == 5;                   // shortcut chunk / plain conv: x itself, rounded to the operand type
@@ -1305,7 +1317,7 @@ conv_halo_fused_kernel(const __grid_constant__ ConvTcParams P) {
                 if (w4 == 0) tc::mbar_wait_idle(&raw_full[sa], (uint32_t)(ia / NA) & 1u);
                 tc::named_bar_sync(1, HF_TWARPS * 32);
                 const uint32_t raw_s = tc::smem_u32(smem + sa * S::RAW_STRIDE);
-                const uint32_t op_s = tc::smem_u32(smem + S::OFF_OP + sa * HF_OP_STRIDE_BF16);
+                const uint32_t op_s = tc::smem_u32(smem + S::OFF_OP + so * HF_OP_STRIDE_BF16);
                 // A lane owns 10 pixels x 4 channels of the chunk: all ten loads are issued before the first SiLU so that the shared-memory and
                 // MUFU latencies overlap (explicit ld/st.shared: generic accesses made the compiler serialise load -> store -> load).  BF16: the
                 // raw slot goes back to the TMA producer as soon as the values sit in registers -- the 64-channel layers are bound by bytes in
@@ -1318,7 +1330,7 @@ conv_halo_fused_kernel(const __grid_constant__ ConvTcParams P) {
                 if (BF16) {
                     __syncwarp();
                     if (lane == 0) tc::mbar_arrive(&raw_empty[sa]);                      // raw tile consumed (its values live in registers)
-                    if (w4 == 0) tc::mbar_wait_idle(&a_empty[sa], ((uint32_t)(ia / NA) & 1u) ^ 1u);      // the operand buffer of this stage is free
+                    if (w4 == 0) tc::mbar_wait_idle(&a_empty[so], pho ^ 1u);                            // the operand buffer of this stage is free
                     tc::named_bar_sync(1, HF_TWARPS * 32);
                 }
                 if (work) {
@@ -1333,7 +1345,17 @@ conv_halo_fused_kernel(const __grid_constant__ ConvTcParams P) {
                             tc::sts128_or_zero(raw_s + roff[j], make_float4(tf32_rn_hw(o.x), tf32_rn_hw(o.y), tf32_rn_hw(o.z), tf32_rn_hw(o.w)), inside);
                         }
                     };
-                    if (do_silu) {
+                    if (do_silu && BF16 && P.silu_tanh) {
+                        // bf16 operands: silu(y) = h + h * tanh(h), h = y / 2 -- ONE MUFU (tanh.approx, |error| <= 2^-11) and two FMAs per element
+                        // instead of ex2 + rcp and four; the approximation error stays below the bf16 rounding of the operand that follows
+                        const float4 sch = make_float4(0.5f * sc.x, 0.5f * sc.y, 0.5f * sc.z, 0.5f * sc.w), shh = make_float4(0.5f * sh.x, 0.5f * sh.y, 0.5f * sh.z, 0.5f * sh.w);
+#pragma unroll
+                        for (int j = 0; j < PER; ++j) {
+                            float4 h;
+                            h.x = fmaf(v[j].x, sch.x, shh.x); h.y = fmaf(v[j].y, sch.y, shh.y); h.z = fmaf(v[j].z, sch.z, shh.z); h.w = fmaf(v[j].w, sch.w, shh.w);
+                            emit(j, make_float4(fmaf(h.x, tanh_approx(h.x), h.x), fmaf(h.y, tanh_approx(h.y), h.y), fmaf(h.z, tanh_approx(h.z), h.z), fmaf(h.w, tanh_approx(h.w), h.w)));
+                        }
+                    } else if (do_silu) {
 #pragma unroll
                         for (int j = 0; j < PER; ++j) {
                             float4 y, e;
@@ -1350,7 +1372,7 @@ conv_halo_fused_kernel(const __grid_constant__ ConvTcParams P) {
                 }
                 tc::fence_proxy_async();                 // generic-proxy writes -> visible to the tensor core's async proxy
                 __syncwarp();
-                if (lane == 0) tc::mbar_arrive(&a_ready[sa]);
+                if (lane == 0) tc::mbar_arrive(&a_ready[so]);
             }
         }
     } else if (warp >= 4 && warp < 12) {
@@ -1578,6 +1600,8 @@ int conv_tc_prepare(ConvTcParams& P, const ConvTcDesc& d) {
     P.out_lo = d.out_lo; P.vt_lo = d.vt_lo; P.qkv_bf16 = d.qkv_bf16;
     IPDM_REQUIRE(!d.n_ident || (P.fused && !d.passthrough && d.stride == 1), "conv_tc: a folded shortcut needs the GroupNorm-fused halo kernel");
     P.bias_mod = d.bias_mod; P.fold = d.fold;
+    static const bool silu_tanh = !(getenv("IPDM_SILU_TANH") && atoi(getenv("IPDM_SILU_TANH")) == 0);
+    P.silu_tanh = silu_tanh;
     P.masked = 0;
     for (int t = 0; t < 9; ++t) { P.kmask[t] = d.kmask[t]; if (d.kmask[t]) P.masked = 1; }
     IPDM_REQUIRE(!P.masked || (P.halo && P.persistent && !P.bf16 && d.ntaps == 9 && P.nk0 + P.nk1 + P.nk2 <= 16),
@@ -1644,7 +1668,14 @@ int conv_tc_launch(const ConvTcParams& P, cudaStream_t st) {
     ProfScope prof(P.fold ? PROF_CONV_DIRECT : (P.halo && P.persistent ? PROF_CONV_HALO_PERS : PROF_CONV_TC), st,
                    P.fold ? 4.0 * P.batch * (double)P.H * P.W * ((P.nk0 + P.nk1 + P.nk2) * P.kc + P.cout) : conv_tc_flops(P), abytes);
     if (P.fused) {
-        if (P.bf16) { if (P.block_n == 128) return launch_halo_fused<128, 8, true>(P, st); if (P.block_n == 64) return launch_halo_fused<64, 12, true>(P, st); }
+        if (P.bf16) {
+            // N = 64 (image net, HBM-bound: 3.2 GB per launch): a third raw slot instead of half of the weight ring -- bytes in flight bound these layers
+            // (IPDM_RAW3=1, measured at 16 x 512 x 512: 64 -> 64 0.735 -> 0.751 ms, 128 -> 64 1.811 -> 1.787 ms: these layers are not bound by
+            // bytes in flight but by the transform stage, so the deeper weight ring stays the default)
+            static const bool raw3 = getenv("IPDM_RAW3") && atoi(getenv("IPDM_RAW3")) == 1;
+            if (P.block_n == 128) return launch_halo_fused<128, 8, true>(P, st);
+            if (P.block_n == 64) return raw3 ? launch_halo_fused<64, 6, true, 3>(P, st) : launch_halo_fused<64, 12, true>(P, st);
+        }
         else {
             if (P.block_n == 128) return launch_halo_fused<128, 6, false>(P, st);
             if (P.block_n == 64) return P.masked ? launch_halo_fused<64, 6, false, 3>(P, st) : launch_halo_fused<64, 10, false>(P, st);

@@ -75,6 +75,7 @@ struct ConvTcParams {
     float* stats_out; int stats_rows;                  // set by prepare only for the persistent kernels (else nullptr / 0)
     int fused; const float* gn_scale; const float* gn_shift; int gn_c0, gn_c1, gn_act;    // conv_halo_fused_kernel
     uint64_t kmask[9]; int gn_m0, gn_m1, bias_mod, masked, fold;                          // width-folded thin layers
+    int silu_tanh;                                                                        // bf16 operand path: SiLU through tanh.approx (one MUFU)
     int ph_log2; uint32_t tapmask[4];                                                     // upsample conv phases: tap positions used by each
     double flops;                                                                         // MMA work issued per launch (prepare)
 };
