@@ -15,9 +15,12 @@
 // Operands are fp32 words rounded to TF32 (kind::tf32; tf32 and fp32 modes, K chunk = 32 channels) or bf16 (kind::f16;
 // bf16 mode, K chunk = 64 channels); accumulation is fp32 in TMEM in every mode.
 //
-// Four kernels share this file (conv_tc_prepare picks one per layer, see there):
-//   conv_halo_persistent_kernel  stride-1 3x3, the dominant kernel: one halo tile per K chunk feeds all nine taps, persistent
-//                                CTAs, double-buffered accumulator pairs, two epilogue warpgroups          (~0.8 of the bf16 peak)
+// Five kernels share this file (conv_tc_prepare picks one per layer, see there):
+//   conv_halo_fused_kernel       the dominant kernel (round 2): GroupNorm + SiLU -> stride-1 3x3 as ONE launch over the raw fp32 tensors
+//                                (operand transform warps between TMA and MMA), the width-folded thin layers of the 2000x912 / 1000x456
+//                                levels (with the ResBlock shortcut as identity K chunks), the Upsample convs as four output-parity phases
+//   conv_halo_persistent_kernel  stride-1 3x3 from an operand tensor: one halo tile per K chunk feeds all nine taps, persistent
+//                                CTAs, double-buffered accumulator pairs, two epilogue warpgroups    (0.82-0.84 of the sustained bf16 peak)
 //   conv_tc_persistent_kernel    per-tap variant for 1x1 / stride-2 / small images (L2 -> SM bound on 3x3 layers)
 //   conv_halo_kernel             one halo tile per CTA, for the N = 16 layer
 //   conv_tc_kernel               one tile per CTA: the 3xTF32 split of the fp32 mode and the qkv epilogue
