@@ -208,6 +208,7 @@ __device__ __forceinline__ void tc_epilogue(const ConvTcParams& P, uint32_t tmem
 // so that 8 lanes cover one pixel's 128 contiguous bytes: every global load (residual) and store is a full line.
 constexpr int EPI_PITCH = 36;
 constexpr int EPI_WARP_FLOATS = 32 * EPI_PITCH;
+constexpr int EPI_ROW_BYTES = 32 * 128;               // EpilogueRow: one [32 px][32 ch] SWIZZLE_128B tile per warp
 template <int BLOCK_N, int CHUNK_W = 32>
 __device__ __forceinline__ void tc_epilogue_coalesced(const ConvTcParams& P, uint32_t tmem_acc, int quarter, int lane, int b, int x0, int y0,
                                                       int n0, const float* sbias, float* stile, int tw_valid, float* stats_row) {
@@ -295,14 +296,14 @@ template <int BLOCK_N, int CHUNK_W = 32>
 struct EpilogueRow {
     static constexpr int CHUNK = BLOCK_N < 32 ? 16 : CHUNK_W;
     static constexpr int LPP = CHUNK / 4, PPI = 32 / LPP, NJ = 32 / PPI;
-    int c4, psub, nvalid, n0, ostep, rstep, oo, ro; uint32_t vmask; bool has_res;
+    int c4, psub, nvalid, n0, ostep, rstep, oo, ro, tx0, tpy, tb; uint32_t vmask; bool has_res;
     size_t pix0; float* obase; const float* rbase;
     float4 rres[NJ];                                   // residual lines of the chunk being processed
 
     // coordinates of this warp's row (pixels x0 .. x0+31 of image row py of slice b, output channels n0 ...)
     // ph: output-parity phase of an upsample conv (ph_log2 = 2): tile pixel (py, x) is output pixel (2 py + ph / 2, 2 x + ph % 2)
     __device__ __forceinline__ void setup(const ConvTcParams& P, int lane, int b, int x0, int py, int n0_, int tw_valid, int ph = 0) {
-        c4 = (lane % LPP) * 4; psub = lane / LPP; n0 = n0_;
+        c4 = (lane % LPP) * 4; psub = lane / LPP; n0 = n0_; tx0 = x0; tpy = py; tb = b;
         nvalid = py < P.H ? min(tw_valid, P.W - x0) : 0;
         vmask = 0;                                     // bit j: pixel j * PPI + psub is an output
 #pragma unroll
@@ -334,7 +335,15 @@ struct EpilogueRow {
                         asm volatile("prefetch.global.L2 [%0];" :: "l"(rbase + (ro + c2 + j * rstep)));
         }
     }
+    // Staging tile: [32 px][128 B] with the 128-byte swizzle (16-byte chunk ^ (pixel & 7)) -- conflict-free both for the lane-per-pixel
+    // writes of the accumulator rows and for the 8-lanes-per-pixel reads, and exactly the layout a SWIZZLE_128B tensor map stores from:
+    // with P.tma_store the finished values go back into the tile and ONE cp.async.bulk.tensor per chunk writes the 30 x 32-channel box
+    // (TMA clips at the image edge); otherwise the lanes store full lines themselves (upsample phases: strided pixels; N = 16 tiles).
     __device__ __forceinline__ void run(const ConvTcParams& P, uint32_t tmem_acc, int quarter, int lane, const float* sbias, float* stile, float* stats_row) {
+        const uint32_t st = tc::smem_u32(stile);
+        const bool tma = P.tma_store && CHUNK == 32;
+        const uint32_t wr = st + (uint32_t)lane * 128u;                       // this lane's pixel row (staging writes)
+        const int q = lane % LPP;                                             // 16-byte chunk this lane reads back
 #pragma unroll 1
         for (int cc = 0; cc < BLOCK_N; cc += CHUNK) {
             const int n = n0 + cc + c4;
@@ -348,23 +357,32 @@ struct EpilogueRow {
                 for (int i = 0; i < 16; ++i) r[i] = r16[i]; }
             if (cc > 0) load_res(P, cc);
             tc::tmem_ld_wait();
+            if (tma && lane == 0) tc::tma_store_wait_read();   // the previous chunk's bulk store has read the tile
             __syncwarp();                              // previous chunk's readers are done with the tile
-            float4* row = reinterpret_cast<float4*>(stile + lane * EPI_PITCH);
 #pragma unroll
             for (int i = 0; i < CHUNK / 4; ++i)
-                row[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+                tc::sts128(wr + (uint32_t)((i ^ (lane & 7)) << 4),
+                           make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3])));
             __syncwarp();
             const float4 bq = *reinterpret_cast<const float4*>(sbias + cc + c4);
             float4 ss = make_float4(0.f, 0.f, 0.f, 0.f), sq = ss;          // GroupNorm partials of this lane's 4 channels
 #pragma unroll
             for (int j = 0; j < NJ; ++j) {
                 if ((vm >> j) & 1u) {
-                    float4 v = *reinterpret_cast<const float4*>(stile + (j * PPI + psub) * EPI_PITCH + c4);
+                    const int p = j * PPI + psub;
+                    const uint32_t at = st + (uint32_t)p * 128u + (uint32_t)((q ^ (p & 7)) << 4);
+                    float4 v = tc::lds128(at);
                     v.x += bq.x + rres[j].x; v.y += bq.y + rres[j].y; v.z += bq.z + rres[j].z; v.w += bq.w + rres[j].w;
-                    st_stream(reinterpret_cast<float4*>(obase + (oo + cc + j * ostep)), v);
+                    if (tma) tc::sts128(at, v);
+                    else st_stream(reinterpret_cast<float4*>(obase + (oo + cc + j * ostep)), v);
                     ss.x += v.x; ss.y += v.y; ss.z += v.z; ss.w += v.w;
                     sq.x = fmaf(v.x, v.x, sq.x); sq.y = fmaf(v.y, v.y, sq.y); sq.z = fmaf(v.z, v.z, sq.z); sq.w = fmaf(v.w, v.w, sq.w);
                 }
+            }
+            if (tma) {
+                tc::fence_proxy_async();               // generic-proxy writes of the tile -> visible to the TMA engine
+                __syncwarp();
+                if (lane == 0 && nvalid > 0) tc::tma_store_4d(&P.mapOut, st, n0 + cc, tx0, tpy, tb);
             }
             if (stats_row) {
 #pragma unroll
@@ -830,8 +848,8 @@ struct HaloPersSmem {
     static constexpr int BAR_OFF = OFF_B + NB * B_BYTES;
     static constexpr int BIAS_OFF = BAR_OFF + 512;
     static constexpr int MAX_COUT = 768;
-    static constexpr int EPI_OFF = BIAS_OFF + MAX_COUT * 4;
-    static constexpr int TOTAL = EPI_OFF + 8 * EPI_WARP_FLOATS * 4 + 1024;
+    static constexpr int EPI_OFF = (BIAS_OFF + MAX_COUT * 4 + 1023) / 1024 * 1024;      // 8 x [32 px][128 B] SWIZZLE_128B tiles (EpilogueRow)
+    static constexpr int TOTAL = EPI_OFF + 8 * EPI_ROW_BYTES + 1024;
     static_assert((2 * NB + 8) * 8 + 16 <= 512, "barrier block");
 };
 
@@ -977,7 +995,7 @@ conv_halo_persistent_kernel(const __grid_constant__ ConvTcParams P) {
         __syncwarp();
     } else if (warp >= 4) {
         const int mt = (warp - 4) >> 2;                              // warpgroup <-> accumulator (tile rows 4*mt .. 4*mt+3)
-        float* stile = (float*)(smem + S::EPI_OFF) + (warp - 4) * EPI_WARP_FLOATS;
+        float* stile = (float*)(smem + S::EPI_OFF + (warp - 4) * EPI_ROW_BYTES);
         int tl = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
             const int buf = tl & 1;
@@ -996,6 +1014,7 @@ conv_halo_persistent_kernel(const __grid_constant__ ConvTcParams P) {
             tc::tc_fence_before();
             tc::mbar_arrive(&tempty[buf]);
         }
+        if (lane == 0) tc::tma_store_wait_all();                     // the staging tile must outlive its last bulk store
     }
     tc::tc_fence_before();
     __syncthreads();
@@ -1034,8 +1053,8 @@ struct HaloFusedSmem {
     static constexpr int BAR_OFF = OFF_B + NB * B_BYTES;
     static constexpr int BIAS_OFF = BAR_OFF + 512;
     static constexpr int MAX_COUT = 512;
-    static constexpr int EPI_OFF = BIAS_OFF + MAX_COUT * 4;
-    static constexpr int TOTAL = EPI_OFF + 8 * EPI_WARP_FLOATS * 4 + 1024;
+    static constexpr int EPI_OFF = (BIAS_OFF + MAX_COUT * 4 + 1023) / 1024 * 1024;      // 8 x [32 px][128 B] SWIZZLE_128B tiles (EpilogueRow)
+    static constexpr int TOTAL = EPI_OFF + 8 * EPI_ROW_BYTES + 1024;
     static_assert((2 * NB + 4 * NA + 6) * 8 + 16 <= 512, "barrier block");
 
 };
@@ -1331,6 +1350,15 @@ conv_halo_fused_kernel(const __grid_constant__ ConvTcParams P) {
                     for (int j = 0; j < PER; ++j) v[j] = tc::lds128(raw_s + roff[j]);
                 }
                 if (BF16) {
+                    // The slot goes back to the TMA producer only when the loaded values HAVE ARRIVED in registers: ld.shared is asynchronous
+                    // and mbarrier.arrive does not wait for it, so every lane first consumes one word of each of its loads (an intermittent
+                    // whole-tile corruption in the bf16 mode was traced to the producer overwriting a tile with loads still in flight).
+                    if (work) {
+                        uint32_t dep = 0;
+#pragma unroll
+                        for (int j = 0; j < PER; ++j) dep ^= __float_as_uint(v[j].x) ^ __float_as_uint(v[j].w);
+                        asm volatile("" :: "r"(dep) : "memory");
+                    }
                     __syncwarp();
                     if (lane == 0) tc::mbar_arrive(&raw_empty[sa]);                      // raw tile consumed (its values live in registers)
                     if (w4 == 0) tc::mbar_wait_idle(&a_empty[so], pho ^ 1u);                            // the operand buffer of this stage is free
@@ -1380,7 +1408,7 @@ conv_halo_fused_kernel(const __grid_constant__ ConvTcParams P) {
         }
     } else if (warp >= 4 && warp < 12) {
         const int mt = (warp - 4) >> 2;
-        float* stile = (float*)(smem + S::EPI_OFF) + (warp - 4) * EPI_WARP_FLOATS;
+        float* stile = (float*)(smem + S::EPI_OFF + (warp - 4) * EPI_ROW_BYTES);
         int tl = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl, walk.next()) {
             const int buf = tl & 1;
@@ -1400,6 +1428,7 @@ conv_halo_fused_kernel(const __grid_constant__ ConvTcParams P) {
             tc::tc_fence_before();
             tc::mbar_arrive(&tempty[buf]);
         }
+        if (lane == 0) tc::tma_store_wait_all();                     // the staging tile must outlive its last bulk store
     }
     tc::tc_fence_before();
     __syncthreads();
@@ -1623,6 +1652,16 @@ int conv_tc_prepare(ConvTcParams& P, const ConvTcDesc& d) {
         // an upsample conv counts as the 3x3 conv on the upsampled image that it replaces (the algorithmic work of the layer):
         // 9 taps x 4 output pixels per source pixel; the tensor pipe issues 16/36 of that
         P.flops = 2.0 * P.batch * P.H * P.W * (double)P.cout * ksteps * kel * (P.ph_log2 ? 9.0 : 1.0);
+    }
+    // TMA-store epilogue of the persistent halo kernels: a [30 px][32 ch] box of one output row per warp and chunk (EpilogueRow)
+    static const bool tma_store_off = getenv("IPDM_TMA_STORE") && atoi(getenv("IPDM_TMA_STORE")) == 0;
+    P.tma_store = 0;
+    if (!tma_store_off && P.halo && P.persistent && !d.phase_up && !d.qkv_mode && P.block_n >= 32 && d.cout % 32 == 0 && ((uintptr_t)d.out.p % 16) == 0) {
+        const uint64_t od[4] = {(uint64_t)d.out.cs, (uint64_t)d.out.w, (uint64_t)d.out.h, (uint64_t)d.out.n};
+        const uint64_t os[3] = {(uint64_t)d.out.cs * 4, (uint64_t)d.out.w * d.out.cs * 4, (uint64_t)d.out.h * d.out.w * d.out.cs * 4};
+        const uint32_t ob[4] = {32, HALO_TWV, 1, 1};
+        IPDM_CHECK(tmap_encode(&P.mapOut, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, d.out.p, od, os, ob, CU_TENSOR_MAP_SWIZZLE_128B));
+        P.tma_store = 1;
     }
     P.stats_out = P.persistent ? d.stats_out : nullptr;              // only the persistent kernels' epilogue produces statistics
     P.stats_rows = P.stats_out ? (P.tiles_x * P.tiles_y * (P.halo ? 2 : 1) * 4) << P.ph_log2 : 0;

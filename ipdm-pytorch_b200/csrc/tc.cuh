@@ -117,6 +117,16 @@ __device__ __forceinline__ void tma_load_4d(void* smem, const CUtensorMap* m, ui
                  :: "r"(smem_u32(smem)), "l"((uint64_t)m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 
+// TMA store of a shared-memory tile (generic-proxy writes must be fenced with fence_proxy_async first) as one bulk async-group;
+// tma_store_wait_read: the tile may be overwritten (the engine has read it), not that the bytes are globally visible
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, uint32_t saddr, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 :: "l"((uint64_t)m), "r"(saddr), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // ---- tensor memory -------------------------------------------------------------------------
 // one full warp allocates `ncols` (power of two >= 32) columns and publishes the base address in smem
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {

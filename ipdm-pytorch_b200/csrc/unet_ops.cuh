@@ -63,6 +63,7 @@ bool conv_tc_can_fuse_norm(int H, int W, int batch, int cout, int ntaps, int str
 struct ConvTcParams {
     CUtensorMap mapA[4];
     CUtensorMap mapB, mapBlo;
+    CUtensorMap mapOut; int tma_store;                 // halo kernels: the epilogue stores [30 px][32 ch] boxes of the output by TMA
     int split, bf16, kc, halo, persistent;
     int H, W, tiles_x, tiles_y, tw_log2, batch;
     int ntaps, stride, nk0, nk1, nk2, nk_gn;           // K chunks per source; chunks >= nk_gn are identity (shortcut) chunks
