@@ -276,6 +276,13 @@ int ipdm_debug_attention(const float* qk_dev, const float* vt_dev, const float* 
 /* the bf16 operand mode of the same kernel: qk_dev [B][T][3C] and vt_dev [B][heads][64][t_pad] hold bf16, t_pad % 8 == 0 */
 int ipdm_debug_attention_bf16(const void* qk_dev, const void* vt_dev, float* out_dev, int batch, int T, int t_pad, int heads, int C,
                               void* stream);
+/* Host-only: the width-folded weights of a thin layer ([tap][f*C_out][f*(c0+c1)], tf32-rounded, + the masks of the structurally non-zero
+ * 8-column k-steps) and the four-phase weights of an Upsample conv ([phase 4][tap 9][C_out][round_up(C_in, 32)]) -- the two weight
+ * transformations behind ConvTcDesc::fold / phase_up, exposed so that the CPU tests can check them against torch convolutions.
+ * out == NULL returns the dimensions only; fold_out == 0 means the shape has no folded form. */
+int ipdm_debug_fold_pack(const float* w_host, int cout, int c0, int c1, int k, float* out, unsigned long long* masks_out,
+                         int* fold_out, int* n_out, int* k_out);
+int ipdm_debug_phase_pack(const float* w_host, int cout, int cin, float* out, int* k_out);
 int ipdm_debug_upsample(const float* src_dev, int n, int hs, int ws, int cs, float* dst_dev, int hd, int wd, void* stream);
 
 #ifdef __cplusplus

@@ -39,6 +39,9 @@ _SIGNATURES = {
     "ipdm_launch_count_reset": (None, []),
     "ipdm_profile_enable": (None, [ctypes.c_int]),
     "ipdm_profile_collect": (ctypes.c_int, [c_double_p, c_double_p, ctypes.POINTER(ctypes.c_longlong)]),
+    "ipdm_debug_fold_pack": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, ctypes.POINTER(ctypes.c_int),
+                                            ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]),
+    "ipdm_debug_phase_pack": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, vp, ctypes.POINTER(ctypes.c_int)]),
     "ipdm_profile_roofline": (ctypes.c_int, [ctypes.c_int, ctypes.c_double, ctypes.c_double, c_double_p, c_double_p, c_double_p]),
     "ipdm_fbp_plan_create": (ctypes.c_int, [ctypes.POINTER(vp), ctypes.c_int]),
     "ipdm_fbp_plan_destroy": (ctypes.c_int, [vp]),

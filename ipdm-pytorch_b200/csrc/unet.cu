@@ -251,14 +251,13 @@ static int fold_factor(const int* cs, int nsrc, int cout) {
 
 // General form: the folded conv reads `nsrc` dense sources of cs[s] channels; source s is contracted with wsrc[s] (a 3x3 conv, or a
 // 1x1 conv = the ResBlock shortcut folded into conv2: centre tap, same pixel only), whose input channels ci_off[s] ... belong to it.
-static int pack_fold_multi(ipdm_unet* net, ConvW& c, int nsrc, const int* cs, const ConvW* const* wsrc, const int* ci_off, const float* bias_host) {
-    c.fold = 0;
-    if (!(net->precision == IPDM_PREC_BF16 || net->force_fold)) return IPDM_OK;
+// host part: folded weights p = [tap][f * C_out][f * sum(cs)] and the k-step masks; returns the fold factor (0: shape not eligible)
+static int fold_pack_host(ConvW& c, int nsrc, const int* cs, const ConvW* const* wsrc, const int* ci_off, std::vector<float>& p) {
     const int f = fold_factor(cs, nsrc, c.cout);
-    if (!f) return IPDM_OK;
+    if (!f) return 0;
     int ctot = 0; for (int s = 0; s < nsrc; ++s) ctot += cs[s];
     const int kmain = wsrc[0]->k, N = f * c.cout, K = f * ctot, nt = kmain == 3 ? 9 : 1;
-    std::vector<float> p((size_t)nt * N * K, 0.f);
+    p.assign((size_t)nt * N * K, 0.f);
     for (int t = 0; t < 9; ++t) c.fold_mask[t] = 0;
     for (int tap = 0; tap < nt; ++tap) {
         const int dy = kmain == 3 ? tap / 3 : 1, bdx = kmain == 3 ? tap % 3 : 1;
@@ -283,9 +282,19 @@ static int pack_fold_multi(ipdm_unet* net, ConvW& c, int nsrc, const int* cs, co
             col0 += f * cs[s];
         }
     }
+    c.fold_c0 = cs[0]; c.fold_c1 = nsrc > 1 ? cs[1] : 0; c.fold_c2 = nsrc > 2 ? cs[2] : 0; c.fold_k = K;
+    return f;
+}
+
+static int pack_fold_multi(ipdm_unet* net, ConvW& c, int nsrc, const int* cs, const ConvW* const* wsrc, const int* ci_off, const float* bias_host) {
+    c.fold = 0;
+    if (!(net->precision == IPDM_PREC_BF16 || net->force_fold)) return IPDM_OK;
+    std::vector<float> p;
+    const int f = fold_pack_host(c, nsrc, cs, wsrc, ci_off, p);
+    if (!f) return IPDM_OK;
     IPDM_CHECK(upload(net, p, &c.w_dev_fold));
     if (bias_host && !c.b_dev) IPDM_CHECK(upload(net, std::vector<float>(bias_host, bias_host + c.cout), &c.b_dev));
-    c.fold = f; c.fold_c0 = cs[0]; c.fold_c1 = nsrc > 1 ? cs[1] : 0; c.fold_c2 = nsrc > 2 ? cs[2] : 0; c.fold_k = K;
+    c.fold = f;
     return IPDM_OK;
 }
 
@@ -347,12 +356,9 @@ static int pack_conv2_shortcut(ipdm_unet* net, ResW& w, int c0, int c1) {
 // (ConvTcDesc::phase_up).  Output row 2i+py reads upsampled rows 2i+py-1 .. 2i+py+1 = source rows floor((2i+py+ky-1)/2): for py = 0
 // {i-1: ky 0; i: ky 1, 2}, for py = 1 {i: ky 0, 1; i+1: ky 2}; columns alike.  In halo-tile coordinates (origin (i-1, j-1)) phase
 // (py, px) uses the tap positions (py + a, px + b), a, b in {0, 1}, with the sums of the 3x3 weights that land there.
-static int pack_phase(ipdm_unet* net, ConvW& c) {
-    static const bool off = getenv("IPDM_PHASE_UP") && atoi(getenv("IPDM_PHASE_UP")) == 0;
-    c.w_dev_phase = nullptr;
-    if (off || !c.tc || c.k != 3 || net->precision == IPDM_PREC_FP32 || c.cout % 64 != 0) return IPDM_OK;
+static void phase_pack_host(const ConvW& c, std::vector<float>& p) {          // p = [phase 4][tap 9][C_out][round_up(C_in, 32)], fp32 sums
     const int K = round_up(c.cin, 32);
-    std::vector<float> p((size_t)4 * 9 * c.cout * K, 0.f);
+    p.assign((size_t)4 * 9 * c.cout * K, 0.f);
     auto taps_of = [](int parity, int a, int* k) {           // 3x3 taps that land on source offset `a` of this parity; returns the count
         if (parity == 0) { if (a == 0) { k[0] = 0; return 1; } k[0] = 1; k[1] = 2; return 2; }
         if (a == 0) { k[0] = 0; k[1] = 1; return 2; } k[0] = 2; return 1;
@@ -373,6 +379,15 @@ static int pack_phase(ipdm_unet* net, ConvW& c) {
                     }
             }
     }
+}
+
+static int pack_phase(ipdm_unet* net, ConvW& c) {
+    static const bool off = getenv("IPDM_PHASE_UP") && atoi(getenv("IPDM_PHASE_UP")) == 0;
+    c.w_dev_phase = nullptr;
+    if (off || !c.tc || c.k != 3 || net->precision == IPDM_PREC_FP32 || c.cout % 64 != 0) return IPDM_OK;
+    const int K = round_up(c.cin, 32);
+    std::vector<float> p;
+    phase_pack_host(c, p);
     if (net->precision == IPDM_PREC_BF16) {
         std::vector<float> packed((p.size() + 1) / 2, 0.f);
         uint16_t* h = reinterpret_cast<uint16_t*>(packed.data());
@@ -1240,6 +1255,30 @@ extern "C" int ipdm_debug_conv_time(int c0, int c1, int n, int h, int w, int cou
     *ms_out = ms / iters;
     if (flops_out) *flops_out = 2.0 * n * ho * wo * (double)cw.cin * cout * k * k;
     cudaFree(s0); cudaFree(s1); cudaFree(out); cudaFree(res); cudaFree(nsc); cudaFree(nsh); cudaFree(tstats); cudaEventDestroy(a); cudaEventDestroy(b);
+    return IPDM_OK;
+}
+
+// Host-only views of the two weight transformations of round 2, for the CPU tests (tests/test_host.py): no device is touched.
+// out == nullptr: only the dimensions are returned.
+extern "C" int ipdm_debug_fold_pack(const float* w_host, int cout, int c0, int c1, int k, float* out, unsigned long long* masks_out,
+                                    int* fold_out, int* n_out, int* k_out) {
+    IPDM_REQUIRE(w_host && fold_out && n_out && k_out && (k == 1 || k == 3) && c0 > 0 && c1 >= 0 && cout > 0, "ipdm_debug_fold_pack: bad arguments");
+    ConvW cw; cw.cin = c0 + c1; cw.cout = cout; cw.k = k;
+    cw.w_host.assign(w_host, w_host + (size_t)cout * cw.cin * k * k);
+    const int cs[2] = {c0, c1}; const ConvW* ws[2] = {&cw, &cw}; const int off[2] = {0, c0};
+    std::vector<float> p;
+    const int f = fold_pack_host(cw, c1 ? 2 : 1, cs, ws, off, p);
+    *fold_out = f; *n_out = f * cout; *k_out = f * cw.cin;
+    if (f && out) memcpy(out, p.data(), p.size() * sizeof(float));
+    if (f && masks_out) for (int t = 0; t < 9; ++t) masks_out[t] = cw.fold_mask[t];
+    return IPDM_OK;
+}
+extern "C" int ipdm_debug_phase_pack(const float* w_host, int cout, int cin, float* out, int* k_out) {
+    IPDM_REQUIRE(w_host && k_out && cout > 0 && cin > 0, "ipdm_debug_phase_pack: bad arguments");
+    ConvW cw; cw.cin = cin; cw.cout = cout; cw.k = 3;
+    cw.w_host.assign(w_host, w_host + (size_t)cout * cin * 9);
+    *k_out = round_up(cin, 32);
+    if (out) { std::vector<float> p; phase_pack_host(cw, p); memcpy(out, p.data(), p.size() * sizeof(float)); }
     return IPDM_OK;
 }
 

@@ -163,3 +163,95 @@ def test_ddim_coefficients_follow_the_reference_formulas():
                 torch.sqrt(1.0 - a_t) / torch.sqrt(a_t), torch.sqrt(a_p), torch.tensor(0.0), eta * tab.at("posterior_variance", t),
                 torch.sqrt(1 - a_p - sig ** 2)]
         np.testing.assert_allclose(np.array(c, dtype=np.float64), np.array([float(w) for w in want]), rtol=3e-7, atol=1e-12)
+
+
+# ---- round 2: the two weight transformations behind the fused halo kernel, checked on the CPU against torch convolutions ----
+def _fold_pack(w, c0, c1):
+    import ctypes
+    import numpy as np
+    from ipdm_pytorch_b200 import _lib
+    L = _lib.lib()
+    cout, cin, k, _ = w.shape
+    wh = np.ascontiguousarray(w.numpy(), dtype=np.float32)
+    f, n, kk = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    _lib.check(L.ipdm_debug_fold_pack(wh.ctypes.data, cout, c0, c1, k, None, None, ctypes.byref(f), ctypes.byref(n), ctypes.byref(kk)), "fold_pack")
+    if f.value == 0:
+        return 0, None, None
+    nt = 9 if k == 3 else 1
+    out = np.zeros((nt, n.value, kk.value), dtype=np.float32)
+    masks = (ctypes.c_ulonglong * 9)()
+    _lib.check(L.ipdm_debug_fold_pack(wh.ctypes.data, cout, c0, c1, k, out.ctypes.data, masks, ctypes.byref(f), ctypes.byref(n), ctypes.byref(kk)), "fold_pack")
+    return f.value, out, [int(m) for m in masks]
+
+
+@pytest.mark.parametrize("c0,c1,cout,k", [(8, 0, 8, 3), (16, 0, 16, 3), (4, 0, 8, 3), (8, 0, 16, 3), (16, 8, 8, 3), (8, 4, 8, 3), (128, 16, 16, 3),
+                                         (16, 8, 8, 1), (8, 8, 8, 1), (16, 16, 16, 1)])
+def test_width_folded_weights_are_the_same_convolution(c0, c1, cout, k):
+    """pack_fold (csrc/unet.cu): a [H][W][C] tensor read as [H][W/f][f*C] and convolved with the folded weights gives the SAME result as the
+    3x3 / 1x1 convolution of the reference layer (Model/model.py:101, 113, 117), up to the tf32 rounding of the packed weights; the masks
+    name exactly the 8-column k-steps that can be non-zero."""
+    import numpy as np
+    import torch
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(c0 * 100 + c1 * 10 + cout + k)
+    C = c0 + c1
+    w = torch.randn(cout, C, k, k, generator=g) * 0.2
+    f, wf, masks = _fold_pack(w, c0, c1)
+    assert f in (2, 4, 8) and (f * cout) in (32, 64) and (f * c0) % 32 == 0 and (f * c1) % 32 == 0
+    H, W = 7, 6 * f
+    x = torch.randn(1, C, H, W, generator=g)
+    want = F.conv2d(x, w, padding=k // 2)
+    # folded input: sources one after the other, inside a source pixel-major (bi, ci)
+    parts, o = [], 0
+    for cs in (c0, c1):
+        if cs:
+            xs = x[:, o:o + cs]                                                  # [1, cs, H, W]
+            parts.append(xs.reshape(1, cs, H, W // f, f).permute(0, 4, 1, 2, 3).reshape(1, f * cs, H, W // f))
+            o += cs
+    xf = torch.cat(parts, 1)
+    wt = torch.from_numpy(wf)                                                    # [tap][N][K]
+    if k == 3:
+        wconv = wt.reshape(3, 3, f * cout, xf.shape[1]).permute(2, 3, 0, 1).contiguous()      # taps are (dy, folded dx)
+        got_f = F.conv2d(xf, wconv, padding=1)
+    else:
+        got_f = F.conv2d(xf, wt[0][:, :, None, None])
+    got = got_f.reshape(1, f, cout, H, W // f).permute(0, 2, 3, 4, 1).reshape(1, cout, H, W)   # output channel = (bo, co)
+    err = float((got - want).norm() / want.norm())
+    assert err < 6e-4, err                                                       # tf32-rounded weights (2^-11 relative)
+    # masks: bit 4 * chunk + kstep set  <=>  those 8 columns of that tap hold a non-zero weight (random weights: structure == values)
+    for tap in range(wt.shape[0]):
+        for ks in range(wt.shape[2] // 8):
+            nz = bool((wt[tap][:, 8 * ks:8 * ks + 8] != 0).any())
+            assert nz == bool((masks[tap] >> ks) & 1), (tap, ks)
+    if k == 3:
+        used = sum(bin(m).count("1") for m in masks)
+        assert used < 9 * (wt.shape[2] // 8)                                     # the left / right neighbours contribute one pixel each
+
+
+def test_upsample_conv_phase_weights_are_the_same_convolution():
+    """pack_phase (csrc/unet.cu): Upsample(nearest, 2x) + conv3x3 (reference Model/model.py:163-170) equals four 2x2-tap convolutions of
+    the low-resolution tensor, one per output parity, with the 3x3 taps summed per source pixel."""
+    import ctypes
+    import numpy as np
+    import torch
+    import torch.nn.functional as F
+    from ipdm_pytorch_b200 import _lib
+    g = torch.Generator().manual_seed(5)
+    cin, cout, H, W = 40, 64, 6, 9
+    w = torch.randn(cout, cin, 3, 3, generator=g) * 0.1
+    x = torch.randn(2, cin, H, W, generator=g)
+    want = F.conv2d(F.interpolate(x, size=(2 * H, 2 * W), mode="nearest"), w, padding=1)
+    wh = np.ascontiguousarray(w.numpy(), dtype=np.float32)
+    K = ctypes.c_int()
+    _lib.check(_lib.lib().ipdm_debug_phase_pack(wh.ctypes.data, cout, cin, None, ctypes.byref(K)), "phase_pack")
+    out = np.zeros((4, 9, cout, K.value), dtype=np.float32)
+    _lib.check(_lib.lib().ipdm_debug_phase_pack(wh.ctypes.data, cout, cin, out.ctypes.data, ctypes.byref(K)), "phase_pack")
+    wp = torch.from_numpy(out)[..., :cin]                                        # [phase][tap][cout][cin]
+    got = torch.zeros_like(want)
+    for ph in range(4):
+        py, px = ph >> 1, ph & 1
+        wk = wp[ph].reshape(3, 3, cout, cin).permute(2, 3, 0, 1).contiguous()    # tap positions of the halo tile (origin (i-1, j-1))
+        nz = {(dy, dx) for dy in range(3) for dx in range(3) if bool((wk[:, :, dy, dx] != 0).any())}
+        assert nz == {(py + a, px + b) for a in (0, 1) for b in (0, 1)}           # four of the nine tap positions
+        got[:, :, py::2, px::2] = F.conv2d(x, wk, padding=1)
+    assert float((got - want).norm() / want.norm()) < 1e-6
