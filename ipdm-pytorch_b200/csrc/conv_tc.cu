@@ -1036,8 +1036,9 @@ conv_halo_persistent_kernel(const __grid_constant__ ConvTcParams P) {
 //                   then fence.proxy.async + arrive on `a_ready`
 //   warp 1          MMA issuer: as conv_halo_persistent_kernel, operands from the transformed tile
 //   warps 4-11      two epilogue warpgroups (unchanged)
-// The per-(slice, channel) scale / shift come from gn_finalize (statistics from the producer conv's epilogue), so the results are
-// bit-identical to apply + conv.
+// The per-(slice, channel) scale / shift come from gn_finalize (statistics from the producer conv's epilogue).  The operand values equal
+// those of the unfused apply pass up to the last bit of the SiLU (exponent argument as one fma; bf16 mode: tanh.approx form) -- within the
+// operand rounding that follows, and checked against torch in tests/test_unet_kernels_gpu.py::test_tc_conv_fused_groupnorm.
 // ================================================================================================
 constexpr int HF_THREADS = 640;       // warps 0 weights TMA, 1 MMA, 2 TMEM alloc + raw-tile TMA, 4-11 epilogue, 12-19 transform
 constexpr int HF_TWARPS = 8;

@@ -223,8 +223,8 @@ def test_tc_conv_halo_reuse_variant(cuda, c0, c1, cout, k, stride, hw):
 def test_tc_conv_fused_groupnorm(cuda, c0, c1, cout, hw):
     """conv_halo_fused_kernel: GroupNorm affine + SiLU applied on the operand path of the persistent halo conv (raw fp32 sources,
     virtual concat, zero padding applied AFTER the activation, ragged edges, padded skip channels, one or two N tiles).
-    tf32 operands: bit-identical to the unfused pair (apply pass -> operand tensor -> conv_halo_persistent_kernel) and within the tf32
-    tolerance of torch; bf16 operands: within the bf16 tolerance."""
+    tf32 operands: within the tf32 tolerance of torch; bf16 operands: within the bf16 tolerance of torch and within 3e-4 of a torch conv
+    on bf16-rounded operands (the device SiLU is approximate: a few operands round to the neighbouring bf16 value)."""
     from ipdm_pytorch_b200 import _lib
     n, C = 2, c0 + c1
     x0 = rnd(n, c0, *hw, seed=1) + 0.3
